@@ -1,0 +1,278 @@
+"""TEST INFRASTRUCTURE: numpy model of the *device* algorithm (not of the reference).
+
+The CUDA pipeline in ``hcore_b200/csrc`` does not call LAPACK; it uses
+  1. a flat-tree tall-skinny Householder QR (first row block: plain blocked
+     Householder; every further row block: triangular-on-top-of-dense "TPQRT" step
+     against the running R), column sub-panels of width W with compact-WY T factors,
+  2. a one-sided Jacobi SVD of ``T = R_u R_v^T`` (columns), sorted, truncated with the
+     reference's rule, ``W = T^T U_r`` instead of accumulating V,
+  3. application of the stored block reflectors to ``[Y; 0]``.
+This file restates exactly that arithmetic in numpy so that (a) the math can be
+validated against the oracle on the CPU, and (b) per-stage device dumps can be
+compared with it when debugging.  It is never used by the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+W = 16      # sub-panel width
+H = 128     # row-block height
+
+
+def _house(alpha, sigma2):
+    """LAPACK dlarfg semantics given alpha and the squared norm of the tail."""
+    if sigma2 == 0.0:
+        return alpha, 0.0, 0.0          # beta, tau, 1/(alpha-beta) (unused)
+    beta = -np.copysign(np.sqrt(alpha * alpha + sigma2), alpha)
+    tau = (beta - alpha) / beta
+    return beta, tau, 1.0 / (alpha - beta)
+
+
+def tsqr_factor(x, h=H, w=W):
+    """Factor ``x`` (m x n, m >= n).  Returns dict with R (n x n), per-block reflector
+    storage V[j] (rows of block j x n), T[j][s] (w x w upper) and the block row ranges."""
+    x = np.array(x, dtype=np.float64, copy=True)
+    m, n = x.shape
+    assert m >= n
+    h0 = min(m, h)
+    assert h0 >= n
+    bounds = [(0, h0)]
+    r0 = h0
+    while r0 < m:
+        bounds.append((r0, min(m, r0 + h)))
+        r0 += h
+    nsp = (n + w - 1) // w
+    R = np.zeros((n, n))
+    Vs, Ts = [], []
+    for j, (lo, hi) in enumerate(bounds):
+        B = x[lo:hi]            # view, modified in place -> becomes V
+        Tj = []
+        for s in range(nsp):
+            c0, c1 = s * w, min(n, s * w + w)
+            pw = c1 - c0
+            taus = np.zeros(pw)
+            Tm = np.zeros((w, w))
+            Vpan = np.zeros((hi - lo, pw))
+            for ii in range(pw):
+                i = c0 + ii
+                if j == 0:
+                    xi = B[i + 1:, i].copy()
+                    alpha = B[i, i]
+                else:
+                    xi = B[:, i].copy()
+                    alpha = R[i, i]
+                # one batched reduction: dots of the current column tail with all panel columns
+                if j == 0:
+                    d = B[i + 1:, c0:c1].T @ xi
+                    dprev = Vpan[i + 1:, :ii].T @ xi     # previous reflectors (tails below row i)
+                else:
+                    d = B[:, c0:c1].T @ xi
+                    dprev = d[:ii]
+                sigma2 = d[ii]
+                beta, tau, scal = _house(alpha, sigma2)
+                taus[ii] = tau
+                if tau == 0.0:
+                    v = np.zeros_like(xi)
+                else:
+                    v = xi * scal
+                # in-panel update of the columns to the right
+                for cc in range(ii + 1, pw):
+                    c = c0 + cc
+                    if j == 0:
+                        wv = tau * (B[i, c] + d[cc] * scal)
+                        B[i, c] -= wv
+                        B[i + 1:, c] -= v * wv
+                    else:
+                        wv = tau * (R[i, c] + d[cc] * scal)
+                        R[i, c] -= wv
+                        B[:, c] -= v * wv
+                if j == 0:
+                    B[i, i] = beta
+                    B[i + 1:, i] = v
+                    Vpan[i, ii] = 1.0
+                    Vpan[i + 1:, ii] = v
+                else:
+                    R[i, i] = beta
+                    B[:, i] = v
+                    Vpan[:, ii] = v
+                # T column (larft, forward/columnwise): T[:ii, ii] = -tau * T[:ii,:ii] @ (V[:, :ii]^T v_ii)
+                Tm[ii, ii] = tau
+                if ii > 0 and tau != 0.0:
+                    if j == 0:
+                        z = Vpan[:, :ii].T @ Vpan[:, ii]
+                    else:
+                        z = dprev * scal
+                    Tm[:ii, ii] = -tau * (Tm[:ii, :ii] @ z)
+            # trailing update
+            if c1 < n:
+                if j == 0:
+                    S = Vpan.T @ B[:, c1:]
+                    S2 = Tm[:pw, :pw].T @ S
+                    B[:, c1:] -= Vpan @ S2
+                else:
+                    S = R[c0:c1, c1:] + Vpan.T @ B[:, c1:]
+                    S2 = Tm[:pw, :pw].T @ S
+                    R[c0:c1, c1:] -= S2
+                    B[:, c1:] -= Vpan @ S2
+            Tj.append(Tm)
+        if j == 0:
+            R[:, :] = np.triu(B[:n, :n])
+        Vs.append(B)
+        Ts.append(Tj)
+    return dict(R=R, V=Vs, T=Ts, bounds=bounds, n=n, m=m, w=w)
+
+
+def _vpanel(f, j, s):
+    """Explicit reflector panel (rows of block j x pw) for block j, sub-panel s."""
+    n, w = f["n"], f["w"]
+    c0, c1 = s * w, min(n, s * w + w)
+    B = f["V"][j]
+    if j > 0:
+        return B[:, c0:c1]
+    Vp = np.tril(B[:, c0:c1], -c0 - 1 + 0)  # strictly below the global diagonal
+    # np.tril with k=-c0-1 keeps element (row, cc) when row - cc >= c0 + 1, i.e. row > c0 + cc
+    for cc in range(c1 - c0):
+        Vp[c0 + cc, cc] = 1.0
+    return Vp
+
+
+def tsqr_apply(f, y):
+    """Return ``Q @ [y; 0]`` (m x r) for ``y`` of shape (n, r)."""
+    n, m, w = f["n"], f["m"], f["w"]
+    nsp = (n + w - 1) // w
+    r = y.shape[1]
+    Y = np.array(y, dtype=np.float64, copy=True)
+    out = np.zeros((m, r))
+    for j in range(len(f["bounds"]) - 1, 0, -1):
+        lo, hi = f["bounds"][j]
+        Z = np.zeros((hi - lo, r))
+        for s in range(nsp - 1, -1, -1):
+            c0, c1 = s * w, min(n, s * w + w)
+            pw = c1 - c0
+            Vp = _vpanel(f, j, s)
+            S = Y[c0:c1] + Vp.T @ Z
+            S2 = f["T"][j][s][:pw, :pw] @ S
+            Y[c0:c1] -= S2
+            Z -= Vp @ S2
+        out[lo:hi] = Z
+    lo, hi = f["bounds"][0]
+    Yf = np.zeros((hi - lo, r))
+    Yf[:n] = Y
+    for s in range(nsp - 1, -1, -1):
+        pw = min(n, s * w + w) - s * w
+        Vp = _vpanel(f, 0, s)
+        S2 = f["T"][0][s][:pw, :pw] @ (Vp.T @ Yf)
+        Yf -= Vp @ S2
+    out[lo:hi] = Yf
+    return out
+
+
+def qrcp(a):
+    """Householder QR with column pivoting on squared partial column norms that are
+    down-dated (no LAPACK-style recomputation safeguard: the permutation only has to be
+    a good *preconditioner* for the Jacobi sweeps, any permutation is backward stable).
+    Returns (R upper triangular, perm) with ``a[:, perm] = Q R``."""
+    a = np.array(a, dtype=np.float64, copy=True)
+    n = a.shape[1]
+    perm = np.arange(n)
+    vn = np.sum(a * a, axis=0)
+    for i in range(n):
+        p = i + int(np.argmax(vn[i:]))
+        if p != i:
+            a[:, [i, p]] = a[:, [p, i]]
+            perm[[i, p]] = perm[[p, i]]
+            vn[[i, p]] = vn[[p, i]]
+        x = a[i:, i]
+        beta, tau, scal = _house(x[0], float(x[1:] @ x[1:]))
+        if tau != 0.0:
+            v = np.concatenate([[1.0], x[1:] * scal])
+            wv = tau * (v @ a[i:, i + 1:])
+            a[i:, i + 1:] -= np.outer(v, wv)
+        a[i, i] = beta
+        a[i + 1:, i] = 0.0
+        vn[i + 1:] = np.maximum(vn[i + 1:] - a[i, i + 1:] ** 2, 0.0)
+    return np.triu(a), perm
+
+
+def rr_pair(n, step, k):
+    """Pair ``k`` (0..n/2-1) of round-robin step ``step`` (0..n-2), n even: closed form
+    used by the kernel (no schedule table)."""
+    if k == 0:
+        a, b = n - 1, step
+    else:
+        a, b = (step + k) % (n - 1), (step - k + n - 1) % (n - 1)
+    return (a, b) if a < b else (b, a)
+
+
+def round_robin_pairs(n):
+    return [[rr_pair(n, st, k) for k in range(n // 2)] for st in range(n - 1)]
+
+
+TOL_ROT = 1e-15     # rotate a pair when |cos| above this
+TOL_STOP = 1e-7     # a sweep whose largest pre-rotation |cos| is below this is the last one
+
+
+def jacobi_svd_cols(t, max_sweeps=30):
+    """One-sided (Hestenes) Jacobi on the columns of ``t``: t @ J = U * diag(sigma).
+    Quadratic convergence: once a sweep's largest cosine is <= TOL_STOP the rotations
+    of that same sweep bring every cosine to ~TOL_STOP**2, so no checking sweep is run.
+    Returns (G = t @ J unsorted, sweeps)."""
+    g = np.array(t, dtype=np.float64, copy=True)
+    n = g.shape[1]
+    assert n % 2 == 0
+    steps = round_robin_pairs(n)
+    sweeps = 0
+    for sweep in range(max_sweeps):
+        big = False
+        for st in steps:
+            for (p, q) in st:
+                app = g[:, p] @ g[:, p]
+                aqq = g[:, q] @ g[:, q]
+                apq = g[:, p] @ g[:, q]
+                den = np.sqrt(app * aqq)
+                if den == 0.0 or abs(apq) <= TOL_ROT * den:
+                    continue
+                if abs(apq) > TOL_STOP * den:
+                    big = True
+                zeta = (aqq - app) / (2.0 * apq)
+                tt = np.copysign(1.0, zeta) / (abs(zeta) + np.sqrt(1.0 + zeta * zeta))
+                c = 1.0 / np.sqrt(1.0 + tt * tt)
+                sn = c * tt
+                gp = g[:, p].copy()
+                g[:, p] = c * gp - sn * g[:, q]
+                g[:, q] = sn * gp + c * g[:, q]
+        sweeps += 1
+        if not big:
+            break
+    return g, sweeps
+
+
+def core_svd_model(ru, rv, rk, acc):
+    """SVD stage of the device pipeline: T' = R_v R_u^T, QRCP, Jacobi on the columns of
+    R^T, sort, truncate, U_r = P * normalised columns, W = R_v (R_u^T U_r)."""
+    from oracle.tlr_oracle import truncation_rank
+    tp = rv @ ru.T
+    r_up, perm = qrcp(tp)
+    g, sweeps = jacobi_svd_cols(r_up.T)
+    sig = np.sqrt(np.sum(g * g, axis=0))
+    order = np.argsort(-sig, kind="stable")
+    sig = sig[order]
+    g = g[:, order]
+    r = truncation_rank(sig, rk, acc)
+    ut = np.where(sig[:r] > 0, g[:, :r] / np.where(sig[:r] > 0, sig[:r], 1.0), 0.0)
+    u = np.zeros_like(ut)
+    u[perm, :] = ut                       # U = P * U~
+    w = rv @ (ru.T @ u)
+    return u, w, sig, r, sweeps
+
+
+def tlr_gemm_model(au, av, bu, bv, cu, cv, *, alpha, beta, rk, maxrk, acc):
+    """Whole device pipeline in numpy (math orientation, nb x rank inputs)."""
+    from oracle.tlr_oracle import truncation_rank
+    xu = np.hstack([beta * cu, alpha * au])
+    p = av.T @ bv
+    xv = np.hstack([cv, bu @ p.T])
+    fu = tsqr_factor(xu)
+    fv = tsqr_factor(xv)
+    u, wv, sig, r, sweeps = core_svd_model(fu["R"], fv["R"], rk, acc)
+    return tsqr_apply(fu, u), tsqr_apply(fv, wv), r, sig, sweeps
