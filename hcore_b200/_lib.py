@@ -1,0 +1,79 @@
+"""ctypes loader for ``hcore_b200/lib/libhcore_b200.so`` (the C ABI in ``include/hcore_b200.h``).
+
+The library is the product; this module only declares argument types.  There is no
+Python or CPU fallback: if the shared library is missing, importing any compute entry
+point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhcore_b200.so")
+
+#: every symbol ``include/hcore_b200.h`` / ``include/hcore_d.h`` declare
+EXPORTED_SYMBOLS = [
+    "hcore_b200_create", "hcore_b200_destroy", "hcore_b200_set_chunk", "hcore_b200_last_error",
+    "hcore_b200_version", "hcore_b200_launch_count", "hcore_b200_shard_range",
+    "HCORE_dgemm_batched", "HCORE_dgemm_batched_strided", "HCORE_dgemm_batched_host",
+    "HCORE_dgemmcd_batched_strided", "HCORE_dsyrk_batched_strided", "hcore_b200_gemm_flops",
+    "hcore_b200_debug_fetch", "hcore_b200_debug_set_stages", "hcore_b200_set_stage_timing",
+    "hcore_b200_stage_ms",
+    "HCORE_dgemm", "HCORE_dgemmcd", "HCORE_dsyrk",
+    "use_trmm", "gemm_print_index", "gemm_print_mat", "hc_nelm_limit", "syrk_print_index",
+    "gemmcd_print_index", "gemmcd_print_mat", "gemmcd_use_scratch",
+]
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C hcore_b200/csrc`. hcore_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, i64, d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.hcore_b200_create.argtypes = [C.POINTER(vp), i]
+    L.hcore_b200_destroy.argtypes = [vp]
+    L.hcore_b200_set_chunk.argtypes = [vp, i]
+    L.hcore_b200_last_error.argtypes = [vp]
+    L.hcore_b200_last_error.restype = C.c_char_p
+    L.hcore_b200_version.restype = C.c_char_p
+    L.hcore_b200_launch_count.argtypes = [vp]
+    L.hcore_b200_launch_count.restype = i64
+    L.hcore_b200_shard_range.argtypes = [i64, i, i, C.POINTER(i64), C.POINTER(i64)]
+    L.hcore_b200_shard_range.restype = None
+    L.hcore_b200_gemm_flops.argtypes = [i, i, i, i, i]
+    L.hcore_b200_gemm_flops.restype = C.c_uint64
+    L.HCORE_dgemm_batched.argtypes = [vp, i, i, d, vp, vp, vp, i, vp, vp, vp, i, d, vp, vp, vp, i, i, i, d, vp, vp]
+    L.HCORE_dgemm_batched_strided.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
+                                              vp, vp, vp, i, i64, i, i, d, vp, vp]
+    L.HCORE_dgemm_batched_host.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
+                                           vp, vp, vp, i, i64, i, i, d, vp]
+    L.HCORE_dgemmcd_batched_strided.argtypes = [vp, i, i, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp]
+    L.HCORE_dsyrk_batched_strided.argtypes = [vp, i, i, d, vp, vp, vp, i64, vp, i64, vp]
+    L.hcore_b200_debug_fetch.argtypes = [vp, i, i, vp, C.c_size_t]
+    L.hcore_b200_debug_set_stages.argtypes = [vp, i]
+    L.hcore_b200_set_stage_timing.argtypes = [vp, i]
+    L.hcore_b200_stage_ms.argtypes = [vp, i]
+    L.hcore_b200_stage_ms.restype = d
+    # legacy drop-in symbols (reference src/include/hcore_d.h:25-46, 68-86, 107-116)
+    dp = C.POINTER(C.c_double)
+    L.HCORE_dgemm.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, dp, dp, i, d, dp, dp, dp, i, i, i, d, dp, vp]
+    L.HCORE_dgemm.restype = None
+    L.HCORE_dgemmcd.argtypes = [i, i, i, d, dp, dp, i, i, dp, dp, i, i, d, dp, i, i, dp, vp]
+    L.HCORE_dgemmcd.restype = None
+    L.HCORE_dsyrk.argtypes = [i, i, i, i, d, dp, i, dp, i, d, dp, i, dp, vp]
+    L.HCORE_dsyrk.restype = None
+    _lib = L
+    return L

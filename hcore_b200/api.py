@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference interface for the TLR update path.
+
+Names and argument meaning follow the reference C API (``src/include/hcore_d.h``):
+``hcore_dgemm`` <-> ``HCORE_dgemm`` (:25-46), ``hcore_dgemmcd`` <-> ``HCORE_dgemmcd`` (:68-86),
+``hcore_dsyrk`` <-> ``HCORE_dsyrk`` (:107-116).  The legacy functions take HOST numpy
+arrays and call the drop-in C symbols of ``libhcore_b200.so`` directly; ``Context`` wraps
+the batched device-pointer entry points for torch CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+HCORE_NoTrans, HCORE_Trans = 111, 112
+HCORE_Lower = 122
+
+STATUS_NAMES = {0: "OK", 1: "ZERO_RANK", 2: "MAXRK", 3: "UNSUPPORTED", 4: "NEWRANK", 5: "NO_CONVERGE"}
+
+
+class FlopCounter(C.Structure):
+    """``flop_counter`` (reference src/misc/include/flop_util_structs.h:5-36; include/hcore_b200_flops.h)."""
+    _fields_ = [("pad1", C.c_ulong), ("pad2", C.c_ulong), ("copy", C.c_ulong), ("flop", C.c_ulong),
+                ("tid", C.c_int), ("potrf", C.c_ulong), ("trsm", C.c_ulong), ("syrk", C.c_ulong),
+                ("update", C.c_ulong), ("geqrfu", C.c_ulong), ("geqrfv", C.c_ulong),
+                ("geqrfv_gemm", C.c_ulong), ("gesvd", C.c_ulong), ("gesvd_gemm", C.c_ulong),
+                ("gesvd_lasetu", C.c_ulong), ("gesvd_lasetv", C.c_ulong), ("gesvd_lacpyu", C.c_ulong),
+                ("gesvd_lacpyv", C.c_ulong), ("gesvd_dscal", C.c_ulong), ("ormqru", C.c_ulong),
+                ("ormqru_laset", C.c_ulong), ("ormqru_lacpy", C.c_ulong), ("ormqrv", C.c_ulong),
+                ("ormqrv_laset", C.c_ulong), ("ormqrv_lacpy", C.c_ulong), ("omatcopy", C.c_ulong),
+                ("numthreads", C.c_int), ("pad3", C.c_ulong), ("pad4", C.c_ulong)]
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check_colmajor(x, name):
+    if x.dtype != np.float64 or not x.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"{name}: need a C-contiguous float64 array holding the column-major matrix as (cols, ld)")
+
+
+# ---- legacy single-tile calls (host arrays) -------------------------------------------------
+
+def hcore_dgemm(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BU, BV, Brk, LDB, beta, CU, CV, Crk, LDC,
+                rk, maxrk, acc, work=None, flops=None):
+    """``HCORE_dgemm`` (reference src/compute/hcore_dgemm.c:703-1012), same arguments.
+
+    Arrays are numpy ``(cols, ld)`` float64 (i.e. the column-major matrices the C code sees);
+    ``Ark, Brk, Crk`` are 1-element float64 arrays (the reference passes ranks as ``double*``);
+    ``CU, CV`` are overwritten with the new factors and ``Crk[0]`` with the new rank.
+    Errors terminate the process like the reference (``exit(-1)``)."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+        _check_colmajor(x, nm)
+    fl = C.byref(flops) if flops is not None else None
+    L.HCORE_dgemm(int(transA), int(transB), int(M), int(N), float(alpha), _dp(AU), _dp(AV), _dp(Ark), int(LDA),
+                  _dp(BU), _dp(BV), _dp(Brk), int(LDB), float(beta), _dp(CU), _dp(CV), _dp(Crk), int(LDC),
+                  int(rk), int(maxrk), float(acc), None, fl)
+
+
+def hcore_dgemmcd(transA, transB, M, alpha, Au, Av, Arank, LDA, Bu, Bv, Brank, LDB, beta, CD, LDC, maxrank,
+                  work=None, flops=None):
+    """``HCORE_dgemmcd`` (reference src/compute/hcore_dgemmcd.c:36-107): ``CD -= (Au Av^T)(Bu Bv^T)^T``."""
+    L = _lib.load()
+    for nm, x in (("Au", Au), ("Av", Av), ("Bu", Bu), ("Bv", Bv), ("CD", CD)):
+        _check_colmajor(x, nm)
+    L.HCORE_dgemmcd(int(transA), int(transB), int(M), float(alpha), _dp(Au), _dp(Av), int(Arank), int(LDA),
+                    _dp(Bu), _dp(Bv), int(Brank), int(LDB), float(beta), _dp(CD), int(LDC), int(maxrank), None,
+                    C.byref(flops) if flops is not None else None)
+
+
+def hcore_dsyrk(uplo, trans, N, K, alpha, AU, LDAU, AV, LDAV, beta, CD, LDCD, work=None, flops=None):
+    """``HCORE_dsyrk`` (reference src/compute/hcore_dsyrk.c:47-189)."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("AV", AV), ("CD", CD)):
+        _check_colmajor(x, nm)
+    L.HCORE_dsyrk(int(uplo), int(trans), int(N), int(K), float(alpha), _dp(AU), int(LDAU), _dp(AV), int(LDAV),
+                  float(beta), _dp(CD), int(LDCD), None, C.byref(flops) if flops is not None else None)
+
+
+def gemm_flops(m, a, b, c, r):
+    """Reference flop model of one ``HCORE_dgemm`` call (``flops->update``)."""
+    return int(_lib.load().hcore_b200_gemm_flops(int(m), int(a), int(b), int(c), int(r)))
+
+
+def shard_range(ntiles, world, rank):
+    first, count = C.c_int64(), C.c_int64()
+    _lib.load().hcore_b200_shard_range(int(ntiles), int(world), int(rank), C.byref(first), C.byref(count))
+    return first.value, count.value
+
+
+# ---- batched context -----------------------------------------------------------------------------
+
+class HcoreError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """Owns a ``hcore_b200_handle_t`` (device workspace) on one CUDA device."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise HcoreError("hcore_b200 needs a CUDA device (no CPU fallback)")
+        self._L = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        rc = self._L.hcore_b200_create(C.byref(h), self.device)
+        if rc != 0:
+            raise HcoreError(f"hcore_b200_create failed ({rc})")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.hcore_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers --
+    def _check(self, rc):
+        if rc != 0:
+            raise HcoreError(f"hcore_b200 error {rc}: {self._L.hcore_b200_last_error(self._h).decode()}")
+
+    def _dev_f64(self, t, name):
+        import torch
+        if t.dtype != torch.float64 or not t.is_cuda or t.device.index != self.device or not t.is_contiguous():
+            raise TypeError(f"{name}: need a contiguous float64 tensor on cuda:{self.device}")
+
+    def _dev_i32(self, t, name):
+        import torch
+        if t.dtype != torch.int32 or not t.is_cuda or t.device.index != self.device or not t.is_contiguous():
+            raise TypeError(f"{name}: need a contiguous int32 tensor on cuda:{self.device}")
+
+    @staticmethod
+    def _stream_ptr(stream):
+        import torch
+        s = torch.cuda.current_stream() if stream is None else stream
+        return C.c_void_p(s.cuda_stream)
+
+    @property
+    def launches(self):
+        return int(self._L.hcore_b200_launch_count(self._h))
+
+    def set_chunk(self, n):
+        self._check(self._L.hcore_b200_set_chunk(self._h, int(n)))
+
+    def set_stage_timing(self, on):
+        self._check(self._L.hcore_b200_set_stage_timing(self._h, 1 if on else 0))
+
+    def stage_ms(self):
+        return [float(self._L.hcore_b200_stage_ms(self._h, i)) for i in range(4)]
+
+    def debug_set_stages(self, n):
+        self._check(self._L.hcore_b200_debug_set_stages(self._h, int(n)))
+
+    def debug_fetch(self, what, tile, nelem):
+        out = np.zeros(nelem, np.float64)
+        self._check(self._L.hcore_b200_debug_fetch(self._h, int(what), int(tile), out.ctypes.data, nelem))
+        return out
+
+    # -- batched TLR update --
+    def dgemm_batched(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc,
+                      status=None, stream=None):
+        """Batched ``HCORE_dgemm`` on strided device tensors.
+
+        ``AU, AV``: (T, ka, nb) float64 CUDA tensors (tile t is the column-major nb x ka matrix),
+        ``BU, BV``: (T, kb, nb); ``CU, CV``: (T, >=maxrk, nb) in/out; ``Ark, Brk, Crk``: (T,) int32
+        (``Crk`` in/out); ``status``: optional (T,) int32 out."""
+        T, ka, nb = AU.shape
+        for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+            self._dev_f64(x, nm)
+        for nm, x in (("Ark", Ark), ("Brk", Brk), ("Crk", Crk)):
+            self._dev_i32(x, nm)
+        if status is not None:
+            self._dev_i32(status, "status")
+        kb, kc = BU.shape[1], CU.shape[1]
+        if kc < maxrk:
+            raise ValueError("CU/CV need room for maxrk columns")
+        rc = self._L.HCORE_dgemm_batched_strided(
+            self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb,
+            _ptr(BU), _ptr(BV), _ptr(Brk), nb, kb * nb, float(beta), _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
+            int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))
+        self._check(rc)
+
+    def dgemm_batched_host(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc, status=None):
+        """Same on HOST tensors/arrays (pinned torch tensors recommended): the end-to-end path."""
+        T, ka, nb = AU.shape
+        kb, kc = BU.shape[1], CU.shape[1]
+
+        def hp(x):
+            return None if x is None else C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data)
+
+        rc = self._L.HCORE_dgemm_batched_host(
+            self._h, T, nb, float(alpha), hp(AU), hp(AV), hp(Ark), nb, ka * nb, hp(BU), hp(BV), hp(Brk), nb, kb * nb,
+            float(beta), hp(CU), hp(CV), hp(Crk), nb, kc * nb, int(rk), int(maxrk), float(acc), hp(status))
+        self._check(rc)
+
+    # -- batched dense-C updates --
+    def dgemmcd_batched(self, AU, AV, Ark, BU, BV, Brk, CD, stream=None):
+        """Batched ``HCORE_dgemmcd``: ``CD[t] -= (AU AV^T)(BU BV^T)^T``; ``CD``: (T, nb, nb) column-major."""
+        T, ka, nb = AU.shape
+        kb = BU.shape[1]
+        for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CD", CD)):
+            self._dev_f64(x, nm)
+        rc = self._L.HCORE_dgemmcd_batched_strided(self._h, T, nb, _ptr(AU), _ptr(AV), _ptr(Ark), ka * nb,
+                                                   _ptr(BU), _ptr(BV), _ptr(Brk), kb * nb, _ptr(CD), nb * nb,
+                                                   self._stream_ptr(stream))
+        self._check(rc)
+
+    def dsyrk_batched(self, alpha, AU, AV, Ark, CD, stream=None):
+        """Batched ``HCORE_dsyrk``: ``CD[t] += alpha (AU AV^T)(AU AV^T)^T``, strict upper triangle zeroed."""
+        T, ka, nb = AU.shape
+        for nm, x in (("AU", AU), ("AV", AV), ("CD", CD)):
+            self._dev_f64(x, nm)
+        rc = self._L.HCORE_dsyrk_batched_strided(self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark),
+                                                 ka * nb, _ptr(CD), nb * nb, self._stream_ptr(stream))
+        self._check(rc)

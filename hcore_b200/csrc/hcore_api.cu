@@ -1,0 +1,592 @@
+// Host side of libhcore_b200.so: context, workspace, kernel launches, the batched C ABI
+// (include/hcore_b200.h) and the legacy single-tile drop-in symbols (include/hcore_d.h).
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <mutex>
+
+#include "tlr_kernels.cuh"
+#include "dense_kernels.cuh"
+#include "../../include/hcore_d.h"
+
+using namespace hcore_b200;
+
+// ---- link-compatible tunables of the reference library (accepted, ignored) ---------------
+extern "C" {
+int use_trmm = 0, gemm_print_index = 0, gemm_print_mat = 0, hc_nelm_limit = 512;
+int syrk_print_index = 0, gemmcd_print_index = 0, gemmcd_print_mat = 0, gemmcd_use_scratch = 0;
+}
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace
+
+struct hcore_b200_context {
+    int device = 0;
+    int chunk_limit = 0;            // user override, 0 = default
+    int num_sms = 148;
+    int64_t launches = 0;
+    std::string err;
+    // TLR workspace
+    DevBuf panel, R, T, Y, sigma, ints, ptrs;
+    // dense workspace
+    DevBuf X;
+    // host-staging (HCORE_dgemm_batched_host and the legacy wrappers)
+    DevBuf stage[2];
+    DevBuf stage_ints[2];
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    // debug / profiling
+    int debug_stages = 4;
+    bool stage_timing = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double stage_ms[4] = {0, 0, 0, 0};
+    // geometry of the last chunk (for debug_fetch)
+    TlrWorkspace last_ws{};
+    int last_N = 0;
+};
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return HCORE_B200_ERR_CUDA;                                                      \
+        }                                                                                    \
+    } while (0)
+
+int pick_width(int maxrk) {
+    const int w = std::min(maxrk, HCORE_B200_MAX_STACK);
+    if (w <= 32) return 32;
+    if (w <= 64) return 64;
+    return 128;
+}
+
+size_t per_tile_ws_bytes(int N, int m_pad, int nblk) {
+    size_t b = 0;
+    b += 2ull * m_pad * (N + 8) * 8;            // panels
+    b += 2ull * N * N * 8;                      // R
+    b += 2ull * nblk * (N / 16) * 256 * 8;      // T
+    b += 2ull * N * N * 8;                      // Y
+    b += (size_t)N * 8 + 16;                    // sigma + ints
+    return b;
+}
+
+int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
+    if (ctx->chunk_limit > 0) return ctx->chunk_limit;
+    // a few waves of CTAs per launch, bounded to ~6 GiB of workspace
+    size_t per = per_tile_ws_bytes(N, m_pad, nblk);
+    size_t cap = (6ull << 30) / per;
+    int c = ctx->num_sms * 16;
+    if ((size_t)c > cap) c = (int)cap;
+    return std::max(c, 1);
+}
+
+template <int N>
+int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
+    const size_t sm_stack = (size_t)N * (N + 4) * sizeof(double);
+    {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_stack_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stack));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<N>::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_svd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SvdSmem<N>::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_apply_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ApplySmem<N>::kBytes));
+    }
+    const bool tm = ctx->stage_timing;
+    if (tm) cudaEventRecord(ctx->ev[0], st);
+    if (ctx->debug_stages >= 1) {
+        tlr_stack_kernel<N><<<ar.ntiles, 512, sm_stack, st>>>(ar, ws);
+        ctx->launches++;
+    }
+    if (tm) cudaEventRecord(ctx->ev[1], st);
+    if (ctx->debug_stages >= 2) {
+        tlr_tsqr_kernel<N><<<2 * ar.ntiles, 512, TsqrSmem<N>::kBytes, st>>>(ws);
+        ctx->launches++;
+    }
+    if (tm) cudaEventRecord(ctx->ev[2], st);
+    if (ctx->debug_stages >= 3) {
+        tlr_svd_kernel<N><<<ar.ntiles, 512, SvdSmem<N>::kBytes, st>>>(ar, ws);
+        ctx->launches++;
+    }
+    if (tm) cudaEventRecord(ctx->ev[3], st);
+    if (ctx->debug_stages >= 4) {
+        dim3 grid(N / kApplyCols, 2, ar.ntiles);
+        tlr_apply_kernel<N><<<grid, 256, ApplySmem<N>::kBytes, st>>>(ar, ws);
+        ctx->launches++;
+    }
+    if (tm) {
+        cudaEventRecord(ctx->ev[4], st);
+        cudaEventSynchronize(ctx->ev[4]);
+        for (int i = 0; i < 4; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]);
+            ctx->stage_ms[i] += ms;
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+__global__ void fill_ptrs_kernel(const double **out, const double *base, int64_t stride, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = base + (size_t)i * stride;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hcore_b200_version(void) { return "hcore_b200 0.1 (sm_100a, FP64 DMMA)"; }
+
+int hcore_b200_create(hcore_b200_handle_t *handle, int device) {
+    if (!handle) return HCORE_B200_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        fprintf(stderr, "hcore_b200: no CUDA device available -- this library has no CPU fallback\n");
+        return HCORE_B200_ERR_CUDA;
+    }
+    auto *ctx = new hcore_b200_context();
+    if (device < 0) cudaGetDevice(&device);
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HCORE_B200_ERR_CUDA; }
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &s : ctx->streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    *handle = ctx;
+    return HCORE_B200_OK;
+}
+
+int hcore_b200_destroy(hcore_b200_handle_t ctx) {
+    if (!ctx) return HCORE_B200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&ctx->panel, &ctx->R, &ctx->T, &ctx->Y, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X,
+                      &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
+        b->release();
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &s : ctx->streams) if (s) cudaStreamDestroy(s);
+    delete ctx;
+    return HCORE_B200_OK;
+}
+
+int hcore_b200_set_chunk(hcore_b200_handle_t ctx, int tiles_per_chunk) {
+    if (!ctx || tiles_per_chunk < 0) return HCORE_B200_ERR_ARG;
+    ctx->chunk_limit = tiles_per_chunk;
+    return HCORE_B200_OK;
+}
+
+const char *hcore_b200_last_error(hcore_b200_handle_t ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
+int64_t hcore_b200_launch_count(hcore_b200_handle_t ctx) { return ctx ? ctx->launches : 0; }
+
+void hcore_b200_shard_range(int64_t ntiles, int world, int rank, int64_t *first, int64_t *count) {
+    // contiguous blocks, the first (ntiles % world) ranks get one extra tile
+    const int64_t base = ntiles / world, rem = ntiles % world;
+    const int64_t f = rank * base + std::min<int64_t>(rank, rem);
+    if (first) *first = f;
+    if (count) *count = base + (rank < rem ? 1 : 0);
+}
+
+uint64_t hcore_b200_gemm_flops(int m_, int a_, int b_, int c_, int r_) {
+    // reference src/misc/descutil/flop_counts.c:3-70 (float divisions and truncations included)
+    const uint64_t m = m_, a = a_, b = b_, r = r_, n = (uint64_t)a_ + c_;
+    auto geqrf = [](uint64_t mm, uint64_t nn) {
+        return 2 * mm * nn * nn - (uint64_t)(2 * nn * nn * nn / 3.0f) + 2 * mm * nn + (uint64_t)(17 * nn / 3.0f);
+    };
+    uint64_t f = 0;
+    f += geqrf(m, n);                                   // __qra  (hcore_dgemm.c:125)
+    f += a * b * m * 2 + m * a * b * 2;                 // __qrb GEMMs (:179, :208)
+    f += geqrf(m, n);                                   // __qrb QR (:224)
+    f += 22 * n * n * n;                                // gesvd model (:434)
+    f += r * n;                                         // sigma scaling (:493)
+    f += 4 * r * m * n - 2 * r * n * n + 3 * r * n;     // ormqr 'L' (:595)  (m,n,k) = (m,r,n)
+    f += 4 * m * r * n - 2 * r * n * n + 2 * r * n + m * n - n * n / 2 + n / 2;  // ormqr 'R' (:666) (m,n,k)=(r,m,n)
+    return f;
+}
+
+int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
+                        double beta, double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = pick_width(maxrk);
+    const int m_pad = round_up(std::max(nb, kBlockH), kBlockH);
+    const int nblk = m_pad / kBlockH;
+    const int chunk = std::min(ntiles, default_chunk(ctx, N, m_pad, nblk));
+
+    CUDA_TRY(ctx, ctx->panel.reserve(2ull * chunk * m_pad * (N + 8) * 8));
+    CUDA_TRY(ctx, ctx->R.reserve(2ull * chunk * N * N * 8));
+    CUDA_TRY(ctx, ctx->T.reserve(2ull * chunk * nblk * (N / 16) * 256 * 8));
+    CUDA_TRY(ctx, ctx->Y.reserve(2ull * chunk * N * N * 8));
+    CUDA_TRY(ctx, ctx->sigma.reserve((size_t)chunk * N * 8));
+    CUDA_TRY(ctx, ctx->ints.reserve((size_t)chunk * 4 * sizeof(int)));
+
+    TlrWorkspace ws{};
+    ws.panel = (double *)ctx->panel.p;
+    ws.R = (double *)ctx->R.p;
+    ws.T = (double *)ctx->T.p;
+    ws.Y = (double *)ctx->Y.p;
+    ws.sigma = (double *)ctx->sigma.p;
+    ws.ncols = (int *)ctx->ints.p;
+    ws.newrank = ws.ncols + chunk;
+    ws.st = ws.newrank + chunk;
+    ws.sweeps = ws.st + chunk;
+    ws.chunk = chunk;
+    ws.m_pad = m_pad;
+    ws.nblk = nblk;
+    ctx->last_ws = ws;
+    ctx->last_N = N;
+    if (ctx->stage_timing) for (double &x : ctx->stage_ms) x = 0;
+
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        TlrArgs ar{};
+        ar.AU = d_AU; ar.AV = d_AV; ar.BU = d_BU; ar.BV = d_BV; ar.CU = d_CU; ar.CV = d_CV;
+        ar.Ark = d_Ark; ar.Brk = d_Brk; ar.Crk = d_Crk; ar.status = d_status;
+        ar.nb = nb; ar.lda = lda; ar.ldb = ldb; ar.ldc = ldc;
+        ar.alpha = alpha; ar.beta = beta; ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc;
+        ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
+        int rc;
+        switch (N) {
+            case 32: rc = launch_chunk<32>(ctx, ar, ws, st); break;
+            case 64: rc = launch_chunk<64>(ctx, ar, ws, st); break;
+            default: rc = launch_chunk<128>(ctx, ar, ws, st); break;
+        }
+        if (rc != HCORE_B200_OK) return rc;
+    }
+    return HCORE_B200_OK;
+}
+
+int HCORE_dgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double beta, double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ctx, ctx->ptrs.reserve(6ull * ntiles * sizeof(double *)));
+    const double **pp = (const double **)ctx->ptrs.p;
+    const double *bases[6] = {d_AU, d_AV, d_BU, d_BV, d_CU, d_CV};
+    const int64_t strides[6] = {strideA, strideA, strideB, strideB, strideC, strideC};
+    const int thr = 256, blk = (ntiles + thr - 1) / thr;
+    for (int i = 0; i < 6; ++i) {
+        fill_ptrs_kernel<<<blk, thr, 0, st>>>(pp + (size_t)i * ntiles, bases[i], strides[i], ntiles);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_dgemm_batched(ctx, ntiles, nb, alpha, pp, pp + ntiles, d_Ark, lda, pp + 2 * (size_t)ntiles,
+                               pp + 3 * (size_t)ntiles, d_Brk, ldb, beta, (double *const *)(pp + 4 * (size_t)ntiles),
+                               (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, rk, maxrk, acc, d_status, stream);
+}
+
+int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *h_AU, const double *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
+                        const double *h_BU, const double *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
+                        double beta, double *h_CU, double *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *h_status) {
+    if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // Slices of `hc` tiles ping-pong over two device staging buffers / streams so that the
+    // H2D copy of slice i+1 and the D2H copy of slice i-1 overlap the kernels of slice i.
+    // The kernels themselves share the context workspace, so they are serialised by an
+    // event chain (compute of slice i+1 waits for compute of slice i).
+    const int hc = std::min(ntiles, 512);
+    const size_t perA = (size_t)strideA * 8, perB = (size_t)strideB * 8, perC = (size_t)strideC * 8;
+    const size_t per_tile = 2 * perA + 2 * perB + 2 * perC;
+    for (int s = 0; s < 2; ++s) {
+        CUDA_TRY(ctx, ctx->stage[s].reserve(per_tile * hc));
+        CUDA_TRY(ctx, ctx->stage_ints[s].reserve((size_t)hc * 4 * sizeof(int)));
+    }
+    cudaEvent_t done[2];
+    for (auto &e : done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = HCORE_B200_OK;
+    int slice = 0;
+    for (int t0 = 0; t0 < ntiles && rc == HCORE_B200_OK; t0 += hc, ++slice) {
+        const int s = slice & 1;
+        const int cnt = std::min(hc, ntiles - t0);
+        cudaStream_t st = ctx->streams[s];
+        char *base = (char *)ctx->stage[s].p;
+        double *dAU = (double *)base, *dAV = (double *)(base + perA * hc);
+        double *dBU = (double *)(base + 2 * perA * hc), *dBV = (double *)(base + 2 * perA * hc + perB * hc);
+        double *dCU = (double *)(base + 2 * perA * hc + 2 * perB * hc);
+        double *dCV = (double *)(base + 2 * perA * hc + 2 * perB * hc + perC * hc);
+        int *di = (int *)ctx->stage_ints[s].p;
+        int *dArk = di, *dBrk = di + hc, *dCrk = di + 2 * hc, *dSt = di + 3 * hc;
+        cudaMemcpyAsync(dAU, h_AU + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dAV, h_AV + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dBU, h_BU + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dBV, h_BV + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dCU, h_CU + (size_t)t0 * strideC, perC * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dCV, h_CV + (size_t)t0 * strideC, perC * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dArk, h_Ark + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dBrk, h_Brk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dCrk, h_Crk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
+        if (slice > 0) cudaStreamWaitEvent(st, done[s ^ 1], 0);   // workspace is shared
+        rc = HCORE_dgemm_batched_strided(ctx, cnt, nb, alpha, dAU, dAV, dArk, lda, strideA, dBU, dBV, dBrk, ldb,
+                                         strideB, beta, dCU, dCV, dCrk, ldc, strideC, rk, maxrk, acc, dSt, st);
+        cudaEventRecord(done[s], st);
+        cudaMemcpyAsync(h_CU + (size_t)t0 * strideC, dCU, perC * cnt, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_CV + (size_t)t0 * strideC, dCV, perC * cnt, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_Crk + t0, dCrk, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
+        if (h_status) cudaMemcpyAsync(h_status + t0, dSt, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
+        // the staging buffer `s` is reused two slices later: wait for its stream then
+        if (slice >= 1) cudaStreamSynchronize(ctx->streams[s ^ 1]);
+    }
+    cudaStreamSynchronize(ctx->streams[0]);
+    cudaStreamSynchronize(ctx->streams[1]);
+    for (auto &e : done) cudaEventDestroy(e);
+    if (rc != HCORE_B200_OK) return rc;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+// ---- dense-C updates ----------------------------------------------------------------------
+static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scale, int syrk,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB,
+                        double *d_CD, int64_t strideC, void *stream) {
+    if (!ctx || ntiles < 0 || nb <= 0) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kmax8 = HCORE_B200_MAX_STACK;      // ranks up to 128
+    const int m_pad = round_up(nb, 8);
+    const size_t sm_prep = (size_t)HCORE_B200_MAX_STACK * kDenseLdP * sizeof(double);
+    const size_t sm_upd = 2ull * kmax8 * (kBlockH + 4) * sizeof(double);
+    {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(dense_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_prep));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(dense_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_upd));
+    }
+    const int chunk = std::min(ntiles, 4096);
+    CUDA_TRY(ctx, ctx->X.reserve((size_t)chunk * m_pad * kmax8 * 8));
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        const int cnt = std::min(chunk, ntiles - t0);
+        DenseArgs ar{};
+        ar.AU = d_AU + (size_t)t0 * strideA; ar.AV = d_AV + (size_t)t0 * strideA;
+        ar.BU = d_BU + (size_t)t0 * strideB; ar.BV = d_BV + (size_t)t0 * strideB;
+        ar.Ark = d_Ark + t0; ar.Brk = d_Brk + t0;
+        ar.strideA = strideA; ar.strideB = strideB; ar.strideC = strideC;
+        ar.CD = d_CD + (size_t)t0 * strideC;
+        ar.X = (double *)ctx->X.p;
+        ar.scale = scale; ar.nb = nb; ar.m_pad = m_pad; ar.kmax8 = kmax8; ar.syrk = syrk;
+        dense_prep_kernel<<<cnt, 256, sm_prep, st>>>(ar);
+        const int nbk = (nb + kBlockH - 1) / kBlockH;
+        dense_update_kernel<<<dim3(nbk, nbk, cnt), 256, sm_upd, st>>>(ar);
+        ctx->launches += 2;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+int HCORE_dgemmcd_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB,
+                        double *d_CD, int64_t strideC, void *stream) {
+    return dense_launch(ctx, ntiles, nb, -1.0, 0, d_AU, d_AV, d_Ark, strideA, d_BU, d_BV, d_Brk, strideB, d_CD,
+                        strideC, stream);
+}
+
+int HCORE_dsyrk_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
+                        double *d_CD, int64_t strideC, void *stream) {
+    return dense_launch(ctx, ntiles, nb, alpha, 1, d_AU, d_AV, d_Ark, strideA, d_AU, d_AV, d_Ark, strideA, d_CD,
+                        strideC, stream);
+}
+
+// ---- debug / profiling -------------------------------------------------------------------------
+int hcore_b200_debug_set_stages(hcore_b200_handle_t ctx, int nstages) {
+    if (!ctx) return HCORE_B200_ERR_ARG;
+    ctx->debug_stages = nstages;
+    return HCORE_B200_OK;
+}
+int hcore_b200_set_stage_timing(hcore_b200_handle_t ctx, int enable) {
+    if (!ctx) return HCORE_B200_ERR_ARG;
+    ctx->stage_timing = enable != 0;
+    return HCORE_B200_OK;
+}
+double hcore_b200_stage_ms(hcore_b200_handle_t ctx, int stage) {
+    return (ctx && stage >= 0 && stage < 4) ? ctx->stage_ms[stage] : -1.0;
+}
+
+int hcore_b200_debug_fetch(hcore_b200_handle_t ctx, int what, int tile, double *h_out, size_t nelem) {
+    if (!ctx || !h_out || ctx->last_N == 0) return HCORE_B200_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    const TlrWorkspace &ws = ctx->last_ws;
+    const int N = ctx->last_N;
+    const size_t pan = (size_t)ws.m_pad * (N + 8), nn = (size_t)N * N, tt = (size_t)ws.nblk * (N / 16) * 256;
+    const double *src = nullptr;
+    size_t avail = 0;
+    switch (what) {
+        case 0: case 8: src = ws.panel + ((size_t)0 * ws.chunk + tile) * pan; avail = pan; break;
+        case 1: src = ws.panel + ((size_t)1 * ws.chunk + tile) * pan; avail = pan; break;
+        case 2: src = ws.R + ((size_t)0 * ws.chunk + tile) * nn; avail = nn; break;
+        case 3: src = ws.R + ((size_t)1 * ws.chunk + tile) * nn; avail = nn; break;
+        case 4: src = ws.Y + ((size_t)0 * ws.chunk + tile) * nn; avail = nn; break;
+        case 5: src = ws.Y + ((size_t)1 * ws.chunk + tile) * nn; avail = nn; break;
+        case 6: src = ws.sigma + (size_t)tile * N; avail = N; break;
+        case 7: src = ws.T + ((size_t)0 * ws.chunk + tile) * tt; avail = tt; break;
+        case 9: {   // ints: ncols, newrank, status, sweeps (as doubles)
+            int v[4];
+            CUDA_TRY(ctx, cudaMemcpy(&v[0], ws.ncols + tile, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(&v[1], ws.newrank + tile, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(&v[2], ws.st + tile, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(&v[3], ws.sweeps + tile, 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < std::min<size_t>(4, nelem); ++i) h_out[i] = v[i];
+            return HCORE_B200_OK;
+        }
+        default: return HCORE_B200_ERR_ARG;
+    }
+    CUDA_TRY(ctx, cudaMemcpy(h_out, src, std::min(avail, nelem) * 8, cudaMemcpyDeviceToHost));
+    return HCORE_B200_OK;
+}
+
+// ==================================================================================================
+// Legacy single-tile drop-in symbols (host pointers).  A process-wide context is created on
+// first use; calls are serialised by a mutex (the reference is re-entrant only with
+// use_scratch = 0; HiCMA calls it from one worker thread per core).
+// ==================================================================================================
+static hcore_b200_handle_t g_ctx = nullptr;
+static std::mutex g_mu;
+
+static hcore_b200_handle_t legacy_ctx(const char *who) {
+    if (!g_ctx) {
+        if (hcore_b200_create(&g_ctx, -1) != HCORE_B200_OK) {
+            fprintf(stderr, "%s: cannot create a CUDA context (no GPU?). hcore_b200 has no CPU path.\n", who);
+            exit(-1);
+        }
+    }
+    return g_ctx;
+}
+
+static void legacy_fail(const char *who, const char *what, int code) {
+    // same convention as the reference: message on stderr, then exit(-1)
+    fprintf(stderr, "%s: %s (code %d)\n", who, what, code);
+    exit(-1);
+}
+
+void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha, double *AU, double *AV, double *Ark,
+                 int LDA, double *BU, double *BV, double *Brk, int LDB, double beta, double *CU, double *CV,
+                 double *Crk, int LDC, int rk, int maxrk, double acc, double *work, flop_counter *flops) {
+    (void)transA; (void)transB; (void)N; (void)work;   // never read by the reference either (hcore_dgemm.c:703-755)
+    std::lock_guard<std::mutex> lock(g_mu);
+    hcore_b200_handle_t ctx = legacy_ctx("HCORE_dgemm");
+    const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
+    if (a == 0 || b == 0 || c == 0) legacy_fail("HCORE_dgemm", "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
+    if (maxrk < a + c) legacy_fail("HCORE_dgemm", "increase maxrank (maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
+    cudaSetDevice(ctx->device);
+    // Only the columns the reference reads (c) and writes (new rank) are moved, so callers
+    // whose CU/CV buffers are smaller than LDC x maxrk keep working (reference test:
+    // testing/testing_dgemm.c:287-290 allocates M x storage_maxrank).
+    const size_t fa = (size_t)LDA * a * 8, fb = (size_t)LDB * b * 8, fcin = (size_t)LDC * c * 8;
+    const size_t fc = (size_t)LDC * (a + c) * 8;
+    if (ctx->stage[0].reserve(2 * fa + 2 * fb + 2 * fc) != cudaSuccess ||
+        ctx->stage_ints[0].reserve(8 * sizeof(int)) != cudaSuccess)
+        legacy_fail("HCORE_dgemm", "device allocation failed", HCORE_B200_ERR_CUDA);
+    char *base = (char *)ctx->stage[0].p;
+    double *dAU = (double *)base, *dAV = (double *)(base + fa), *dBU = (double *)(base + 2 * fa),
+           *dBV = (double *)(base + 2 * fa + fb), *dCU = (double *)(base + 2 * fa + 2 * fb),
+           *dCV = (double *)(base + 2 * fa + 2 * fb + fc);
+    int *di = (int *)ctx->stage_ints[0].p;
+    int hi[4] = {a, b, c, 0};
+    cudaStream_t st = ctx->streams[0];
+    cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    int rc = HCORE_dgemm_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU,
+                                         dCV, di + 2, LDC, 0, rk, maxrk, acc, di + 3, st);
+    if (rc != HCORE_B200_OK) legacy_fail("HCORE_dgemm", hcore_b200_last_error(ctx), rc);
+    cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail("HCORE_dgemm", "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (hi[3] != HCORE_B200_OK) legacy_fail("HCORE_dgemm", "tile update failed", hi[3]);
+    const int rnew = hi[2];
+    cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail("HCORE_dgemm", "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
+    Crk[0] = (double)rnew;
+}
+
+static void legacy_dense(const char *who, int syrk, int M, double scale, const double *Au, const double *Av, int a,
+                         const double *Bu, const double *Bv, int b, double *CD) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    cudaSetDevice(ctx->device);
+    const size_t fa = (size_t)M * a * 8, fb = (size_t)M * b * 8, fc = (size_t)M * M * 8;
+    if (ctx->stage[0].reserve(2 * fa + 2 * fb + fc) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
+        legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+    char *base = (char *)ctx->stage[0].p;
+    double *dAu = (double *)base, *dAv = (double *)(base + fa), *dBu = (double *)(base + 2 * fa),
+           *dBv = (double *)(base + 2 * fa + fb), *dC = (double *)(base + 2 * fa + 2 * fb);
+    int *di = (int *)ctx->stage_ints[0].p;
+    int hi[2] = {a, b};
+    cudaStream_t st = ctx->streams[0];
+    cudaMemcpyAsync(dAu, Au, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dAv, Av, fa, cudaMemcpyHostToDevice, st);
+    if (!syrk) {
+        cudaMemcpyAsync(dBu, Bu, fb, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dBv, Bv, fb, cudaMemcpyHostToDevice, st);
+    }
+    cudaMemcpyAsync(dC, CD, fc, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    int rc = syrk ? dense_launch(ctx, 1, M, scale, 1, dAu, dAv, di, 0, dAu, dAv, di, 0, dC, 0, st)
+                  : dense_launch(ctx, 1, M, scale, 0, dAu, dAv, di, 0, dBu, dBv, di + 1, 0, dC, 0, st);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+    cudaMemcpyAsync(CD, dC, fc, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+}
+
+void HCORE_dgemmcd(HCORE_enum transA, HCORE_enum transB, int M, double alpha, double *Au, double *Av, int Arank,
+                   int LDA, double *Bu, double *Bv, int Brank, int LDB, double beta, double *CD, int LDC, int maxrank,
+                   double *work, flop_counter *flops) {
+    // alpha, beta and the leading dimensions are ignored by the reference too (-1/+1 and M,
+    // src/compute/hcore_dgemmcd.c:66-99); flops is never touched there.
+    (void)transA; (void)transB; (void)alpha; (void)LDA; (void)LDB; (void)beta; (void)LDC; (void)maxrank;
+    (void)work; (void)flops;
+    legacy_dense("HCORE_dgemmcd", 0, M, -1.0, Au, Av, Arank, Bu, Bv, Brank, CD);
+}
+
+void HCORE_dsyrk(HCORE_enum uplo, HCORE_enum trans, int N, int K, double alpha, const double *AU, int LDAU,
+                 const double *AV, int LDAV, double beta, double *CD, int LDCD, double *work, flop_counter *flops) {
+    // uplo, trans, beta and LDAV are ignored by the reference (src/compute/hcore_dsyrk.c:47-189).
+    (void)uplo; (void)trans; (void)LDAV; (void)beta; (void)LDAU; (void)LDCD; (void)work;
+    legacy_dense("HCORE_dsyrk", 1, N, alpha, AU, AV, K, AU, AV, K, CD);
+    if (flops) {   // reference hcore_dsyrk.c:104,145,172,188 with its contraction length N = LDAU
+        const unsigned long n = (unsigned long)LDAU, k = (unsigned long)K, m = (unsigned long)N;
+        flops->syrk += 2 * k * k * n + 2 * m * k * k + 2 * m * m * k;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+/*
+ * hcore_b200.h -- C ABI of the B200-native tile-low-rank (TLR) update path.
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes
+ * only.  It has two layers:
+ *
+ *  1. The LEGACY single-tile symbols of ecrc/hcore with byte-for-byte identical
+ *     prototypes (host pointers, column-major, ranks passed as floating point):
+ *       HCORE_dgemm    replaces reference src/include/hcore_d.h:25-46
+ *                      (definition src/compute/hcore_dgemm.c:703-1012)
+ *       HCORE_dgemmcd  replaces reference src/include/hcore_d.h:68-86
+ *                      (definition src/compute/hcore_dgemmcd.c:36-107)
+ *       HCORE_dsyrk    replaces reference src/include/hcore_d.h:107-116
+ *                      (definition src/compute/hcore_dsyrk.c:47-189)
+ *     They are declared in include/hcore_d.h (same file name the reference installs)
+ *     and run as a batch of one on the GPU.  There is NO CPU fallback: without a
+ *     CUDA device they print an error and exit(-1), the reference's own error
+ *     convention (src/compute/hcore_dgemm.c:743-746).
+ *
+ *  2. The BATCHED entry points this library adds (north star: "the existing C entry
+ *     points ... gain a batched variant over thousands of independent tiles").
+ *     All array arguments are DEVICE pointers; tiles are independent; errors that
+ *     make the reference exit(-1) become a per-tile int32 status.
+ *
+ * Matrix conventions are the reference's: column-major, a tile is U * V^T with
+ * U, V of size nb x rank and leading dimension ld (effectively nb, reference
+ * src/compute/hcore_dgemm.c:96-113), the operation is always
+ *     C <- alpha * A * B^T + beta * C
+ * whatever transA/transB say (they are never read by the reference,
+ * src/compute/hcore_dgemm.c:703-755).
+ */
+#ifndef HCORE_B200_H
+#define HCORE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (per tile, and as function return values) -------------------------- */
+#define HCORE_B200_OK                0
+#define HCORE_B200_ERR_ZERO_RANK     1  /* Ark, Brk or Crk == 0   (ref hcore_dgemm.c:743-746: exit)      */
+#define HCORE_B200_ERR_MAXRK         2  /* maxrk < Ark + Crk      (ref hcore_dgemm.c:924-927: exit)      */
+#define HCORE_B200_ERR_UNSUPPORTED   3  /* Ark+Crk above the compiled stack width (128) or > nb           */
+#define HCORE_B200_ERR_NEWRANK       4  /* rank after truncation > maxrk (ref hcore_dgemm.c:465-468)     */
+#define HCORE_B200_ERR_NO_CONVERGE   5  /* Jacobi SVD hit its sweep limit (ref: dgesvd info != 0, :407)  */
+#define HCORE_B200_ERR_CUDA        100  /* a CUDA runtime call failed (function return value only)       */
+#define HCORE_B200_ERR_ARG         101  /* invalid argument           (function return value only)       */
+
+/* Largest stacked width Ark + Crk the kernels are compiled for. */
+#define HCORE_B200_MAX_STACK       128
+
+typedef struct hcore_b200_context *hcore_b200_handle_t;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device` (-1: current device).  The context owns the
+ * workspace (reflector panels, R factors, T factors) and grows it on demand.            */
+int  hcore_b200_create(hcore_b200_handle_t *handle, int device);
+int  hcore_b200_destroy(hcore_b200_handle_t handle);
+/* Upper bound on the number of tiles processed per kernel wave (workspace = chunk *
+ * about 2.8 MiB at nb=1024, stack 128).  0 selects the default.                          */
+int  hcore_b200_set_chunk(hcore_b200_handle_t handle, int tiles_per_chunk);
+const char *hcore_b200_last_error(hcore_b200_handle_t handle);
+const char *hcore_b200_version(void);
+/* Number of kernels launched by this context so far (bench.py reports it). */
+int64_t hcore_b200_launch_count(hcore_b200_handle_t handle);
+
+/* ---- tile scheduler ------------------------------------------------------------------ */
+/* Contiguous block partition of `ntiles` over `world` ranks by tile index
+ * (SURVEY.md section 8(e)); rank r owns [*first, *first + *count).                       */
+void hcore_b200_shard_range(int64_t ntiles, int world, int rank, int64_t *first, int64_t *count);
+
+/* ---- batched TLR update + recompression (device pointers) ----------------------------- */
+/* Batched HCORE_dgemm (reference src/compute/hcore_dgemm.c:703-1012) over `ntiles`
+ * independent tiles.
+ *   d_AU[t], d_AV[t] : nb x Ark[t] (ld lda)      d_BU[t], d_BV[t] : nb x Brk[t] (ld ldb)
+ *   d_CU[t], d_CV[t] : buffers of nb x maxrk (ld ldc); first Crk[t] columns valid on
+ *                      entry, first (new) Crk[t] columns valid on exit
+ *   d_Ark, d_Brk     : int32 ranks (in)           d_Crk : int32 ranks (in/out)
+ *   rk   != 0 : fixed-rank truncation min(rk, Ark+Crk)      (ref hcore_dgemm.c:448-452)
+ *   rk   == 0 : first i >= 1 with sigma_i < acc (absolute)  (ref hcore_dgemm.c:453-464)
+ *   d_status  : int32 per tile, HCORE_B200_OK or an error code; a failed tile is left
+ *               untouched.  May be NULL.
+ * `stream` is a cudaStream_t (NULL: default stream).  Asynchronous w.r.t. the host.     */
+int HCORE_dgemm_batched(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
+                        double beta,
+                        double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_status, void *stream);
+
+/* Same, for factors stored at a fixed element stride between consecutive tiles. */
+int HCORE_dgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double beta,
+                        double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_status, void *stream);
+
+/* Host-buffer variant: every pointer is a HOST pointer (pinned memory gives overlap);
+ * the call stages chunks through the device (H2D, compute, D2H overlapped on internal
+ * streams) and returns when the results are back in host memory.  This is the
+ * "reference-facing" end-to-end path bench.py reports as `e2e`.                          */
+int HCORE_dgemm_batched_host(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *h_AU, const double *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
+                        const double *h_BU, const double *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
+                        double beta,
+                        double *h_CU, double *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc,
+                        int32_t *h_status);
+
+/* ---- batched dense-C updates (device pointers) ---------------------------------------- */
+/* Batched HCORE_dgemmcd (reference src/compute/hcore_dgemmcd.c:36-107):
+ *   CD[t] <- CD[t] - (Au Av^T)(Bu Bv^T)^T ; alpha/beta are hard-wired to -1/+1 there. */
+int HCORE_dgemmcd_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB,
+                        double *d_CD, int64_t strideC, void *stream);
+
+/* Batched HCORE_dsyrk (reference src/compute/hcore_dsyrk.c:47-189):
+ *   CD[t] <- CD[t] + alpha * AU (AV^T AV) AU^T, strict upper triangle set to 0 (:174-181). */
+int HCORE_dsyrk_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
+                        double *d_CD, int64_t strideC, void *stream);
+
+/* ---- flop model ------------------------------------------------------------------------ */
+/* The reference's own accounting of one HCORE_dgemm call (flops->update; reference
+ * src/misc/descutil/flop_counts.c:3-70 with the call sites of hcore_dgemm.c), used for
+ * "effective GFLOP/s".  m = nb, r = rank after truncation.                               */
+uint64_t hcore_b200_gemm_flops(int m, int a, int b, int c, int r);
+
+/* ---- stage-level entry points (tests / profiling) -------------------------------------- */
+/* Run only the first `nstages` kernels of the pipeline on a strided batch and leave the
+ * intermediates in the context workspace; hcore_b200_debug_fetch copies one of them to
+ * host memory.  what: 0 = U panel after QR (reflectors), 1 = V panel, 2 = R_u, 3 = R_v,
+ * 4 = Yu (U_r), 5 = Yv (W), 6 = sigma, 7 = T factors of the U panel, 8 = U panel before QR */
+int hcore_b200_debug_fetch(hcore_b200_handle_t handle, int what, int tile, double *h_out, size_t nelem);
+int hcore_b200_debug_set_stages(hcore_b200_handle_t handle, int nstages);
+/* Per-stage device time (ms) of the last batched call, measured with CUDA events when
+ * enabled (adds synchronisation; off by default).  stage: 0 stack, 1 tsqr, 2 svd, 3 apply */
+int hcore_b200_set_stage_timing(hcore_b200_handle_t handle, int enable);
+double hcore_b200_stage_ms(hcore_b200_handle_t handle, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCORE_B200_H */

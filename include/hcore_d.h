@@ -1,0 +1,51 @@
+/*
+ * Drop-in replacement for the hot-path part of the reference's src/include/hcore_d.h.
+ * Only the three double-precision kernels on the TLR update path are provided
+ * (SURVEY.md section 8, rows a1, a11, a12); the prototypes are identical to the
+ * reference's so existing callers compile and link unchanged:
+ *     HCORE_dgemm    reference src/include/hcore_d.h:25-46
+ *     HCORE_dgemmcd  reference src/include/hcore_d.h:68-86
+ *     HCORE_dsyrk    reference src/include/hcore_d.h:107-116
+ * All pointers are HOST pointers, exactly as in the reference; each call runs as a batch
+ * of one on the GPU (see include/hcore_b200.h for the batched device-pointer API).
+ */
+#ifndef HCORE_B200_DROPIN_HCORE_D_H
+#define HCORE_B200_DROPIN_HCORE_D_H
+#include "flop_util_structs.h"
+#include "hcore.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* C(U,V) <- alpha * A * B^T + beta * C, recompressed; Crk[0] receives the new rank. */
+void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha,
+                 double *AU, double *AV, double *Ark, int LDA,
+                 double *BU, double *BV, double *Brk, int LDB,
+                 double beta,
+                 double *CU, double *CV, double *Crk, int LDC,
+                 int rk, int maxrk, double acc, double *work, flop_counter *flops);
+
+/* CD <- CD - (Au Av^T)(Bu Bv^T)^T, CD dense M x M. */
+void HCORE_dgemmcd(HCORE_enum transA, HCORE_enum transB, int M, double alpha,
+                   double *Au, double *Av, int Arank, int LDA,
+                   double *Bu, double *Bv, int Brank, int LDB,
+                   double beta, double *CD, int LDC, int maxrank,
+                   double *work, flop_counter *flops);
+
+/* CD <- CD + alpha * (AU AV^T)(AU AV^T)^T, strict upper triangle of CD zeroed. */
+void HCORE_dsyrk(HCORE_enum uplo, HCORE_enum trans, int N, int K, double alpha,
+                 const double *AU, int LDAU, const double *AV, int LDAV,
+                 double beta, double *CD, int LDCD, double *work, flop_counter *flops);
+
+/* Link-compatible tunables the reference library defines (reference
+ * src/compute/hcore_dgemm.c:37-43, hcore_dsyrk.c:21, hcore_dgemmcd.c:24-26).  They are
+ * accepted and ignored: there is no scratch protocol and no printing on the GPU path.
+ * `use_scratch` stays an application-defined symbol in the reference and is not
+ * referenced by this library at all. */
+extern int use_trmm, gemm_print_index, gemm_print_mat, hc_nelm_limit;
+extern int syrk_print_index, gemmcd_print_index, gemmcd_print_mat, gemmcd_use_scratch;
+
+#ifdef __cplusplus
+}
+#endif
+#endif
