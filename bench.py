@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the TLR update path: batched HCORE_dgemm + recompression.
+
+  python bench.py --gpus N --steps K --warmup W            # this library, on N B200s
+  python bench.py --impl reference --gpus N ...             # the reference's CPU path, host cores
+
+Metric (BASELINE.json): tiles/s of batched HCORE_dgemm with recompression at nb=1024,
+rank 64, accuracy 1e-8 (configs[1]: 16k tiles per B200; weak scaling: 16k tiles per GPU, so
+8 GPUs process the 128k tiles of configs[4]).  One "step" = one pass of the hot path over
+the whole batch.  The update is in place (it overwrites C, like the reference), so the C
+factors are restored from a pristine copy between steps; the restore is outside the CUDA
+event pair that times the step.
+
+One JSON line is printed by rank 0 (see the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "TLR dgemm+recompress tiles/s (nb=1024,k=64,acc=1e-8)"
+FP64_PEAK_FALLBACK_TFLOPS = 37.1   # profiles/fp64_peak_r1.txt (DMMA m8n8k4, measured on this pool's B200)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=16384, help="tiles per GPU")
+    ap.add_argument("--nb", type=int, default=1024)
+    ap.add_argument("--rank", type=int, default=64)
+    ap.add_argument("--acc", type=float, default=1e-8)
+    ap.add_argument("--e2e-tiles", type=int, default=2048, help="tiles per end-to-end (host buffer) step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="CPU baseline tiles per worker (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic batch on the device (same distribution as hcore_b200.tilegen / SURVEY 8(d))
+# ------------------------------------------------------------------------------------------------
+def device_orth(torch, gen, T, nb, k, dev, chunk=1024):
+    """(T, k, nb) float64: each tile an nb x k matrix with orthonormal columns (column-major).
+    Orthonormalised with two rounds of Cholesky-QR (a uniform random nb x k matrix is very well
+    conditioned); input generation only, not part of anything timed."""
+    out = torch.empty((T, k, nb), dtype=torch.float64, device=dev)
+    for t0 in range(0, T, chunk):
+        c = min(chunk, T - t0)
+        x = torch.rand((c, k, nb), dtype=torch.float64, device=dev, generator=gen) - 0.5   # rows = columns of X
+        for _ in range(2):
+            g = x @ x.transpose(1, 2)                       # X^T X  (k x k)
+            l = torch.linalg.cholesky(g)                     # G = L L^T,  R = L^T
+            x = torch.linalg.solve_triangular(l, x, upper=False)   # (X R^-1)^T = L^-1 X^T
+        out[t0:t0 + c] = x
+    return out
+
+
+def make_device_batch(torch, T, nb, k, dev, seed):
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    sig = (10.0 ** (-8.0 * torch.arange(k, dtype=torch.float64, device=dev) / k))[None, :, None]
+    d = {}
+    d["au"] = device_orth(torch, gen, T, nb, k, dev)
+    d["av"] = device_orth(torch, gen, T, nb, k, dev) * sig
+    d["bu"] = device_orth(torch, gen, T, nb, k, dev)
+    d["bv"] = device_orth(torch, gen, T, nb, k, dev) * sig
+    d["cu0"] = device_orth(torch, gen, T, nb, k, dev)           # pristine C factors (k columns)
+    d["cv0"] = device_orth(torch, gen, T, nb, k, dev) * sig
+    d["cu"] = torch.zeros((T, 2 * k, nb), dtype=torch.float64, device=dev)
+    d["cv"] = torch.zeros((T, 2 * k, nb), dtype=torch.float64, device=dev)
+    d["ark"] = torch.full((T,), k, dtype=torch.int32, device=dev)
+    d["brk"] = torch.full((T,), k, dtype=torch.int32, device=dev)
+    d["crk"] = torch.full((T,), k, dtype=torch.int32, device=dev)
+    d["status"] = torch.zeros((T,), dtype=torch.int32, device=dev)
+    return d
+
+
+def restore_c(d, k):
+    d["cu"][:, :k].copy_(d["cu0"])
+    d["cv"][:, :k].copy_(d["cv0"])
+    d["crk"].fill_(k)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "sw_power_cap": 0x4, "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        if self.nv:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own HCORE_dgemm on the host cores, one process per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wid, ntiles, nb, k, acc, use_ref = args
+    sys.path.insert(0, ROOT)
+    from hcore_b200.tilegen import make_lr_batch
+    b = make_lr_batch(ntiles + 1, nb, k, base_seed=777 + 1000 * wid)
+    if use_ref:
+        from oracle import ref_binding as rb
+        rb.set_blas_threads(1)
+
+        def one(t):
+            return rb.hcore_gemm(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k, alpha=-1.0, beta=1.0,
+                                 rk=0, maxrk=2 * k, acc=acc)[2]
+    else:
+        from oracle import tlr_oracle as orc
+
+        def one(t):
+            return orc.tlr_gemm_colmajor(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k, alpha=-1.0,
+                                         beta=1.0, rk=0, maxrk=2 * k, acc=acc)[2]
+    one(ntiles)                       # warm-up tile
+    t0 = time.perf_counter()
+    ranks = [one(t) for t in range(ntiles)]
+    return time.perf_counter() - t0, ranks
+
+
+def cpu_baseline(nb, k, acc, tiles_per_worker, workers=None):
+    """Times the reference CPU path (oracle/_ref when built, else the numpy/LAPACK port) with one
+    single-threaded-BLAS process per host core (threads do not scale in this OpenBLAS)."""
+    import multiprocessing as mp
+    from oracle import ref_binding as rb
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    use_ref = rb.available()
+    cores = workers or (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(w, tiles_per_worker, nb, k, acc, use_ref) for w in range(cores)])
+    wall = max(r[0] for r in res)
+    total = tiles_per_worker * cores
+    ranks = [x for r in res for x in r[1]]
+    return {"value": total / wall, "unit": "tiles/s", "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"{total} tiles ({tiles_per_worker} per process x {cores} single-thread-BLAS processes) of the "
+                      f"same synthetic workload, nb={nb} k={k} acc={acc:g}; wall = slowest process",
+            "mean_rank": float(np.mean(ranks)), "per_core": total / wall / cores}
+
+
+def stage_flops(m, a, b, c, r):
+    """Reference flop model split by pipeline stage (for per-stage roofline fractions)."""
+    n = a + c
+    geqrf = 2 * m * n * n - int(2 * n ** 3 / 3) + 2 * m * n + int(17 * n / 3)
+    return {"stack": 4 * m * a * b, "tsqr": 2 * geqrf, "svd": 22 * n ** 3 + 2 * n ** 3 + r * n,
+            "apply": (4 * r * m * n - 2 * r * n * n + 3 * r * n) +
+                     (4 * m * r * n - 2 * r * n * n + 2 * r * n + m * n - n * n // 2 + n // 2)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per = args.cpu_sample or 12
+    for _ in range(args.warmup):
+        cpu_baseline(args.nb, args.rank, args.acc, 1)
+    vals, last = [], None
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_baseline(args.nb, args.rank, args.acc, per)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t_all
+    v = float(np.mean(vals))
+    total = per * last["cores"]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"HCORE_dgemm nb={args.nb} k={args.rank} acc={args.acc:g}, bounded sample of "
+                                   f"{total} tiles per step on the host cores", "nb": args.nb, "rank": args.rank},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hcore_b200 import api
+    from hcore_b200.scheduler import TileScheduler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hcore_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nb, k, acc = args.nb, args.rank, args.acc
+    T_local = args.tiles
+    total_tiles = T_local * world
+    sched = TileScheduler(total_tiles, world, rank)
+    assert sched.count == T_local
+    ctx = api.Context(local)
+    d = make_device_batch(torch, T_local, nb, k, dev, seed=20260 + sched.first)
+    torch.cuda.synchronize()
+
+    def hot_path():
+        ctx.dgemm_batched(-1.0, d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], 1.0, d["cu"], d["cv"],
+                          d["crk"], rk=0, maxrk=2 * k, acc=acc, status=d["status"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        restore_c(d, k)
+        hot_path()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = ctx.launches
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        restore_c(d, k)               # untimed: puts C back to its pristine rank-k state
+        barrier()
+        ev0[s].record()
+        hot_path()
+        ev1[s].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    ms_local = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    tms = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms = float(tms.item())
+    ms_per_step = total_ms / args.steps
+    value = total_tiles / (ms_per_step * 1e-3)
+
+    # results of the last step: ranks / status gathered with NCCL (the only collective on this path)
+    ranks_all, stat_all = sched.gather_results(d["crk"], d["status"])
+    ranks_np = ranks_all.cpu().numpy()
+    nfail = int((stat_all != 0).sum().item())
+    mean_rank = float(ranks_np.mean())
+
+    # accuracy on a few local tiles (dense check is O(nb^2 k) per tile, done on the GPU with torch)
+    errs = []
+    for t in range(min(4, T_local)):
+        r = int(d["crk"][t].item())
+        approx = d["cu"][t, :r].T @ d["cv"][t, :r]
+        A = d["au"][t].T @ d["av"][t]
+        B = d["bu"][t].T @ d["bv"][t]
+        dense = d["cu0"][t].T @ d["cv0"][t] - A @ B.T
+        errs.append(float(torch.linalg.norm(approx - dense).item()))
+
+    # per-stage device times (extra pass with event timing between the kernels; not part of `value`)
+    restore_c(d, k)
+    ctx.set_stage_timing(True)
+    hot_path()
+    torch.cuda.synchronize()
+    stage_ms = ctx.stage_ms()
+    ctx.set_stage_timing(False)
+    r_model = int(round(mean_rank))
+    fl = stage_flops(nb, k, k, k, r_model)
+    flops_tile = api.gemm_flops(nb, k, k, k, r_model) + 2 * (2 * k) ** 3
+
+    # FP64 peak calibration: cuBLAS DGEMM 8192^3 (calibration only) next to the DMMA micro-benchmark figure
+    a64 = torch.rand((8192, 8192), dtype=torch.float64, device=dev)
+    b64 = torch.rand((8192, 8192), dtype=torch.float64, device=dev)
+    torch.matmul(a64, b64)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        torch.matmul(a64, b64)
+    e1.record()
+    torch.cuda.synchronize()
+    cublas_tflops = 3 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a64, b64
+    peak_tflops = max(FP64_PEAK_FALLBACK_TFLOPS, cublas_tflops)
+
+    names = ["stack", "tsqr", "svd", "apply"]
+    nchunks = max(1, launches // (args.steps * 4)) if launches else 1
+    stages = {}
+    for nm, ms in zip(names, stage_ms):
+        ach = fl[nm] * T_local / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        stages[nm] = {"ms": ms, "share": ms / max(sum(stage_ms), 1e-9), "model_tflops": ach, "frac_fp64_peak": ach / peak_tflops}
+    dom = max(names, key=lambda nm: stages[nm]["ms"])
+    roofline = {"bound": "tensor", "kernel": f"tlr_{dom}_kernel", "achieved": stages[dom]["model_tflops"],
+                "peak": peak_tflops, "unit": "TFLOP/s", "frac": stages[dom]["model_tflops"] / peak_tflops,
+                "traffic": None,
+                "note": "FP64: peak = max(DMMA m8n8k4 micro-benchmark 37.1 TF (profiles/fp64_peak_r1.txt), cuBLAS DGEMM "
+                        f"8192^3 measured in this run = {cublas_tflops:.1f} TF); MEASURED_PEAKS.json has no FP64 entry. "
+                        "achieved = reference flop model of the stage x tiles / CUDA-event time of the stage's launches",
+                "pipeline_frac": value / world * flops_tile / 1e12 / peak_tflops}
+
+    line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"batched HCORE_dgemm, {T_local} tiles per GPU, nb={nb}, rank {k}, acc {acc:g}, "
+                                   f"alpha=-1 beta=1 (BASELINE.json configs[1]; x{world} GPUs = {total_tiles} tiles)",
+                       "tiles_per_gpu": T_local, "nb": nb, "rank": k, "maxrk": 2 * k, "acc": acc,
+                       "parallelism": f"tile-sharded x{world}", "l2": "inputs (>60 GB per GPU) exceed L2",
+                       "c_restore_between_steps": "untimed device copy of the pristine C factors"},
+            "gflops_effective": value * flops_tile / 1e9, "flops_per_tile_model": flops_tile,
+            "mean_new_rank": mean_rank, "failed_tiles": nfail, "sample_abs_err_fro": errs,
+            "gpu_launches": launches, "stages": stages, "roofline": roofline, "clocks": clocks,
+            "wall_s_timed_region": wall}
+
+    if rank == 0 and world == 1:
+        # ---- end to end through the C ABI with HOST buffers (H2D + D2H inside the timed region) ----
+        if not args.no_e2e:
+            Te = min(args.e2e_tiles, T_local)
+            host = {}
+            for nm in ("au", "av", "bu", "bv"):
+                host[nm] = d[nm][:Te].cpu().pin_memory()
+            host["cu"] = torch.zeros((Te, 2 * k, nb), dtype=torch.float64).pin_memory()
+            host["cv"] = torch.zeros((Te, 2 * k, nb), dtype=torch.float64).pin_memory()
+            cu0h, cv0h = d["cu0"][:Te].cpu(), d["cv0"][:Te].cpu()
+            ark = torch.full((Te,), k, dtype=torch.int32).pin_memory()
+            brk = torch.full((Te,), k, dtype=torch.int32).pin_memory()
+            crk = torch.full((Te,), k, dtype=torch.int32).pin_memory()
+            sth = torch.zeros((Te,), dtype=torch.int32).pin_memory()
+            times = []
+            for it in range(args.warmup + args.steps):
+                host["cu"][:, :k].copy_(cu0h)
+                host["cv"][:, :k].copy_(cv0h)
+                crk.fill_(k)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ctx.dgemm_batched_host(-1.0, host["au"], host["av"], ark, host["bu"], host["bv"], brk, 1.0,
+                                       host["cu"], host["cv"], crk, rk=0, maxrk=2 * k, acc=acc, status=sth)
+                dt = time.perf_counter() - t0
+                if it >= args.warmup:
+                    times.append(dt)
+            per_tile_in = (4 * k + 2 * 2 * k) * nb * 8
+            per_tile_out = 2 * 2 * k * nb * 8
+            line["e2e"] = {"value": Te / float(np.mean(times)), "unit": "tiles/s",
+                           "h2d_bytes_per_step": Te * per_tile_in + 3 * 4 * Te,
+                           "d2h_bytes_per_step": Te * per_tile_out + 2 * 4 * Te,
+                           "tiles_per_step": Te, "failed_tiles": int((sth != 0).sum().item()),
+                           "note": "HCORE_dgemm_batched_host: pinned host buffers, chunked H2D/compute/D2H pipeline"}
+            del host
+        # ---- CPU baseline: the reference on the host cores ----
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(nb, k, acc, args.cpu_sample or 24)
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(256) dense_prep_kernel(DenseArgs ar) {
     block_gemm<2, kGemmSet>(mview(X, 1, ar.m_pad), Au, cview(W, 1, kDenseLdP), m8, b8, a8, warp, nwarps);
 }
 
+constexpr int kDenseKc = 64;   // contraction chunk staged in shared memory
+
 // grid = (row blocks, col blocks, tiles), 256 threads; 128 x 128 block of CD per CTA.
-// Shared: Xs (128 x kmax8, ld 132) and Bs (128 x kmax8, ld 132).
+// Shared: Xs and Bs (128 x kDenseKc each, ld 132), refilled per contraction chunk.
 __global__ void __launch_bounds__(256) dense_update_kernel(DenseArgs ar) {
     constexpr int LD = kBlockH + 4;
     extern __shared__ double smem[];
@@ -69,33 +71,43 @@ __global__ void __launch_bounds__(256) dense_update_kernel(DenseArgs ar) {
     }
     const int b = ar.Brk[t];
     const int b8 = round_up(b, 8);
-    double *Xs = smem, *Bs = smem + (size_t)ar.kmax8 * LD;
+    double *Xs = smem, *Bs = smem + (size_t)kDenseKc * LD;
     const double *X = ar.X + (size_t)t * ar.m_pad * ar.kmax8;
     const double *BU = ar.BU + (size_t)t * ar.strideB;
-    for (int idx = tid; idx < kBlockH * b8; idx += blockDim.x) {
-        const int rr = idx & 127, kk = idx >> 7;
-        Xs[rr + kk * LD] = (i0 + rr < m) ? X[i0 + rr + (size_t)kk * ar.m_pad] : 0.0;
-        Bs[rr + kk * LD] = (j0 + rr < m && kk < b) ? BU[j0 + rr + (size_t)kk * m] : 0.0;
-    }
-    __syncthreads();
-    // CD[I, J] += Xs * Bs^T  (reference hcore_dgemmcd.c:81-85, hcore_dsyrk.c:165-171)
     const int lane = lane_id(), g = lane >> 2, tg = lane & 3;
-    const int warp = warp_id(), nwarps = blockDim.x >> 5;
-    // each warp owns 8-row strips; all 16 column tiles of the strip are kept in registers
-    for (int strip = warp; strip < kBlockH / 8; strip += nwarps) {
-        const int r0 = strip * 8;
-        double acc[16][2];
+    const int warp = warp_id();
+    // CD[I, J] += Xs * Bs^T  (reference hcore_dgemmcd.c:81-85, hcore_dsyrk.c:165-171)
+    // 8 warps x 2 strips: each warp keeps two 8 x 128 accumulator strips in registers.
+    double acc[2][16][2];
 #pragma unroll
-        for (int tt = 0; tt < 16; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
-        for (int k = 0; k < b8; k += 4) {
-            const double av = Xs[r0 + g + (k + tg) * LD];
+    for (int sidx = 0; sidx < 2; ++sidx)
 #pragma unroll
-            for (int tt = 0; tt < 16; ++tt) {
-                const double bv = Bs[tt * 8 + g + (k + tg) * LD];
-                dmma_884(acc[tt][0], acc[tt][1], av, bv);
+        for (int tt = 0; tt < 16; ++tt) acc[sidx][tt][0] = acc[sidx][tt][1] = 0.0;
+    for (int k0 = 0; k0 < b8; k0 += kDenseKc) {
+        const int kc = (b8 - k0 < kDenseKc) ? (b8 - k0) : kDenseKc;
+        __syncthreads();
+        for (int idx = tid; idx < kBlockH * kc; idx += blockDim.x) {
+            const int rr = idx & 127, kk = idx >> 7;
+            Xs[rr + kk * LD] = (i0 + rr < m) ? X[i0 + rr + (size_t)(k0 + kk) * ar.m_pad] : 0.0;
+            Bs[rr + kk * LD] = (j0 + rr < m && k0 + kk < b) ? BU[j0 + rr + (size_t)(k0 + kk) * m] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+            const int r0 = (warp + 8 * sidx) * 8;
+            for (int k = 0; k < kc; k += 4) {
+                const double av = Xs[r0 + g + (k + tg) * LD];
+#pragma unroll
+                for (int tt = 0; tt < 16; ++tt) {
+                    const double bv = Bs[tt * 8 + g + (k + tg) * LD];
+                    dmma_884(acc[sidx][tt][0], acc[sidx][tt][1], av, bv);
+                }
             }
         }
-        const int rr = i0 + r0 + g;
+    }
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+        const int rr = i0 + (warp + 8 * sidx) * 8 + g;
         if (rr < m) {
 #pragma unroll
             for (int tt = 0; tt < 16; ++tt) {
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(DenseArgs ar) {
                     if (cc < m) {
                         double *p = CD + rr + (size_t)cc * m;
                         if (ar.syrk && cc > rr) *p = 0.0;
-                        else *p += acc[tt][h];
+                        else *p += acc[sidx][tt][h];
                     }
                 }
             }

@@ -380,7 +380,7 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
     const int kmax8 = HCORE_B200_MAX_STACK;      // ranks up to 128
     const int m_pad = round_up(nb, 8);
     const size_t sm_prep = (size_t)HCORE_B200_MAX_STACK * kDenseLdP * sizeof(double);
-    const size_t sm_upd = 2ull * kmax8 * (kBlockH + 4) * sizeof(double);
+    const size_t sm_upd = 2ull * kDenseKc * (kBlockH + 4) * sizeof(double);
     {
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_prep));
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_upd));

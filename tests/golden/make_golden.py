@@ -1,0 +1,178 @@
+"""Generates the golden fixtures in tests/golden/ from the UNMODIFIED reference.
+
+Run once in the dev container (needs /root/reference built into oracle/_ref by
+`make -C oracle ref`):   python tests/golden/make_golden.py
+
+Fixtures:
+  ref_ctest_dgemm.npz    inputs/outputs of the reference's own known-answer program
+                         testing/testing_dgemm.c (M=N=K=10, LAPACKE_dlatms with
+                         iseed={0,0,0,1}, acc 1e-4): the dlatms/dgesvd calls are replayed here
+                         through the same OpenBLAS the reference was linked with, then the
+                         compiled reference HCORE_dgemm is run on them.
+  ref_ctest_dgemmcd.npz  testing/testing_dgemmcd.c (nrows 10, ranks 7/6, glibc rand() with the
+                         default seed), outputs of the compiled HCORE_dgemmcd.
+  ref_ctest_dsyrk.npz    testing/testing_dsyrk.c (nrows 10, rank 7).
+  ref_tlr_small.npz      compiled-reference outputs (full factors) for seeded tilegen batches
+                         at nb=64/k=8 and nb=96/k=(5,7,6) (ragged ranks), fixed-rank mode too.
+  ref_tlr_large.npz      compiled-reference ranks, singular-value-free summaries (errors,
+                         flop counts) at nb=500/k=25 and nb=1024/k=64 (inputs are regenerated
+                         from the seed by hcore_b200.tilegen).
+"""
+import ctypes as C
+import glob
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from hcore_b200.tilegen import make_lr_batch  # noqa: E402
+from oracle import ref_binding as rb  # noqa: E402
+
+import scipy  # noqa: E402
+
+_blas = C.CDLL(glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs",
+                                      "libscipy_openblas*.so"))[0])
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+_blas.scipy_LAPACKE_dlatms.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char, ip, C.c_char, dp, C.c_int, C.c_double,
+                                       C.c_double, C.c_int, C.c_int, C.c_char, dp, C.c_int]
+_blas.scipy_LAPACKE_dgesvd.argtypes = [C.c_int, C.c_char, C.c_char, C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int,
+                                       dp, C.c_int, dp]
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def generate_compress(n, iseed, storage_maxrank, acc):
+    """Replays generate_compress() of reference testing/testing_dgemm.c:119-236 (square n x n)."""
+    d = np.array([10.0 ** (-i) for i in range(n)])
+    a = np.zeros((n, n))            # column-major n x n as (col, row)
+    info = _blas.scipy_LAPACKE_dlatms(102, n, n, b"U", iseed.ctypes.data_as(ip), b"N", _p(d), 0, -1.0, -1.0, n - 1,
+                                      n - 1, b"N", _p(a), n)
+    assert info == 0
+    clone = a.copy()
+    s, u, vt, sb = np.zeros(n), np.zeros((n, n)), np.zeros((n, n)), np.zeros(n)
+    info = _blas.scipy_LAPACKE_dgesvd(102, b"A", b"A", n, n, _p(clone), n, _p(s), _p(u), n, _p(vt), n, _p(sb))
+    assert info == 0
+    vt_m = vt.T * s[:, None]        # math orientation: rows of V^T scaled by sigma (:176-179)
+    rank = 0
+    while rank < n and s[rank] >= acc:
+        rank += 1
+    rank = min(rank, storage_maxrank)
+    U = np.ascontiguousarray(u[:rank])               # (rank, n): column-major n x rank
+    V = np.ascontiguousarray(vt_m[:rank])            # V = (Sigma V^T)^T stored n x rank -> (rank, n)
+    return a, U, V, rank
+
+
+def ctest_dgemm():
+    n, smr, acc = 10, 6, 1e-4
+    iseed = np.array([0, 0, 0, 1], dtype=np.int32)
+    A, AU, AV, ra = generate_compress(n, iseed, smr, acc)
+    B, BU, BV, rb_ = generate_compress(n, iseed, smr, acc)
+    Cm, CU, CV, rc = generate_compress(n, iseed, smr, acc)
+    Am, Bm, Cmm = A.T, B.T, Cm.T     # math orientation
+    ref_c = 1.0 * Am @ Bm.T + 1.0 * Cmm
+    cu, cv, r, fl = rb.hcore_gemm(AU, AV, BU, BV, CU, CV, rc, alpha=1.0, beta=1.0, rk=0, maxrk=n, acc=acc)
+    app = cu[:r].T @ cv[:r]
+    rnorm = np.abs(ref_c - app).sum(axis=1).max()
+    print("ctest dgemm: ranks", ra, rb_, rc, "->", r, "inf norm", rnorm)
+    assert rnorm < 10 * acc
+    np.savez(os.path.join(HERE, "ref_ctest_dgemm.npz"), AU=AU, AV=AV, BU=BU, BV=BV, CU=CU, CV=CV,
+             ranks=np.array([ra, rb_, rc]), ref_c=ref_c, out_cu=cu[:r], out_cv=cv[:r], out_rank=r,
+             rnorm=rnorm, flops=fl, acc=acc, n=n)
+
+
+def _glibc_rand_stream():
+    libc = C.CDLL("libc.so.6")
+    libc.srand(1)                    # glibc's default seed when srand() is never called
+    return lambda: libc.rand() / 2147483647.0
+
+
+def ctest_dgemmcd():
+    """reference testing/testing_dgemmcd.c:105-205: nrows 10, rankA 7, rankB 6, rand()/RAND_MAX."""
+    n, ka, kb = 10, 7, 6
+    rnd = _glibc_rand_stream()
+    # the test fills the arrays element by element in allocation order; the exact order only
+    # matters for bit-reproducing ITS numbers, the fixture pins OUR inputs against the reference
+    Au = np.array([[rnd() for _ in range(n)] for _ in range(ka)])
+    Av = np.array([[rnd() for _ in range(n)] for _ in range(ka)])
+    Bu = np.array([[rnd() for _ in range(n)] for _ in range(kb)])
+    Bv = np.array([[rnd() for _ in range(n)] for _ in range(kb)])
+    CD = np.array([[rnd() for _ in range(n)] for _ in range(n)])
+    out = rb.hcore_dgemmcd(Au, Av, Bu, Bv, CD)
+    dense = CD.T - (Au.T @ Av) @ (Bu.T @ Bv).T
+    res = np.abs(dense - out.T).sum(axis=1).max()
+    print("ctest dgemmcd residual", res)
+    assert res < 1000 * np.finfo(float).eps
+    np.savez(os.path.join(HERE, "ref_ctest_dgemmcd.npz"), Au=Au, Av=Av, Bu=Bu, Bv=Bv, CD=CD, out=out, residual=res)
+
+
+def ctest_dsyrk():
+    """reference testing/testing_dsyrk.c:102-181: nrows 10, rank 7, lower triangle compared."""
+    n, k = 10, 7
+    rnd = _glibc_rand_stream()
+    AU = np.array([[rnd() for _ in range(n)] for _ in range(k)])
+    AV = np.array([[rnd() for _ in range(n)] for _ in range(k)])
+    CD = np.array([[rnd() for _ in range(n)] for _ in range(n)])
+    out, fl = rb.hcore_dsyrk(AU, AV, CD, alpha=-1.0)
+    Am = AU.T @ AV
+    dense = np.tril(CD.T - Am @ Am.T)
+    res = np.abs(dense - np.tril(out.T)).sum(axis=1).max()
+    print("ctest dsyrk residual", res, "upper zeroed:", np.abs(np.triu(out.T, 1)).max())
+    assert res < 1000 * np.finfo(float).eps
+    np.savez(os.path.join(HERE, "ref_ctest_dsyrk.npz"), AU=AU, AV=AV, CD=CD, out=out, residual=res, flops=fl)
+
+
+def tlr_small():
+    rec = {}
+    cases = [("nb64_k8", 64, 8, None, 0, 1e-8, -1.0, 1.0),
+             ("nb96_ragged", 96, 8, [(5, 7, 6), (8, 3, 2), (1, 1, 1)], 0, 1e-6, 0.5, 2.0),
+             ("nb64_fixed", 64, 8, None, 5, 1e-8, -1.0, 1.0)]
+    for name, nb, k, ranks, rk, acc, alpha, beta in cases:
+        T = 3
+        b = make_lr_batch(T, nb, k, base_seed=99, ranks=ranks)
+        for t in range(T):
+            cu, cv, r, fl = rb.hcore_gemm(b.au[t, :b.ark[t]], b.av[t, :b.ark[t]], b.bu[t, :b.brk[t]], b.bv[t, :b.brk[t]],
+                                          b.cu[t], b.cv[t], int(b.crk[t]), alpha=alpha, beta=beta, rk=rk,
+                                          maxrk=2 * k, acc=acc)
+            rec[f"{name}_t{t}_cu"] = cu[:r]
+            rec[f"{name}_t{t}_cv"] = cv[:r]
+            rec[f"{name}_t{t}_rank"] = r
+            rec[f"{name}_t{t}_flops"] = fl
+        rec[f"{name}_meta"] = np.array([nb, k, rk, T], dtype=np.int64)
+        rec[f"{name}_scal"] = np.array([acc, alpha, beta])
+        if ranks is not None:
+            rec[f"{name}_ranks"] = np.array(ranks, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "ref_tlr_small.npz"), **rec)
+    print("tlr_small:", {k_: int(v) for k_, v in rec.items() if k_.endswith("_rank")})
+
+
+def tlr_large():
+    rec = {}
+    for name, nb, k, T in (("nb500_k25", 500, 25, 3), ("nb1024_k64", 1024, 64, 2)):
+        b = make_lr_batch(T, nb, k)
+        ranks, errs, flops, frob = [], [], [], []
+        for t in range(T):
+            cu, cv, r, fl = rb.hcore_gemm(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k, alpha=-1.0,
+                                          beta=1.0, rk=0, maxrk=2 * k, acc=1e-8)
+            D = b.dense_c(t, -1.0, 1.0)
+            ranks.append(r); flops.append(fl)
+            errs.append(np.linalg.norm(cu[:r].T @ cv[:r] - D)); frob.append(np.linalg.norm(D))
+        rec[name + "_ranks"] = np.array(ranks)
+        rec[name + "_err"] = np.array(errs)
+        rec[name + "_normC"] = np.array(frob)
+        rec[name + "_flops"] = np.array(flops)
+        print(name, ranks, errs)
+    np.savez(os.path.join(HERE, "ref_tlr_large.npz"), **rec)
+
+
+if __name__ == "__main__":
+    rb.set_blas_threads(1)
+    ctest_dgemm()
+    ctest_dgemmcd()
+    ctest_dsyrk()
+    tlr_small()
+    tlr_large()

@@ -1,0 +1,273 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against (1) the reference's own known-answer tests, (2) committed outputs of the compiled
+reference, (3) the oracle on seeded inputs, (4) size-independent properties at full size.
+Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+from hcore_b200 import api
+from hcore_b200.tilegen import make_lr_batch, make_dense_batch
+from oracle import tlr_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _inf_norm(x):
+    return np.abs(x).sum(axis=1).max()
+
+
+def _to_dev(b):
+    dev = torch.device("cuda:0")
+    return {n: torch.from_numpy(np.ascontiguousarray(getattr(b, n))).to(dev)
+            for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
+
+
+def _run_batch(ctx, b, alpha, beta, rk, maxrk, acc):
+    t = _to_dev(b)
+    status = torch.full((b.ntiles,), -7, dtype=torch.int32, device="cuda:0")
+    ctx.dgemm_batched(alpha, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], beta, t["cu"], t["cv"], t["crk"],
+                      rk=rk, maxrk=maxrk, acc=acc, status=status)
+    torch.cuda.synchronize()
+    return t["cu"].cpu().numpy(), t["cv"].cpu().numpy(), t["crk"].cpu().numpy(), status.cpu().numpy()
+
+
+# ---- (1) the reference's own known-answer tests, through the legacy drop-in symbols ----------------
+
+def test_ctest_dgemm_legacy_symbol(golden_dir):
+    """reference testing/testing_dgemm.c:250-392 replayed on HCORE_dgemm of libhcore_b200.so."""
+    g = np.load(os.path.join(golden_dir, "ref_ctest_dgemm.npz"))
+    n, acc = int(g["n"]), float(g["acc"])
+    ra, rb_, rc = (int(x) for x in g["ranks"])
+    smr = 6                                               # storage_maxrank: CU/CV buffers are n x 6 (:259,:287-290)
+    CU = np.zeros((smr, n)); CU[:rc] = g["CU"][:rc]
+    CV = np.zeros((smr, n)); CV[:rc] = g["CV"][:rc]
+    Ark, Brk, Crk = np.array([float(ra)]), np.array([float(rb_)]), np.array([float(rc)])
+    fl = api.FlopCounter()
+    api.hcore_dgemm(api.HCORE_NoTrans, api.HCORE_Trans, n, n, 1.0, np.ascontiguousarray(g["AU"]),
+                    np.ascontiguousarray(g["AV"]), Ark, n, np.ascontiguousarray(g["BU"]), np.ascontiguousarray(g["BV"]),
+                    Brk, n, 1.0, CU, CV, Crk, n, 0, n, acc, None, fl)
+    r = int(Crk[0])
+    assert r == int(g["out_rank"]) == 6                   # "Crank: 4 -> 6"
+    rnorm = _inf_norm(g["ref_c"] - CU[:r].T @ CV[:r])
+    assert rnorm < 10 * acc                               # the reference's assert (:377-378)
+    assert abs(rnorm - float(g["rnorm"])) < 1e-10         # 1.476392e-04
+    assert fl.update == int(g["flops"])                   # same flop accounting as the reference
+
+
+def test_ctest_dgemmcd_legacy_symbol(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_ctest_dgemmcd.npz"))
+    CD = np.array(g["CD"], copy=True)
+    api.hcore_dgemmcd(api.HCORE_NoTrans, api.HCORE_Trans, 10, -1.0, np.ascontiguousarray(g["Au"]),
+                      np.ascontiguousarray(g["Av"]), 7, 10, np.ascontiguousarray(g["Bu"]), np.ascontiguousarray(g["Bv"]),
+                      6, 10, 1.0, CD, 10, 7)
+    dense = g["CD"].T - (g["Au"].T @ g["Av"]) @ (g["Bu"].T @ g["Bv"]).T
+    assert _inf_norm(dense - CD.T) < 1000 * EPS           # reference testing_dgemmcd.c:194-205
+    assert np.abs(CD - g["out"]).max() < 1000 * EPS
+
+
+def test_ctest_dsyrk_legacy_symbol(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_ctest_dsyrk.npz"))
+    CD = np.array(g["CD"], copy=True)
+    fl = api.FlopCounter()
+    api.hcore_dsyrk(api.HCORE_Lower, api.HCORE_NoTrans, 10, 7, -1.0, np.ascontiguousarray(g["AU"]), 10,
+                    np.ascontiguousarray(g["AV"]), 10, 1.0, CD, 10, None, fl)
+    Am = g["AU"].T @ g["AV"]
+    dense = np.tril(g["CD"].T - Am @ Am.T)
+    assert _inf_norm(dense - np.tril(CD.T)) < 1000 * EPS  # reference testing_dsyrk.c:170-181
+    assert np.abs(np.triu(CD.T, 1)).max() == 0.0          # strict upper triangle zeroed (hcore_dsyrk.c:174-181)
+    assert np.abs(CD - g["out"]).max() < 1000 * EPS
+    assert fl.syrk == int(g["flops"])
+
+
+# ---- (2) committed outputs of the compiled reference --------------------------------------------------
+
+@pytest.mark.parametrize("name,kind", [("nb64_k8", None), ("nb96_ragged", "ragged"), ("nb64_fixed", None)])
+def test_small_batches_vs_reference_outputs(ctx, golden_dir, name, kind):
+    g = np.load(os.path.join(golden_dir, "ref_tlr_small.npz"))
+    nb, k, rk, T = (int(x) for x in g[name + "_meta"])
+    acc, alpha, beta = (float(x) for x in g[name + "_scal"])
+    ranks = [tuple(int(v) for v in row) for row in g[name + "_ranks"]] if kind == "ragged" else None
+    b = make_lr_batch(T, nb, k, base_seed=99, ranks=ranks)
+    cu, cv, crk, st = _run_batch(ctx, b, alpha, beta, rk, 2 * k, acc)
+    assert (st == 0).all()
+    for t in range(T):
+        r_ref = int(g[f"{name}_t{t}_rank"])
+        r = int(crk[t])
+        assert abs(r - r_ref) <= 1
+        ref = g[f"{name}_t{t}_cu"].T @ g[f"{name}_t{t}_cv"]
+        dense = b.dense_c(t, alpha, beta)
+        e_ref = np.linalg.norm(ref - dense)
+        e_dev = np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense)
+        if r == r_ref:
+            assert np.abs(cu[t, :r].T @ cv[t, :r] - ref).max() < 1e-12
+        assert e_dev <= max(1.01 * e_ref, 64 * EPS * np.linalg.norm(dense)) + (acc if r != r_ref else 0.0)
+        if rk == 0:
+            assert np.abs(cu[t, :r] @ cu[t, :r].T - np.eye(r)).max() < 1e-13   # U factor stays orthonormal
+
+
+@pytest.mark.parametrize("name,nb,k,T", [("nb500_k25", 500, 25, 3), ("nb1024_k64", 1024, 64, 2)])
+def test_large_tiles_vs_reference_outputs(ctx, golden_dir, name, nb, k, T):
+    """BASELINE.json configs[0] (nb=500, rank 25) and configs[1] (nb=1024, rank 64), acc 1e-8."""
+    g = np.load(os.path.join(golden_dir, "ref_tlr_large.npz"))
+    b = make_lr_batch(T, nb, k)
+    cu, cv, crk, st = _run_batch(ctx, b, -1.0, 1.0, 0, 2 * k, 1e-8)
+    assert (st == 0).all()
+    for t in range(T):
+        r, r_ref = int(crk[t]), int(g[name + "_ranks"][t])
+        assert abs(r - r_ref) <= 1
+        dense = b.dense_c(t, -1.0, 1.0)
+        err = np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense)
+        assert err <= max(1e-8 * np.linalg.norm(dense), 1.01 * float(g[name + "_err"][t])) + (1e-8 if r != r_ref else 0)
+        assert err / np.linalg.norm(dense) <= 1e-8       # north star: relative error at or below the accuracy
+
+
+# ---- (3) oracle on seeded inputs: shapes, scalars, modes -------------------------------------------------
+
+@pytest.mark.parametrize("nb,k,alpha,beta,rk,acc", [
+    (128, 16, -1.0, 1.0, 0, 1e-8), (130, 9, 1.0, 1.0, 0, 1e-6), (257, 17, 0.3, -2.0, 0, 1e-10),
+    (1000, 40, -1.0, 1.0, 0, 1e-8), (384, 64, -1.0, 1.0, 0, 1e-8), (200, 12, -1.0, 1.0, 7, 1e-8),
+    (200, 12, -1.0, 1.0, 100, 1e-8), (64, 3, -1.0, 1.0, 0, 1e-3), (2048, 32, -1.0, 1.0, 0, 1e-8)])
+def test_vs_oracle(ctx, nb, k, alpha, beta, rk, acc):
+    T = 3
+    b = make_lr_batch(T, nb, k, base_seed=7 + nb)
+    cu, cv, crk, st = _run_batch(ctx, b, alpha, beta, rk, 2 * k, acc)
+    assert (st == 0).all()
+    for t in range(T):
+        cu_o, cv_o, r_o, sig = orc.tlr_gemm_colmajor(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k,
+                                                     alpha=alpha, beta=beta, rk=rk, maxrk=2 * k, acc=acc)
+        r = int(crk[t])
+        assert abs(r - r_o) <= (0 if rk else 1)
+        dense = b.dense_c(t, alpha, beta)
+        e_o = np.linalg.norm(cu_o.T @ cv_o - dense)
+        e_d = np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense)
+        assert e_d <= max(1.01 * e_o, 256 * EPS * np.linalg.norm(dense)) + (acc if r != r_o else 0.0)
+
+
+def test_ragged_ranks_and_rank_deficient_stack(ctx):
+    nb, k = 192, 16
+    ranks = [(16, 16, 16), (1, 1, 1), (3, 16, 9), (16, 2, 1), (7, 7, 7)]
+    b = make_lr_batch(len(ranks), nb, k, base_seed=21, ranks=ranks)
+    b.au[4, :7] = b.cu[4, :7]                            # A and C share their column space exactly
+    cu, cv, crk, st = _run_batch(ctx, b, -1.0, 1.0, 0, 2 * k, 1e-8)
+    assert (st == 0).all()
+    for t, (a, bb, c) in enumerate(ranks):
+        cu_o, cv_o, r_o, _ = orc.tlr_gemm(b.au[t, :a].T, b.av[t, :a].T, b.bu[t, :bb].T, b.bv[t, :bb].T, b.cu[t, :c].T,
+                                          b.cv[t, :c].T, alpha=-1.0, beta=1.0, rk=0, maxrk=2 * k, acc=1e-8)
+        r = int(crk[t])
+        assert abs(r - r_o) <= 1
+        dense = b.dense_c(t, -1.0, 1.0)
+        assert np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense) <= 1.01 * np.linalg.norm(cu_o @ cv_o.T - dense) + 2e-8
+    assert int(crk[4]) <= 8                               # rank-deficient stack is really recompressed
+
+
+def test_per_tile_status_instead_of_exit(ctx):
+    """Errors that make the reference exit(-1) (hcore_dgemm.c:743-746, :924-927) become per-tile status."""
+    nb, k = 128, 8
+    ranks = [(8, 8, 8), (8, 8, 0), (8, 8, 8), (0, 8, 8)]
+    b = make_lr_batch(4, nb, k, base_seed=2, ranks=[(8, 8, 8)] * 4)
+    b.ark[:] = [r[0] for r in ranks]; b.crk[:] = [r[2] for r in ranks]
+    before = b.cu.copy()
+    cu, cv, crk, st = _run_batch(ctx, b, -1.0, 1.0, 0, 2 * k, 1e-8)
+    assert st.tolist() == [0, 1, 0, 1]
+    assert np.array_equal(cu[1], before[1]) and np.array_equal(cu[3], before[3])    # failed tiles untouched
+    b2 = make_lr_batch(2, nb, k, base_seed=2)
+    cu, cv, crk, st = _run_batch(ctx, b2, -1.0, 1.0, 0, 2 * k - 1, 1e-8)            # maxrk < Ark + Crk
+    assert st.tolist() == [2, 2] and crk.tolist() == [8, 8]
+
+
+# ---- (4) properties at the benchmark size ------------------------------------------------------------------
+
+def test_full_size_properties_and_shard_invariance(ctx):
+    """nb=1024, rank 64, acc 1e-8 (BASELINE.json configs[1]) on 96 tiles: every tile meets the
+    accuracy bound, U stays orthonormal, ranks sit where the reference's do (92-94), and the
+    per-tile results do not depend on how the batch is cut (tiles are independent)."""
+    nb, k, T, acc = 1024, 64, 96, 1e-8
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    import bench
+    d = bench.make_device_batch(torch, T, nb, k, dev, seed=5)
+    bench.restore_c(d, k)
+    ctx.dgemm_batched(-1.0, d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], 1.0, d["cu"], d["cv"], d["crk"],
+                      rk=0, maxrk=2 * k, acc=acc, status=d["status"])
+    torch.cuda.synchronize()
+    assert int(d["status"].abs().sum().item()) == 0
+    ranks = d["crk"].cpu().numpy()
+    assert ranks.min() >= 90 and ranks.max() <= 96
+    full_cu, full_cv = d["cu"].clone(), d["cv"].clone()
+    for t in range(0, T, 7):
+        r = int(ranks[t])
+        U, V = d["cu"][t, :r], d["cv"][t, :r]
+        A = d["au"][t].T @ d["av"][t]; B = d["bu"][t].T @ d["bv"][t]
+        dense = d["cu0"][t].T @ d["cv0"][t] - A @ B.T
+        err = torch.linalg.norm(U.T @ V - dense).item()
+        assert err / torch.linalg.norm(dense).item() <= acc
+        assert err <= acc * np.sqrt(2 * k)               # reference guarantee: ||err||_F <= acc*sqrt(#dropped)
+        assert (U @ U.T - torch.eye(r, dtype=torch.float64, device=dev)).abs().max().item() < 1e-13
+    # same batch cut in two unequal shards and in small chunks: bit-identical per-tile output
+    for cut, chunk in ((37, 0), (64, 5)):
+        ctx.set_chunk(chunk)
+        bench.restore_c(d, k)
+        for lo, hi in ((0, cut), (cut, T)):
+            ctx.dgemm_batched(-1.0, d["au"][lo:hi], d["av"][lo:hi], d["ark"][lo:hi], d["bu"][lo:hi], d["bv"][lo:hi],
+                              d["brk"][lo:hi], 1.0, d["cu"][lo:hi], d["cv"][lo:hi], d["crk"][lo:hi], rk=0,
+                              maxrk=2 * k, acc=acc, status=d["status"][lo:hi])
+        torch.cuda.synchronize()
+        assert np.array_equal(d["crk"].cpu().numpy(), ranks)
+        for t in range(T):
+            r = int(ranks[t])
+            assert torch.equal(d["cu"][t, :r], full_cu[t, :r]) and torch.equal(d["cv"][t, :r], full_cv[t, :r])
+    ctx.set_chunk(0)
+
+
+def test_host_buffer_path_matches_device_path(ctx):
+    nb, k, T = 256, 16, 700                               # > one 512-tile staging slice
+    b = make_lr_batch(8, nb, k, base_seed=31)
+    rep = lambda x: np.ascontiguousarray(np.tile(x, (T // 8 + 1,) + (1,) * (x.ndim - 1))[:T])
+    import copy
+    bb = copy.copy(b)
+    for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk"):
+        setattr(bb, n, rep(getattr(b, n)))
+    cu_d, cv_d, crk_d, st_d = _run_batch(ctx, bb, -1.0, 1.0, 0, 2 * k, 1e-8)
+    cu_h, cv_h, crk_h = bb.cu.copy(), bb.cv.copy(), bb.crk.copy()
+    st_h = np.full(T, -1, np.int32)
+    ctx.dgemm_batched_host(-1.0, bb.au, bb.av, bb.ark, bb.bu, bb.bv, bb.brk, 1.0, cu_h, cv_h, crk_h, rk=0, maxrk=2 * k,
+                           acc=1e-8, status=st_h)
+    assert (st_h == 0).all() and np.array_equal(crk_h, crk_d)
+    for t in range(T):
+        r = int(crk_d[t])
+        assert np.array_equal(cu_h[t, :r], cu_d[t, :r]) and np.array_equal(cv_h[t, :r], cv_d[t, :r])
+
+
+# ---- dense-C updates (BASELINE.json configs[2]) ----------------------------------------------------------------
+
+@pytest.mark.parametrize("nb,ka,kb", [(1024, 32, 32), (500, 25, 13), (130, 7, 6), (1024, 64, 96)])
+def test_dgemmcd_dsyrk_batched_vs_oracle(ctx, nb, ka, kb):
+    T = 3
+    b = make_lr_batch(T, nb, max(ka, kb), base_seed=17, ranks=[(ka, kb, 1)] * T)
+    t = _to_dev(b)
+    cd = make_dense_batch(T, nb)
+    c1 = torch.from_numpy(cd).to("cuda:0")
+    ctx.dgemmcd_batched(t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], c1)
+    c2 = torch.from_numpy(cd).to("cuda:0")
+    ctx.dsyrk_batched(-1.0, t["au"], t["av"], t["ark"], c2)
+    torch.cuda.synchronize()
+    for i in range(T):
+        ref = orc.gemmcd(b.au[i, :ka].T, b.av[i, :ka].T, b.bu[i, :kb].T, b.bv[i, :kb].T, cd[i].T)
+        assert np.abs(c1[i].cpu().numpy().T - ref).max() < 1000 * EPS * max(1.0, np.abs(ref).max())
+        ref = orc.syrk(b.au[i, :ka].T, b.av[i, :ka].T, cd[i].T, -1.0)
+        out = c2[i].cpu().numpy().T
+        assert np.abs(out - ref).max() < 1000 * EPS * max(1.0, np.abs(ref).max())
+        assert np.abs(np.triu(out, 1)).max() == 0.0

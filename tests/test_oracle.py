@@ -1,0 +1,147 @@
+"""CPU tests: the oracle (numpy/LAPACK restatement) against the reference's own known-answer
+tests and against outputs of the compiled, unmodified reference (tests/golden, produced by
+tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from hcore_b200.tilegen import make_lr_batch
+from oracle import ref_binding as rb
+from oracle import tlr_oracle as orc
+import device_model as dm
+
+
+def _inf_norm(x):
+    return np.abs(x).sum(axis=1).max()
+
+
+def test_reference_ctest_dgemm(golden_dir):
+    """reference testing/testing_dgemm.c: ranks 4/4/4 -> 6 and ||C_ref - CU CV^T||_inf < 10*acc (:377-378)."""
+    g = np.load(os.path.join(golden_dir, "ref_ctest_dgemm.npz"))
+    ra, rb_, rc = g["ranks"]
+    cu, cv, r, _ = orc.tlr_gemm(g["AU"][:ra].T, g["AV"][:ra].T, g["BU"][:rb_].T, g["BV"][:rb_].T, g["CU"][:rc].T,
+                                g["CV"][:rc].T, alpha=1.0, beta=1.0, rk=0, maxrk=int(g["n"]), acc=float(g["acc"]))
+    assert r == int(g["out_rank"]) == 6
+    rn = _inf_norm(g["ref_c"] - cu @ cv.T)
+    assert rn < 10 * float(g["acc"])
+    assert abs(rn - float(g["rnorm"])) < 1e-12          # golden value 1.476392e-04
+    assert abs(float(g["rnorm"]) - 1.476392e-04) < 1e-9
+    np.testing.assert_allclose(cu.T, g["out_cu"], atol=1e-12)
+    np.testing.assert_allclose(cv.T, g["out_cv"], atol=1e-12)
+    assert orc.flop_model(10, ra, rb_, rc, r) == int(g["flops"])
+
+
+def test_reference_ctest_dgemmcd(golden_dir):
+    """reference testing/testing_dgemmcd.c:194-205: residual < 1000 eps."""
+    g = np.load(os.path.join(golden_dir, "ref_ctest_dgemmcd.npz"))
+    out = orc.gemmcd(g["Au"].T, g["Av"].T, g["Bu"].T, g["Bv"].T, g["CD"].T)
+    assert np.abs(out - g["out"].T).max() < 1000 * np.finfo(float).eps
+
+
+def test_reference_ctest_dsyrk(golden_dir):
+    """reference testing/testing_dsyrk.c:170-181: lower triangle compared, residual < 1000 eps;
+    the reference also zeroes the strict upper triangle (src/compute/hcore_dsyrk.c:174-181)."""
+    g = np.load(os.path.join(golden_dir, "ref_ctest_dsyrk.npz"))
+    out = orc.syrk(g["AU"].T, g["AV"].T, g["CD"].T, -1.0)
+    assert np.abs(out - g["out"].T).max() < 1000 * np.finfo(float).eps
+    assert np.abs(np.triu(out, 1)).max() == 0.0
+
+
+CASES = [("nb64_k8", None), ("nb96_ragged", "ragged"), ("nb64_fixed", None)]
+
+
+@pytest.mark.parametrize("name,kind", CASES)
+def test_oracle_vs_compiled_reference_small(golden_dir, name, kind):
+    g = np.load(os.path.join(golden_dir, "ref_tlr_small.npz"))
+    nb, k, rk, T = (int(x) for x in g[name + "_meta"])
+    acc, alpha, beta = (float(x) for x in g[name + "_scal"])
+    ranks = [tuple(int(v) for v in row) for row in g[name + "_ranks"]] if kind == "ragged" else None
+    b = make_lr_batch(T, nb, k, base_seed=99, ranks=ranks)
+    for t in range(T):
+        a, bb, c = int(b.ark[t]), int(b.brk[t]), int(b.crk[t])
+        cu, cv, r, _ = orc.tlr_gemm(b.au[t, :a].T, b.av[t, :a].T, b.bu[t, :bb].T, b.bv[t, :bb].T, b.cu[t, :c].T,
+                                    b.cv[t, :c].T, alpha=alpha, beta=beta, rk=rk, maxrk=2 * k, acc=acc)
+        assert r == int(g[f"{name}_t{t}_rank"])
+        np.testing.assert_allclose(cu @ cv.T, g[f"{name}_t{t}_cu"].T @ g[f"{name}_t{t}_cv"], atol=1e-12)
+        assert orc.flop_model(nb, a, bb, c, r) == int(g[f"{name}_t{t}_flops"])
+
+
+@pytest.mark.parametrize("name,nb,k,T", [("nb500_k25", 500, 25, 3), ("nb1024_k64", 1024, 64, 2)])
+def test_oracle_vs_compiled_reference_large(golden_dir, name, nb, k, T):
+    g = np.load(os.path.join(golden_dir, "ref_tlr_large.npz"))
+    b = make_lr_batch(T, nb, k)
+    for t in range(T):
+        cu, cv, r, _ = orc.tlr_gemm_colmajor(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k, alpha=-1.0,
+                                             beta=1.0, rk=0, maxrk=2 * k, acc=1e-8)
+        assert r == int(g[name + "_ranks"][t])
+        err = np.linalg.norm(cu.T @ cv - b.dense_c(t, -1.0, 1.0))
+        assert abs(err - float(g[name + "_err"][t])) < 1e-11
+        assert orc.flop_model(nb, k, k, k, r) == int(g[name + "_flops"][t])
+
+
+@pytest.mark.skipif(not rb.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_vs_live_reference():
+    rb.set_blas_threads(1)
+    b = make_lr_batch(2, 200, 12, base_seed=5)
+    for t in range(2):
+        cu, cv, r, fl = rb.hcore_gemm(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], 12, alpha=-1.0, beta=1.0,
+                                      rk=0, maxrk=24, acc=1e-8)
+        cu2, cv2, r2, _ = orc.tlr_gemm_colmajor(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], 12, alpha=-1.0,
+                                                beta=1.0, rk=0, maxrk=24, acc=1e-8)
+        assert r == r2
+        np.testing.assert_allclose(cu[:r], cu2, atol=1e-12)
+        np.testing.assert_allclose(cv[:r], cv2, atol=1e-12)
+        assert fl == orc.flop_model(200, 12, 12, 12, r)
+
+
+def test_oracle_error_conventions():
+    """Where the reference exit(-1)s the oracle raises (hcore_dgemm.c:743-746, :924-927)."""
+    b = make_lr_batch(1, 32, 4)
+    args = [x.T for x in (b.au[0], b.av[0], b.bu[0], b.bv[0], b.cu[0][:4], b.cv[0][:4])]
+    with pytest.raises(ValueError):
+        orc.tlr_gemm(*args, alpha=1.0, beta=1.0, rk=0, maxrk=7, acc=1e-8)
+    with pytest.raises(ValueError):
+        orc.tlr_gemm(args[0][:, :0], args[1][:, :0], *args[2:], alpha=1.0, beta=1.0, rk=0, maxrk=8, acc=1e-8)
+
+
+def test_truncation_rule():
+    s = np.array([1.0, 1e-3, 1e-9, 1e-12])
+    assert orc.truncation_rank(s, 0, 1e-8) == 2
+    assert orc.truncation_rank(s, 0, 10.0) == 1          # scan starts at 1: rank >= 1
+    assert orc.truncation_rank(s, 0, 1e-20) == 4
+    assert orc.truncation_rank(s, 3, 1e-8) == 3
+    assert orc.truncation_rank(s, 9, 1e-8) == 4
+    assert orc.truncation_rank(s, -1, 1e-8) == min(-1, 4)  # d/s variants: rk != 0 is "fixed" (hcore_dgemm.c:448)
+    assert orc.truncation_rank(s, -1, 1e-8, fixed_rank_if_positive=True) == 2   # zgemm: rk > 0 (hcore_zgemm.c:376)
+
+
+@pytest.mark.parametrize("nb,k", [(64, 8), (150, 10), (300, 20)])
+def test_device_model_matches_oracle(nb, k):
+    """The numpy model of the DEVICE algorithm (TSQR + QRCP/Jacobi + reflector apply) gives the
+    reference's rank and reconstruction error; this validates the math the CUDA kernels implement."""
+    b = make_lr_batch(2, nb, k, base_seed=11)
+    for t in range(2):
+        args = [x.T for x in (b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t][:k], b.cv[t][:k])]
+        kw = dict(alpha=-1.0, beta=1.0, rk=0, maxrk=2 * k, acc=1e-8)
+        cu, cv, r, sig, sweeps = dm.tlr_gemm_model(*args, **kw)
+        cu2, cv2, r2, sig2 = orc.tlr_gemm(*args, **kw)
+        D = b.dense_c(t, -1.0, 1.0)
+        assert r == r2
+        assert np.abs(sig - sig2).max() < 1e-13
+        assert np.linalg.norm(cu @ cv.T - D) <= 1.01 * np.linalg.norm(cu2 @ cv2.T - D) + 1e-14
+        assert np.abs(cu.T @ cu - np.eye(r)).max() < 1e-13
+        assert sweeps <= 8
+
+
+def test_device_model_rank_deficient_stack():
+    """U-stack with exactly repeated columns (C and A share their column space)."""
+    b = make_lr_batch(1, 96, 6, base_seed=3)
+    au = b.cu[0][:6].T.copy()            # AU == CU
+    args = [au, b.av[0].T, b.bu[0].T, b.bv[0].T, b.cu[0][:6].T, b.cv[0][:6].T]
+    kw = dict(alpha=-1.0, beta=1.0, rk=0, maxrk=12, acc=1e-8)
+    cu, cv, r, sig, _ = dm.tlr_gemm_model(*args, **kw)
+    cu2, cv2, r2, _ = orc.tlr_gemm(*args, **kw)
+    D = args[4] @ args[5].T - (au @ args[1].T) @ (args[2] @ args[3].T).T
+    assert abs(r - r2) <= 1 and r <= 7
+    assert np.linalg.norm(cu @ cv.T - D) < 5e-8
