@@ -131,6 +131,10 @@ __device__ __forceinline__ void block_gemm(MatView C, AView A, BView B, int M, i
 
 // LAPACK dlarfg on (alpha, squared norm of the tail): returns beta, tau and the scale
 // 1/(alpha-beta) to apply to the tail.  sigma2 == 0 -> H = I (tau = 0), as LAPACK does.
+// Written with one rsqrt and one reciprocal instead of sqrt + two divisions (the scalar
+// chain sits on the critical path of every Householder step):
+//   nrm = sqrt(alpha^2 + sigma2),  beta = -sign(alpha) nrm,
+//   tau = (beta - alpha)/beta = 1 + |alpha|/nrm,   1/(alpha - beta) = sign(alpha)/(|alpha| + nrm)
 struct Householder {
     double beta, tau, scal;
 };
@@ -141,12 +145,61 @@ __device__ __forceinline__ Householder make_householder(double alpha, double sig
         h.tau = 0.0;
         h.scal = 0.0;
     } else {
-        const double nrm = sqrt(fma(alpha, alpha, sigma2));
+        const double s2 = fma(alpha, alpha, sigma2);
+        const double rinv = rsqrt(s2);
+        const double nrm = s2 * rinv;
+        const double aabs = fabs(alpha);
         h.beta = -copysign(nrm, alpha);
-        h.tau = (h.beta - alpha) / h.beta;
-        h.scal = 1.0 / (alpha - h.beta);
+        h.tau = fma(aabs, rinv, 1.0);
+        h.scal = copysign(__drcp_rn(aabs + nrm), alpha);
     }
     return h;
+}
+
+// Named barrier for a subset of the CTA's warps (ids 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp by recursive halving: after the call
+// every lane holds in the return value the warp total of column reduce16_col(lane).
+// 16 double exchanges instead of the 80 of 16 separate butterflies.
+__device__ __forceinline__ int reduce16_col(int lane) { return (lane >> 1) & 15; }
+__device__ __forceinline__ double reduce16(const double (&p)[16], int lane) {
+    double a8[8], a4[4], a2[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double keep = up ? p[j + 8] : p[j];
+            const double send = up ? p[j] : p[j + 8];
+            a8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double keep = up ? a8[j + 4] : a8[j];
+            const double send = up ? a8[j] : a8[j + 4];
+            a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double keep = up ? a4[j + 2] : a4[j];
+            const double send = up ? a4[j] : a4[j + 2];
+            a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool up = lane & 2;
+    const double keep = up ? a2[1] : a2[0];
+    const double send = up ? a2[0] : a2[1];
+    double v = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
 }
 
 // Round-robin (chess tournament) pairing, closed form: pair k of step `step`, n even.

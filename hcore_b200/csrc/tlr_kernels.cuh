@@ -144,23 +144,35 @@ __global__ void __launch_bounds__(512) tlr_stack_kernel(TlrArgs ar, TlrWorkspace
 // ========================================================================================
 // 2. tall-skinny QR kernel
 // ========================================================================================
+// Flat-tree TSQR: the panel is processed in 128-row blocks that live in shared memory.
+// Block 0 is a plain blocked Householder QR (reflectors below the diagonal, R on top);
+// every further block B_j is eliminated against the running R ("triangle on top of a dense
+// block"): reflector i = [e_i ; v_i] touches row i of R and all of B_j.  Column sub-panels of
+// width 16; per sub-panel
+//   (a) panel factorisation by warps 0-3: one row per thread, the 16 panel columns in
+//       registers; per Householder step ONE batched 16-value reduction (the dots of the
+//       current column with every panel column give the norm, the in-panel update AND the
+//       V^T v products for the compact-WY T factor), one 128-thread named barrier;
+//   (b) block-reflector update of the trailing columns with three DMMA GEMMs
+//       S = R_strip + V^T B,  S2 = T^T S,  B -= V S2,  R_strip -= S2   (all 16 warps).
 template <int N>
 struct TsqrSmem {
     using G = Geometry<N>;
     static constexpr int kB = 0;
     static constexpr int kVp = kB + N * G::kLdB;
-    static constexpr int kRs = kVp + kPanelW * G::kLdB;
-    static constexpr int kS = kRs + N * G::kLdS;
+    static constexpr int kS = kVp + kPanelW * G::kLdB;
     static constexpr int kS2 = kS + N * G::kLdS;
     static constexpr int kTs = kS2 + N * G::kLdS;
-    static constexpr int kRfin = kTs + 256;
-    static constexpr int kZm = kRfin + 256;
-    static constexpr int kRed = kZm + 256;
-    static constexpr int kXcol = kRed + 64;
-    static constexpr int kTau = kXcol + kBlockH;
+    static constexpr int kRd = kTs + 256;       // diagonal 16x16 block of the R strip, row-major
+    static constexpr int kRfin = kRd + 256;     // its final value, row-major
+    static constexpr int kRed = kRfin + 256;    // [2][4 warps][16] reduction partials
+    static constexpr int kTau = kRed + 128;
     static constexpr int kTotal = kTau + 16;
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
+
+constexpr int kPanelThreads = 128;   // warps 0-3 factor the sub-panel
+constexpr int kPanelBarrier = 1;
 
 // One CTA (512 threads) per panel: blockIdx.x = 2 * tile + panel.
 template <int N>
@@ -169,9 +181,9 @@ __global__ void __launch_bounds__(512, 1) tlr_tsqr_kernel(TlrWorkspace ws) {
     using SM = TsqrSmem<N>;
     constexpr int LDB = G::kLdB, LDS = G::kLdS;
     extern __shared__ double smem[];
-    double *B = smem + SM::kB, *Vp = smem + SM::kVp, *Rs = smem + SM::kRs, *S = smem + SM::kS,
-           *S2 = smem + SM::kS2, *Ts = smem + SM::kTs, *Rfin = smem + SM::kRfin, *Zm = smem + SM::kZm,
-           *red = smem + SM::kRed, *xcol = smem + SM::kXcol, *tauv = smem + SM::kTau;
+    double *B = smem + SM::kB, *Vp = smem + SM::kVp, *S = smem + SM::kS, *S2 = smem + SM::kS2,
+           *Ts = smem + SM::kTs, *Rd = smem + SM::kRd, *Rfin = smem + SM::kRfin, *red = smem + SM::kRed,
+           *tauv = smem + SM::kTau;
 
     const int t = blockIdx.x >> 1, pnl = blockIdx.x & 1;
     if (ws.st[t] != HCORE_B200_OK) return;
@@ -183,10 +195,6 @@ __global__ void __launch_bounds__(512, 1) tlr_tsqr_kernel(TlrWorkspace ws) {
     double *panel = ws.panel + panel_offset(ws, pnl, t, G::kPanelCols);
     double *Rg = ws.R + nn_offset(ws, pnl, t, N);
     double *Tg = ws.T + t_offset(ws, pnl, t, G::kNsp);
-
-    const int r = tid & (kBlockH - 1);   // row of the block owned in the panel factorisation
-    const int q = tid >> 7;              // column quarter (4 of the 16 sub-panel columns)
-    const int rw = warp & 3;             // row-warp index inside the quarter
 
     for (int j = 0; j < ws.nblk; ++j) {
         const bool blk0 = (j == 0);
@@ -200,110 +208,114 @@ __global__ void __launch_bounds__(512, 1) tlr_tsqr_kernel(TlrWorkspace ws) {
         for (int s = 0; s < nsp; ++s) {
             const int c0 = s * kPanelW, c1 = c0 + kPanelW;
             const int ntrail = n16 - c1;
-            double v[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) v[l] = B[r + (c0 + 4 * q + l) * LDB];
-            if (!blk0) {
-                // strip of the running R: rows c0..c0+15, columns c0..n16-1
-                for (int idx = tid; idx < kPanelW * (n16 - c0); idx += blockDim.x) {
-                    const int ii = idx & 15, cc = c0 + (idx >> 4);
-                    Rs[ii + cc * LDS] = Rg[(size_t)(c0 + ii) + (size_t)cc * N];
-                }
-            }
-            if (tid < 256) { Zm[tid] = 0.0; Rfin[tid] = 0.0; }
-            __syncthreads();
 
-            // ---- panel factorisation: 16 Householder steps ----------------------------
-            for (int ii = 0; ii < kPanelW; ++ii) {
-                const int i = c0 + ii;           // global column (and diagonal row in block 0)
-                const int qi = ii >> 2, li = ii & 3;
-                if (q == qi) xcol[r] = v[li];
-                if (blk0 && r == i) {
+            if (warp < kPanelThreads / 32) {
+                // ================= (a) panel factorisation, warps 0-3 =====================
+                const int r = tid;                   // row of the block owned by this thread
+                double v[kPanelW];
 #pragma unroll
-                    for (int l = 0; l < 4; ++l) Rs[ii + (c0 + 4 * q + l) * LDS] = v[l];
-                }
-                __syncthreads();
-                double xi = xcol[r];
-                if (blk0 && r <= i) xi = 0.0;
-                double pd[4];
-#pragma unroll
-                for (int l = 0; l < 4; ++l) pd[l] = warp_sum(xi * v[l]);
-                if (lane == 0) {
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) red[rw * 16 + 4 * q + l] = pd[l];
-                }
-                __syncthreads();
-                const double sigma2 = red[ii] + red[16 + ii] + red[32 + ii] + red[48 + ii];
-                const double alpha = Rs[ii + i * LDS];
-                const Householder h = make_householder(alpha, sigma2);
-                const double vr = xi * h.scal;
-                const bool writer = (r == kBlockH - 1);
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    const int cc = 4 * q + l;
-                    const double dc = red[cc] + red[16 + cc] + red[32 + cc] + red[48 + cc];
-                    const double y = Rs[ii + (c0 + cc) * LDS] + dc * h.scal;
-                    if (cc > ii) {
-                        const double w = h.tau * y;
-                        v[l] -= vr * w;
-                        if (writer) Rfin[ii + cc * 16] = Rs[ii + (c0 + cc) * LDS] - w;
-                    } else if (cc < ii) {
-                        if (writer) Zm[cc + ii * 16] = y;
-                    } else {
-                        // column ii now holds the reflector tail; in block 0 the rows on and
-                        // above the diagonal keep their R entries
-                        if (!(blk0 && r <= i)) v[l] = vr;
-                        if (writer) { Rfin[ii + ii * 16] = h.beta; tauv[ii] = h.tau; }
+                for (int c = 0; c < kPanelW; ++c) v[c] = B[r + (c0 + c) * LDB];
+                if (!blk0) {
+                    // diagonal block of the running R (rows/cols c0..c0+15), row-major
+                    for (int idx = tid; idx < 256; idx += kPanelThreads) {
+                        const int ii = idx >> 4, c = idx & 15;
+                        Rd[idx] = Rg[(size_t)(c0 + ii) + (size_t)(c0 + c) * N];
                     }
                 }
-                // no barrier needed here: the next step's first barrier orders the reuse
-                // of xcol / red, and Rfin / Zm / tauv are only read after the loop.
-            }
-            __syncthreads();
+                for (int idx = tid; idx < 256; idx += kPanelThreads) { Ts[idx] = 0.0; Rfin[idx] = 0.0; }
+                named_barrier(kPanelBarrier, kPanelThreads);
 
-            // ---- compact-WY T (forward, columnwise): row k of T depends only on row k --
-            if (warp == 0 && lane < kPanelW) {
-                const int k = lane;
-                double trow[kPanelW];
 #pragma unroll
                 for (int ii = 0; ii < kPanelW; ++ii) {
-                    double val = 0.0;
-                    if (k == ii) val = tauv[ii];
-                    else if (k < ii) {
+                    const int i = c0 + ii;           // global column (= diagonal row in block 0)
+                    double *redb = red + (ii & 1) * 64;
+                    if (blk0 && r == i) {            // this row becomes row ii of the R strip
+#pragma unroll
+                        for (int c = 0; c < kPanelW; ++c) Rd[ii * 16 + c] = v[c];
+                    }
+                    double xi = v[ii];
+                    if (blk0 && r <= i) xi = 0.0;    // block 0: only rows below the diagonal take part
+                    double pr[kPanelW];
+#pragma unroll
+                    for (int c = 0; c < kPanelW; ++c) pr[c] = xi * v[c];
+                    const double wsum = reduce16(pr, lane);
+                    if ((lane & 1) == 0) redb[warp * 16 + reduce16_col(lane)] = wsum;
+                    named_barrier(kPanelBarrier, kPanelThreads);
+
+                    // totals d[c] = x_i . column c  (all of them only in warp 0, which builds T)
+                    double d[kPanelW];
+#pragma unroll
+                    for (int c = 0; c < kPanelW; c += 2) {
+                        if (c + 1 >= ii || warp == 0) {
+                            const double2 p0 = *reinterpret_cast<const double2 *>(redb + c);
+                            const double2 p1 = *reinterpret_cast<const double2 *>(redb + 16 + c);
+                            const double2 p2 = *reinterpret_cast<const double2 *>(redb + 32 + c);
+                            const double2 p3 = *reinterpret_cast<const double2 *>(redb + 48 + c);
+                            d[c] = (p0.x + p1.x) + (p2.x + p3.x);
+                            d[c + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+                        } else {
+                            d[c] = d[c + 1] = 0.0;
+                        }
+                    }
+                    const double alpha = Rd[ii * 16 + ii];
+                    const Householder h = make_householder(alpha, d[ii]);
+                    const double vr = xi * h.scal;
+                    const bool writer = (r == kPanelThreads - 1);
+#pragma unroll
+                    for (int c = ii + 1; c < kPanelW; ++c) {
+                        const double rd = Rd[ii * 16 + c];
+                        const double w = h.tau * fma(d[c], h.scal, rd);
+                        v[c] = fma(-vr, w, v[c]);
+                        if (writer) Rfin[ii * 16 + c] = rd - w;
+                    }
+                    // column ii now holds the reflector tail; in block 0 the rows on and above
+                    // the diagonal keep their R entries
+                    if (!(blk0 && r <= i)) v[ii] = vr;
+                    if (writer) { Rfin[ii * 16 + ii] = h.beta; tauv[ii] = h.tau; }
+                    // compact-WY T, column ii (forward/columnwise larft): lane k of warp 0 owns row k
+                    //   T[k][ii] = -tau * sum_{c=k}^{ii-1} T[k][c] * z_c,  z_c = V[:,c]^T v_ii
+                    if (warp == 0 && lane < kPanelW) {
+                        const int k = lane;
                         double accv = 0.0;
 #pragma unroll
-                        for (int cc = 0; cc < kPanelW; ++cc)
-                            if (cc >= k && cc < ii) accv = fma(trow[cc], Zm[cc + ii * 16], accv);
-                        val = -tauv[ii] * accv;
+                        for (int c = 0; c < ii; ++c) {
+                            const double z = fma(d[c], h.scal, Rd[ii * 16 + c]);
+                            if (c >= k) accv = fma(Ts[k + c * 16], z, accv);
+                        }
+                        Ts[k + ii * 16] = (k < ii) ? -h.tau * accv : (k == ii ? h.tau : 0.0);
                     }
-                    trow[ii] = val;
-                    Ts[k + ii * 16] = val;
                 }
-            }
-            // ---- explicit reflector panel, write-back of the block columns -------------
+                named_barrier(kPanelBarrier, kPanelThreads);   // Rfin complete
+
+                // explicit reflector panel + write-back of the block columns
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const int cc = 4 * q + l, col = c0 + cc;
-                double vv = v[l], bb = v[l];
-                if (blk0) {
-                    if (r < col) vv = 0.0;
-                    else if (r == col) vv = 1.0;
-                    if (r >= c0 && r <= col) bb = Rfin[(r - c0) + cc * 16];
+                for (int c = 0; c < kPanelW; ++c) {
+                    const int col = c0 + c;
+                    double vv = v[c], bb = v[c];
+                    if (blk0) {
+                        if (r < col) vv = 0.0;
+                        else if (r == col) vv = 1.0;
+                        if (r >= c0 && r <= col) bb = Rfin[(r - c0) * 16 + c];
+                    }
+                    Vp[r + c * LDB] = vv;
+                    B[r + col * LDB] = bb;
                 }
-                Vp[r + cc * LDB] = vv;
-                B[r + col * LDB] = bb;
-            }
-            if (!blk0 && tid < 256) {   // finished diagonal block of the running R
-                const int ii = tid & 15, cc = tid >> 4;
-                Rg[(size_t)(c0 + ii) + (size_t)(c0 + cc) * N] = (cc >= ii) ? Rfin[ii + cc * 16] : 0.0;
-            }
-            // S <- R strip (trailing columns) or zero
-            for (int idx = tid; idx < kPanelW * ntrail; idx += blockDim.x) {
-                const int ii = idx & 15, jj = idx >> 4;
-                S[ii + jj * LDS] = blk0 ? 0.0 : Rs[ii + (c1 + jj) * LDS];
+                if (!blk0) {   // finished diagonal block of the running R
+                    for (int idx = tid; idx < 256; idx += kPanelThreads) {
+                        const int ii = idx >> 4, c = idx & 15;
+                        Rg[(size_t)(c0 + ii) + (size_t)(c0 + c) * N] = (c >= ii) ? Rfin[idx] : 0.0;
+                    }
+                }
+            } else {
+                // warps 4-15 meanwhile stage S <- trailing part of the R strip (or zero)
+                for (int idx = tid - kPanelThreads; idx < kPanelW * ntrail; idx += (int)blockDim.x - kPanelThreads) {
+                    const int ii = idx & 15, jj = idx >> 4;
+                    S[ii + jj * LDS] = blk0 ? 0.0 : Rg[(size_t)(c0 + ii) + (size_t)(c1 + jj) * N];
+                }
             }
             __syncthreads();
 
+            // ================= (b) trailing update, all warps ==============================
             if (ntrail > 0) {
                 // S += Vp^T * B_trail
                 block_gemm<1, kGemmAdd>(mview(S, 1, LDS), cview(Vp, LDB, 1), cview(B + c1 * LDB, 1, LDB),
@@ -313,11 +325,11 @@ __global__ void __launch_bounds__(512, 1) tlr_tsqr_kernel(TlrWorkspace ws) {
                 block_gemm<1, kGemmSet>(mview(S2, 1, LDS), cview(Ts, 16, 1), cview(S, 1, LDS), kPanelW,
                                         ntrail, kPanelW, warp, nwarps);
                 __syncthreads();
-                // R strip -= S2 ; B_trail -= Vp * S2
+                // R strip -= S2 (straight to global) ; B_trail -= Vp * S2
                 if (!blk0) {
                     for (int idx = tid; idx < kPanelW * ntrail; idx += blockDim.x) {
                         const int ii = idx & 15, jj = idx >> 4;
-                        Rg[(size_t)(c0 + ii) + (size_t)(c1 + jj) * N] = Rs[ii + (c1 + jj) * LDS] - S2[ii + jj * LDS];
+                        Rg[(size_t)(c0 + ii) + (size_t)(c1 + jj) * N] -= S2[ii + jj * LDS];
                     }
                 }
                 block_gemm<2, kGemmSub>(mview(B + c1 * LDB, 1, LDB), cview(Vp, 1, LDB), cview(S2, 1, LDS),
@@ -506,8 +518,11 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     __syncthreads();
 
     // ---- one-sided Jacobi on the columns of L ---------------------------------------------
-    // 8 lanes per column pair; lane l8 owns rows l8, l8+8, ...
-    const int grp = tid >> 3, l8 = tid & 7;
+    // 8 lanes per column pair; lane l8 owns rows l8, l8+8, ...  The four pairs of a warp are
+    // taken in the order k, k+2, k+1, k+3 so that the two 8-lane groups of a half-warp read
+    // columns two apart (64-byte segments 16 banks apart: conflict-free with ld = N+4).
+    const int l8 = tid & 7;
+    const int grp = ((tid >> 5) << 2) | ((tid >> 4) & 1) | (((tid >> 3) & 1) << 1);
     const int npairs = n16 >> 1;
     int sweeps = 0;
     bool converged = false;
@@ -535,12 +550,15 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
                     aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
                     apq += __shfl_xor_sync(0xffffffffu, apq, o);
                 }
-                const double den = sqrt(app * aqq);
-                const double aapq = fabs(apq);
-                if (den > 0.0 && aapq > kTolRot * den) {
-                    if (aapq > kTolStop * den) big = 1;
-                    const double zeta = (aqq - app) / (2.0 * apq);
-                    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
+                const double den2 = app * aqq, apq2 = apq * apq;
+                if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
+                    if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
+                    // tan(theta) = sign(d) * 2apq / (|d| + sqrt(d^2 + 4 apq^2)),  d = aqq - app
+                    const double dd = aqq - app, h2 = 2.0 * apq;
+                    const double s2 = fma(dd, dd, h2 * h2);
+                    const double hyp = s2 * rsqrt(s2);
+                    const double tt = (dd >= 0.0 ? h2 : -h2) * __drcp_rn(fabs(dd) + hyp);
                     const double cs = rsqrt(fma(tt, tt, 1.0));
                     const double sn = cs * tt;
 #pragma unroll
