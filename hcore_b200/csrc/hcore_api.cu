@@ -123,7 +123,7 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     }
     if (tm) cudaEventRecord(ctx->ev[1], st);
     if (ctx->debug_stages >= 2) {
-        tlr_tsqr_kernel<N><<<2 * ar.ntiles, 512, TsqrSmem<N>::kBytes, st>>>(ws);
+        tlr_tsqr_kernel<N><<<2 * ar.ntiles, kTsqrThreads, TsqrSmem<N>::kBytes, st>>>(ws);
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[2], st);

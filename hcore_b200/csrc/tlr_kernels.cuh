@@ -108,19 +108,31 @@ __global__ void __launch_bounds__(512) tlr_stack_kernel(TlrArgs ar, TlrWorkspace
 
     // X_u = [beta*CU | alpha*AU | 0], X_v[:, :c] = CV, everything else of X_v zeroed
     // (G is written by the GEMM below); rows m..m_pad-1 are zero padding.
-    for (size_t idx = tid; idx < (size_t)m_pad * N; idx += blockDim.x) {
-        const int r = (int)(idx % m_pad), col = (int)(idx / m_pad);
-        double xu = 0.0, xv = 0.0;
-        if (r < m) {
-            if (col < c) {
-                xu = ar.beta * CU[r + (size_t)col * ar.ldc];
-                xv = CV[r + (size_t)col * ar.ldc];
-            } else if (col < n) {
-                xu = ar.alpha * AU[r + (size_t)(col - c) * ar.lda];
+    // One warp per column, lanes along the rows (coalesced), four loads in flight per lane.
+    {
+        const int warp = warp_id(), lane = lane_id(), nwarps = blockDim.x >> 5;
+        for (int col = warp; col < N; col += nwarps) {
+            const double *su = nullptr, *sv = nullptr;
+            double scale = 0.0;
+            if (col < c) { su = CU + (size_t)col * ar.ldc; sv = CV + (size_t)col * ar.ldc; scale = ar.beta; }
+            else if (col < n) { su = AU + (size_t)(col - c) * ar.lda; scale = ar.alpha; }
+            double *du = XU + (size_t)col * m_pad, *dv = XV + (size_t)col * m_pad;
+            for (int r0 = 0; r0 < m_pad; r0 += 128) {
+                double xu[4], xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + lane + 32 * u;
+                    xu[u] = (su && r < m) ? __ldg(su + r) : 0.0;
+                    xv[u] = (sv && r < m) ? __ldg(sv + r) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + lane + 32 * u;      // m_pad is a multiple of 128
+                    du[r] = scale * xu[u];
+                    dv[r] = xv[u];
+                }
             }
         }
-        XU[idx] = xu;
-        XV[idx] = xv;
     }
 
     // P = AV^T * BV   (a x b, contraction over the m rows)
@@ -128,7 +140,7 @@ __global__ void __launch_bounds__(512) tlr_stack_kernel(TlrArgs ar, TlrWorkspace
     {
         GuardedView Av{AV, (long)ar.lda, 1, a, m};   // A(i, k) = AV[k + i*lda]
         GuardedView Bv{BV, 1, (long)ar.ldb, m, b};   // B(k, j) = BV[k + j*ldb]
-        block_gemm<2, kGemmSet>(mview(P, 1, G::kLdL), Av, Bv, a8, b8, m4, warp_id(), blockDim.x >> 5);
+        block_gemm<4, kGemmSet>(mview(P, 1, G::kLdL), Av, Bv, a8, b8, m4, warp_id(), blockDim.x >> 5);
     }
     __syncthreads();
     // G = BU * P^T  -> X_v[:, c : c+a]
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(512) tlr_stack_kernel(TlrArgs ar, TlrWorkspace
         const int m8 = round_up(m, 8);
         GuardedView Bu{BU, 1, (long)ar.ldb, m, b};   // A(i, k) = BU[i + k*ldb]
         CMatView Pt = cview(P, G::kLdL, 1);          // B(k, j) = P[j + k*ldl]
-        block_gemm<2, kGemmSet>(mview(XV + (size_t)c * m_pad, 1, m_pad), Bu, Pt, m8, a8, b8, warp_id(),
+        block_gemm<4, kGemmSet>(mview(XV + (size_t)c * m_pad, 1, m_pad), Bu, Pt, m8, a8, b8, warp_id(),
                                 blockDim.x >> 5);
     }
 }
@@ -148,21 +160,31 @@ __global__ void __launch_bounds__(512) tlr_stack_kernel(TlrArgs ar, TlrWorkspace
 // Block 0 is a plain blocked Householder QR (reflectors below the diagonal, R on top);
 // every further block B_j is eliminated against the running R ("triangle on top of a dense
 // block"): reflector i = [e_i ; v_i] touches row i of R and all of B_j.  Column sub-panels of
-// width 16; per sub-panel
+// width 16 with compact-WY T factors.
+//
+// The columns are processed LEFT-LOOKING in groups of kGroupW = 64: for group g the CTA walks
+// over all row blocks, first applies the stored reflectors of the earlier groups to the
+// group's 64 columns, then factors the group's own four sub-panels.  Only a 128 x 64 slice of
+// a block is resident (110 KiB of shared memory), so two CTAs share an SM and one CTA's
+// latency-bound panel steps overlap the other's GEMM phases; the arithmetic (and its order
+// per matrix element) is the same as in the right-looking formulation.
+//
+// Per sub-panel
 //   (a) panel factorisation by warps 0-3: one row per thread, the 16 panel columns in
 //       registers; per Householder step ONE batched 16-value reduction (the dots of the
 //       current column with every panel column give the norm, the in-panel update AND the
 //       V^T v products for the compact-WY T factor), one 128-thread named barrier;
 //   (b) block-reflector update of the trailing columns with three DMMA GEMMs
-//       S = R_strip + V^T B,  S2 = T^T S,  B -= V S2,  R_strip -= S2   (all 16 warps).
+//       S = R_strip + V^T B,  S2 = T^T S,  B -= V S2,  R_strip -= S2   (all warps).
 template <int N>
 struct TsqrSmem {
     using G = Geometry<N>;
+    static constexpr int kGroupW = (N < 64) ? N : 64;
     static constexpr int kB = 0;
-    static constexpr int kVp = kB + N * G::kLdB;
+    static constexpr int kVp = kB + kGroupW * G::kLdB;
     static constexpr int kS = kVp + kPanelW * G::kLdB;
-    static constexpr int kS2 = kS + N * G::kLdS;
-    static constexpr int kTs = kS2 + N * G::kLdS;
+    static constexpr int kS2 = kS + kGroupW * G::kLdS;
+    static constexpr int kTs = kS2 + kGroupW * G::kLdS;
     static constexpr int kRd = kTs + 256;       // diagonal 16x16 block of the R strip, row-major
     static constexpr int kRfin = kRd + 256;     // its final value, row-major
     static constexpr int kRed = kRfin + 256;    // [2][4 warps][16] reduction partials
@@ -171,15 +193,41 @@ struct TsqrSmem {
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
 
+constexpr int kTsqrThreads = 256;
 constexpr int kPanelThreads = 128;   // warps 0-3 factor the sub-panel
 constexpr int kPanelBarrier = 1;
 
-// One CTA (512 threads) per panel: blockIdx.x = 2 * tile + panel.
+// Block-reflector update of `ncols` columns of the resident block slice (B + col_off*LDB):
+//   S (pre-loaded with the R strip or zero) += Vp^T B ; S2 = T^T S ; R strip -= S2 ; B -= Vp S2
+// rrow0 / rcol0 locate the strip in the global R.  Ends with a __syncthreads().
 template <int N>
-__global__ void __launch_bounds__(512, 1) tlr_tsqr_kernel(TlrWorkspace ws) {
+__device__ __forceinline__ void tsqr_block_update(double *Bc, const double *Vp, const double *Ts, double *S,
+                                                  double *S2, double *Rg, bool blk0, int rrow0, int rcol0,
+                                                  int ncols, int tid, int warp, int nwarps) {
+    constexpr int LDB = Geometry<N>::kLdB, LDS = Geometry<N>::kLdS;
+    block_gemm<1, kGemmAdd>(mview(S, 1, LDS), cview(Vp, LDB, 1), cview(Bc, 1, LDB), kPanelW, ncols, kBlockH, warp,
+                            nwarps);
+    __syncthreads();
+    block_gemm<1, kGemmSet>(mview(S2, 1, LDS), cview(Ts, 16, 1), cview(S, 1, LDS), kPanelW, ncols, kPanelW, warp,
+                            nwarps);
+    __syncthreads();
+    if (!blk0) {
+        for (int idx = tid; idx < kPanelW * ncols; idx += kTsqrThreads) {
+            const int ii = idx & 15, jj = idx >> 4;
+            Rg[(size_t)(rrow0 + ii) + (size_t)(rcol0 + jj) * N] -= S2[ii + jj * LDS];
+        }
+    }
+    block_gemm<2, kGemmSub>(mview(Bc, 1, LDB), cview(Vp, 1, LDB), cview(S2, 1, LDS), kBlockH, ncols, kPanelW, warp,
+                            nwarps);
+    __syncthreads();
+}
+
+// One CTA (256 threads) per panel: blockIdx.x = 2 * tile + panel.
+template <int N>
+__global__ void __launch_bounds__(kTsqrThreads, 2) tlr_tsqr_kernel(TlrWorkspace ws) {
     using G = Geometry<N>;
     using SM = TsqrSmem<N>;
-    constexpr int LDB = G::kLdB, LDS = G::kLdS;
+    constexpr int LDB = G::kLdB, LDS = G::kLdS, GW = SM::kGroupW;
     extern __shared__ double smem[];
     double *B = smem + SM::kB, *Vp = smem + SM::kVp, *S = smem + SM::kS, *S2 = smem + SM::kS2,
            *Ts = smem + SM::kTs, *Rd = smem + SM::kRd, *Rfin = smem + SM::kRfin, *red = smem + SM::kRed,
@@ -188,171 +236,180 @@ __global__ void __launch_bounds__(512, 1) tlr_tsqr_kernel(TlrWorkspace ws) {
     const int t = blockIdx.x >> 1, pnl = blockIdx.x & 1;
     if (ws.st[t] != HCORE_B200_OK) return;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
-    const int nwarps = blockDim.x >> 5;
+    const int nwarps = kTsqrThreads / 32;
     const int n16 = round_up(ws.ncols[t], kPanelW);
-    const int nsp = n16 / kPanelW;
     const int m_pad = ws.m_pad;
     double *panel = ws.panel + panel_offset(ws, pnl, t, G::kPanelCols);
     double *Rg = ws.R + nn_offset(ws, pnl, t, N);
     double *Tg = ws.T + t_offset(ws, pnl, t, G::kNsp);
 
-    for (int j = 0; j < ws.nblk; ++j) {
-        const bool blk0 = (j == 0);
-        // ---- load the row block ------------------------------------------------------
-        for (int idx = tid; idx < kBlockH * n16; idx += blockDim.x) {
-            const int rr = idx & (kBlockH - 1), cc = idx >> 7;
-            B[rr + cc * LDB] = panel[(size_t)j * kBlockH + rr + (size_t)cc * m_pad];
-        }
-        __syncthreads();
-
-        for (int s = 0; s < nsp; ++s) {
-            const int c0 = s * kPanelW, c1 = c0 + kPanelW;
-            const int ntrail = n16 - c1;
-
-            if (warp < kPanelThreads / 32) {
-                // ================= (a) panel factorisation, warps 0-3 =====================
-                const int r = tid;                   // row of the block owned by this thread
-                double v[kPanelW];
-#pragma unroll
-                for (int c = 0; c < kPanelW; ++c) v[c] = B[r + (c0 + c) * LDB];
-                if (!blk0) {
-                    // diagonal block of the running R (rows/cols c0..c0+15), row-major
-                    for (int idx = tid; idx < 256; idx += kPanelThreads) {
-                        const int ii = idx >> 4, c = idx & 15;
-                        Rd[idx] = Rg[(size_t)(c0 + ii) + (size_t)(c0 + c) * N];
-                    }
+    for (int gc0 = 0; gc0 < n16; gc0 += GW) {                     // column groups, left to right
+        const int gcols = (n16 - gc0 < GW) ? (n16 - gc0) : GW;    // multiple of 16
+        for (int j = 0; j < ws.nblk; ++j) {
+            const bool blk0 = (j == 0);
+            // ---- load the group's slice of the row block --------------------------------
+            for (int idx = tid; idx < kBlockH * gcols; idx += kTsqrThreads) {
+                const int rr = idx & (kBlockH - 1), cc = idx >> 7;
+                B[rr + cc * LDB] = panel[(size_t)j * kBlockH + rr + (size_t)(gc0 + cc) * m_pad];
+            }
+            // ---- (1) reflectors of the earlier groups (left-looking) ------------------------
+            for (int sp = 0; sp < gc0 / kPanelW; ++sp) {
+                const int pc0 = sp * kPanelW;
+                for (int idx = tid; idx < kBlockH * kPanelW; idx += kTsqrThreads) {
+                    const int rr = idx & 127, cc = idx >> 7, col = pc0 + cc;
+                    double x = panel[(size_t)j * kBlockH + rr + (size_t)col * m_pad];
+                    if (blk0) x = (rr > col) ? x : (rr == col ? 1.0 : 0.0);
+                    Vp[rr + cc * LDB] = x;
                 }
-                for (int idx = tid; idx < 256; idx += kPanelThreads) { Ts[idx] = 0.0; Rfin[idx] = 0.0; }
-                named_barrier(kPanelBarrier, kPanelThreads);
+                Ts[tid] = Tg[((size_t)j * G::kNsp + sp) * 256 + tid];
+                for (int idx = tid; idx < kPanelW * gcols; idx += kTsqrThreads) {
+                    const int ii = idx & 15, jj = idx >> 4;
+                    S[ii + jj * LDS] = blk0 ? 0.0 : Rg[(size_t)(pc0 + ii) + (size_t)(gc0 + jj) * N];
+                }
+                __syncthreads();
+                tsqr_block_update<N>(B, Vp, Ts, S, S2, Rg, blk0, pc0, gc0, gcols, tid, warp, nwarps);
+            }
+            __syncthreads();
 
+            // ---- (2) the group's own sub-panels ----------------------------------------------
+            for (int c0 = gc0; c0 < gc0 + gcols; c0 += kPanelW) {
+                const int s = c0 / kPanelW;
+                const int c1 = c0 + kPanelW;
+                const int lc0 = c0 - gc0, lc1 = c1 - gc0;          // local column offsets in the slice
+                const int ntrail = gcols - lc1;
+
+                if (warp < kPanelThreads / 32) {
+                    // ================= (a) panel factorisation, warps 0-3 =====================
+                    const int r = tid;                   // row of the block owned by this thread
+                    double v[kPanelW];
 #pragma unroll
-                for (int ii = 0; ii < kPanelW; ++ii) {
-                    const int i = c0 + ii;           // global column (= diagonal row in block 0)
-                    double *redb = red + (ii & 1) * 64;
-                    if (blk0 && r == i) {            // this row becomes row ii of the R strip
-#pragma unroll
-                        for (int c = 0; c < kPanelW; ++c) Rd[ii * 16 + c] = v[c];
+                    for (int c = 0; c < kPanelW; ++c) v[c] = B[r + (lc0 + c) * LDB];
+                    if (!blk0) {
+                        // diagonal block of the running R (rows/cols c0..c0+15), row-major
+                        for (int idx = tid; idx < 256; idx += kPanelThreads) {
+                            const int ii = idx >> 4, c = idx & 15;
+                            Rd[idx] = Rg[(size_t)(c0 + ii) + (size_t)(c0 + c) * N];
+                        }
                     }
-                    double xi = v[ii];
-                    if (blk0 && r <= i) xi = 0.0;    // block 0: only rows below the diagonal take part
-                    double pr[kPanelW];
-#pragma unroll
-                    for (int c = 0; c < kPanelW; ++c) pr[c] = xi * v[c];
-                    const double wsum = reduce16(pr, lane);
-                    if ((lane & 1) == 0) redb[warp * 16 + reduce16_col(lane)] = wsum;
+                    for (int idx = tid; idx < 256; idx += kPanelThreads) { Ts[idx] = 0.0; Rfin[idx] = 0.0; }
                     named_barrier(kPanelBarrier, kPanelThreads);
 
-                    // totals d[c] = x_i . column c  (all of them only in warp 0, which builds T)
-                    double d[kPanelW];
 #pragma unroll
-                    for (int c = 0; c < kPanelW; c += 2) {
-                        if (c + 1 >= ii || warp == 0) {
-                            const double2 p0 = *reinterpret_cast<const double2 *>(redb + c);
-                            const double2 p1 = *reinterpret_cast<const double2 *>(redb + 16 + c);
-                            const double2 p2 = *reinterpret_cast<const double2 *>(redb + 32 + c);
-                            const double2 p3 = *reinterpret_cast<const double2 *>(redb + 48 + c);
-                            d[c] = (p0.x + p1.x) + (p2.x + p3.x);
-                            d[c + 1] = (p0.y + p1.y) + (p2.y + p3.y);
-                        } else {
-                            d[c] = d[c + 1] = 0.0;
+                    for (int ii = 0; ii < kPanelW; ++ii) {
+                        const int i = c0 + ii;           // global column (= diagonal row in block 0)
+                        double *redb = red + (ii & 1) * 64;
+                        if (blk0 && r == i) {            // this row becomes row ii of the R strip
+#pragma unroll
+                            for (int c = 0; c < kPanelW; ++c) Rd[ii * 16 + c] = v[c];
+                        }
+                        double xi = v[ii];
+                        if (blk0 && r <= i) xi = 0.0;    // block 0: only rows below the diagonal take part
+                        double pr[kPanelW];
+#pragma unroll
+                        for (int c = 0; c < kPanelW; ++c) pr[c] = xi * v[c];
+                        const double wsum = reduce16(pr, lane);
+                        if ((lane & 1) == 0) redb[warp * 16 + reduce16_col(lane)] = wsum;
+                        named_barrier(kPanelBarrier, kPanelThreads);
+
+                        // totals d[c] = x_i . column c  (all of them only in warp 0, which builds T)
+                        double d[kPanelW];
+#pragma unroll
+                        for (int c = 0; c < kPanelW; c += 2) {
+                            if (c + 1 >= ii || warp == 0) {
+                                const double2 p0 = *reinterpret_cast<const double2 *>(redb + c);
+                                const double2 p1 = *reinterpret_cast<const double2 *>(redb + 16 + c);
+                                const double2 p2 = *reinterpret_cast<const double2 *>(redb + 32 + c);
+                                const double2 p3 = *reinterpret_cast<const double2 *>(redb + 48 + c);
+                                d[c] = (p0.x + p1.x) + (p2.x + p3.x);
+                                d[c + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+                            } else {
+                                d[c] = d[c + 1] = 0.0;
+                            }
+                        }
+                        const double alpha = Rd[ii * 16 + ii];
+                        const Householder h = make_householder(alpha, d[ii]);
+                        const double vr = xi * h.scal;
+                        const bool writer = (r == kPanelThreads - 1);
+#pragma unroll
+                        for (int c = ii + 1; c < kPanelW; ++c) {
+                            const double rd = Rd[ii * 16 + c];
+                            const double w = h.tau * fma(d[c], h.scal, rd);
+                            v[c] = fma(-vr, w, v[c]);
+                            if (writer) Rfin[ii * 16 + c] = rd - w;
+                        }
+                        // column ii now holds the reflector tail; in block 0 the rows on and above
+                        // the diagonal keep their R entries
+                        if (!(blk0 && r <= i)) v[ii] = vr;
+                        if (writer) { Rfin[ii * 16 + ii] = h.beta; tauv[ii] = h.tau; }
+                        // compact-WY T, column ii (forward/columnwise larft): lane k of warp 0 owns row k
+                        //   T[k][ii] = -tau * sum_{c=k}^{ii-1} T[k][c] * z_c,  z_c = V[:,c]^T v_ii
+                        if (warp == 0 && lane < kPanelW) {
+                            const int k = lane;
+                            double accv = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ii; ++c) {
+                                const double z = fma(d[c], h.scal, Rd[ii * 16 + c]);
+                                if (c >= k) accv = fma(Ts[k + c * 16], z, accv);
+                            }
+                            Ts[k + ii * 16] = (k < ii) ? -h.tau * accv : (k == ii ? h.tau : 0.0);
                         }
                     }
-                    const double alpha = Rd[ii * 16 + ii];
-                    const Householder h = make_householder(alpha, d[ii]);
-                    const double vr = xi * h.scal;
-                    const bool writer = (r == kPanelThreads - 1);
+                    named_barrier(kPanelBarrier, kPanelThreads);   // Rfin complete
+
+                    // explicit reflector panel + write-back of the block columns
 #pragma unroll
-                    for (int c = ii + 1; c < kPanelW; ++c) {
-                        const double rd = Rd[ii * 16 + c];
-                        const double w = h.tau * fma(d[c], h.scal, rd);
-                        v[c] = fma(-vr, w, v[c]);
-                        if (writer) Rfin[ii * 16 + c] = rd - w;
-                    }
-                    // column ii now holds the reflector tail; in block 0 the rows on and above
-                    // the diagonal keep their R entries
-                    if (!(blk0 && r <= i)) v[ii] = vr;
-                    if (writer) { Rfin[ii * 16 + ii] = h.beta; tauv[ii] = h.tau; }
-                    // compact-WY T, column ii (forward/columnwise larft): lane k of warp 0 owns row k
-                    //   T[k][ii] = -tau * sum_{c=k}^{ii-1} T[k][c] * z_c,  z_c = V[:,c]^T v_ii
-                    if (warp == 0 && lane < kPanelW) {
-                        const int k = lane;
-                        double accv = 0.0;
-#pragma unroll
-                        for (int c = 0; c < ii; ++c) {
-                            const double z = fma(d[c], h.scal, Rd[ii * 16 + c]);
-                            if (c >= k) accv = fma(Ts[k + c * 16], z, accv);
+                    for (int c = 0; c < kPanelW; ++c) {
+                        const int col = c0 + c;
+                        double vv = v[c], bb = v[c];
+                        if (blk0) {
+                            if (r < col) vv = 0.0;
+                            else if (r == col) vv = 1.0;
+                            if (r >= c0 && r <= col) bb = Rfin[(r - c0) * 16 + c];
                         }
-                        Ts[k + ii * 16] = (k < ii) ? -h.tau * accv : (k == ii ? h.tau : 0.0);
+                        Vp[r + c * LDB] = vv;
+                        B[r + (lc0 + c) * LDB] = bb;
                     }
-                }
-                named_barrier(kPanelBarrier, kPanelThreads);   // Rfin complete
-
-                // explicit reflector panel + write-back of the block columns
-#pragma unroll
-                for (int c = 0; c < kPanelW; ++c) {
-                    const int col = c0 + c;
-                    double vv = v[c], bb = v[c];
-                    if (blk0) {
-                        if (r < col) vv = 0.0;
-                        else if (r == col) vv = 1.0;
-                        if (r >= c0 && r <= col) bb = Rfin[(r - c0) * 16 + c];
+                    if (!blk0) {   // finished diagonal block of the running R
+                        for (int idx = tid; idx < 256; idx += kPanelThreads) {
+                            const int ii = idx >> 4, c = idx & 15;
+                            Rg[(size_t)(c0 + ii) + (size_t)(c0 + c) * N] = (c >= ii) ? Rfin[idx] : 0.0;
+                        }
                     }
-                    Vp[r + c * LDB] = vv;
-                    B[r + col * LDB] = bb;
-                }
-                if (!blk0) {   // finished diagonal block of the running R
-                    for (int idx = tid; idx < 256; idx += kPanelThreads) {
-                        const int ii = idx >> 4, c = idx & 15;
-                        Rg[(size_t)(c0 + ii) + (size_t)(c0 + c) * N] = (c >= ii) ? Rfin[idx] : 0.0;
-                    }
-                }
-            } else {
-                // warps 4-15 meanwhile stage S <- trailing part of the R strip (or zero)
-                for (int idx = tid - kPanelThreads; idx < kPanelW * ntrail; idx += (int)blockDim.x - kPanelThreads) {
-                    const int ii = idx & 15, jj = idx >> 4;
-                    S[ii + jj * LDS] = blk0 ? 0.0 : Rg[(size_t)(c0 + ii) + (size_t)(c1 + jj) * N];
-                }
-            }
-            __syncthreads();
-
-            // ================= (b) trailing update, all warps ==============================
-            if (ntrail > 0) {
-                // S += Vp^T * B_trail
-                block_gemm<1, kGemmAdd>(mview(S, 1, LDS), cview(Vp, LDB, 1), cview(B + c1 * LDB, 1, LDB),
-                                        kPanelW, ntrail, kBlockH, warp, nwarps);
-                __syncthreads();
-                // S2 = T^T * S
-                block_gemm<1, kGemmSet>(mview(S2, 1, LDS), cview(Ts, 16, 1), cview(S, 1, LDS), kPanelW,
-                                        ntrail, kPanelW, warp, nwarps);
-                __syncthreads();
-                // R strip -= S2 (straight to global) ; B_trail -= Vp * S2
-                if (!blk0) {
-                    for (int idx = tid; idx < kPanelW * ntrail; idx += blockDim.x) {
+                } else {
+                    // warps 4-7 meanwhile stage S <- trailing part of the R strip (or zero)
+                    for (int idx = tid - kPanelThreads; idx < kPanelW * ntrail; idx += kTsqrThreads - kPanelThreads) {
                         const int ii = idx & 15, jj = idx >> 4;
-                        Rg[(size_t)(c0 + ii) + (size_t)(c1 + jj) * N] -= S2[ii + jj * LDS];
+                        S[ii + jj * LDS] = blk0 ? 0.0 : Rg[(size_t)(c0 + ii) + (size_t)(c1 + jj) * N];
                     }
                 }
-                block_gemm<2, kGemmSub>(mview(B + c1 * LDB, 1, LDB), cview(Vp, 1, LDB), cview(S2, 1, LDS),
-                                        kBlockH, ntrail, kPanelW, warp, nwarps);
-            }
-            // T factor of this (block, sub-panel) to global
-            if (tid < 256) Tg[((size_t)j * G::kNsp + s) * 256 + tid] = Ts[tid];
-            __syncthreads();
-        }  // sub-panels
+                __syncthreads();
 
-        // ---- store the block (reflectors; block 0 also carries R) ---------------------
-        for (int idx = tid; idx < kBlockH * n16; idx += blockDim.x) {
-            const int rr = idx & (kBlockH - 1), cc = idx >> 7;
-            panel[(size_t)j * kBlockH + rr + (size_t)cc * m_pad] = B[rr + cc * LDB];
-        }
-        if (blk0) {
-            for (int idx = tid; idx < N * N; idx += blockDim.x) {
-                const int i = idx % N, cc = idx / N;
-                Rg[idx] = (i <= cc && cc < n16) ? B[i + cc * LDB] : 0.0;
+                // T factor of this (block, sub-panel) to global
+                Tg[((size_t)j * G::kNsp + s) * 256 + tid] = Ts[tid];
+                // ================= (b) trailing update inside the group, all warps ================
+                if (ntrail > 0)
+                    tsqr_block_update<N>(B + lc1 * LDB, Vp, Ts, S, S2, Rg, blk0, c0, c1, ntrail, tid, warp, nwarps);
+                else
+                    __syncthreads();
+            }  // sub-panels
+
+            // ---- store the slice (reflectors; block 0 also carries R) ---------------------
+            for (int idx = tid; idx < kBlockH * gcols; idx += kTsqrThreads) {
+                const int rr = idx & (kBlockH - 1), cc = idx >> 7;
+                panel[(size_t)j * kBlockH + rr + (size_t)(gc0 + cc) * m_pad] = B[rr + cc * LDB];
             }
-        }
-        __syncthreads();   // R / panel writes visible to this CTA's later loads, B free for reuse
-    }
+            if (blk0) {
+                for (int idx = tid; idx < N * gcols; idx += kTsqrThreads) {
+                    const int i = idx % N, cc = idx / N, col = gc0 + cc;
+                    Rg[(size_t)i + (size_t)col * N] = (i <= col) ? B[i + cc * LDB] : 0.0;
+                }
+                if (gc0 + gcols >= n16) {     // zero the padding columns n16..N-1 once
+                    for (int idx = tid; idx < N * (N - n16); idx += kTsqrThreads) Rg[(size_t)n16 * N + idx] = 0.0;
+                }
+            }
+            __syncthreads();   // R / panel writes visible to this CTA's later loads, B free for reuse
+        }  // row blocks
+    }  // column groups
 }
 
 // ========================================================================================
