@@ -51,7 +51,7 @@ struct hcore_b200_context {
     int64_t launches = 0;
     std::string err;
     // TLR workspace
-    DevBuf panel, R, T, Y, sigma, ints, ptrs;
+    DevBuf rec, G, R, Y, sigma, ints, ptrs;
     // dense workspace
     DevBuf X;
     // host-staging (HCORE_dgemm_batched_host and the legacy wrappers)
@@ -88,9 +88,9 @@ int pick_width(int maxrk) {
 
 size_t per_tile_ws_bytes(int N, int m_pad, int nblk) {
     size_t b = 0;
-    b += 2ull * m_pad * (N + 8) * 8;            // panels
+    b += 2ull * nblk * (N / 16) * kRecBytes;    // block-reflector records
+    b += (size_t)m_pad * N * 8;                 // G
     b += 2ull * N * N * 8;                      // R
-    b += 2ull * nblk * (N / 16) * 256 * 8;      // T
     b += 2ull * N * N * 8;                      // Y
     b += (size_t)N * 8 + 16;                    // sigma + ints
     return b;
@@ -106,24 +106,28 @@ int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
     return std::max(c, 1);
 }
 
+constexpr int kTsqrWarps = 8;     // 64-column groups
+constexpr int kApplyWarps = 4;    // 32 output columns per CTA
+
 template <int N>
 int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
-    const size_t sm_stack = (size_t)N * (N + 4) * sizeof(double);
     {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_stack_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stack));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<N>::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_pg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PgSmem::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N, kTsqrWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TsqrSmem<kTsqrWarps>::kBytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_svd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SvdSmem<N>::kBytes));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_apply_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ApplySmem<N>::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_apply_kernel<N, kApplyWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ApplySmem<kApplyWarps>::kBytes));
     }
     const bool tm = ctx->stage_timing;
     if (tm) cudaEventRecord(ctx->ev[0], st);
     if (ctx->debug_stages >= 1) {
-        tlr_stack_kernel<N><<<ar.ntiles, 512, sm_stack, st>>>(ar, ws);
+        tlr_pg_kernel<N><<<ar.ntiles, 256, PgSmem::kBytes, st>>>(ar, ws);
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[1], st);
     if (ctx->debug_stages >= 2) {
-        tlr_tsqr_kernel<N><<<2 * ar.ntiles, kTsqrThreads, TsqrSmem<N>::kBytes, st>>>(ws);
+        tlr_tsqr_kernel<N, kTsqrWarps><<<2 * ar.ntiles, 32 * kTsqrWarps, TsqrSmem<kTsqrWarps>::kBytes, st>>>(ar, ws);
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[2], st);
@@ -133,8 +137,8 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     }
     if (tm) cudaEventRecord(ctx->ev[3], st);
     if (ctx->debug_stages >= 4) {
-        dim3 grid(N / kApplyCols, 2, ar.ntiles);
-        tlr_apply_kernel<N><<<grid, 256, ApplySmem<N>::kBytes, st>>>(ar, ws);
+        dim3 grid((N + 8 * kApplyWarps - 1) / (8 * kApplyWarps), 2, ar.ntiles);
+        tlr_apply_kernel<N, kApplyWarps><<<grid, 32 * kApplyWarps, ApplySmem<kApplyWarps>::kBytes, st>>>(ar, ws);
         ctx->launches++;
     }
     if (tm) {
@@ -183,7 +187,7 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
     if (!ctx) return HCORE_B200_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->panel, &ctx->R, &ctx->T, &ctx->Y, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X,
+    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X,
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -240,17 +244,17 @@ int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alph
     const int nblk = m_pad / kBlockH;
     const int chunk = std::min(ntiles, default_chunk(ctx, N, m_pad, nblk));
 
-    CUDA_TRY(ctx, ctx->panel.reserve(2ull * chunk * m_pad * (N + 8) * 8));
+    CUDA_TRY(ctx, ctx->rec.reserve(2ull * chunk * nblk * (N / 16) * kRecBytes));
+    CUDA_TRY(ctx, ctx->G.reserve((size_t)chunk * m_pad * N * 8));
     CUDA_TRY(ctx, ctx->R.reserve(2ull * chunk * N * N * 8));
-    CUDA_TRY(ctx, ctx->T.reserve(2ull * chunk * nblk * (N / 16) * 256 * 8));
     CUDA_TRY(ctx, ctx->Y.reserve(2ull * chunk * N * N * 8));
     CUDA_TRY(ctx, ctx->sigma.reserve((size_t)chunk * N * 8));
     CUDA_TRY(ctx, ctx->ints.reserve((size_t)chunk * 4 * sizeof(int)));
 
     TlrWorkspace ws{};
-    ws.panel = (double *)ctx->panel.p;
+    ws.rec = (double *)ctx->rec.p;
+    ws.G = (double *)ctx->G.p;
     ws.R = (double *)ctx->R.p;
-    ws.T = (double *)ctx->T.p;
     ws.Y = (double *)ctx->Y.p;
     ws.sigma = (double *)ctx->sigma.p;
     ws.ncols = (int *)ctx->ints.p;
@@ -442,18 +446,18 @@ int hcore_b200_debug_fetch(hcore_b200_handle_t ctx, int what, int tile, double *
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     const TlrWorkspace &ws = ctx->last_ws;
     const int N = ctx->last_N;
-    const size_t pan = (size_t)ws.m_pad * (N + 8), nn = (size_t)N * N, tt = (size_t)ws.nblk * (N / 16) * 256;
+    const size_t nn = (size_t)N * N, rr = (size_t)ws.nblk * (N / 16) * kRecDoubles, gg = (size_t)ws.m_pad * N;
     const double *src = nullptr;
     size_t avail = 0;
     switch (what) {
-        case 0: case 8: src = ws.panel + ((size_t)0 * ws.chunk + tile) * pan; avail = pan; break;
-        case 1: src = ws.panel + ((size_t)1 * ws.chunk + tile) * pan; avail = pan; break;
+        case 0: src = ws.rec + ((size_t)0 * ws.chunk + tile) * rr; avail = rr; break;   // raw records, U panel
+        case 1: src = ws.rec + ((size_t)1 * ws.chunk + tile) * rr; avail = rr; break;   // raw records, V panel
         case 2: src = ws.R + ((size_t)0 * ws.chunk + tile) * nn; avail = nn; break;
         case 3: src = ws.R + ((size_t)1 * ws.chunk + tile) * nn; avail = nn; break;
         case 4: src = ws.Y + ((size_t)0 * ws.chunk + tile) * nn; avail = nn; break;
         case 5: src = ws.Y + ((size_t)1 * ws.chunk + tile) * nn; avail = nn; break;
         case 6: src = ws.sigma + (size_t)tile * N; avail = N; break;
-        case 7: src = ws.T + ((size_t)0 * ws.chunk + tile) * tt; avail = tt; break;
+        case 7: src = ws.G + (size_t)tile * gg; avail = gg; break;
         case 9: {   // ints: ncols, newrank, status, sweeps (as doubles)
             int v[4];
             CUDA_TRY(ctx, cudaMemcpy(&v[0], ws.ncols + tile, 4, cudaMemcpyDeviceToHost));
