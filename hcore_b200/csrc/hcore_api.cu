@@ -60,6 +60,7 @@ struct hcore_b200_context {
     cudaStream_t streams[2] = {nullptr, nullptr};
     // debug / profiling
     int debug_stages = 4;
+    int tsqr_warps = 8;
     bool stage_timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double stage_ms[4] = {0, 0, 0, 0};
@@ -106,18 +107,15 @@ int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
     return std::max(c, 1);
 }
 
-constexpr int kTsqrWarps = 8;     // 64-column groups
-constexpr int kApplyWarps = 4;    // 32 output columns per CTA
-
-template <int N>
+template <int N, int TW, int AW>
 int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
     {
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_pg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PgSmem::kBytes));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N, kTsqrWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)TsqrSmem<kTsqrWarps>::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TsqrSmem<TW>::kBytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_svd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SvdSmem<N>::kBytes));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_apply_kernel<N, kApplyWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)ApplySmem<kApplyWarps>::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_apply_kernel<N, AW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ApplySmem<AW>::kBytes));
     }
     const bool tm = ctx->stage_timing;
     if (tm) cudaEventRecord(ctx->ev[0], st);
@@ -127,7 +125,7 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     }
     if (tm) cudaEventRecord(ctx->ev[1], st);
     if (ctx->debug_stages >= 2) {
-        tlr_tsqr_kernel<N, kTsqrWarps><<<2 * ar.ntiles, 32 * kTsqrWarps, TsqrSmem<kTsqrWarps>::kBytes, st>>>(ar, ws);
+        tlr_tsqr_kernel<N, TW><<<2 * ar.ntiles, 32 * TW, TsqrSmem<TW>::kBytes, st>>>(ar, ws);
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[2], st);
@@ -137,8 +135,8 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     }
     if (tm) cudaEventRecord(ctx->ev[3], st);
     if (ctx->debug_stages >= 4) {
-        dim3 grid((N + 8 * kApplyWarps - 1) / (8 * kApplyWarps), 2, ar.ntiles);
-        tlr_apply_kernel<N, kApplyWarps><<<grid, 32 * kApplyWarps, ApplySmem<kApplyWarps>::kBytes, st>>>(ar, ws);
+        dim3 grid((N + 8 * AW - 1) / (8 * AW), 2, ar.ntiles);
+        tlr_apply_kernel<N, AW><<<grid, 32 * AW, ApplySmem<AW>::kBytes, st>>>(ar, ws);
         ctx->launches++;
     }
     if (tm) {
@@ -152,6 +150,13 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return HCORE_B200_OK;
+}
+
+template <int N>
+int launch_chunk_n(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
+    // kernel shapes: warps per QR CTA (8 columns each) and per apply CTA; tunable for experiments
+    if (ctx->tsqr_warps == 4) return launch_chunk<N, 4, 4>(ctx, ar, ws, st);
+    return launch_chunk<N, 8, 4>(ctx, ar, ws, st);
 }
 
 __global__ void fill_ptrs_kernel(const double **out, const double *base, int64_t stride, int n) {
@@ -177,6 +182,7 @@ int hcore_b200_create(hcore_b200_handle_t *handle, int device) {
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HCORE_B200_ERR_CUDA; }
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char *e = getenv("HCORE_B200_TSQR_WARPS")) ctx->tsqr_warps = atoi(e);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &s : ctx->streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     *handle = ctx;
@@ -277,9 +283,9 @@ int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alph
         ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
         int rc;
         switch (N) {
-            case 32: rc = launch_chunk<32>(ctx, ar, ws, st); break;
-            case 64: rc = launch_chunk<64>(ctx, ar, ws, st); break;
-            default: rc = launch_chunk<128>(ctx, ar, ws, st); break;
+            case 32: rc = launch_chunk_n<32>(ctx, ar, ws, st); break;
+            case 64: rc = launch_chunk_n<64>(ctx, ar, ws, st); break;
+            default: rc = launch_chunk_n<128>(ctx, ar, ws, st); break;
         }
         if (rc != HCORE_B200_OK) return rc;
     }

@@ -408,28 +408,60 @@ __device__ __forceinline__ ColSrc panel_column(const TlrArgs &ar, const double *
     return s;
 }
 
-template <int LPC>   // lanes per column (power of two <= 32); `mask` names the lanes of the group
-__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+// Warp all-reduce (sum) of one double per lane through the FP64 tensor core: two dependent
+// DMMAs with a matrix of ones (~70 cycles) instead of five shuffle rounds (~175-250 cycles).
+//   stage 1: B[k = tg][n = g] = v(lane)  ->  D[.][n] = column sums cs(n) = sum_tg v(4n + tg);
+//            lane (g, tg) receives cs(2tg), cs(2tg+1)
+//   stage 2: B[k = tg][n = g] = cs(2tg) + cs(2tg+1)  ->  D = total, in every lane.
+template <int NV>
+__device__ __forceinline__ void warp_allsum_dmma(double (&v)[NV]) {
+    double d0[NV], d1[NV];
 #pragma unroll
-    for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-    return v;
+    for (int q = 0; q < NV; ++q) { d0[q] = 0.0; d1[q] = 0.0; dmma_884(d0[q], d1[q], 1.0, v[q]); }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) { const double p = d0[q] + d1[q]; d0[q] = 0.0; d1[q] = 0.0; dmma_884(d0[q], d1[q], 1.0, p); }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = d0[q];
+}
+
+// Column jc of the compact-WY factor (forward columnwise larft), computed by one warp:
+//   T[r][jc] = -tau_jc * sum_{q=r}^{jc-1} T[r][q] z_q ,  z_q = v_q^T v_jc,  r < jc.
+// Fully unrolled and predicated so that all shared-memory loads are issued up front (this sits
+// on the path to the next CTA barrier).
+__device__ __forceinline__ void t_column(double *Ts, const double *zb, const double *taus, int jc, int lane) {
+    const double *z = zb + (jc & 1) * 16;
+    const double mtau = -taus[jc];
+    const int r = lane;
+    if (r < jc) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < kPanelW - 1; ++q) {
+            const bool on = (q >= r) && (q < jc);
+            const double tv = on ? Ts[r + 16 * q] : 0.0, zv = z[q];
+            if (q & 1) a1 = fma(tv, zv, a1);
+            else a0 = fma(tv, zv, a0);
+        }
+        Ts[r + 16 * jc] = mtau * (a0 + a1);
+    }
 }
 
 // Householder factorisation of the 128 x 16 sub-panel held in Pf (plain column-major, ld kLdPf).
 // Produces the record (V swizzled, T, T^T) in `rec`, the R entries in Rg and (blocks > 0) uses /
-// updates the 16 x 16 diagonal block of the running R.  All NW warps participate; column cc is
-// owned by the LPC = 2*NW lanes tid/LPC == cc, lane l of the group owns rows l + LPC*k.
+// updates the 16 x 16 diagonal block of the running R.  All NW warps participate: warp w owns the
+// columns w, w + NW, ... (CPW = 16 / NW of them), lane l owns rows l, l+32, l+64, l+96.  Every
+// role decision is warp-uniform, so all shuffles run converged.  One CTA barrier per step.
 template <int N, int NW>
 __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *Rg, bool blk0, int c0, int tid) {
     using SM = TsqrSmem<NW>;
-    constexpr int LPC = 2 * NW, RPT = kBlockH / LPC;     // rows per thread
+    constexpr int CPW = kPanelW / NW, RPT = kBlockH / 32;     // columns per warp, rows per lane
     double *Pf = smem + SM::kPf, *vbuf = smem + SM::kVbuf, *Rd = smem + SM::kRd, *Ts = smem + SM::kTs,
            *taus = smem + SM::kTau, *zb = smem + SM::kZ;
-    const int cc = tid / LPC, l = tid % LPC;
-    const unsigned gmask = (LPC == 32) ? 0xffffffffu : (((1u << (LPC & 31)) - 1u) << (LPC * ((tid & 31) / LPC)));
-    double x[RPT];
+    const int w = tid >> 5, l = tid & 31;
+    double x[CPW][RPT];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) x[k] = Pf[(l + LPC * k) + cc * kLdPf];
+    for (int q = 0; q < CPW; ++q)
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) x[q][k] = Pf[(l + 32 * k) + (w + NW * q) * kLdPf];
     if (!blk0) {
         for (int idx = tid; idx < 256; idx += 32 * NW)
             Rd[idx] = Rg[(size_t)(c0 + (idx & 15)) + (size_t)(c0 + (idx >> 4)) * N];
@@ -440,90 +472,107 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
 #pragma unroll 1
     for (int ii = 0; ii < kPanelW; ++ii) {
         const int i = c0 + ii;                 // global column = diagonal row in block 0
+        const int so = ii / NW;                // slot of column ii in its owner warp
         double *vb = vbuf + (ii & 1) * kBlockH;
-        if (cc == ii) {                        // ---- owner group: build the reflector ----------------
-            double s2 = 0.0, xi[RPT];
+        if (w == ii % NW) {                    // ---- owner warp: build the reflector ------------------
+            double xo[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
-                const int row = l + LPC * k;
-                xi[k] = (blk0 && row <= i) ? 0.0 : x[k];
-                s2 = fma(xi[k], xi[k], s2);
+                double v = x[0][k];
+#pragma unroll
+                for (int q = 1; q < CPW; ++q) v = (q == so) ? x[q][k] : v;
+                xo[k] = v;
             }
-            s2 = group_sum<LPC>(s2, gmask);
+            double s2a = 0.0, s2b = 0.0, xi[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int row = l + 32 * k;
+                xi[k] = (blk0 && row <= i) ? 0.0 : xo[k];
+                if (k & 1) s2b = fma(xi[k], xi[k], s2b);
+                else s2a = fma(xi[k], xi[k], s2a);
+            }
+            double s2v[1] = {s2a + s2b};
+            warp_allsum_dmma<1>(s2v);
+            const double s2 = s2v[0];
             double alpha;
             if (blk0) {
                 double sel = 0.0;
 #pragma unroll
-                for (int k = 0; k < RPT; ++k) sel = (k == i / LPC) ? x[k] : sel;
-                alpha = __shfl_sync(gmask, sel, i % LPC, LPC);
+                for (int k = 0; k < RPT; ++k) sel = (k == (i >> 5)) ? xo[k] : sel;
+                alpha = __shfl_sync(0xffffffffu, sel, i & 31);
             } else {
                 alpha = Rd[ii + 16 * ii];
             }
             const Householder h = make_householder(alpha, s2);
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
-                const int row = l + LPC * k;
+                const int row = l + 32 * k;
                 double v = xi[k] * h.scal;
                 if (blk0 && row == i) v = 1.0;
                 vb[row] = v;
-                if (blk0) x[k] = (row > i) ? v : (row == i ? h.beta : x[k]);
-                else x[k] = v;
+                const double keep = blk0 ? ((row > i) ? v : (row == i ? h.beta : xo[k])) : v;
+#pragma unroll
+                for (int q = 0; q < CPW; ++q) x[q][k] = (q == so) ? keep : x[q][k];
             }
             if (l == 0) {
                 taus[ii] = h.tau;
+                Ts[ii + 16 * ii] = h.tau;
                 if (!blk0) Rd[ii + 16 * ii] = h.beta;
             }
         }
         __syncthreads();
-        if (cc != ii) {
+        {
             const double tau = taus[ii];
-            double vv[RPT], dot = 0.0;
+            double vv[RPT], dot[CPW];
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                vv[k] = vb[l + LPC * k];
-                dot = fma(vv[k], x[k], dot);
+            for (int k = 0; k < RPT; ++k) vv[k] = vb[l + 32 * k];
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) {
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    if (k & 1) d1 = fma(vv[k], x[q][k], d1);
+                    else d0 = fma(vv[k], x[q][k], d0);
+                }
+                dot[q] = d0 + d1;
             }
-            dot = group_sum<LPC>(dot, gmask);
-            if (cc > ii) {
-                const double rd = blk0 ? 0.0 : Rd[ii + 16 * cc];
-                const double w = tau * (rd + dot);
+            double rdv[CPW];
 #pragma unroll
-                for (int k = 0; k < RPT; ++k) x[k] = fma(-vv[k], w, x[k]);
-                if (!blk0 && l == 0) Rd[ii + 16 * cc] = rd - w;
-            } else if (l == 0) {
-                zb[(ii & 1) * 16 + cc] = dot;         // z_c = v_c^T v_ii for the T factor
+            for (int q = 0; q < CPW; ++q) rdv[q] = blk0 ? 0.0 : Rd[ii + 16 * (w + NW * q)];
+            warp_allsum_dmma<CPW>(dot);
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) {
+                const int cc = w + NW * q;
+                if (cc > ii) {
+                    const double rd = rdv[q];
+                    const double wv = tau * (rd + dot[q]);
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) x[q][k] = fma(-vv[k], wv, x[q][k]);
+                    if (!blk0 && l == 0) Rd[ii + 16 * cc] = rd - wv;
+                } else if (cc < ii && l == 0) {
+                    zb[(ii & 1) * 16 + cc] = dot[q];      // z_c = v_c^T v_ii for the T factor
+                }
             }
         }
-        // T column ii-1 (forward columnwise larft) by the group that owned it; its z values were
-        // published during step ii-1, one barrier ago.
-        if (ii > 0 && cc == ii - 1 && l < ii - 1) {
-            const int jc = ii - 1;
-            const double *z = zb + (jc & 1) * 16;
-            double accv = 0.0;
-            for (int q = l; q < jc; ++q) accv = fma(Ts[l + 16 * q], z[q], accv);
-            Ts[l + 16 * jc] = -taus[jc] * accv;
-        }
-        if (cc == ii && l == 0) Ts[ii + 16 * ii] = taus[ii];
+        // T column ii-1 by the warp that owned it; its z values were published during step ii-1
+        if (ii > 1 && w == (ii - 1) % NW) t_column(Ts, zb, taus, ii - 1, l);
     }
     __syncthreads();
-    if (cc == kPanelW - 1 && l < kPanelW - 1) {          // last T column
-        const int jc = kPanelW - 1;
-        const double *z = zb + (jc & 1) * 16;
-        double accv = 0.0;
-        for (int q = l; q < jc; ++q) accv = fma(Ts[l + 16 * q], z[q], accv);
-        Ts[l + 16 * jc] = -taus[jc] * accv;
-    }
+    if (w == (kPanelW - 1) % NW) t_column(Ts, zb, taus, kPanelW - 1, l);          // last T column
     // ---- outputs: explicit reflector panel (swizzled), R entries ------------------------------------
-    const int col = c0 + cc;
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-        const int row = l + LPC * k;
-        double v = x[k];
-        if (blk0) {
-            v = (row > col) ? x[k] : (row == col ? 1.0 : 0.0);
-            if (row < N) Rg[(size_t)row + (size_t)col * N] = (row <= col) ? x[k] : 0.0;
+    for (int q = 0; q < CPW; ++q) {
+        const int cc = w + NW * q, col = c0 + cc;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int row = l + 32 * k;
+            double v = x[q][k];
+            if (blk0) {
+                v = (row > col) ? x[q][k] : (row == col ? 1.0 : 0.0);
+                if (row < N) Rg[(size_t)row + (size_t)col * N] = (row <= col) ? x[q][k] : 0.0;
+            }
+            rec[vswz(row, cc)] = v;
         }
-        rec[vswz(row, cc)] = v;
     }
     __syncthreads();
     for (int idx = tid; idx < 256; idx += 32 * NW) {
@@ -542,7 +591,7 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
 
 // One CTA (NW warps) per panel: blockIdx.x = 2 * tile + panel.
 template <int N, int NW>
-__global__ void __launch_bounds__(32 * NW, 2) tlr_tsqr_kernel(TlrArgs ar, TlrWorkspace ws) {
+__global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, TlrWorkspace ws) {
     using SM = TsqrSmem<NW>;
     constexpr int GW = 8 * NW, NSP = N / kPanelW, NT = 32 * NW;
     extern __shared__ __align__(16) double smem[];
@@ -685,7 +734,7 @@ struct ApplySmem {
 };
 
 template <int N, int NW>
-__global__ void __launch_bounds__(32 * NW) tlr_apply_kernel(TlrArgs ar, TlrWorkspace ws) {
+__global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar, TlrWorkspace ws) {
     using SM = ApplySmem<NW>;
     constexpr int NSP = N / kPanelW;
     extern __shared__ __align__(16) double smem[];
