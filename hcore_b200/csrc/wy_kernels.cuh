@@ -385,7 +385,8 @@ struct TsqrSmem {
     static constexpr int kTs = kRd + 256;                 // T, Ts[k + 16 c]
     static constexpr int kTau = kTs + 256;                // [16]
     static constexpr int kZ = kTau + 16;                  // [2][16]
-    static constexpr int kBar = kZ + 32;                  // 2 mbarriers
+    static constexpr int kHs = kZ + 32;                   // tau, scal of the current step
+    static constexpr int kBar = kHs + 2;                  // 2 mbarriers
     static constexpr int kTotal = kBar + 2;
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
@@ -448,116 +449,132 @@ __device__ __forceinline__ void t_column(double *Ts, const double *zb, const dou
 // Householder factorisation of the 128 x 16 sub-panel held in Pf (plain column-major, ld kLdPf).
 // Produces the record (V swizzled, T, T^T) in `rec`, the R entries in Rg and (blocks > 0) uses /
 // updates the 16 x 16 diagonal block of the running R.  All NW warps participate: warp w owns the
-// columns w, w + NW, ... (CPW = 16 / NW of them), lane l owns rows l, l+32, l+64, l+96.  Every
-// role decision is warp-uniform, so all shuffles run converged.  One CTA barrier per step.
-template <int N, int NW>
-__device__ __forceinline__ void panel_factor(double *smem, double *rec, double *Rg, bool blk0, int c0, int tid) {
+// columns w, w + NW, ... (CPW = 16 / NW of them), lane l owns rows l, l+32, l+64, l+96; every role
+// decision is warp-uniform.
+//
+// Step ii is split so that the latency-critical scalar work overlaps the dot products:
+//   phase A  the RAW (unscaled) tail y of column ii is already in shared memory; every warp forms
+//            d_c = y^T x_c for its columns (for the owner's own column this IS the squared norm)
+//            and, in block 0, extracts its row-i elements; one DMMA all-reduce; the owner derives
+//            (beta, tau, scal) and publishes them                                   -> barrier
+//   phase B  w_c = tau (r_c + scal d_c),  x_c -= y (scal w_c)  [v = scal y is never formed for the
+//            update], the owner scales its column to v, the NEXT owner publishes its raw updated
+//            column                                                                 -> barrier
+template <int N, int NW, bool BLK0>
+__device__ __forceinline__ void panel_factor(double *smem, double *rec, double *Rg, int c0, int tid) {
     using SM = TsqrSmem<NW>;
     constexpr int CPW = kPanelW / NW, RPT = kBlockH / 32;     // columns per warp, rows per lane
+    constexpr int NV = BLK0 ? 2 * CPW : CPW;
     double *Pf = smem + SM::kPf, *vbuf = smem + SM::kVbuf, *Rd = smem + SM::kRd, *Ts = smem + SM::kTs,
-           *taus = smem + SM::kTau, *zb = smem + SM::kZ;
+           *taus = smem + SM::kTau, *zb = smem + SM::kZ, *hs = smem + SM::kHs;
     const int w = tid >> 5, l = tid & 31;
     double x[CPW][RPT];
 #pragma unroll
     for (int q = 0; q < CPW; ++q)
 #pragma unroll
         for (int k = 0; k < RPT; ++k) x[q][k] = Pf[(l + 32 * k) + (w + NW * q) * kLdPf];
-    if (!blk0) {
+    if (!BLK0) {
         for (int idx = tid; idx < 256; idx += 32 * NW)
             Rd[idx] = Rg[(size_t)(c0 + (idx & 15)) + (size_t)(c0 + (idx >> 4)) * N];
     }
     for (int idx = tid; idx < 256; idx += 32 * NW) Ts[idx] = 0.0;
+    if (w == 0) {       // raw tail of column 0
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) vbuf[l + 32 * k] = (BLK0 && l + 32 * k <= c0) ? 0.0 : x[0][k];
+    }
     __syncthreads();
 
 #pragma unroll 1
     for (int ii = 0; ii < kPanelW; ++ii) {
         const int i = c0 + ii;                 // global column = diagonal row in block 0
         const int so = ii / NW;                // slot of column ii in its owner warp
-        double *vb = vbuf + (ii & 1) * kBlockH;
-        if (w == ii % NW) {                    // ---- owner warp: build the reflector ------------------
-            double xo[RPT];
+        const int ki = i >> 5, li = i & 31;    // block 0: row i lives in lane li, register ki
+        const double *vb = vbuf + (ii & 1) * kBlockH;
+        // ---------------- phase A -------------------------------------------------------------------
+        double yb[RPT], vals[NV], rd[CPW];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) yb[k] = vb[l + 32 * k];
+        if (!BLK0) {
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) rd[q] = Rd[ii + 16 * (w + NW * q)];
+        }
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                if (k & 1) d1 = fma(yb[k], x[q][k], d1);
+                else d0 = fma(yb[k], x[q][k], d0);
+            }
+            vals[q] = d0 + d1;
+            if (BLK0) {
+                double xs = x[q][0];
+#pragma unroll
+                for (int k = 1; k < RPT; ++k) xs = (k == ki) ? x[q][k] : xs;
+                vals[CPW + q] = (l == li) ? xs : 0.0;
+            }
+        }
+        warp_allsum_dmma<NV>(vals);
+        if (BLK0) {
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) rd[q] = vals[CPW + q];
+        }
+        double beta = 0.0;
+        if (w == ii % NW) {                    // owner warp: reflector scalars
+            double s2 = vals[0], alpha = rd[0];
+#pragma unroll
+            for (int q = 1; q < CPW; ++q) { s2 = (q == so) ? vals[q] : s2; alpha = (q == so) ? rd[q] : alpha; }
+            const Householder h = make_householder(alpha, s2);
+            beta = h.beta;
+            if (l == 0) {
+                hs[0] = h.tau;
+                hs[1] = h.scal;
+                taus[ii] = h.tau;
+                Ts[ii + 16 * ii] = h.tau;
+                if (!BLK0) Rd[ii + 16 * ii] = h.beta;
+            }
+        }
+        // T column ii-1 by the warp that owned it (its z values were published in step ii-1)
+        if (ii > 1 && w == (ii - 1) % NW) t_column(Ts, zb, taus, ii - 1, l);
+        __syncthreads();
+        // ---------------- phase B -------------------------------------------------------------------
+        const double tau = hs[0], scal = hs[1];
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            const int cc = w + NW * q;
+            const double zc = fma(scal, vals[q], rd[q]);          // r_c + scal * d_c
+            if (cc > ii) {
+                const double wv = tau * zc, f = scal * wv;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    x[q][k] = fma(-yb[k], f, x[q][k]);
+                    if (BLK0) x[q][k] = (l == li && k == ki) ? x[q][k] - wv : x[q][k];
+                }
+                if (!BLK0 && l == 0) Rd[ii + 16 * cc] = rd[q] - wv;
+            } else if (cc < ii) {
+                if (l == 0) zb[(ii & 1) * 16 + cc] = zc;          // z_c = v_c^T v_ii for the T factor
+            } else {                                              // my column becomes the reflector
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const double v = yb[k] * scal;
+                    if (BLK0) x[q][k] = (l + 32 * k > i) ? v : ((l == li && k == ki) ? beta : x[q][k]);
+                    else x[q][k] = v;
+                }
+            }
+        }
+        if (ii + 1 < kPanelW && w == (ii + 1) % NW) {             // next owner: publish the raw tail
+            const int so2 = (ii + 1) / NW;
+            double *vn = vbuf + ((ii + 1) & 1) * kBlockH;
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
                 double v = x[0][k];
 #pragma unroll
-                for (int q = 1; q < CPW; ++q) v = (q == so) ? x[q][k] : v;
-                xo[k] = v;
-            }
-            double s2a = 0.0, s2b = 0.0, xi[RPT];
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                const int row = l + 32 * k;
-                xi[k] = (blk0 && row <= i) ? 0.0 : xo[k];
-                if (k & 1) s2b = fma(xi[k], xi[k], s2b);
-                else s2a = fma(xi[k], xi[k], s2a);
-            }
-            double s2v[1] = {s2a + s2b};
-            warp_allsum_dmma<1>(s2v);
-            const double s2 = s2v[0];
-            double alpha;
-            if (blk0) {
-                double sel = 0.0;
-#pragma unroll
-                for (int k = 0; k < RPT; ++k) sel = (k == (i >> 5)) ? xo[k] : sel;
-                alpha = __shfl_sync(0xffffffffu, sel, i & 31);
-            } else {
-                alpha = Rd[ii + 16 * ii];
-            }
-            const Householder h = make_householder(alpha, s2);
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                const int row = l + 32 * k;
-                double v = xi[k] * h.scal;
-                if (blk0 && row == i) v = 1.0;
-                vb[row] = v;
-                const double keep = blk0 ? ((row > i) ? v : (row == i ? h.beta : xo[k])) : v;
-#pragma unroll
-                for (int q = 0; q < CPW; ++q) x[q][k] = (q == so) ? keep : x[q][k];
-            }
-            if (l == 0) {
-                taus[ii] = h.tau;
-                Ts[ii + 16 * ii] = h.tau;
-                if (!blk0) Rd[ii + 16 * ii] = h.beta;
+                for (int q = 1; q < CPW; ++q) v = (q == so2) ? x[q][k] : v;
+                vn[l + 32 * k] = (BLK0 && l + 32 * k <= i + 1) ? 0.0 : v;
             }
         }
         __syncthreads();
-        {
-            const double tau = taus[ii];
-            double vv[RPT], dot[CPW];
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) vv[k] = vb[l + 32 * k];
-#pragma unroll
-            for (int q = 0; q < CPW; ++q) {
-                double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int k = 0; k < RPT; ++k) {
-                    if (k & 1) d1 = fma(vv[k], x[q][k], d1);
-                    else d0 = fma(vv[k], x[q][k], d0);
-                }
-                dot[q] = d0 + d1;
-            }
-            double rdv[CPW];
-#pragma unroll
-            for (int q = 0; q < CPW; ++q) rdv[q] = blk0 ? 0.0 : Rd[ii + 16 * (w + NW * q)];
-            warp_allsum_dmma<CPW>(dot);
-#pragma unroll
-            for (int q = 0; q < CPW; ++q) {
-                const int cc = w + NW * q;
-                if (cc > ii) {
-                    const double rd = rdv[q];
-                    const double wv = tau * (rd + dot[q]);
-#pragma unroll
-                    for (int k = 0; k < RPT; ++k) x[q][k] = fma(-vv[k], wv, x[q][k]);
-                    if (!blk0 && l == 0) Rd[ii + 16 * cc] = rd - wv;
-                } else if (cc < ii && l == 0) {
-                    zb[(ii & 1) * 16 + cc] = dot[q];      // z_c = v_c^T v_ii for the T factor
-                }
-            }
-        }
-        // T column ii-1 by the warp that owned it; its z values were published during step ii-1
-        if (ii > 1 && w == (ii - 1) % NW) t_column(Ts, zb, taus, ii - 1, l);
     }
-    __syncthreads();
     if (w == (kPanelW - 1) % NW) t_column(Ts, zb, taus, kPanelW - 1, l);          // last T column
     // ---- outputs: explicit reflector panel (swizzled), R entries ------------------------------------
 #pragma unroll
@@ -567,7 +584,7 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
         for (int k = 0; k < RPT; ++k) {
             const int row = l + 32 * k;
             double v = x[q][k];
-            if (blk0) {
+            if (BLK0) {
                 v = (row > col) ? x[q][k] : (row == col ? 1.0 : 0.0);
                 if (row < N) Rg[(size_t)row + (size_t)col * N] = (row <= col) ? x[q][k] : 0.0;
             }
@@ -580,7 +597,7 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
         const double tv = Ts[idx];
         rec[kRecV + k + kLdT * q] = tv;                  // T   : B[k][n] = T[k][n]
         rec[kRecV + kRecT + q + kLdT * k] = tv;          // T^T : B[k][n] = T[n][k]
-        if (!blk0) Rg[(size_t)(c0 + k) + (size_t)(c0 + q) * N] = (q >= k) ? Rd[k + 16 * q] : 0.0;
+        if (!BLK0) Rg[(size_t)(c0 + k) + (size_t)(c0 + q) * N] = (q >= k) ? Rd[k + 16 * q] : 0.0;
     }
     for (int idx = tid; idx < 2 * (kLdT - 16) * 16; idx += 32 * NW) {   // padding of the T images
         const int im = idx / ((kLdT - 16) * 16), r = idx % ((kLdT - 16) * 16);
@@ -688,7 +705,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                         *reinterpret_cast<double2 *>(Pf + (8 * i + 2 * tg) + pc * kLdPf) = make_double2(bx[i], by[i]);
                 }
                 __syncthreads();
-                panel_factor<N, NW>(smem, rec, Rg, blk0, c0, tid);
+                if (blk0) panel_factor<N, NW, true>(smem, rec, Rg, c0, tid);
+                else panel_factor<N, NW, false>(smem, rec, Rg, c0, tid);
                 // record -> global (all threads, coalesced)
                 {
                     double *dst = recg + ((size_t)j * NSP + s) * kRecDoubles;

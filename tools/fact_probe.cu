@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(32 * NW) probe(double *Rg_all, long long *cyc,
         }
         __syncthreads();
         long long t0 = clock64();
-        panel_factor<128, NW>(smem, rec, Rg, blk0 != 0, 16 * (r & 3), tid);
+        if (blk0) panel_factor<128, NW, true>(smem, rec, Rg, 16 * (r & 3), tid); else panel_factor<128, NW, false>(smem, rec, Rg, 16 * (r & 3), tid);
         long long t1 = clock64();
         total += t1 - t0;
     }
