@@ -17,6 +17,8 @@ EXPORTED_SYMBOLS = [
     "hcore_b200_create", "hcore_b200_destroy", "hcore_b200_set_chunk", "hcore_b200_last_error",
     "hcore_b200_version", "hcore_b200_launch_count", "hcore_b200_shard_range",
     "HCORE_dgemm_batched", "HCORE_dgemm_batched_strided", "HCORE_dgemm_batched_host",
+    "HCORE_sgemm_batched", "HCORE_sgemm_batched_strided", "HCORE_sgemm",
+    "sgemm_use_trmm", "sgemm_print_index", "sgemm_print_mat",
     "HCORE_dgemmcd_batched_strided", "HCORE_dsyrk_batched_strided", "hcore_b200_gemm_flops",
     "hcore_b200_debug_fetch", "hcore_b200_debug_set_stages", "hcore_b200_set_stage_timing",
     "hcore_b200_stage_ms",
@@ -58,6 +60,10 @@ def load():
     L.HCORE_dgemm_batched.argtypes = [vp, i, i, d, vp, vp, vp, i, vp, vp, vp, i, d, vp, vp, vp, i, i, i, d, vp, vp]
     L.HCORE_dgemm_batched_strided.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
                                               vp, vp, vp, i, i64, i, i, d, vp, vp]
+    f = C.c_float
+    L.HCORE_sgemm_batched.argtypes = [vp, i, i, f, vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, i, i, i, f, vp, vp]
+    L.HCORE_sgemm_batched_strided.argtypes = [vp, i, i, f, vp, vp, vp, i, i64, vp, vp, vp, i, i64, f,
+                                              vp, vp, vp, i, i64, i, i, f, vp, vp]
     L.HCORE_dgemm_batched_host.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
                                            vp, vp, vp, i, i64, i, i, d, vp]
     L.HCORE_dgemmcd_batched_strided.argtypes = [vp, i, i, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp]
@@ -71,6 +77,10 @@ def load():
     dp = C.POINTER(C.c_double)
     L.HCORE_dgemm.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, dp, dp, i, d, dp, dp, dp, i, i, i, d, dp, vp]
     L.HCORE_dgemm.restype = None
+    fp = C.POINTER(C.c_float)
+    # reference src/include/hcore_s.h:25-46
+    L.HCORE_sgemm.argtypes = [i, i, i, i, f, fp, fp, fp, i, fp, fp, fp, i, f, fp, fp, fp, i, i, i, f, fp, vp]
+    L.HCORE_sgemm.restype = None
     L.HCORE_dgemmcd.argtypes = [i, i, i, d, dp, dp, i, i, dp, dp, i, i, d, dp, i, i, dp, vp]
     L.HCORE_dgemmcd.restype = None
     L.HCORE_dsyrk.argtypes = [i, i, i, i, d, dp, i, dp, i, d, dp, i, dp, vp]

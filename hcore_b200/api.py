@@ -61,6 +61,21 @@ def hcore_dgemm(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BU, BV, Brk, LDB,
                   int(rk), int(maxrk), float(acc), None, fl)
 
 
+def hcore_sgemm(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BU, BV, Brk, LDB, beta, CU, CV, Crk, LDC,
+                rk, maxrk, acc, work=None, flops=None):
+    """``HCORE_sgemm`` (reference src/compute/hcore_sgemm.c:703-1012): float32 arrays, ranks as
+    1-element float32 arrays, otherwise as :func:`hcore_dgemm`."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV), ("Ark", Ark), ("Brk", Brk),
+                  ("Crk", Crk)):
+        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{nm}: need a C-contiguous float32 array")
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    L.HCORE_sgemm(int(transA), int(transB), int(M), int(N), float(alpha), fp(AU), fp(AV), fp(Ark), int(LDA),
+                  fp(BU), fp(BV), fp(Brk), int(LDB), float(beta), fp(CU), fp(CV), fp(Crk), int(LDC),
+                  int(rk), int(maxrk), float(acc), None, C.byref(flops) if flops is not None else None)
+
+
 def hcore_dgemmcd(transA, transB, M, alpha, Au, Av, Arank, LDA, Bu, Bv, Brank, LDB, beta, CD, LDC, maxrank,
                   work=None, flops=None):
     """``HCORE_dgemmcd`` (reference src/compute/hcore_dgemmcd.c:36-107): ``CD -= (Au Av^T)(Bu Bv^T)^T``."""
@@ -189,6 +204,25 @@ class Context:
         if kc < maxrk:
             raise ValueError("CU/CV need room for maxrk columns")
         rc = self._L.HCORE_dgemm_batched_strided(
+            self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb,
+            _ptr(BU), _ptr(BV), _ptr(Brk), nb, kb * nb, float(beta), _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
+            int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))
+        self._check(rc)
+
+    def sgemm_batched(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc,
+                      status=None, stream=None):
+        """Batched ``HCORE_sgemm``: as :meth:`dgemm_batched` with float32 factor tensors."""
+        import torch
+        T, ka, nb = AU.shape
+        for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+            if x.dtype != torch.float32 or not x.is_cuda or not x.is_contiguous():
+                raise TypeError(f"{nm}: need a contiguous float32 CUDA tensor")
+        for nm, x in (("Ark", Ark), ("Brk", Brk), ("Crk", Crk)):
+            self._dev_i32(x, nm)
+        kb, kc = BU.shape[1], CU.shape[1]
+        if kc < maxrk:
+            raise ValueError("CU/CV need room for maxrk columns")
+        rc = self._L.HCORE_sgemm_batched_strided(
             self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb,
             _ptr(BU), _ptr(BV), _ptr(Brk), nb, kb * nb, float(beta), _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
             int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))

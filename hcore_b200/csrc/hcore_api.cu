@@ -12,6 +12,7 @@
 #include "tlr_kernels.cuh"
 #include "dense_kernels.cuh"
 #include "../../include/hcore_d.h"
+#include "../../include/hcore_s.h"
 
 using namespace hcore_b200;
 
@@ -19,6 +20,7 @@ using namespace hcore_b200;
 extern "C" {
 int use_trmm = 0, gemm_print_index = 0, gemm_print_mat = 0, hc_nelm_limit = 512;
 int syrk_print_index = 0, gemmcd_print_index = 0, gemmcd_print_mat = 0, gemmcd_use_scratch = 0;
+int sgemm_use_trmm = 0, sgemm_print_index = 0, sgemm_print_mat = 0;
 }
 
 namespace {
@@ -159,9 +161,10 @@ int launch_chunk_n(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspac
     return launch_chunk<N, 8, 4>(ctx, ar, ws, st);
 }
 
-__global__ void fill_ptrs_kernel(const double **out, const double *base, int64_t stride, int n) {
+// out[i] = base + i * stride_bytes (factor arrays at a fixed stride; element size 8 or 4)
+__global__ void fill_ptrs_kernel(const double **out, const char *base, int64_t stride_bytes, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = base + (size_t)i * stride;
+    if (i < n) out[i] = reinterpret_cast<const double *>(base + (size_t)i * stride_bytes);
 }
 
 }  // namespace
@@ -236,11 +239,14 @@ uint64_t hcore_b200_gemm_flops(int m_, int a_, int b_, int c_, int r_) {
     return f;
 }
 
-int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+}  // extern "C"
+
+// Batched update on arrays of device pointers; f32 = 1: the arrays hold float (HCORE_sgemm).
+static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
                         const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
                         const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
                         double beta, double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
-                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32) {
     if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -280,7 +286,7 @@ int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alph
         ar.Ark = d_Ark; ar.Brk = d_Brk; ar.Crk = d_Crk; ar.status = d_status;
         ar.nb = nb; ar.lda = lda; ar.ldb = ldb; ar.ldc = ldc;
         ar.alpha = alpha; ar.beta = beta; ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc;
-        ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
+        ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0); ar.f32 = f32;
         int rc;
         switch (N) {
             case 32: rc = launch_chunk_n<32>(ctx, ar, ws, st); break;
@@ -292,28 +298,69 @@ int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alph
     return HCORE_B200_OK;
 }
 
-int HCORE_dgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
-                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
-                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
-                        double beta, double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
-                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+// strided factor arrays -> pointer arrays (on the device), then the pointer-array path
+static int tlr_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const void *d_AU, const void *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double beta, void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32) {
     if (!ctx || ntiles < 0) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(ctx, ctx->ptrs.reserve(6ull * ntiles * sizeof(double *)));
     const double **pp = (const double **)ctx->ptrs.p;
-    const double *bases[6] = {d_AU, d_AV, d_BU, d_BV, d_CU, d_CV};
+    const void *bases[6] = {d_AU, d_AV, d_BU, d_BV, d_CU, d_CV};
     const int64_t strides[6] = {strideA, strideA, strideB, strideB, strideC, strideC};
+    const int es = f32 ? 4 : 8;
     const int thr = 256, blk = (ntiles + thr - 1) / thr;
     for (int i = 0; i < 6; ++i) {
-        fill_ptrs_kernel<<<blk, thr, 0, st>>>(pp + (size_t)i * ntiles, bases[i], strides[i], ntiles);
+        fill_ptrs_kernel<<<blk, thr, 0, st>>>(pp + (size_t)i * ntiles, (const char *)bases[i], strides[i] * es, ntiles);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    return HCORE_dgemm_batched(ctx, ntiles, nb, alpha, pp, pp + ntiles, d_Ark, lda, pp + 2 * (size_t)ntiles,
-                               pp + 3 * (size_t)ntiles, d_Brk, ldb, beta, (double *const *)(pp + 4 * (size_t)ntiles),
-                               (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, rk, maxrk, acc, d_status, stream);
+    return tlr_batched(ctx, ntiles, nb, alpha, pp, pp + ntiles, d_Ark, lda, pp + 2 * (size_t)ntiles,
+                       pp + 3 * (size_t)ntiles, d_Brk, ldb, beta, (double *const *)(pp + 4 * (size_t)ntiles),
+                       (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, rk, maxrk, acc, d_status, stream, f32);
+}
+
+extern "C" {
+
+int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
+                        double beta, double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    return tlr_batched(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, d_BU, d_BV, d_Brk, ldb, beta, d_CU, d_CV, d_Crk, ldc,
+                       rk, maxrk, acc, d_status, stream, 0);
+}
+
+int HCORE_sgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, float alpha,
+                        const float *const *d_AU, const float *const *d_AV, const int32_t *d_Ark, int lda,
+                        const float *const *d_BU, const float *const *d_BV, const int32_t *d_Brk, int ldb,
+                        float beta, float *const *d_CU, float *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, float acc, int32_t *d_status, void *stream) {
+    return tlr_batched(ctx, ntiles, nb, alpha, (const double *const *)d_AU, (const double *const *)d_AV, d_Ark, lda,
+                       (const double *const *)d_BU, (const double *const *)d_BV, d_Brk, ldb, beta, (double *const *)d_CU,
+                       (double *const *)d_CV, d_Crk, ldc, rk, maxrk, acc, d_status, stream, 1);
+}
+
+int HCORE_dgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double beta, double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    return tlr_batched_strided(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, strideA, d_BU, d_BV, d_Brk, ldb, strideB, beta,
+                               d_CU, d_CV, d_Crk, ldc, strideC, rk, maxrk, acc, d_status, stream, 0);
+}
+
+int HCORE_sgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, float alpha,
+                        const float *d_AU, const float *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const float *d_BU, const float *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        float beta, float *d_CU, float *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, float acc, int32_t *d_status, void *stream) {
+    return tlr_batched_strided(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, strideA, d_BU, d_BV, d_Brk, ldb, strideB, beta,
+                               d_CU, d_CV, d_Crk, ldc, strideC, rk, maxrk, acc, d_status, stream, 1);
 }
 
 int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
@@ -339,6 +386,19 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
     for (auto &e : done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int rc = HCORE_B200_OK;
     int slice = 0;
+    struct Pending { int t0, cnt; double *dCU, *dCV; } pending[2] = {{0, 0, nullptr, nullptr}, {0, 0, nullptr, nullptr}};
+    auto flush = [&](int s) {
+        Pending &p = pending[s];
+        if (p.cnt == 0) return;
+        cudaStream_t st = ctx->streams[s];
+        cudaStreamSynchronize(st);                       // ranks of this slice are on the host now
+        int rmax = 1;
+        for (int t = 0; t < p.cnt; ++t) rmax = std::max(rmax, (int)h_Crk[p.t0 + t]);
+        const size_t wout = std::min(perC, (size_t)ldc * rmax * 8);
+        cudaMemcpy2DAsync(h_CU + (size_t)p.t0 * strideC, perC, p.dCU, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st);
+        cudaMemcpy2DAsync(h_CV + (size_t)p.t0 * strideC, perC, p.dCV, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st);
+        p.cnt = 0;
+    };
     for (int t0 = 0; t0 < ntiles && rc == HCORE_B200_OK; t0 += hc, ++slice) {
         const int s = slice & 1;
         const int cnt = std::min(hc, ntiles - t0);
@@ -354,8 +414,13 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
         cudaMemcpyAsync(dAV, h_AV + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(dBU, h_BU + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(dBV, h_BV + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dCU, h_CU + (size_t)t0 * strideC, perC * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dCV, h_CV + (size_t)t0 * strideC, perC * cnt, cudaMemcpyHostToDevice, st);
+        // Only the columns that carry data cross PCIe: the first max(Crk) columns of CU/CV go in,
+        // the first max(new Crk) columns come back (2-D copies, one row per tile).
+        int cmax = 1;
+        for (int t = 0; t < cnt; ++t) cmax = std::max(cmax, (int)h_Crk[t0 + t]);
+        const size_t win = std::min(perC, (size_t)ldc * cmax * 8);
+        cudaMemcpy2DAsync(dCU, perC, h_CU + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st);
+        cudaMemcpy2DAsync(dCV, perC, h_CV + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(dArk, h_Ark + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(dBrk, h_Brk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(dCrk, h_Crk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
@@ -363,13 +428,14 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
         rc = HCORE_dgemm_batched_strided(ctx, cnt, nb, alpha, dAU, dAV, dArk, lda, strideA, dBU, dBV, dBrk, ldb,
                                          strideB, beta, dCU, dCV, dCrk, ldc, strideC, rk, maxrk, acc, dSt, st);
         cudaEventRecord(done[s], st);
-        cudaMemcpyAsync(h_CU + (size_t)t0 * strideC, dCU, perC * cnt, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(h_CV + (size_t)t0 * strideC, dCV, perC * cnt, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(h_Crk + t0, dCrk, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
         if (h_status) cudaMemcpyAsync(h_status + t0, dSt, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
-        // the staging buffer `s` is reused two slices later: wait for its stream then
-        if (slice >= 1) cudaStreamSynchronize(ctx->streams[s ^ 1]);
+        pending[s] = {t0, cnt, dCU, dCV};
+        // while slice `slice` computes, finish the previous one: its new ranks are known once its
+        // stream has drained, then its factors come back on that stream
+        if (slice >= 1) flush(s ^ 1);
     }
+    if (slice >= 1) flush((slice - 1) & 1);
     cudaStreamSynchronize(ctx->streams[0]);
     cudaStreamSynchronize(ctx->streams[1]);
     for (auto &e : done) cudaEventDestroy(e);
@@ -503,28 +569,27 @@ static void legacy_fail(const char *who, const char *what, int code) {
     exit(-1);
 }
 
-void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha, double *AU, double *AV, double *Ark,
-                 int LDA, double *BU, double *BV, double *Brk, int LDB, double beta, double *CU, double *CV,
-                 double *Crk, int LDC, int rk, int maxrk, double acc, double *work, flop_counter *flops) {
-    (void)transA; (void)transB; (void)N; (void)work;   // never read by the reference either (hcore_dgemm.c:703-755)
+// Shared body of the legacy HCORE_dgemm / HCORE_sgemm: host arrays of element size `es`.
+static int legacy_gemm(const char *who, int es, int M, double alpha, const void *AU, const void *AV, int a, int LDA,
+                       const void *BU, const void *BV, int b, int LDB, double beta, void *CU, void *CV, int c, int LDC,
+                       int rk, int maxrk, double acc) {
     std::lock_guard<std::mutex> lock(g_mu);
-    hcore_b200_handle_t ctx = legacy_ctx("HCORE_dgemm");
-    const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
-    if (a == 0 || b == 0 || c == 0) legacy_fail("HCORE_dgemm", "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
-    if (maxrk < a + c) legacy_fail("HCORE_dgemm", "increase maxrank (maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    if (a == 0 || b == 0 || c == 0) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
+    if (maxrk < a + c) legacy_fail(who, "increase maxrank (maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
     cudaSetDevice(ctx->device);
     // Only the columns the reference reads (c) and writes (new rank) are moved, so callers
     // whose CU/CV buffers are smaller than LDC x maxrk keep working (reference test:
     // testing/testing_dgemm.c:287-290 allocates M x storage_maxrank).
-    const size_t fa = (size_t)LDA * a * 8, fb = (size_t)LDB * b * 8, fcin = (size_t)LDC * c * 8;
-    const size_t fc = (size_t)LDC * (a + c) * 8;
-    if (ctx->stage[0].reserve(2 * fa + 2 * fb + 2 * fc) != cudaSuccess ||
+    const size_t fa = (size_t)LDA * a * es, fb = (size_t)LDB * b * es, fcin = (size_t)LDC * c * es;
+    const size_t fc = ((size_t)LDC * (a + c) * es + 15) / 16 * 16;
+    const size_t fa16 = (fa + 15) / 16 * 16, fb16 = (fb + 15) / 16 * 16;
+    if (ctx->stage[0].reserve(2 * fa16 + 2 * fb16 + 2 * fc) != cudaSuccess ||
         ctx->stage_ints[0].reserve(8 * sizeof(int)) != cudaSuccess)
-        legacy_fail("HCORE_dgemm", "device allocation failed", HCORE_B200_ERR_CUDA);
+        legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
     char *base = (char *)ctx->stage[0].p;
-    double *dAU = (double *)base, *dAV = (double *)(base + fa), *dBU = (double *)(base + 2 * fa),
-           *dBV = (double *)(base + 2 * fa + fb), *dCU = (double *)(base + 2 * fa + 2 * fb),
-           *dCV = (double *)(base + 2 * fa + 2 * fb + fc);
+    char *dAU = base, *dAV = base + fa16, *dBU = base + 2 * fa16, *dBV = base + 2 * fa16 + fb16,
+         *dCU = base + 2 * fa16 + 2 * fb16, *dCV = base + 2 * fa16 + 2 * fb16 + fc;
     int *di = (int *)ctx->stage_ints[0].p;
     int hi[4] = {a, b, c, 0};
     cudaStream_t st = ctx->streams[0];
@@ -535,18 +600,38 @@ void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha, doub
     cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
-    int rc = HCORE_dgemm_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU,
-                                         dCV, di + 2, LDC, 0, rk, maxrk, acc, di + 3, st);
-    if (rc != HCORE_B200_OK) legacy_fail("HCORE_dgemm", hcore_b200_last_error(ctx), rc);
+    int rc = tlr_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV, di + 2,
+                                 LDC, 0, rk, maxrk, acc, di + 3, st, es == 4);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
     cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail("HCORE_dgemm", "CUDA failure", HCORE_B200_ERR_CUDA);
-    if (hi[3] != HCORE_B200_OK) legacy_fail("HCORE_dgemm", "tile update failed", hi[3]);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
     const int rnew = hi[2];
-    cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * 8, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * 8, cudaMemcpyDeviceToHost, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail("HCORE_dgemm", "CUDA failure", HCORE_B200_ERR_CUDA);
+    cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    return rnew;
+}
+
+void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha, double *AU, double *AV, double *Ark,
+                 int LDA, double *BU, double *BV, double *Brk, int LDB, double beta, double *CU, double *CV,
+                 double *Crk, int LDC, int rk, int maxrk, double acc, double *work, flop_counter *flops) {
+    (void)transA; (void)transB; (void)N; (void)work;   // never read by the reference either (hcore_dgemm.c:703-755)
+    const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
+    const int rnew = legacy_gemm("HCORE_dgemm", 8, M, alpha, AU, AV, a, LDA, BU, BV, b, LDB, beta, CU, CV, c, LDC, rk, maxrk, acc);
     if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
     Crk[0] = (double)rnew;
+}
+
+// reference src/compute/hcore_sgemm.c:703 (float clone of HCORE_dgemm; ranks travel as float)
+void HCORE_sgemm(HCORE_enum transA, HCORE_enum transB, int M, int N, float alpha, float *AU, float *AV, float *Ark,
+                 int LDA, float *BU, float *BV, float *Brk, int LDB, float beta, float *CU, float *CV, float *Crk,
+                 int LDC, int rk, int maxrk, float acc, float *work, flop_counter *flops) {
+    (void)transA; (void)transB; (void)N; (void)work;
+    const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
+    const int rnew = legacy_gemm("HCORE_sgemm", 4, M, alpha, AU, AV, a, LDA, BU, BV, b, LDB, beta, CU, CV, c, LDC, rk, maxrk, acc);
+    if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
+    Crk[0] = (float)rnew;
 }
 
 static void legacy_dense(const char *who, int syrk, int M, double scale, const double *Au, const double *Av, int a,

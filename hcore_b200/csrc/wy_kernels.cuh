@@ -166,7 +166,18 @@ struct TlrArgs {
     double acc;
     int tile0;            // first tile of this chunk in the user arrays
     int ntiles;           // tiles in this chunk
+    int f32;              // 1: the user arrays hold float (HCORE_sgemm); arithmetic stays FP64
 };
+
+// User-array element access: the factor arrays are double, or float when ar.f32 is set (the
+// pointers are then float arrays behind a double* type).  `idx` is an ELEMENT index.
+__device__ __forceinline__ double ld_user(const double *base, size_t idx, int f32) {
+    return f32 ? (double)__ldg(reinterpret_cast<const float *>(base) + idx) : __ldg(base + idx);
+}
+__device__ __forceinline__ void st_user(double *base, size_t idx, double v, int f32) {
+    if (f32) reinterpret_cast<float *>(base)[idx] = (float)v;
+    else base[idx] = v;
+}
 
 // Per-chunk scratch owned by the context.  Index [panel][tile] with panel 0 = U, 1 = V.
 struct TlrWorkspace {
@@ -208,8 +219,9 @@ struct PgSmem {
 };
 
 // rows [r0, r0+32) x ncol columns (padded with zeros to ncol8) of a column-major matrix -> dst (ld kPgLd)
-__device__ __forceinline__ void pg_stage(double *dst, const double *src, int ld, int m, int r0, int ncol, int ncol8,
-                                         bool vec_ok, int tid) {
+__device__ __forceinline__ void pg_stage(double *dst, const double *src, size_t col0, int ld, int m, int r0, int ncol,
+                                         int ncol8, bool vec_ok, int f32, int tid) {
+    if (!f32) src += col0 * ld;
     if (vec_ok && r0 + kPgRows <= m) {
         for (int idx = tid; idx < (kPgRows / 2) * ncol; idx += 256) {
             const int rp = idx & 15, c = idx >> 4;
@@ -218,7 +230,8 @@ __device__ __forceinline__ void pg_stage(double *dst, const double *src, int ld,
     } else {
         for (int idx = tid; idx < kPgRows * ncol; idx += 256) {
             const int r = idx & 31, c = idx >> 5;
-            dst[r + c * kPgLd] = (r0 + r < m) ? __ldg(src + (size_t)c * ld + r0 + r) : 0.0;
+            dst[r + c * kPgLd] = (r0 + r >= m) ? 0.0
+                                 : (f32 ? ld_user(src, (col0 + c) * ld + r0 + r, 1) : __ldg(src + (size_t)c * ld + r0 + r));
         }
     }
     for (int idx = tid; idx < kPgRows * (ncol8 - ncol); idx += 256) {
@@ -253,8 +266,9 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
     const double *AV = ar.AV[gt], *BU = ar.BU[gt], *BV = ar.BV[gt];
     const int m_pad = ws.m_pad;
     const int nchunks = (m + kPgRows - 1) / kPgRows, nchunks_pad = m_pad / kPgRows;
-    const bool va = ((reinterpret_cast<uintptr_t>(AV) & 15) == 0) && ((ar.lda & 1) == 0);
-    const bool vb = ((reinterpret_cast<uintptr_t>(BV) & 15) == 0) && ((reinterpret_cast<uintptr_t>(BU) & 15) == 0) &&
+    const int f32 = ar.f32;
+    const bool va = !f32 && ((reinterpret_cast<uintptr_t>(AV) & 15) == 0) && ((ar.lda & 1) == 0);
+    const bool vb = !f32 && ((reinterpret_cast<uintptr_t>(BV) & 15) == 0) && ((reinterpret_cast<uintptr_t>(BU) & 15) == 0) &&
                     ((ar.ldb & 1) == 0);
     double *Gt = ws.G + (size_t)t * m_pad * N;
 
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
         const int as = (a - ia < kPgKC) ? (a - ia) : kPgKC, as8 = round_up(as, 8);
         for (int jb = 0; jb < b; jb += kPgKC) {
             const int bs = (b - jb < kPgKC) ? (b - jb) : kPgKC, bs8 = round_up(bs, 8);
-            const double *AVs = AV + (size_t)ia * ar.lda, *BVs = BV + (size_t)jb * ar.ldb, *BUs = BU + (size_t)jb * ar.ldb;
+            const double *AVs = AV, *BVs = BV, *BUs = BU;      // slab offsets are passed as column indices
             // ---- P slab = AV[:, ia..]^T BV[:, jb..]: warp -> 8-row strip of P, all column tiles -----
             {
                 const bool active = 8 * warp < as8;
@@ -270,15 +284,15 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
                 double acc[8][2];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-                pg_stage(smem, AVs, ar.lda, m, 0, as, as8, va, tid);
-                pg_stage(smem + kPgKC * kPgLd, BVs, ar.ldb, m, 0, bs, bs8, vb, tid);
+                pg_stage(smem, AVs, ia, ar.lda, m, 0, as, as8, va, f32, tid);
+                pg_stage(smem + kPgKC * kPgLd, BVs, jb, ar.ldb, m, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const double *cur = smem + (ch & 1) * SM::kStage;
                     if (ch + 1 < nchunks) {
                         double *nxt = smem + ((ch + 1) & 1) * SM::kStage;
-                        pg_stage(nxt, AVs, ar.lda, m, (ch + 1) * kPgRows, as, as8, va, tid);
-                        pg_stage(nxt + kPgKC * kPgLd, BVs, ar.ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, tid);
+                        pg_stage(nxt, AVs, ia, ar.lda, m, (ch + 1) * kPgRows, as, as8, va, f32, tid);
+                        pg_stage(nxt + kPgKC * kPgLd, BVs, jb, ar.ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
                         cp_async_commit();
                         cp_async_wait<1>();
                     } else {
@@ -315,12 +329,12 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
             // ---- G[:, ia..] (+)= BU[:, jb..] P^T: warp -> (8-row strip of the chunk, 4 column tiles) ------
             {
                 const int strip = warp & 3, q0 = 4 * (warp >> 2);
-                pg_stage(smem, BUs, ar.ldb, m, 0, bs, bs8, vb, tid);
+                pg_stage(smem, BUs, jb, ar.ldb, m, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
                 for (int ch = 0; ch < nchunks_pad; ++ch) {
                     const double *cur = smem + (ch & 1) * SM::kStage;
                     if (ch + 1 < nchunks_pad) {
-                        pg_stage(smem + ((ch + 1) & 1) * SM::kStage, BUs, ar.ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, tid);
+                        pg_stage(smem + ((ch + 1) & 1) * SM::kStage, BUs, jb, ar.ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
                         cp_async_commit();
                         cp_async_wait<1>();
                     } else {
@@ -391,20 +405,25 @@ struct TsqrSmem {
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
 
-// Source of one stacked-panel column: pointer to its first row and the scalar applied on load.
+// Source of one stacked-panel column: array, element offset of its first row, the scalar applied
+// on load and whether the array holds floats.
 struct ColSrc {
     const double *p;
+    size_t off;
     double scale;
+    int f32;
 };
 __device__ __forceinline__ ColSrc panel_column(const TlrArgs &ar, const double *Gt, int m_pad, int gt, int pnl,
                                                int col, int c, int n) {
-    ColSrc s{nullptr, 0.0};
+    ColSrc s{nullptr, 0, 0.0, 0};
     if (col < c) {
-        s.p = (pnl == 0 ? ar.CU[gt] : ar.CV[gt]) + (size_t)col * ar.ldc;
+        s.p = (pnl == 0 ? ar.CU[gt] : ar.CV[gt]);
+        s.off = (size_t)col * ar.ldc;
         s.scale = pnl == 0 ? ar.beta : 1.0;
+        s.f32 = ar.f32;
     } else if (col < n) {
-        if (pnl == 0) { s.p = ar.AU[gt] + (size_t)(col - c) * ar.lda; s.scale = ar.alpha; }
-        else { s.p = Gt + (size_t)(col - c) * m_pad; s.scale = 1.0; }
+        if (pnl == 0) { s.p = ar.AU[gt]; s.off = (size_t)(col - c) * ar.lda; s.scale = ar.alpha; s.f32 = ar.f32; }
+        else { s.p = Gt; s.off = (size_t)(col - c) * m_pad; s.scale = 1.0; }
     }
     return s;
 }
@@ -652,17 +671,17 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
             }
             // ---- my 8 columns of the row block -> registers -----------------------------------------
             double bx[16], by[16];
-            const bool v16 = src.p && ((reinterpret_cast<uintptr_t>(src.p) & 15) == 0);
+            const bool v16 = src.p && !src.f32 && ((reinterpret_cast<uintptr_t>(src.p + src.off) & 15) == 0);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int row = j * kBlockH + 8 * i + 2 * tg;
                 if (v16 && row + 1 < m) {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(src.p + row));
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(src.p + src.off + row));
                     bx[i] = src.scale * v.x;
                     by[i] = src.scale * v.y;
                 } else {
-                    bx[i] = (src.p && row < m) ? src.scale * __ldg(src.p + row) : 0.0;
-                    by[i] = (src.p && row + 1 < m) ? src.scale * __ldg(src.p + row + 1) : 0.0;
+                    bx[i] = (src.p && row < m) ? src.scale * ld_user(src.p, src.off + row, src.f32) : 0.0;
+                    by[i] = (src.p && row + 1 < m) ? src.scale * ld_user(src.p, src.off + row + 1, src.f32) : 0.0;
                 }
             }
             // ---- (1) reflectors of the earlier groups ------------------------------------------------
@@ -774,7 +793,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar,
     const bool col_on = mycol < rnew;
     const double *recg = ws.rec + rec_offset(ws, pnl, t, NSP);
     double *Yg = ws.Y + nn_offset(ws, pnl, t, N) + (size_t)mycol * N;     // my column of U_r / W
-    double *out = (pnl == 0 ? ar.CU[gt] : ar.CV[gt]) + (size_t)mycol * ar.ldc;
+    double *outb = (pnl == 0 ? ar.CU[gt] : ar.CV[gt]);
+    const size_t outo = (size_t)mycol * ar.ldc;          // element offset of my output column
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -828,15 +848,15 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar,
                 for (int q = 0; q < 2; ++q) { ys[8 * q] -= sx[q]; ys[8 * q + 1] -= sy[q]; }
             }
             if (s == 0 && col_on) {      // row block finished -> output
-                const bool v16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+                const bool v16 = !ar.f32 && (reinterpret_cast<uintptr_t>(outb + outo) & 15) == 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int row = j * kBlockH + 8 * i + 2 * tg;
                     if (v16 && row + 1 < m) {
-                        *reinterpret_cast<double2 *>(out + row) = make_double2(bx[i], by[i]);
+                        *reinterpret_cast<double2 *>(outb + outo + row) = make_double2(bx[i], by[i]);
                     } else {
-                        if (row < m) out[row] = bx[i];
-                        if (row + 1 < m) out[row + 1] = by[i];
+                        if (row < m) st_user(outb, outo + row, bx[i], ar.f32);
+                        if (row + 1 < m) st_user(outb, outo + row + 1, by[i], ar.f32);
                     }
                 }
             }

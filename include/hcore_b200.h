@@ -12,7 +12,9 @@
  *                      (definition src/compute/hcore_dgemmcd.c:36-107)
  *       HCORE_dsyrk    replaces reference src/include/hcore_d.h:107-116
  *                      (definition src/compute/hcore_dsyrk.c:47-189)
- *     They are declared in include/hcore_d.h (same file name the reference installs)
+ *       HCORE_sgemm    replaces reference src/include/hcore_s.h:25-46
+ *                      (definition src/compute/hcore_sgemm.c:703-1012)
+ *     They are declared in include/hcore_d.h / hcore_s.h (same file names the reference installs)
  *     and run as a batch of one on the GPU.  There is NO CPU fallback: without a
  *     CUDA device they print an error and exit(-1), the reference's own error
  *     convention (src/compute/hcore_dgemm.c:743-746).
@@ -101,6 +103,25 @@ int HCORE_dgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         double beta,
                         double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
                         int rk, int maxrk, double acc,
+                        int32_t *d_status, void *stream);
+
+/* Batched HCORE_sgemm (reference src/compute/hcore_sgemm.c:703): same contract with float
+ * factor arrays; the arithmetic is carried out in FP64 and the new factors are rounded to float. */
+int HCORE_sgemm_batched(hcore_b200_handle_t handle, int ntiles, int nb,
+                        float alpha,
+                        const float *const *d_AU, const float *const *d_AV, const int32_t *d_Ark, int lda,
+                        const float *const *d_BU, const float *const *d_BV, const int32_t *d_Brk, int ldb,
+                        float beta,
+                        float *const *d_CU, float *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, float acc,
+                        int32_t *d_status, void *stream);
+int HCORE_sgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        float alpha,
+                        const float *d_AU, const float *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const float *d_BU, const float *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        float beta,
+                        float *d_CU, float *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, float acc,
                         int32_t *d_status, void *stream);
 
 /* Host-buffer variant: every pointer is a HOST pointer (pinned memory gives overlap);

@@ -46,6 +46,52 @@ def _p(a):
     return a.ctypes.data_as(dp)
 
 
+fpp = C.POINTER(C.c_float)
+_blas.scipy_LAPACKE_slatms.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char, ip, C.c_char, fpp, C.c_int, C.c_float,
+                                       C.c_float, C.c_int, C.c_int, C.c_char, fpp, C.c_int]
+_blas.scipy_LAPACKE_sgesvd.argtypes = [C.c_int, C.c_char, C.c_char, C.c_int, C.c_int, fpp, C.c_int, fpp, fpp, C.c_int,
+                                       fpp, C.c_int, fpp]
+
+
+def generate_compress_s(n, iseed, storage_maxrank, acc):
+    """float clone: generate_compress() of reference testing/testing_sgemm.c:119-236."""
+    f = lambda a: a.ctypes.data_as(fpp)  # noqa: E731
+    d = np.array([10.0 ** (-i) for i in range(n)], np.float32)
+    a = np.zeros((n, n), np.float32)
+    info = _blas.scipy_LAPACKE_slatms(102, n, n, b"U", iseed.ctypes.data_as(ip), b"N", f(d), 0, -1.0, -1.0, n - 1,
+                                      n - 1, b"N", f(a), n)
+    assert info == 0
+    clone = a.copy()
+    s, u, vt, sb = (np.zeros(n, np.float32), np.zeros((n, n), np.float32), np.zeros((n, n), np.float32),
+                    np.zeros(n, np.float32))
+    info = _blas.scipy_LAPACKE_sgesvd(102, b"A", b"A", n, n, f(clone), n, f(s), f(u), n, f(vt), n, f(sb))
+    assert info == 0
+    vt_m = vt.T * s[:, None]
+    rank = 0
+    while rank < n and s[rank] >= acc:
+        rank += 1
+    rank = min(rank, storage_maxrank)
+    return a, np.ascontiguousarray(u[:rank]), np.ascontiguousarray(vt_m[:rank]), rank
+
+
+def ctest_sgemm():
+    """reference testing/testing_sgemm.c (M=N=K=10, storage_maxrank 10 (:259), acc 1e-4)."""
+    n, smr, acc = 10, 10, 1e-4
+    iseed = np.array([0, 0, 0, 1], dtype=np.int32)
+    A, AU, AV, ra = generate_compress_s(n, iseed, smr, acc)
+    B, BU, BV, rb_ = generate_compress_s(n, iseed, smr, acc)
+    Cm, CU, CV, rc = generate_compress_s(n, iseed, smr, acc)
+    ref_c = (A.T.astype(np.float32) @ B.T.astype(np.float32).T + Cm.T).astype(np.float32)
+    cu, cv, r, fl = rb.hcore_gemm(AU, AV, BU, BV, CU, CV, rc, alpha=1.0, beta=1.0, rk=0, maxrk=n, acc=acc)
+    app = cu[:r].T @ cv[:r]
+    rnorm = np.abs(ref_c - app).sum(axis=1).max()
+    print("ctest sgemm: ranks", ra, rb_, rc, "->", r, "inf norm", rnorm)
+    assert rnorm < 10 * acc
+    np.savez(os.path.join(HERE, "ref_ctest_sgemm.npz"), AU=AU, AV=AV, BU=BU, BV=BV, CU=CU, CV=CV,
+             ranks=np.array([ra, rb_, rc]), ref_c=ref_c, out_cu=cu[:r], out_cv=cv[:r], out_rank=r,
+             rnorm=rnorm, flops=fl, acc=acc, n=n)
+
+
 def generate_compress(n, iseed, storage_maxrank, acc):
     """Replays generate_compress() of reference testing/testing_dgemm.c:119-236 (square n x n)."""
     d = np.array([10.0 ** (-i) for i in range(n)])
@@ -172,6 +218,7 @@ def tlr_large():
 if __name__ == "__main__":
     rb.set_blas_threads(1)
     ctest_dgemm()
+    ctest_sgemm()
     ctest_dgemmcd()
     ctest_dsyrk()
     tlr_small()

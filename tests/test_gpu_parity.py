@@ -67,6 +67,54 @@ def test_ctest_dgemm_legacy_symbol(golden_dir):
     assert fl.update == int(g["flops"])                   # same flop accounting as the reference
 
 
+def test_ctest_sgemm_legacy_symbol(golden_dir):
+    """reference testing/testing_sgemm.c replayed on HCORE_sgemm of libhcore_b200.so (float in/out,
+    FP64 arithmetic inside): same rank, same assert, residual no worse than the reference's."""
+    g = np.load(os.path.join(golden_dir, "ref_ctest_sgemm.npz"))
+    n, acc = int(g["n"]), float(g["acc"])
+    ra, rb_, rc = (int(x) for x in g["ranks"])
+    CU = np.zeros((n, n), np.float32); CU[:rc] = g["CU"][:rc]
+    CV = np.zeros((n, n), np.float32); CV[:rc] = g["CV"][:rc]
+    Ark, Brk, Crk = (np.array([float(x)], np.float32) for x in (ra, rb_, rc))
+    fl = api.FlopCounter()
+    api.hcore_sgemm(api.HCORE_NoTrans, api.HCORE_Trans, n, n, 1.0, np.ascontiguousarray(g["AU"]),
+                    np.ascontiguousarray(g["AV"]), Ark, n, np.ascontiguousarray(g["BU"]), np.ascontiguousarray(g["BV"]),
+                    Brk, n, 1.0, CU, CV, Crk, n, 0, n, acc, None, fl)
+    r = int(Crk[0])
+    assert r == int(g["out_rank"]) == 6
+    rnorm = _inf_norm(g["ref_c"].astype(np.float64) - CU[:r].T.astype(np.float64) @ CV[:r].astype(np.float64))
+    assert rnorm < 10 * acc                               # the reference's assert (testing_sgemm.c:377-378)
+    assert rnorm <= float(g["rnorm"]) * 1.05
+    assert fl.update == int(g["flops"])
+
+
+@pytest.mark.parametrize("nb,k,acc", [(256, 16, 1e-4), (1024, 64, 1e-4), (500, 25, 1e-3)])
+def test_sgemm_batched_vs_oracle(ctx, nb, k, acc):
+    """HCORE_sgemm_batched (config 4, float leg) against the float32 oracle (sgeqrf/sgesvd/sormqr)."""
+    T = 3
+    b = make_lr_batch(T, nb, k, base_seed=41, dtype=np.float32, decades=4.0)
+    dev = torch.device("cuda:0")
+    t = {n: torch.from_numpy(np.ascontiguousarray(getattr(b, n))).to(dev)
+         for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
+    status = torch.full((T,), -7, dtype=torch.int32, device=dev)
+    ctx.sgemm_batched(-1.0, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], 1.0, t["cu"], t["cv"], t["crk"],
+                      rk=0, maxrk=2 * k, acc=acc, status=status)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    cu, cv, crk = t["cu"].cpu().numpy(), t["cv"].cpu().numpy(), t["crk"].cpu().numpy()
+    assert cu.dtype == np.float32
+    for i in range(T):
+        cu_o, cv_o, r_o, _ = orc.tlr_gemm_colmajor(b.au[i], b.av[i], b.bu[i], b.bv[i], b.cu[i], b.cv[i], k,
+                                                   alpha=np.float32(-1.0), beta=np.float32(1.0), rk=0, maxrk=2 * k, acc=acc)
+        r = int(crk[i])
+        assert abs(r - r_o) <= 1
+        dense = b.dense_c(i, -1.0, 1.0).astype(np.float64)
+        e_o = np.linalg.norm(cu_o.T.astype(np.float64) @ cv_o.astype(np.float64) - dense)
+        e_d = np.linalg.norm(cu[i, :r].T.astype(np.float64) @ cv[i, :r].astype(np.float64) - dense)
+        # FP64 inside: no worse than the float reference (plus float rounding of the output factors)
+        assert e_d <= 1.01 * e_o + 8 * np.finfo(np.float32).eps * np.linalg.norm(dense) + (acc if r != r_o else 0.0)
+
+
 def test_ctest_dgemmcd_legacy_symbol(golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_ctest_dgemmcd.npz"))
     CD = np.array(g["CD"], copy=True)

@@ -32,6 +32,25 @@ def test_reference_ctest_dgemm(golden_dir):
     assert orc.flop_model(10, ra, rb_, rc, r) == int(g["flops"])
 
 
+def test_reference_ctest_sgemm(golden_dir):
+    """reference testing/testing_sgemm.c (float clone, storage_maxrank 10): ranks 4/5/5 -> 6,
+    ||C_ref - CU CV^T||_inf = 8.181651e-05 < 10*acc."""
+    g = np.load(os.path.join(golden_dir, "ref_ctest_sgemm.npz"))
+    ra, rb_, rc = g["ranks"]
+    assert (int(ra), int(rb_), int(rc)) == (4, 5, 5)
+    assert g["AU"].dtype == np.float32
+    cu, cv, r, _ = orc.tlr_gemm(g["AU"][:ra].T, g["AV"][:ra].T, g["BU"][:rb_].T, g["BV"][:rb_].T, g["CU"][:rc].T,
+                                g["CV"][:rc].T, alpha=np.float32(1.0), beta=np.float32(1.0), rk=0, maxrk=int(g["n"]),
+                                acc=float(g["acc"]))
+    assert cu.dtype == np.float32
+    assert r == int(g["out_rank"]) == 6
+    rn = _inf_norm(g["ref_c"] - cu @ cv.T)
+    assert rn < 10 * float(g["acc"])
+    assert abs(float(g["rnorm"]) - 8.181651e-05) < 1e-9
+    assert abs(rn - float(g["rnorm"])) < 1e-5            # float LAPACK: last digits depend on the BLAS
+    np.testing.assert_allclose(cu @ cv.T, g["out_cu"].T @ g["out_cv"], atol=2e-5)
+
+
 def test_reference_ctest_dgemmcd(golden_dir):
     """reference testing/testing_dgemmcd.c:194-205: residual < 1000 eps."""
     g = np.load(os.path.join(golden_dir, "ref_ctest_dgemmcd.npz"))
