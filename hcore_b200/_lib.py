@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "hcore_b200_version", "hcore_b200_launch_count", "hcore_b200_shard_range",
     "HCORE_dgemm_batched", "HCORE_dgemm_batched_strided", "HCORE_dgemm_batched_host",
     "HCORE_sgemm_batched", "HCORE_sgemm_batched_strided", "HCORE_sgemm",
+    "HCORE_zgemm_batched_strided", "HCORE_zgemm",
     "sgemm_use_trmm", "sgemm_print_index", "sgemm_print_mat",
     "HCORE_dgemmcd_batched_strided", "HCORE_dsyrk_batched_strided", "hcore_b200_gemm_flops",
     "hcore_b200_debug_fetch", "hcore_b200_debug_set_stages", "hcore_b200_set_stage_timing",
@@ -28,6 +29,16 @@ EXPORTED_SYMBOLS = [
 ]
 
 _lib = None
+
+
+class DComplex(C.Structure):
+    """``hcore_b200_dcomplex``: complex double scalar passed by value (layout of C99 double _Complex)."""
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+    @classmethod
+    def of(cls, z):
+        z = complex(z)
+        return cls(z.real, z.imag)
 
 
 class LibraryMissing(RuntimeError):
@@ -64,6 +75,8 @@ def load():
     L.HCORE_sgemm_batched.argtypes = [vp, i, i, f, vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, i, i, i, f, vp, vp]
     L.HCORE_sgemm_batched_strided.argtypes = [vp, i, i, f, vp, vp, vp, i, i64, vp, vp, vp, i, i64, f,
                                               vp, vp, vp, i, i64, i, i, f, vp, vp]
+    L.HCORE_zgemm_batched_strided.argtypes = [vp, i, i, DComplex, vp, vp, vp, i, i64, vp, vp, vp, i, i64, DComplex,
+                                              vp, vp, vp, i, i64, i, i, d, vp, vp]
     L.HCORE_dgemm_batched_host.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
                                            vp, vp, vp, i, i64, i, i, d, vp]
     L.HCORE_dgemmcd_batched_strided.argtypes = [vp, i, i, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp]
@@ -81,6 +94,9 @@ def load():
     # reference src/include/hcore_s.h:25-46
     L.HCORE_sgemm.argtypes = [i, i, i, i, f, fp, fp, fp, i, fp, fp, fp, i, f, fp, fp, fp, i, i, i, f, fp, vp]
     L.HCORE_sgemm.restype = None
+    # reference src/include/hcore_z.h:27-48
+    L.HCORE_zgemm.argtypes = [i, i, i, i, DComplex, vp, vp, dp, i, vp, vp, dp, i, DComplex, vp, vp, dp, i, i, i, d, vp, vp]
+    L.HCORE_zgemm.restype = None
     L.HCORE_dgemmcd.argtypes = [i, i, i, d, dp, dp, i, i, dp, dp, i, i, d, dp, i, i, dp, vp]
     L.HCORE_dgemmcd.restype = None
     L.HCORE_dsyrk.argtypes = [i, i, i, i, d, dp, i, dp, i, d, dp, i, dp, vp]

@@ -76,6 +76,20 @@ def hcore_sgemm(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BU, BV, Brk, LDB,
                   int(rk), int(maxrk), float(acc), None, C.byref(flops) if flops is not None else None)
 
 
+def hcore_zgemm(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BU, BV, Brk, LDB, beta, CU, CV, Crk, LDC,
+                rk, maxrk, acc, work=None, flops=None):
+    """``HCORE_zgemm`` (reference src/compute/hcore_zgemm.c:663-975): complex128 arrays, complex
+    ``alpha``/``beta``, ranks as 1-element float64 arrays; tiles are ``U @ V.T`` (plain transpose)."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+        if x.dtype != np.complex128 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{nm}: need a C-contiguous complex128 array")
+    vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    L.HCORE_zgemm(int(transA), int(transB), int(M), int(N), _lib.DComplex.of(alpha), vp(AU), vp(AV), _dp(Ark), int(LDA),
+                  vp(BU), vp(BV), _dp(Brk), int(LDB), _lib.DComplex.of(beta), vp(CU), vp(CV), _dp(Crk), int(LDC),
+                  int(rk), int(maxrk), float(acc), None, C.byref(flops) if flops is not None else None)
+
+
 def hcore_dgemmcd(transA, transB, M, alpha, Au, Av, Arank, LDA, Bu, Bv, Brank, LDB, beta, CD, LDC, maxrank,
                   work=None, flops=None):
     """``HCORE_dgemmcd`` (reference src/compute/hcore_dgemmcd.c:36-107): ``CD -= (Au Av^T)(Bu Bv^T)^T``."""
@@ -226,6 +240,25 @@ class Context:
             self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb,
             _ptr(BU), _ptr(BV), _ptr(Brk), nb, kb * nb, float(beta), _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
             int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))
+        self._check(rc)
+
+    def zgemm_batched(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc,
+                      status=None, stream=None):
+        """Batched ``HCORE_zgemm``: complex128 factor tensors (T, k, nb), complex scalars."""
+        import torch
+        T, ka, nb = AU.shape
+        for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+            if x.dtype != torch.complex128 or not x.is_cuda or not x.is_contiguous():
+                raise TypeError(f"{nm}: need a contiguous complex128 CUDA tensor")
+        for nm, x in (("Ark", Ark), ("Brk", Brk), ("Crk", Crk)):
+            self._dev_i32(x, nm)
+        kb, kc = BU.shape[1], CU.shape[1]
+        if kc < maxrk:
+            raise ValueError("CU/CV need room for maxrk columns")
+        rc = self._L.HCORE_zgemm_batched_strided(
+            self._h, T, nb, _lib.DComplex.of(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb,
+            _ptr(BU), _ptr(BV), _ptr(Brk), nb, kb * nb, _lib.DComplex.of(beta), _ptr(CU), _ptr(CV), _ptr(Crk), nb,
+            kc * nb, int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))
         self._check(rc)
 
     def dgemm_batched_host(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc, status=None):

@@ -11,8 +11,10 @@
 
 #include "tlr_kernels.cuh"
 #include "dense_kernels.cuh"
+#include "zgemm_kernels.cuh"
 #include "../../include/hcore_d.h"
 #include "../../include/hcore_s.h"
+#include "../../include/hcore_z.h"
 
 using namespace hcore_b200;
 
@@ -56,6 +58,8 @@ struct hcore_b200_context {
     DevBuf rec, G, R, Y, sigma, ints, ptrs;
     // dense workspace
     DevBuf X;
+    // complex (zgemm) workspace
+    DevBuf zpanel, ztau, zT, zY, zsigma, zints;
     // host-staging (HCORE_dgemm_batched_host and the legacy wrappers)
     DevBuf stage[2];
     DevBuf stage_ints[2];
@@ -196,7 +200,7 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
     if (!ctx) return HCORE_B200_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X,
+    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -444,6 +448,54 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
     return HCORE_B200_OK;
 }
 
+// ---- complex double (HCORE_zgemm) ------------------------------------------------------------
+int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_dcomplex alpha,
+                        const void *d_AU, const void *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        hcore_b200_dcomplex beta, void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = pick_width(maxrk);
+    const size_t per = (2ull * nb * N + 2ull * N + 3ull * N * N) * sizeof(zc) + N * 8 + 16;
+    int chunk = ctx->chunk_limit > 0 ? ctx->chunk_limit : (int)std::min<size_t>(ctx->num_sms * 4, (4ull << 30) / per);
+    chunk = std::max(1, std::min(chunk, ntiles));
+    CUDA_TRY(ctx, ctx->zpanel.reserve(2ull * chunk * nb * N * sizeof(zc)));
+    CUDA_TRY(ctx, ctx->ztau.reserve(2ull * chunk * N * sizeof(zc)));
+    CUDA_TRY(ctx, ctx->zT.reserve((size_t)chunk * N * N * sizeof(zc)));
+    CUDA_TRY(ctx, ctx->zY.reserve(2ull * chunk * N * N * sizeof(zc)));
+    CUDA_TRY(ctx, ctx->zsigma.reserve((size_t)chunk * N * 8));
+    CUDA_TRY(ctx, ctx->zints.reserve((size_t)chunk * 4 * sizeof(int)));
+    ZWorkspace ws{};
+    ws.panel = (zc *)ctx->zpanel.p; ws.tau = (zc *)ctx->ztau.p; ws.T = (zc *)ctx->zT.p; ws.Y = (zc *)ctx->zY.p;
+    ws.sigma = (double *)ctx->zsigma.p;
+    ws.ncols = (int *)ctx->zints.p; ws.newrank = ws.ncols + chunk; ws.st = ws.newrank + chunk; ws.sweeps = ws.st + chunk;
+    ws.chunk = chunk; ws.N = N;
+    const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = 8ull * nb * sizeof(zc);
+    if (sm_ap > 227 * 1024) { ctx->err = "HCORE_zgemm: nb too large for the apply kernel's shared memory"; return HCORE_B200_ERR_ARG; }
+    CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qr));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ap));
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        ZArgs ar{};
+        ar.AU = (const zc *)d_AU; ar.AV = (const zc *)d_AV; ar.BU = (const zc *)d_BU; ar.BV = (const zc *)d_BV;
+        ar.CU = (zc *)d_CU; ar.CV = (zc *)d_CV;
+        ar.strideA = strideA; ar.strideB = strideB; ar.strideC = strideC;
+        ar.Ark = d_Ark; ar.Brk = d_Brk; ar.Crk = d_Crk; ar.status = d_status;
+        ar.nb = nb; ar.lda = lda; ar.ldb = ldb; ar.ldc = ldc;
+        ar.alpha = make_double2(alpha.re, alpha.im); ar.beta = make_double2(beta.re, beta.im);
+        ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc; ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
+        ztlr_stack_kernel<<<ar.ntiles, 256, 0, st>>>(ar, ws);
+        ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
+        ztlr_svd_kernel<<<ar.ntiles, 512, 0, st>>>(ar, ws);
+        ztlr_apply_kernel<<<dim3((N + 7) / 8, 2, ar.ntiles), 256, sm_ap, st>>>(ar, ws);
+        ctx->launches += 4;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
 // ---- dense-C updates ----------------------------------------------------------------------
 static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scale, int syrk,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
@@ -632,6 +684,50 @@ void HCORE_sgemm(HCORE_enum transA, HCORE_enum transB, int M, int N, float alpha
     const int rnew = legacy_gemm("HCORE_sgemm", 4, M, alpha, AU, AV, a, LDA, BU, BV, b, LDB, beta, CU, CV, c, LDC, rk, maxrk, acc);
     if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
     Crk[0] = (float)rnew;
+}
+
+// reference src/compute/hcore_zgemm.c:663-975.  `double _Complex` by value and a struct of two
+// doubles are passed identically (two SSE registers) under the x86-64 SysV ABI.
+void HCORE_zgemm(HCORE_enum transA, int transB, int M, int N, hcore_b200_dcomplex alpha, void *AU, void *AV,
+                 double *Ark, int LDA, void *BU, void *BV, double *Brk, int LDB, hcore_b200_dcomplex beta, void *CU,
+                 void *CV, double *Crk, int LDC, int rk, int maxrk, double acc, void *work, flop_counter *flops) {
+    (void)transA; (void)transB; (void)N; (void)work;
+    const char *who = "HCORE_zgemm";
+    const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
+    std::lock_guard<std::mutex> lock(g_mu);
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    if (a == 0 || b == 0 || c == 0) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
+    if (maxrk < a + c) legacy_fail(who, "increase maxrank (maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
+    cudaSetDevice(ctx->device);
+    const size_t es = 16;
+    const size_t fa = (size_t)LDA * a * es, fb = (size_t)LDB * b * es, fcin = (size_t)LDC * c * es, fc = (size_t)LDC * (a + c) * es;
+    if (ctx->stage[0].reserve(2 * fa + 2 * fb + 2 * fc) != cudaSuccess || ctx->stage_ints[0].reserve(8 * sizeof(int)) != cudaSuccess)
+        legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+    char *base = (char *)ctx->stage[0].p;
+    char *dAU = base, *dAV = base + fa, *dBU = base + 2 * fa, *dBV = base + 2 * fa + fb, *dCU = base + 2 * fa + 2 * fb,
+         *dCV = base + 2 * fa + 2 * fb + fc;
+    int *di = (int *)ctx->stage_ints[0].p;
+    int hi[4] = {a, b, c, 0};
+    cudaStream_t st = ctx->streams[0];
+    cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    int rc = HCORE_zgemm_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV,
+                                         di + 2, LDC, 0, rk, maxrk, acc, di + 3, st);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+    cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
+    const int rnew = hi[2];
+    cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
+    Crk[0] = (double)rnew;
 }
 
 static void legacy_dense(const char *who, int syrk, int M, double scale, const double *Au, const double *Av, int a,

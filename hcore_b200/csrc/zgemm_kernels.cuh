@@ -1,0 +1,358 @@
+// Complex-double tile-low-rank update + recompression (HCORE_zgemm, reference
+// src/compute/hcore_zgemm.c:663-975) -- first, correctness-oriented CUDA path.
+//
+// Same pipeline as the FP64 path, complex arithmetic on the FP64 FMA pipe, operands in global
+// memory / L2 (the complex 1024 x 128 panel is 2 MiB, the 128 x 128 core 256 KiB: neither fits
+// one CTA's shared memory):
+//   ztlr_stack_kernel  X_u = [beta CU | alpha AU], P = AV^T BV, X_v = [CV | BU P^T]   (__zqra/__zqrb,
+//                      hcore_zgemm.c:65-137, :138-215; PLAIN transposes, :165, :189)
+//   ztlr_qr_kernel     unblocked Householder QR (zgeqr2 semantics: zlarfg, H^H applied) of both panels
+//                      (replaces LAPACKE_zgeqrf, hcore_zgemm.c:123, :205)
+//   ztlr_svd_kernel    T = R_u R_v^T (plain transpose, :309), one-sided Jacobi on its columns with
+//                      complex rotations, sort, truncation (rk > 0 = fixed rank, :376), U_r,
+//                      W = R_v (R_u^T conj(U_r))  (replaces LAPACKE_zgesvd + the conj/zunmqr/conj dance
+//                      of __znewv, :593-632: CV = Q_v W)
+//   ztlr_apply_kernel  CU = Q_u [U_r; 0], CV = Q_v [W; 0] by applying the reflectors to one output
+//                      column per warp held in shared memory (replaces LAPACKE_zunmqr, :470-530, :600-620)
+#pragma once
+#include "common.cuh"
+
+namespace hcore_b200 {
+
+typedef double2 zc;   // x = re, y = im
+
+__device__ __forceinline__ zc zmake(double r, double i) { return make_double2(r, i); }
+__device__ __forceinline__ zc zadd(zc a, zc b) { return zmake(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ zc zsub(zc a, zc b) { return zmake(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ zc zmul(zc a, zc b) { return zmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ zc zconj(zc a) { return zmake(a.x, -a.y); }
+__device__ __forceinline__ zc zscale(zc a, double s) { return zmake(a.x * s, a.y * s); }
+__device__ __forceinline__ zc zfma(zc a, zc b, zc c) {   // a*b + c
+    return zmake(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+__device__ __forceinline__ zc zcfma(zc a, zc b, zc c) {  // conj(a)*b + c
+    return zmake(fma(a.x, b.x, fma(a.y, b.y, c.x)), fma(a.x, b.y, fma(-a.y, b.x, c.y)));
+}
+__device__ __forceinline__ double zabs2(zc a) { return fma(a.x, a.x, a.y * a.y); }
+__device__ __forceinline__ zc zwarp_sum(zc v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+struct ZArgs {
+    const zc *AU, *AV, *BU, *BV;     // strided factor arrays
+    zc *CU, *CV;
+    long strideA, strideB, strideC;
+    const int *Ark, *Brk;
+    int *Crk;
+    int *status;
+    int nb, lda, ldb, ldc;
+    zc alpha, beta;
+    int rk, maxrk;
+    double acc;
+    int tile0, ntiles;
+};
+
+struct ZWorkspace {
+    zc *panel;     // [2][chunk][m * N]     stacked panels -> reflectors + R
+    zc *tau;       // [2][chunk][N]
+    zc *T;         // [chunk][N * N]        P, then the core matrix, then a GEMM temporary
+    zc *Y;         // [2][chunk][N * N]     U_r and W
+    double *sigma; // [chunk][N]
+    int *ncols, *newrank, *st, *sweeps;
+    int chunk, N;
+};
+
+__device__ __forceinline__ zc *zpanel(const ZWorkspace &ws, int pnl, int t, int m) {
+    return ws.panel + ((size_t)pnl * ws.chunk + t) * (size_t)m * ws.N;
+}
+
+// ---- 1. stacking ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ztlr_stack_kernel(ZArgs ar, ZWorkspace ws) {
+    const int t = blockIdx.x, gt = ar.tile0 + t, tid = threadIdx.x;
+    const int a = ar.Ark[gt], b = ar.Brk[gt], c = ar.Crk[gt];
+    const int n = a + c, m = ar.nb, N = ws.N;
+    int st = HCORE_B200_OK;
+    if (a <= 0 || b <= 0 || c <= 0) st = HCORE_B200_ERR_ZERO_RANK;
+    else if (ar.maxrk < n) st = HCORE_B200_ERR_MAXRK;
+    else if (n > N || n > m || b > N) st = HCORE_B200_ERR_UNSUPPORTED;
+    if (tid == 0) {
+        ws.st[t] = st; ws.ncols[t] = n; ws.newrank[t] = c;
+        if (ar.status) ar.status[gt] = st;
+    }
+    if (st != HCORE_B200_OK) return;
+    const zc *AU = ar.AU + (size_t)gt * ar.strideA, *AV = ar.AV + (size_t)gt * ar.strideA;
+    const zc *BU = ar.BU + (size_t)gt * ar.strideB, *BV = ar.BV + (size_t)gt * ar.strideB;
+    const zc *CU = ar.CU + (size_t)gt * ar.strideC, *CV = ar.CV + (size_t)gt * ar.strideC;
+    zc *XU = zpanel(ws, 0, t, m), *XV = zpanel(ws, 1, t, m);
+    zc *P = ws.T + (size_t)t * N * N;                     // P[i + j*N], i < a, j < b
+
+    for (int idx = tid; idx < m * n; idx += blockDim.x) {
+        const int r = idx % m, col = idx / m;
+        if (col < c) {
+            XU[r + (size_t)col * m] = zmul(ar.beta, CU[r + (size_t)col * ar.ldc]);
+            XV[r + (size_t)col * m] = CV[r + (size_t)col * ar.ldc];
+        } else {
+            XU[r + (size_t)col * m] = zmul(ar.alpha, AU[r + (size_t)(col - c) * ar.lda]);
+        }
+    }
+    // P = AV^T BV: one thread per P entry, lanes along i (coalescing comes from the L1: every
+    // thread streams its two columns)
+    for (int idx = tid; idx < a * b; idx += blockDim.x) {
+        const int i = idx % a, j = idx / a;
+        const zc *pa = AV + (size_t)i * ar.lda, *pb = BV + (size_t)j * ar.ldb;
+        zc acc = zmake(0.0, 0.0);
+        for (int k = 0; k < m; ++k) acc = zfma(pa[k], pb[k], acc);
+        P[i + (size_t)j * N] = acc;
+    }
+    __syncthreads();
+    // G = BU P^T -> X_v[:, c : c+a]: one thread per row, 8 outputs at a time
+    for (int r = tid; r < m; r += blockDim.x) {
+        for (int i0 = 0; i0 < a; i0 += 8) {
+            zc acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = zmake(0.0, 0.0);
+            for (int j = 0; j < b; ++j) {
+                const zc bu = BU[r + (size_t)j * ar.ldb];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (i0 + q < a) acc[q] = zfma(bu, P[(i0 + q) + (size_t)j * N], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (i0 + q < a) XV[r + (size_t)(c + i0 + q) * m] = acc[q];
+        }
+    }
+}
+
+// ---- 2. Householder QR (zgeqr2) --------------------------------------------------------------------------
+// grid = 2 * tiles, 512 threads; dynamic shared memory: m complex (current reflector) + 40 doubles.
+__global__ void __launch_bounds__(512) ztlr_qr_kernel(ZArgs ar, ZWorkspace ws) {
+    extern __shared__ __align__(16) double zsm[];
+    const int t = blockIdx.x >> 1, pnl = blockIdx.x & 1;
+    if (ws.st[t] != HCORE_B200_OK) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int n = ws.ncols[t], m = ar.nb;
+    zc *X = zpanel(ws, pnl, t, m);
+    zc *tau_g = ws.tau + ((size_t)pnl * ws.chunk + t) * ws.N;
+    zc *v = reinterpret_cast<zc *>(zsm);
+    double *red = zsm + 2 * (size_t)m;          // [32] partial sums, [32..35] scalars
+    for (int j = 0; j < n; ++j) {
+        zc *xj = X + (size_t)j * m;
+        double s = 0.0;
+        for (int r = j + 1 + tid; r < m; r += blockDim.x) { const zc x = xj[r]; v[r] = x; s += zabs2(x); }
+        s = warp_sum(s);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double xn2 = 0.0;
+            for (int w = 0; w < nwarps; ++w) xn2 += red[w];
+            const zc alpha = xj[j];
+            zc tau = zmake(0.0, 0.0), scale = zmake(0.0, 0.0);
+            double beta = alpha.x;
+            if (xn2 != 0.0 || alpha.y != 0.0) {                       // LAPACK zlarfg
+                beta = -copysign(sqrt(zabs2(alpha) + xn2), alpha.x);
+                tau = zmake((beta - alpha.x) / beta, -alpha.y / beta);
+                const zc d = zmake(alpha.x - beta, alpha.y);
+                const double dn = zabs2(d);
+                scale = zmake(d.x / dn, -d.y / dn);                   // 1 / (alpha - beta)
+                xj[j] = zmake(beta, 0.0);
+            }
+            tau_g[j] = tau;
+            red[32] = tau.x; red[33] = tau.y; red[34] = scale.x; red[35] = scale.y;
+        }
+        __syncthreads();
+        const zc tau = zmake(red[32], red[33]), scale = zmake(red[34], red[35]);
+        for (int r = j + 1 + tid; r < m; r += blockDim.x) { const zc x = zmul(v[r], scale); v[r] = x; xj[r] = x; }
+        __syncthreads();
+        if (tau.x != 0.0 || tau.y != 0.0) {
+            const zc ctau = zconj(tau);                                // H^H = I - conj(tau) v v^H
+            for (int c = j + 1 + warp; c < n; c += nwarps) {
+                zc *xc = X + (size_t)c * m;
+                zc dot = zmake(0.0, 0.0);
+                for (int r = j + 1 + lane; r < m; r += 32) dot = zcfma(v[r], xc[r], dot);
+                dot = zwarp_sum(dot);
+                dot = zadd(dot, xc[j]);
+                const zc tw = zmul(ctau, dot);
+                if (lane == 0) xc[j] = zsub(xc[j], tw);
+                const zc ntw = zmake(-tw.x, -tw.y);
+                for (int r = j + 1 + lane; r < m; r += 32) xc[r] = zfma(ntw, v[r], xc[r]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- 3. core SVD ------------------------------------------------------------------------------------------
+constexpr double kZTolRot = 1e-15, kZTolStop = 1e-7;
+constexpr int kZMaxSweeps = 60;
+
+__global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) {
+    __shared__ double sig[HCORE_B200_MAX_STACK], ssort[HCORE_B200_MAX_STACK];
+    __shared__ int posof[HCORE_B200_MAX_STACK], misc[4];
+    const int t = blockIdx.x;
+    if (ws.st[t] != HCORE_B200_OK) return;
+    const int gt = ar.tile0 + t;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int n = ws.ncols[t], m = ar.nb, N = ws.N;
+    const zc *Ru = zpanel(ws, 0, t, m), *Rv = zpanel(ws, 1, t, m);   // upper triangles, ld m
+    zc *T = ws.T + (size_t)t * N * N;                                 // ld N
+    zc *Yu = ws.Y + ((size_t)0 * ws.chunk + t) * N * N, *Yv = ws.Y + ((size_t)1 * ws.chunk + t) * N * N;
+
+    // T = R_u R_v^T (plain transpose): T(i,j) = sum_{k >= max(i,j)} Ru(i,k) Rv(j,k)
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;
+        zc acc = zmake(0.0, 0.0);
+        for (int k = (i > j ? i : j); k < n; ++k) acc = zfma(Ru[i + (size_t)k * m], Rv[j + (size_t)k * m], acc);
+        T[i + (size_t)j * N] = acc;
+    }
+    __syncthreads();
+
+    // one-sided Jacobi on the columns of T; a warp per pair, lane l owns rows l, l+32, ...
+    const int n2 = n + (n & 1);
+    int sweeps = 0;
+    bool converged = (n2 < 2);
+    for (int sweep = 0; sweep < kZMaxSweeps && !converged; ++sweep) {
+        int big = 0;
+        for (int step = 0; step < n2 - 1; ++step) {
+            for (int k = warp; k < n2 / 2; k += nwarps) {
+                int p, q;
+                rr_pair(n2, step, k, p, q);
+                if (q >= n) continue;
+                zc *cp = T + (size_t)p * N, *cq = T + (size_t)q * N;
+                zc xp[4], xq[4];
+                double app = 0.0, aqq = 0.0;
+                zc apq = zmake(0.0, 0.0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = lane + 32 * e;
+                    xp[e] = (r < n) ? cp[r] : zmake(0.0, 0.0);
+                    xq[e] = (r < n) ? cq[r] : zmake(0.0, 0.0);
+                    app += zabs2(xp[e]); aqq += zabs2(xq[e]);
+                    apq = zcfma(xp[e], xq[e], apq);                  // p^H q
+                }
+                app = warp_sum(app); aqq = warp_sum(aqq); apq = zwarp_sum(apq);
+                const double den2 = app * aqq, g2 = zabs2(apq);
+                if (den2 > 0.0 && g2 > (kZTolRot * kZTolRot) * den2) {
+                    if (g2 > (kZTolStop * kZTolStop) * den2) big = 1;
+                    const double g = sqrt(g2);
+                    const zc ph = zmake(apq.x / g, -apq.y / g);     // conj(theta): q <- q conj(theta) makes p^H q real
+                    const double zeta = (aqq - app) / (2.0 * g);
+                    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = lane + 32 * e;
+                        if (r < n) {
+                            const zc qt = zmul(xq[e], ph);
+                            cp[r] = zmake(cs * xp[e].x - sn * qt.x, cs * xp[e].y - sn * qt.y);
+                            cq[r] = zmake(sn * xp[e].x + cs * qt.x, sn * xp[e].y + cs * qt.y);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        ++sweeps;
+        converged = (__syncthreads_or(big) == 0);
+    }
+
+    // singular values, sort (descending, stable), truncation
+    for (int cc = warp; cc < n; cc += nwarps) {
+        double s2 = 0.0;
+        for (int r = lane; r < n; r += 32) s2 += zabs2(T[r + (size_t)cc * N]);
+        s2 = warp_sum(s2);
+        if (lane == 0) sig[cc] = sqrt(s2);
+    }
+    if (tid == 0) misc[1] = n;
+    __syncthreads();
+    if (tid < n) {
+        const double mine = sig[tid];
+        int pos = 0;
+        for (int jj = 0; jj < n; ++jj) { const double o = sig[jj]; pos += (o > mine || (o == mine && jj < tid)) ? 1 : 0; }
+        posof[tid] = pos;
+        ssort[pos] = mine;
+    }
+    __syncthreads();
+    // reference src/compute/hcore_zgemm.c:376-395: fixed rank iff rk > 0, else the first index
+    // i >= 1 with sigma_i < acc (absolute)
+    if (ar.rk > 0) { if (tid == 0) misc[1] = ar.rk < n ? ar.rk : n; }
+    else if (tid >= 1 && tid < n && ssort[tid] < ar.acc) atomicMin(&misc[1], tid);
+    __syncthreads();
+    const int rnew = misc[1];
+    if (tid < n) ws.sigma[(size_t)t * N + tid] = ssort[tid];
+    int st = converged ? HCORE_B200_OK : HCORE_B200_ERR_NO_CONVERGE;
+    if (rnew > ar.maxrk) st = HCORE_B200_ERR_NEWRANK;
+    if (tid == 0) {
+        ws.newrank[t] = rnew; ws.sweeps[t] = sweeps; ws.st[t] = st;
+        if (ar.status) ar.status[gt] = st;
+        if (st == HCORE_B200_OK) ar.Crk[gt] = rnew;
+    }
+    if (st != HCORE_B200_OK) return;
+    // U_r: normalised columns in sorted order
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, cc = idx / n, pos = posof[cc];
+        if (pos < rnew) {
+            const double sg = sig[cc];
+            Yu[i + (size_t)pos * N] = sg > 0.0 ? zscale(T[i + (size_t)cc * N], 1.0 / sg) : zmake(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+    // tmp = R_u^T conj(U_r)  (n x r) into T;  W = R_v tmp
+    for (int idx = tid; idx < n * rnew; idx += blockDim.x) {
+        const int k = idx % n, c = idx / n;
+        zc acc = zmake(0.0, 0.0);
+        for (int i = 0; i <= k; ++i) acc = zfma(Ru[i + (size_t)k * m], zconj(Yu[i + (size_t)c * N]), acc);
+        T[k + (size_t)c * N] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * rnew; idx += blockDim.x) {
+        const int j = idx % n, c = idx / n;
+        zc acc = zmake(0.0, 0.0);
+        for (int k = j; k < n; ++k) acc = zfma(Rv[j + (size_t)k * m], T[k + (size_t)c * N], acc);
+        Yv[j + (size_t)c * N] = acc;
+    }
+}
+
+// ---- 4. reflector application --------------------------------------------------------------------------------
+// grid = (ceil(N / 8), 2, tiles), 256 threads: every warp owns one output column, kept in shared
+// memory (m complex per warp), and applies H_{n-1}, ..., H_0 to [y; 0].
+__global__ void __launch_bounds__(256) ztlr_apply_kernel(ZArgs ar, ZWorkspace ws) {
+    extern __shared__ __align__(16) double zsm[];
+    const int t = blockIdx.z, pnl = blockIdx.y;
+    if (ws.st[t] != HCORE_B200_OK) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 8 + warp;
+    const int rnew = ws.newrank[t];
+    if (col >= rnew) return;
+    const int gt = ar.tile0 + t;
+    const int n = ws.ncols[t], m = ar.nb, N = ws.N;
+    const zc *X = zpanel(ws, pnl, t, m);
+    const zc *tau_g = ws.tau + ((size_t)pnl * ws.chunk + t) * N;
+    const zc *y = ws.Y + ((size_t)pnl * ws.chunk + t) * N * N + (size_t)col * N;
+    zc *z = reinterpret_cast<zc *>(zsm) + (size_t)warp * m;
+    zc *out = (pnl == 0 ? ar.CU : ar.CV) + (size_t)gt * ar.strideC + (size_t)col * ar.ldc;
+    for (int r = lane; r < m; r += 32) z[r] = (r < n) ? y[r] : zmake(0.0, 0.0);
+    __syncwarp();
+    for (int j = n - 1; j >= 0; --j) {
+        const zc tau = tau_g[j];
+        if (tau.x == 0.0 && tau.y == 0.0) continue;
+        const zc *v = X + (size_t)j * m;
+        zc dot = zmake(0.0, 0.0);
+        for (int r = j + 1 + lane; r < m; r += 32) dot = zcfma(v[r], z[r], dot);
+        dot = zwarp_sum(dot);
+        dot = zadd(dot, z[j]);
+        const zc tw = zmul(tau, dot), ntw = zmake(-tw.x, -tw.y);
+        __syncwarp();
+        if (lane == 0) z[j] = zsub(z[j], tw);
+        for (int r = j + 1 + lane; r < m; r += 32) z[r] = zfma(ntw, v[r], z[r]);
+        __syncwarp();
+    }
+    for (int r = lane; r < m; r += 32) out[r] = z[r];
+}
+
+}  // namespace hcore_b200

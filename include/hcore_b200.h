@@ -14,7 +14,9 @@
  *                      (definition src/compute/hcore_dsyrk.c:47-189)
  *       HCORE_sgemm    replaces reference src/include/hcore_s.h:25-46
  *                      (definition src/compute/hcore_sgemm.c:703-1012)
- *     They are declared in include/hcore_d.h / hcore_s.h (same file names the reference installs)
+ *       HCORE_zgemm    replaces reference src/include/hcore_z.h:27-48
+ *                      (definition src/compute/hcore_zgemm.c:663-975)
+ *     They are declared in include/hcore_d.h / hcore_s.h / hcore_z.h (same file names the reference installs)
  *     and run as a batch of one on the GPU.  There is NO CPU fallback: without a
  *     CUDA device they print an error and exit(-1), the reference's own error
  *     convention (src/compute/hcore_dgemm.c:743-746).
@@ -55,6 +57,9 @@ extern "C" {
 #define HCORE_B200_MAX_STACK       128
 
 typedef struct hcore_b200_context *hcore_b200_handle_t;
+
+/* complex double scalar passed by value (layout of C99 `double _Complex`) */
+typedef struct { double re, im; } hcore_b200_dcomplex;
 
 /* ---- context ------------------------------------------------------------------------- */
 /* Creates a context on CUDA device `device` (-1: current device).  The context owns the
@@ -122,6 +127,18 @@ int HCORE_sgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         float beta,
                         float *d_CU, float *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
                         int rk, int maxrk, float acc,
+                        int32_t *d_status, void *stream);
+
+/* Batched HCORE_zgemm (reference src/compute/hcore_zgemm.c:663-975): complex double factors
+ * (interleaved re/im, i.e. arrays of C99 double _Complex), tiles are U * V^T with a PLAIN
+ * transpose, ranks int32, rk > 0 selects fixed-rank truncation (reference :376).              */
+int HCORE_zgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        hcore_b200_dcomplex alpha,
+                        const void *d_AU, const void *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        hcore_b200_dcomplex beta,
+                        void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc,
                         int32_t *d_status, void *stream);
 
 /* Host-buffer variant: every pointer is a HOST pointer (pinned memory gives overlap);

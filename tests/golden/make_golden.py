@@ -215,6 +215,25 @@ def tlr_large():
     np.savez(os.path.join(HERE, "ref_tlr_large.npz"), **rec)
 
 
+def tlr_complex():
+    """Compiled-reference HCORE_zgemm outputs (the reference has no test of its own for zgemm):
+    seeded complex batches, plain-transpose tiles, adaptive and fixed-rank (rk > 0) modes."""
+    rec = {}
+    for name, nb, k, rk, acc, alpha, beta in (("z_nb64_k6", 64, 6, 0, 1e-8, -1.0 + 0.25j, 1.0 - 0.5j),
+                                              ("z_nb96_fixed", 96, 8, 5, 1e-8, 0.5 - 1.0j, 1.0 + 0.0j)):
+        T = 2
+        b = make_lr_batch(T, nb, k, base_seed=51, dtype=np.complex128)
+        for t in range(T):
+            cu, cv, r, fl = rb.hcore_gemm(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k, alpha=alpha, beta=beta,
+                                          rk=rk, maxrk=2 * k, acc=acc)
+            rec[f"{name}_t{t}_cu"] = cu[:r]; rec[f"{name}_t{t}_cv"] = cv[:r]
+            rec[f"{name}_t{t}_rank"] = r; rec[f"{name}_t{t}_flops"] = fl
+        rec[name + "_meta"] = np.array([nb, k, rk, T], dtype=np.int64)
+        rec[name + "_scal"] = np.array([acc, alpha, beta], dtype=np.complex128)
+    np.savez_compressed(os.path.join(HERE, "ref_tlr_complex.npz"), **rec)
+    print("tlr_complex:", {k_: int(v) for k_, v in rec.items() if k_.endswith("_rank")})
+
+
 if __name__ == "__main__":
     rb.set_blas_threads(1)
     ctest_dgemm()
@@ -223,3 +242,4 @@ if __name__ == "__main__":
     ctest_dsyrk()
     tlr_small()
     tlr_large()
+    tlr_complex()

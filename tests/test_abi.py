@@ -21,7 +21,7 @@ def _declared_functions(header):
 
 def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.load()
-    declared = _declared_functions("hcore_b200.h") | _declared_functions("hcore_d.h") | _declared_functions("hcore_s.h")
+    declared = _declared_functions("hcore_b200.h") | _declared_functions("hcore_d.h") | _declared_functions("hcore_s.h") | _declared_functions("hcore_z.h")
     assert {"HCORE_dgemm", "HCORE_dgemmcd", "HCORE_dsyrk", "HCORE_dgemm_batched"} <= declared
     for sym in declared | set(_lib.EXPORTED_SYMBOLS):
         assert hasattr(L, sym), sym

@@ -115,6 +115,55 @@ def test_sgemm_batched_vs_oracle(ctx, nb, k, acc):
         assert e_d <= 1.01 * e_o + 8 * np.finfo(np.float32).eps * np.linalg.norm(dense) + (acc if r != r_o else 0.0)
 
 
+@pytest.mark.parametrize("nb,k,acc,rk", [(96, 8, 1e-8, 0), (256, 16, 1e-8, 0), (200, 12, 1e-8, 5), (1024, 64, 1e-8, 0)])
+def test_zgemm_batched_vs_oracle(ctx, nb, k, acc, rk):
+    """HCORE_zgemm_batched (config 4, complex leg) against the complex oracle (zgeqrf/zgesvd/zunmqr,
+    plain-transpose tiles, reference src/compute/hcore_zgemm.c:165,189,309)."""
+    T = 2
+    alpha, beta = -1.0 + 0.25j, 1.0 - 0.5j
+    b = make_lr_batch(T, nb, k, base_seed=51, dtype=np.complex128)
+    dev = torch.device("cuda:0")
+    t = {n: torch.from_numpy(np.ascontiguousarray(getattr(b, n))).to(dev)
+         for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
+    status = torch.full((T,), -7, dtype=torch.int32, device=dev)
+    ctx.zgemm_batched(alpha, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], beta, t["cu"], t["cv"], t["crk"],
+                      rk=rk, maxrk=2 * k, acc=acc, status=status)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    cu, cv, crk = t["cu"].cpu().numpy(), t["cv"].cpu().numpy(), t["crk"].cpu().numpy()
+    for i in range(T):
+        cu_o, cv_o, r_o, _ = orc.tlr_gemm_colmajor(b.au[i], b.av[i], b.bu[i], b.bv[i], b.cu[i], b.cv[i], k,
+                                                   alpha=alpha, beta=beta, rk=rk, maxrk=2 * k, acc=acc)
+        r = int(crk[i])
+        assert abs(r - r_o) <= (0 if rk else 1)
+        dense = b.dense_c(i, alpha, beta)
+        e_o = np.linalg.norm(cu_o.T @ cv_o - dense)
+        e_d = np.linalg.norm(cu[i, :r].T @ cv[i, :r] - dense)
+        assert e_d <= max(1.01 * e_o, 256 * EPS * np.linalg.norm(dense)) + (acc if r != r_o else 0.0)
+        if rk == 0:
+            U = cu[i, :r]
+            assert np.abs(U.conj() @ U.T - np.eye(r)).max() < 1e-12     # CU has orthonormal columns
+
+
+def test_zgemm_legacy_symbol(ctx):
+    """HCORE_zgemm drop-in symbol (host arrays, double _Complex scalars by value)."""
+    nb, k = 64, 6
+    alpha, beta = 0.5 - 1.0j, 1.0 + 0.0j
+    b = make_lr_batch(1, nb, k, base_seed=77, dtype=np.complex128)
+    CU, CV = b.cu[0].copy(), b.cv[0].copy()
+    Ark, Brk, Crk = np.array([float(k)]), np.array([float(k)]), np.array([float(k)])
+    fl = api.FlopCounter()
+    api.hcore_zgemm(api.HCORE_NoTrans, api.HCORE_Trans, nb, nb, alpha, b.au[0], b.av[0], Ark, nb, b.bu[0], b.bv[0], Brk, nb,
+                    beta, CU, CV, Crk, nb, 0, 2 * k, 1e-8, None, fl)
+    r = int(Crk[0])
+    cu_o, cv_o, r_o, _ = orc.tlr_gemm_colmajor(b.au[0], b.av[0], b.bu[0], b.bv[0], b.cu[0], b.cv[0], k, alpha=alpha,
+                                               beta=beta, rk=0, maxrk=2 * k, acc=1e-8)
+    assert abs(r - r_o) <= 1
+    dense = b.dense_c(0, alpha, beta)
+    assert np.linalg.norm(CU[:r].T @ CV[:r] - dense) <= 1.01 * np.linalg.norm(cu_o.T @ cv_o - dense) + 1e-8
+    assert fl.update == api.gemm_flops(nb, k, k, k, r)
+
+
 def test_ctest_dgemmcd_legacy_symbol(golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_ctest_dgemmcd.npz"))
     CD = np.array(g["CD"], copy=True)

@@ -86,6 +86,24 @@ def test_oracle_vs_compiled_reference_small(golden_dir, name, kind):
         assert orc.flop_model(nb, a, bb, c, r) == int(g[f"{name}_t{t}_flops"])
 
 
+@pytest.mark.parametrize("name", ["z_nb64_k6", "z_nb96_fixed"])
+def test_oracle_vs_compiled_reference_complex(golden_dir, name):
+    """The complex restatement against outputs of the compiled reference HCORE_zgemm (the
+    reference ships no zgemm test: this fixture is what pins the complex oracle)."""
+    g = np.load(os.path.join(golden_dir, "ref_tlr_complex.npz"))
+    nb, k, rk, T = (int(x.real) for x in g[name + "_meta"])
+    acc, alpha, beta = g[name + "_scal"]
+    b = make_lr_batch(T, nb, k, base_seed=51, dtype=np.complex128)
+    for t in range(T):
+        cu, cv, r, _ = orc.tlr_gemm_colmajor(b.au[t], b.av[t], b.bu[t], b.bv[t], b.cu[t], b.cv[t], k, alpha=alpha,
+                                             beta=beta, rk=rk, maxrk=2 * k, acc=float(acc.real))
+        assert r == int(g[f"{name}_t{t}_rank"])
+        np.testing.assert_allclose(cu.T @ cv, g[f"{name}_t{t}_cu"].T @ g[f"{name}_t{t}_cv"], atol=1e-12)
+        dense = b.dense_c(t, alpha, beta)
+        if rk == 0:
+            assert np.linalg.norm(cu.T @ cv - dense) <= 4 * float(acc.real)
+
+
 @pytest.mark.parametrize("name,nb,k,T", [("nb500_k25", 500, 25, 3), ("nb1024_k64", 1024, 64, 2)])
 def test_oracle_vs_compiled_reference_large(golden_dir, name, nb, k, T):
     g = np.load(os.path.join(golden_dir, "ref_tlr_large.npz"))
