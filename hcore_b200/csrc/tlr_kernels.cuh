@@ -87,90 +87,159 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     if (tid < n16) perm[tid] = tid;
     __syncthreads();
 
-    // ---- QR with column pivoting (preconditioner) ----------------------------------------
-    for (int cc = warp; cc < n16; cc += nwarps) {
-        double s2 = 0.0;
-        for (int rr = lane; rr < n16; rr += 32) { const double x = L[rr + cc * LDL]; s2 = fma(x, x, s2); }
-        s2 = warp_sum(s2);
-        if (lane == 0) vn[cc] = s2;
+    // ---- QR with column pivoting (preconditioner), truncated -----------------------------------
+    // Two barriers per step:
+    //   phase C (warp 0)  pivot = argmax of the 16 per-warp candidates, swap, Householder vector
+    //   phase D (all)     apply the reflector to the trailing columns (a warp owns columns
+    //                     i+1+warp, +16, ...; batches of 4 columns share one DMMA all-reduce),
+    //                     down-date their squared norms (recomputed exactly every 8th step) and
+    //                     leave the warp's best candidate for the next step
+    // The factorisation stops at step kq when the exact Frobenius norm of the remaining block is
+    // below 1% of the truncation threshold (singular values move by less than that, Weyl), or at
+    // rounding level of the largest column in fixed-rank mode.
+    constexpr int RPL = N / 32;                        // rows per lane
+    double *candv = sig;                               // [16] per-warp best squared norm (sig is free until later)
+    int *candi = reinterpret_cast<int *>(ssort);       // [16] and its column
+    {
+        // exact norms of all columns; warp w owns columns w, w+16, ... like phase D of "step -1"
+        double best = -1.0; int bi = 0;
+        for (int cc = warp; cc < n16; cc += nwarps) {
+            double s2 = 0.0;
+            for (int rr = lane; rr < n16; rr += 32) { const double x = L[rr + cc * LDL]; s2 = fma(x, x, s2); }
+            s2 = warp_sum(s2);
+            if (lane == 0) vn[cc] = s2;
+            if (s2 > best) { best = s2; bi = cc; }
+        }
+        if (lane == 0) { candv[warp] = best; candi[warp] = bi; }
     }
     __syncthreads();
+    double tol2;
+    {
+        double mx = 0.0;
+        for (int w = 0; w < nwarps; ++w) mx = fmax(mx, candv[w]);
+        tol2 = (ar.rk == 0) ? 1e-4 * ar.acc * ar.acc : 1e-30 * mx;
+    }
+    int kq = n16;
     for (int i = 0; i < n16; ++i) {
-        if (warp == 0) {      // pivot = argmax of the down-dated squared column norms
-            double best = -1.0; int bi = i;
-            for (int cc = i + lane; cc < n16; cc += 32) { const double x = vn[cc]; if (x > best) { best = x; bi = cc; } }
+        const int ki = i >> 5, li = i & 31;
+        if (warp == 0) {
+            // -- pivot --
+            double best = (lane < nwarps) ? candv[lane] : -1.0;
+            int bi = (lane < nwarps) ? candi[lane] : 0x7fffffff;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = 8; o > 0; o >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            if (lane == 0) misc[0] = bi;
+            best = __shfl_sync(0xffffffffu, best, 0);
+            const int piv = __shfl_sync(0xffffffffu, bi, 0);
+            const bool exact = (i & 7) == 0;           // candidates come from exactly recomputed norms
+            const bool stop = exact && best * (double)(n16 - i) < tol2;
+            if (lane == 0) misc[2] = stop ? 1 : 0;
+            if (!stop) {
+                // -- swap columns i <-> piv, build the reflector of the pivot column --
+                double xi[RPL], xp[RPL];
+#pragma unroll
+                for (int e = 0; e < RPL; ++e) {
+                    const int rr = lane + 32 * e;
+                    xi[e] = (rr < n16) ? L[rr + i * LDL] : 0.0;
+                    xp[e] = (rr < n16) ? L[rr + piv * LDL] : 0.0;
+                }
+                double rv[2] = {0.0, 0.0};             // squared norm below the diagonal, diagonal entry
+#pragma unroll
+                for (int e = 0; e < RPL; ++e) {
+                    const int rr = lane + 32 * e;
+                    if (rr > i) rv[0] = fma(xp[e], xp[e], rv[0]);
+                    if (rr == i) rv[1] = xp[e];
+                }
+                warp_allsum_dmma<2>(rv);
+                const Householder h = make_householder(rv[1], rv[0]);
+#pragma unroll
+                for (int e = 0; e < RPL; ++e) {
+                    const int rr = lane + 32 * e;
+                    if (rr < n16) {
+                        vvec[rr] = (rr == i) ? 1.0 : (rr > i ? xp[e] * h.scal : 0.0);
+                        L[rr + i * LDL] = (rr < i) ? xp[e] : (rr == i ? h.beta : 0.0);
+                        if (piv != i) L[rr + piv * LDL] = xi[e];
+                    }
+                }
+                if (lane == 0) {
+                    dmisc[0] = h.tau;
+                    if (piv != i) {
+                        const int pi = perm[i]; perm[i] = perm[piv]; perm[piv] = pi;
+                        vn[piv] = vn[i];
+                    }
+                }
+            }
         }
         __syncthreads();
-        const int piv = misc[0];
-        if (piv != i) {
-            if (tid < n16) {
-                const double x = L[tid + i * LDL];
-                L[tid + i * LDL] = L[tid + piv * LDL];
-                L[tid + piv * LDL] = x;
-            }
-            if (tid == 0) {
-                const int pi = perm[i]; perm[i] = perm[piv]; perm[piv] = pi;
-                const double x = vn[i]; vn[i] = vn[piv]; vn[piv] = x;
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {      // Householder vector of column i (rows i..n16-1)
-            double s2 = 0.0;
-            for (int rr = i + 1 + lane; rr < n16; rr += 32) { const double x = L[rr + i * LDL]; s2 = fma(x, x, s2); }
-            s2 = warp_sum(s2);
-            const double alpha = L[i + i * LDL];
-            const Householder h = make_householder(alpha, s2);
-            for (int rr = i + lane; rr < n16; rr += 32) {
-                const double x = L[rr + i * LDL];
-                vvec[rr] = (rr == i) ? 1.0 : x * h.scal;
-                L[rr + i * LDL] = (rr == i) ? h.beta : 0.0;
-            }
-            if (lane == 0) dmisc[0] = h.tau;
-        }
-        __syncthreads();
+        if (misc[2]) { kq = i; break; }
         {
             const double tau = dmisc[0];
-            for (int cc = i + 1 + warp; cc < n16; cc += nwarps) {
-                double x[N / 32], vv[N / 32];
-                double dot = 0.0;
+            const bool exact_next = ((i + 1) & 7) == 0;
+            double vv[RPL];
 #pragma unroll
-                for (int e = 0; e < N / 32; ++e) {
-                    const int rr = lane + 32 * e;
-                    const bool on = (rr >= i && rr < n16);
-                    x[e] = on ? L[rr + cc * LDL] : 0.0;
-                    vv[e] = on ? vvec[rr] : 0.0;
-                    dot = fma(x[e], vv[e], dot);
-                }
-                dot = warp_sum(dot) * tau;
-                if (tau != 0.0) {
+            for (int e = 0; e < RPL; ++e) { const int rr = lane + 32 * e; vv[e] = (rr >= i && rr < n16) ? vvec[rr] : 0.0; }
+            double best = -1.0; int bi = 0x7fffffff;
+            for (int c0 = i + 1 + warp; c0 < n16; c0 += 4 * nwarps) {
+                double x[4][RPL], dot[4];
 #pragma unroll
-                    for (int e = 0; e < N / 32; ++e) {
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = c0 + q * nwarps;
+                    double d = 0.0;
+#pragma unroll
+                    for (int e = 0; e < RPL; ++e) {
                         const int rr = lane + 32 * e;
-                        if (rr >= i && rr < n16) {
-                            x[e] = fma(-dot, vv[e], x[e]);
-                            L[rr + cc * LDL] = x[e];
+                        x[q][e] = (cc < n16 && rr < n16) ? L[rr + cc * LDL] : 0.0;
+                        d = fma(x[q][e], vv[e], d);
+                    }
+                    dot[q] = d;
+                }
+                warp_allsum_dmma<4>(dot);
+                double nrm[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = c0 + q * nwarps;
+                    const double w = dot[q] * tau;
+                    double s2 = 0.0;
+#pragma unroll
+                    for (int e = 0; e < RPL; ++e) {
+                        const int rr = lane + 32 * e;
+                        x[q][e] = fma(-w, vv[e], x[q][e]);
+                        if (cc < n16 && rr >= i && rr < n16) L[rr + cc * LDL] = x[q][e];
+                        if (rr > i) s2 = fma(x[q][e], x[q][e], s2);
+                    }
+                    nrm[q] = s2;
+                }
+                if (exact_next) warp_allsum_dmma<4>(nrm);      // exact norms of rows > i
+                if (lane == li) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cc = c0 + q * nwarps;
+                        if (cc < n16) {
+                            double top = x[q][0];
+#pragma unroll
+                            for (int e = 1; e < RPL; ++e) top = (e == ki) ? x[q][e] : top;
+                            double v = exact_next ? nrm[q] : vn[cc] - top * top;
+                            v = v > 0.0 ? v : 0.0;
+                            vn[cc] = v;
+                            if (v > best || (v == best && cc < bi)) { best = v; bi = cc; }
                         }
                     }
                 }
-                // down-date the squared norm with the (updated) entry in row i
-                double xsel = 0.0;
-#pragma unroll
-                for (int e = 0; e < N / 32; ++e) xsel = (e == (i >> 5)) ? x[e] : xsel;
-                const double top = __shfl_sync(0xffffffffu, xsel, i & 31);
-                if (lane == 0) { const double d = vn[cc] - top * top; vn[cc] = d > 0.0 ? d : 0.0; }
             }
+            if (lane == li) { candv[warp] = best; candi[warp] = bi; }
         }
         __syncthreads();
     }
 
-    // ---- L <- R^T (R upper triangular, its strict lower part is already zero) ------------
+    // ---- L <- R^T restricted to the kq factored rows (the remaining block is dropped) -------------
+    for (int idx = tid; idx < n16 * n16; idx += blockDim.x) {
+        const int i = idx % n16, j = idx / n16;
+        if (i >= kq) L[i + j * LDL] = 0.0;
+    }
+    __syncthreads();
     for (int idx = tid; idx < n16 * n16; idx += blockDim.x) {
         const int i = idx % n16, j = idx / n16;
         if (i < j) {
@@ -180,6 +249,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         }
     }
     __syncthreads();
+    const int kq2 = (kq + 1) & ~1;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq2
 
     // ---- one-sided Jacobi on the columns of L ---------------------------------------------
     // 8 lanes per column pair; lane l8 owns rows l8, l8+8, ...  The four pairs of a warp are
@@ -187,15 +257,15 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     // columns two apart (64-byte segments 16 banks apart: conflict-free with ld = N+4).
     const int l8 = tid & 7;
     const int grp = ((tid >> 5) << 2) | ((tid >> 4) & 1) | (((tid >> 3) & 1) << 1);
-    const int npairs = n16 >> 1;
+    const int npairs = kq2 >> 1;
     int sweeps = 0;
-    bool converged = false;
+    bool converged = (kq2 < 2);
     for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
         int big = 0;
-        for (int step = 0; step < n16 - 1; ++step) {
+        for (int step = 0; step < kq2 - 1; ++step) {
             for (int k = grp; k < npairs; k += (int)(blockDim.x >> 3)) {
                 int p, qq;
-                rr_pair(n16, step, k, p, qq);
+                rr_pair(kq2, step, k, p, qq);
                 double xp[N / 8], xq[N / 8];
                 double app = 0.0, aqq = 0.0, apq = 0.0;
 #pragma unroll

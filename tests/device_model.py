@@ -167,16 +167,27 @@ def tsqr_apply(f, y):
     return out
 
 
-def qrcp(a):
+def qrcp(a, tol2=0.0):
     """Householder QR with column pivoting on squared partial column norms that are
-    down-dated (no LAPACK-style recomputation safeguard: the permutation only has to be
-    a good *preconditioner* for the Jacobi sweeps, any permutation is backward stable).
-    Returns (R upper triangular, perm) with ``a[:, perm] = Q R``."""
+    down-dated and recomputed exactly every 8th step (no LAPACK-style safeguard: the
+    permutation only has to be a good *preconditioner* for the Jacobi sweeps, any
+    permutation is backward stable).  The factorisation is TRUNCATED: at a step ``i`` that is
+    a multiple of 8 (exact norms) it stops when ``max_norm2 * (n - i) < tol2``, i.e. when the
+    Frobenius norm of the remaining block is below ``sqrt(tol2)``; the remaining block is
+    dropped.  Returns (R of shape (kq, n) upper trapezoidal, perm, kq) with
+    ``a[:, perm] = Q R + O(sqrt(tol2))``."""
     a = np.array(a, dtype=np.float64, copy=True)
     n = a.shape[1]
     perm = np.arange(n)
     vn = np.sum(a * a, axis=0)
+    kq = n
     for i in range(n):
+        if i % 8 == 0:
+            if i > 0:
+                vn[i:] = np.sum(a[i:, i:] ** 2, axis=0)
+            if vn[i:].max() * (n - i) < tol2:
+                kq = i
+                break
         p = i + int(np.argmax(vn[i:]))
         if p != i:
             a[:, [i, p]] = a[:, [p, i]]
@@ -191,7 +202,7 @@ def qrcp(a):
         a[i, i] = beta
         a[i + 1:, i] = 0.0
         vn[i + 1:] = np.maximum(vn[i + 1:] - a[i, i + 1:] ** 2, 0.0)
-    return np.triu(a), perm
+    return np.triu(a)[:kq], perm, kq
 
 
 def rr_pair(n, step, k):
@@ -252,16 +263,25 @@ def core_svd_model(ru, rv, rk, acc):
     R^T, sort, truncate, U_r = P * normalised columns, W = R_v (R_u^T U_r)."""
     from oracle.tlr_oracle import truncation_rank
     tp = rv @ ru.T
-    r_up, perm = qrcp(tp)
-    g, sweeps = jacobi_svd_cols(r_up.T)
+    n = tp.shape[1]
+    n16 = (n + 15) // 16 * 16                      # the kernel works on the zero-padded n16 x n16 core
+    tpp = np.zeros((n16, n16)); tpp[:n, :n] = tp
+    tol2 = 1e-4 * acc * acc if rk == 0 else 1e-30 * float(np.max(np.sum(tpp * tpp, axis=0)))
+    r_up, perm, kq = qrcp(tpp, tol2)
+    kq2 = (kq + 1) & ~1
+    lt = np.zeros((n16, n16))
+    lt[:, :kq] = r_up.T
+    gj, sweeps = jacobi_svd_cols(lt[:, :kq2]) if kq2 >= 2 else (lt[:, :kq2], 0)
+    g = np.zeros((n16, n16)); g[:, :kq2] = gj
     sig = np.sqrt(np.sum(g * g, axis=0))
     order = np.argsort(-sig, kind="stable")
-    sig = sig[order]
-    g = g[:, order]
+    sig = sig[order][:n]
+    g = g[:, order][:, :n]
     r = truncation_rank(sig, rk, acc)
     ut = np.where(sig[:r] > 0, g[:, :r] / np.where(sig[:r] > 0, sig[:r], 1.0), 0.0)
-    u = np.zeros_like(ut)
-    u[perm, :] = ut                       # U = P * U~
+    up = np.zeros_like(ut)
+    up[perm, :] = ut                      # U = P * U~
+    u = up[:n]
     w = rv @ (ru.T @ u)
     return u, w, sig, r, sweeps
 

@@ -1,0 +1,91 @@
+"""Secondary measurements (GPU box): the other BASELINE.json configs, device-resident inputs, CUDA events.
+  config 2/5: batched HCORE_dgemm sweep nb x rank      config 3: HCORE_dsyrk + HCORE_dgemmcd (dense C), nb=1024 rank 32
+  config 4  : HCORE_sgemm / HCORE_zgemm, nb=1024 rank 64
+usage: python tools/bench_ops.py [out.json]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from hcore_b200 import api  # noqa: E402
+
+dev = torch.device("cuda:0")
+ctx = api.Context(0)
+HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed(fn, restore, reps=3, warm=2):
+    for _ in range(warm):
+        restore(); fn()
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(reps):
+        restore()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    return ms / reps
+
+
+out = {"hbm_gbs_measured": HBM}
+# ---- dgemm sweep -------------------------------------------------------------------------------------
+sweep = []
+for nb, k, T in [(512, 16, 8192), (512, 32, 8192), (512, 64, 4096), (1024, 16, 8192), (1024, 32, 8192), (1024, 64, 4736),
+                 (2048, 32, 2368), (2048, 64, 2368)]:
+    d = bench.make_device_batch(torch, T, nb, k, dev, seed=3)
+    fn = lambda: ctx.dgemm_batched(-1.0, d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], 1.0, d["cu"], d["cv"],
+                                   d["crk"], rk=0, maxrk=2 * k, acc=1e-8, status=d["status"])
+    ms = timed(fn, lambda: bench.restore_c(d, k))
+    r = float(d["crk"].float().mean().item())
+    fl = api.gemm_flops(nb, k, k, k, int(round(r))) + 2 * (2 * k) ** 3
+    sweep.append({"nb": nb, "rank": k, "tiles": T, "tiles_per_s": T / ms * 1e3, "mean_new_rank": r,
+                  "gflops_effective": T / ms * 1e3 * fl / 1e9, "failed": int((d["status"] != 0).sum().item())})
+    print(sweep[-1], flush=True)
+    del d
+    torch.cuda.empty_cache()
+out["dgemm_sweep"] = sweep
+# ---- sgemm / zgemm --------------------------------------------------------------------------------------
+nb, k = 1024, 64
+for name, dt, T, acc in (("sgemm", torch.float32, 4736, 1e-4), ("zgemm", torch.complex128, 592, 1e-8)):
+    d = bench.make_device_batch(torch, T, nb, k, dev, seed=4)
+    conv = {}
+    for nm in ("au", "av", "bu", "bv", "cu0", "cv0", "cu", "cv"):
+        x = d[nm]
+        if dt == torch.complex128:
+            conv[nm] = torch.complex(x, torch.roll(x, 1, dims=2) * 0.5).contiguous()
+        else:
+            conv[nm] = x.to(dt).contiguous()
+    del d["au"], d["av"], d["bu"], d["bv"], d["cu0"], d["cv0"], d["cu"], d["cv"]
+
+    def restore():
+        conv["cu"][:, :k].copy_(conv["cu0"]); conv["cv"][:, :k].copy_(conv["cv0"]); d["crk"].fill_(k)
+    call = ctx.sgemm_batched if name == "sgemm" else ctx.zgemm_batched
+    fn = lambda: call(-1.0, conv["au"], conv["av"], d["ark"], conv["bu"], conv["bv"], d["brk"], 1.0, conv["cu"], conv["cv"],
+                      d["crk"], rk=0, maxrk=2 * k, acc=acc, status=d["status"])
+    ms = timed(fn, restore, reps=2, warm=1)
+    out[name] = {"nb": nb, "rank": k, "tiles": T, "acc": acc, "tiles_per_s": T / ms * 1e3,
+                 "mean_new_rank": float(d["crk"].float().mean().item()), "failed": int((d["status"] != 0).sum().item())}
+    print(name, out[name], flush=True)
+    del conv, d
+    torch.cuda.empty_cache()
+# ---- dense-C updates (config 3) ---------------------------------------------------------------------------
+nb, k, T = 1024, 32, 2048
+d = bench.make_device_batch(torch, T, nb, k, dev, seed=5)
+cd = torch.rand((T, nb, nb), dtype=torch.float64, device=dev)
+for name, fn in (("dgemmcd", lambda: ctx.dgemmcd_batched(d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], cd)),
+                 ("dsyrk", lambda: ctx.dsyrk_batched(-1.0, d["au"], d["av"], d["ark"], cd))):
+    ms = timed(fn, lambda: None)
+    byts = (2 * nb * nb + (4 if name == "dgemmcd" else 2) * nb * k) * 8
+    out[name] = {"nb": nb, "rank": k, "tiles": T, "calls_per_s": T / ms * 1e3, "algorithmic_GBps": T * byts / ms / 1e6,
+                 "frac_of_measured_hbm": T * byts / ms / 1e6 / HBM}
+    print(name, out[name], flush=True)
+ctx.close()
+if len(sys.argv) > 1:
+    json.dump(out, open(sys.argv[1], "w"), indent=1)
