@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhcore_b200.so")
+# HCORE_B200_LIB selects another build of the same library (the instrumented `make prof` one)
+LIB_PATH = os.environ.get("HCORE_B200_LIB") or os.path.join(_HERE, "lib", "libhcore_b200.so")
 
 #: every symbol ``include/hcore_b200.h`` / ``include/hcore_d.h`` declare
 EXPORTED_SYMBOLS = [

@@ -14,6 +14,26 @@ namespace hcore_b200 {
 
 constexpr int kWarp = 32;
 
+// Optional in-kernel phase timing (make prof -> lib/libhcore_b200_prof.so, tools/phase_prof.py):
+// one designated thread per CTA accumulates clock64() deltas between checkpoints.
+#ifdef HCORE_B200_PROF
+__device__ unsigned long long g_prof[64];
+#define PROF_DECL(who) const bool _pw = (who); long long _pt = clock64();
+#define PROF_ADD(slot)                                                              \
+    do {                                                                            \
+        if (_pw) {                                                                  \
+            const long long _n = clock64();                                         \
+            atomicAdd(&g_prof[slot], (unsigned long long)(_n - _pt));               \
+            _pt = clock64();                                                        \
+        }                                                                           \
+    } while (0)
+#define PROF_COUNT(slot, v) do { if (_pw) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
+#else
+#define PROF_DECL(who)
+#define PROF_ADD(slot)
+#define PROF_COUNT(slot, v)
+#endif
+
 // Sub-panel width of the blocked Householder factorisations and row-block height of the
 // flat-tree tall-skinny QR.  tests/device_model.py uses the same constants.
 constexpr int kPanelW = 16;

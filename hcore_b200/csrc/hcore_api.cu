@@ -550,6 +550,21 @@ int HCORE_dsyrk_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, dou
 }
 
 // ---- debug / profiling -------------------------------------------------------------------------
+#ifdef HCORE_B200_PROF
+// phase counters of the instrumented build (tools/phase_prof.py)
+int hcore_b200_prof_read(unsigned long long *out, int n, int reset) {
+    unsigned long long h[64];
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(h, hcore_b200::g_prof, sizeof(h)) != cudaSuccess) return HCORE_B200_ERR_CUDA;
+    for (int i = 0; i < n && i < 64; ++i) out[i] = h[i];
+    if (reset) {
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(hcore_b200::g_prof, h, sizeof(h));
+    }
+    return HCORE_B200_OK;
+}
+#endif
+
 int hcore_b200_debug_set_stages(hcore_b200_handle_t ctx, int nstages) {
     if (!ctx) return HCORE_B200_ERR_ARG;
     ctx->debug_stages = nstages;

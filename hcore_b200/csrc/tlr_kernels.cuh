@@ -81,11 +81,14 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     double *Yu = ws.Y + nn_offset(ws, 0, t, N);
     double *Yv = ws.Y + nn_offset(ws, 1, t, N);
 
+    PROF_DECL(tid == 0)
+    PROF_COUNT(29, 1);
     // ---- T' = R_v * R_u^T --------------------------------------------------------------
     block_gemm<2, kGemmSet>(mview(L, 1, LDL), cview(Rv, 1, N), cview(Ru, N, 1), n16, n16, n16, warp, nwarps,
                             UpperTimesUpperT());
     if (tid < n16) perm[tid] = tid;
     __syncthreads();
+    PROF_ADD(10);
 
     // ---- QR with column pivoting (preconditioner), truncated -----------------------------------
     // Two barriers per step:
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         tol2 = (ar.rk == 0) ? 1e-4 * ar.acc * ar.acc : 1e-30 * mx;
     }
     int kq = n16;
+    PROF_ADD(11);
     for (int i = 0; i < n16; ++i) {
         const int ki = i >> 5, li = i & 31;
         if (warp == 0) {
@@ -234,6 +238,8 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         __syncthreads();
     }
 
+    PROF_ADD(12);
+    PROF_COUNT(20, kq);
     // ---- L <- R^T restricted to the kq factored rows (the remaining block is dropped) -------------
     for (int idx = tid; idx < n16 * n16; idx += blockDim.x) {
         const int i = idx % n16, j = idx / n16;
@@ -249,6 +255,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         }
     }
     __syncthreads();
+    PROF_ADD(13);
     const int kq2 = (kq + 1) & ~1;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq2
 
     // ---- one-sided Jacobi on the columns of L ---------------------------------------------
@@ -311,6 +318,8 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         converged = (__syncthreads_or(big) == 0);
     }
 
+    PROF_ADD(14);
+    PROF_COUNT(21, sweeps);
     // ---- singular values, sort, truncation -------------------------------------------------
     for (int cc = warp; cc < n16; cc += nwarps) {
         double s2 = 0.0;
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         if (st == HCORE_B200_OK) ar.Crk[gt] = rnew;
     }
     if (st != HCORE_B200_OK) return;
+    PROF_ADD(15);
 
     // ---- U_r = P * (normalised, sorted columns) -> Yu (n16 x r8, zero padded) -----------------
     for (int idx = tid; idx < n16 * n16; idx += blockDim.x) {
@@ -364,6 +374,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         }
     }
     __syncthreads();   // Yu (global) visible to the whole CTA; L is free from here on
+    PROF_ADD(16);
 
     // ---- W = R_v * (R_u^T * U_r) -> Yv ----------------------------------------------------------
     block_gemm<2, kGemmSet>(mview(L, 1, LDL), cview(Ru, N, 1), cview(Yu, 1, N), n16, r8, n16, warp, nwarps,
@@ -371,6 +382,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     __syncthreads();
     block_gemm<2, kGemmSet>(mview(Yv, 1, N), cview(Rv, 1, N), cview(L, 1, LDL), n16, r8, n16, warp, nwarps,
                             UpperK());
+    PROF_ADD(17);
 }
 
 }  // namespace hcore_b200

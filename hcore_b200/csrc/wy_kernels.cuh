@@ -502,6 +502,7 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
         for (int k = 0; k < RPT; ++k) vbuf[l + 32 * k] = (BLK0 && l + 32 * k <= c0) ? 0.0 : x[0][k];
     }
     __syncthreads();
+    PROF_DECL(tid == 32 * NW - 32)
 
 #pragma unroll 1
     for (int ii = 0; ii < kPanelW; ++ii) {
@@ -556,6 +557,7 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
         // T column ii-1 by the warp that owned it (its z values were published in step ii-1)
         if (ii > 1 && w == (ii - 1) % NW) t_column(Ts, zb, taus, ii - 1, l);
         __syncthreads();
+        PROF_ADD(30);
         // ---------------- phase B -------------------------------------------------------------------
         const double tau = hs[0], scal = hs[1];
 #pragma unroll
@@ -593,6 +595,7 @@ __device__ __forceinline__ void panel_factor(double *smem, double *rec, double *
             }
         }
         __syncthreads();
+        PROF_ADD(31);
     }
     if (w == (kPanelW - 1) % NW) t_column(Ts, zb, taus, kPanelW - 1, l);          // last T column
     // ---- outputs: explicit reflector panel (swizzled), R entries ------------------------------------
@@ -654,6 +657,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
     }
     __syncthreads();
     uint32_t phase[2] = {0, 0};
+    PROF_DECL(tid == NT - 32)
+    PROF_COUNT(9, 1);
 
     for (int gc0 = 0; gc0 < n16; gc0 += GW) {
         const int gcols = (n16 - gc0 < GW) ? (n16 - gc0) : GW;      // multiple of 16
@@ -684,6 +689,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                     by[i] = (src.p && row + 1 < m) ? src.scale * ld_user(src.p, src.off + row + 1, src.f32) : 0.0;
                 }
             }
+            PROF_ADD(0);
             // ---- (1) reflectors of the earlier groups ------------------------------------------------
             for (int sp = 0; sp < nprev; ++sp) {
                 const int b = sp & 1;
@@ -711,7 +717,9 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                     }
                 }
             }
+            PROF_ADD(1);
             __syncthreads();     // record buffers free (generic reads done), R strips visible
+            PROF_ADD(2);
 
             // ---- (2) the group's own sub-panels ---------------------------------------------------------
             for (int lc0 = 0; lc0 < gcols; lc0 += kPanelW) {
@@ -724,14 +732,17 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                         *reinterpret_cast<double2 *>(Pf + (8 * i + 2 * tg) + pc * kLdPf) = make_double2(bx[i], by[i]);
                 }
                 __syncthreads();
+                PROF_ADD(3);
                 if (blk0) panel_factor<N, NW, true>(smem, rec, Rg, c0, tid);
                 else panel_factor<N, NW, false>(smem, rec, Rg, c0, tid);
+                PROF_ADD(4);
                 // record -> global (all threads, coalesced)
                 {
                     double *dst = recg + ((size_t)j * NSP + s) * kRecDoubles;
                     for (int idx = tid; idx < kRecDoubles / 2; idx += NT)
                         reinterpret_cast<double2 *>(dst)[idx] = reinterpret_cast<const double2 *>(rec)[idx];
                 }
+                PROF_ADD(5);
                 // trailing columns of the group
                 if (have_cols && lc >= lc0 + kPanelW) {
                     double sx[2] = {0.0, 0.0}, sy[2] = {0.0, 0.0};
@@ -746,10 +757,12 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                         for (int q = 0; q < 2; ++q) { rs[8 * q] -= sx[q]; rs[8 * q + 1] -= sy[q]; }
                     }
                 }
+                PROF_ADD(6);
             }
             // async-proxy writes (TMA) into the record buffers follow generic-proxy accesses
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
+            PROF_ADD(7);
         }  // row blocks
     }  // column groups
     // padding columns n16..N-1 of R
