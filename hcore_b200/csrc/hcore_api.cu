@@ -66,7 +66,7 @@ struct hcore_b200_context {
     cudaStream_t streams[2] = {nullptr, nullptr};
     // debug / profiling
     int debug_stages = 4;
-    int tsqr_warps = 8;
+    int tsqr_warps = 4;
     bool stage_timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double stage_ms[4] = {0, 0, 0, 0};
@@ -95,7 +95,7 @@ int pick_width(int maxrk) {
 
 size_t per_tile_ws_bytes(int N, int m_pad, int nblk) {
     size_t b = 0;
-    b += 2ull * nblk * (N / 16) * kRecBytes;    // block-reflector records
+    b += 2ull * nblk * (N / kSubW) * kRecBytes;    // block-reflector records
     b += (size_t)m_pad * N * 8;                 // G
     b += 2ull * N * N * 8;                      // R
     b += 2ull * N * N * 8;                      // Y
@@ -161,8 +161,9 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
 template <int N>
 int launch_chunk_n(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
     // kernel shapes: warps per QR CTA (8 columns each) and per apply CTA; tunable for experiments
-    if (ctx->tsqr_warps == 4) return launch_chunk<N, 4, 4>(ctx, ar, ws, st);
-    return launch_chunk<N, 8, 4>(ctx, ar, ws, st);
+    if (ctx->tsqr_warps == 8) return launch_chunk<N, 8, 4>(ctx, ar, ws, st);
+    if (ctx->tsqr_warps == 2) return launch_chunk<N, 2, 4>(ctx, ar, ws, st);
+    return launch_chunk<N, 4, 4>(ctx, ar, ws, st);
 }
 
 // out[i] = base + i * stride_bytes (factor arrays at a fixed stride; element size 8 or 4)
@@ -260,7 +261,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
     const int nblk = m_pad / kBlockH;
     const int chunk = std::min(ntiles, default_chunk(ctx, N, m_pad, nblk));
 
-    CUDA_TRY(ctx, ctx->rec.reserve(2ull * chunk * nblk * (N / 16) * kRecBytes));
+    CUDA_TRY(ctx, ctx->rec.reserve(2ull * chunk * nblk * (N / kSubW) * kRecBytes));
     CUDA_TRY(ctx, ctx->G.reserve((size_t)chunk * m_pad * N * 8));
     CUDA_TRY(ctx, ctx->R.reserve(2ull * chunk * N * N * 8));
     CUDA_TRY(ctx, ctx->Y.reserve(2ull * chunk * N * N * 8));
@@ -585,7 +586,7 @@ int hcore_b200_debug_fetch(hcore_b200_handle_t ctx, int what, int tile, double *
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     const TlrWorkspace &ws = ctx->last_ws;
     const int N = ctx->last_N;
-    const size_t nn = (size_t)N * N, rr = (size_t)ws.nblk * (N / 16) * kRecDoubles, gg = (size_t)ws.m_pad * N;
+    const size_t nn = (size_t)N * N, rr = (size_t)ws.nblk * (N / kSubW) * kRecDoubles, gg = (size_t)ws.m_pad * N;
     const double *src = nullptr;
     size_t avail = 0;
     switch (what) {

@@ -12,9 +12,9 @@
 //                     copies/transposes around it, src/compute/hcore_dgemm.c:531-598, :645-674,
 //                     :972-982).
 //
-// Common machinery.  A "record" is the block reflector of one (128-row block, 16-column
-// sub-panel): the explicit 128 x 16 reflector panel V in an XOR-swizzled layout plus its 16 x 16
-// compact-WY factor T (and T^T), 22 528 contiguous bytes.  Records are produced once by the
+// Common machinery.  A "record" is the block reflector of one (128-row block, 8-column
+// sub-panel): the explicit 128 x 8 reflector panel V in an XOR-swizzled layout plus its 8 x 8
+// compact-WY factor T (and T^T), 9 216 contiguous bytes.  Records are produced once by the
 // QR kernel and consumed by ONE TMA bulk copy (cp.async.bulk) each, double buffered, both by
 // the left-looking QR itself and by the apply kernel.  The matrix the reflectors act on lives
 // in REGISTERS: a warp owns 8 columns, held transposed as DMMA accumulator fragments
@@ -23,23 +23,25 @@
 // the A operand of the next DMMA, so the whole chain
 //      S^T = [S0^T +] B^T V ,  S2^T = S^T T(^T) ,  B^T -= S2^T V^T
 // runs with no shared-memory round trip and no CTA barrier; only V and T are read from shared
-// memory, conflict-free thanks to the swizzle.
+// memory, conflict-free thanks to the swizzle.  The sub-panel width equals the 8 columns a warp
+// owns, so a sub-panel is FACTORED by its owner warp alone, in registers (warp_factor below).
 #pragma once
 #include "common.cuh"
 
 namespace hcore_b200 {
 
-constexpr int kRecV = kBlockH * kPanelW;           // 2048 doubles: swizzled reflector panel
-constexpr int kLdT = 24;                           // leading dim of the T images (conflict-free LDS.128)
-constexpr int kRecT = kPanelW * kLdT;              // 384
-constexpr int kRecDoubles = kRecV + 2 * kRecT;     // V | T | T^T  = 2816
-constexpr int kRecBytes = kRecDoubles * 8;         // 22 528
+constexpr int kSubW = 8;                           // sub-panel width = columns per warp
+constexpr int kRecV = kBlockH * kSubW;             // 1024 doubles: swizzled reflector panel
+constexpr int kLdT = 8;                            // leading dim of the T images (conflict-free LDS.128)
+constexpr int kRecT = kSubW * kLdT;                // 64
+constexpr int kRecDoubles = kRecV + 2 * kRecT;     // V | T | T^T  = 1152
+constexpr int kRecBytes = kRecDoubles * 8;         // 9 216
 
-// Swizzled position of element (row r, column c) of a 128 x 16 reflector panel.  16-byte slots
+// Swizzled position of element (row r, column c) of a 128 x 8 reflector panel.  16-byte slots
 // hold row pairs; slot = c*64 + ((r/2) ^ h(c)).  h is chosen so that both access patterns of
 // the chain are bank-conflict free:
-//   GEMM1 (LDS.128): lanes (g, tg) read rows (8i+2tg, 8i+2tg+1) of column 8t+g
-//   GEMM3 (LDS.64) : lanes (g, tg) read row 8i+g of columns 8u+2tg and 8u+2tg+1
+//   GEMM1 (LDS.128): lanes (g, tg) read rows (8i+2tg, 8i+2tg+1) of column g
+//   GEMM3 (LDS.64) : lanes (g, tg) read row 8i+g of columns 2tg and 2tg+1
 __host__ __device__ __forceinline__ int vswz(int r, int c) {
     const int h = ((c & 1) << 2) ^ (((c >> 1) & 3) << 1);
     return (((c << 6) + ((r >> 1) ^ h)) << 1) + (r & 1);
@@ -79,56 +81,40 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- the register-resident block-reflector chain ------------------------------------------------
-// bx[i], by[i]: B^T fragments of 128-row tile i (i = 0..15): column g of the warp's 8 columns,
+// bx[i], by[i]: B^T fragments of 8-row tile i (i = 0..15): column g of the warp's 8 columns,
 // rows 8i + 2tg and 8i + 2tg + 1.
-// sx/sy[t]   : in  S0^T fragments (R strip / Y rows / zero): column g, reflectors 8t+2tg, 8t+2tg+1
-//              out S2^T fragments in the same layout.
+// sx, sy     : in  S0^T fragment (R strip / Y rows / zero): column g, reflectors 2tg, 2tg+1 (added AFTER
+//              the B^T V product, so the load that produced it is off the critical path)
+//              out S2^T fragment in the same layout.
 // FORWARD = true : S2 = T^T S (factorisation, Q^T applied);  false: S2 = T S (Q applied).
 template <bool FORWARD>
-__device__ __forceinline__ void wy_chain(double (&bx)[16], double (&by)[16], double (&sx)[2], double (&sy)[2],
+__device__ __forceinline__ void wy_chain(double (&bx)[16], double (&by)[16], double &sx, double &sy,
                                          const double *rec, int lane) {
     const int g = lane >> 2, tg = lane & 3;
-    // ---- GEMM1: S^T += B^T V --------------------------------------------------------------------
+    // ---- GEMM1: S^T += B^T V (four independent accumulator sets) ----------------------------------------
     {
         const int h = ((g & 1) << 2) ^ (((g >> 1) & 3) << 1);
         const int hlo = h & 3, hhi = (h >> 2) & 1;
         const double *base = rec + 2 * ((g << 6) + (tg ^ hlo));
         const double *pe = base + 8 * hhi, *po = base - 8 * hhi;
-        double e0x = 0.0, e0y = 0.0, e1x = 0.0, e1y = 0.0;   // second accumulator set (odd tiles)
+        double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const double *q = ((i & 1) ? po : pe) + 8 * i;
-            const double2 v0 = *reinterpret_cast<const double2 *>(q);
-            const double2 v1 = *reinterpret_cast<const double2 *>(q + 1024);
-            if (i & 1) {
-                dmma_884(e0x, e0y, bx[i], v0.x);
-                dmma_884(e1x, e1y, bx[i], v1.x);
-                dmma_884(e0x, e0y, by[i], v0.y);
-                dmma_884(e1x, e1y, by[i], v1.y);
-            } else {
-                dmma_884(sx[0], sy[0], bx[i], v0.x);
-                dmma_884(sx[1], sy[1], bx[i], v1.x);
-                dmma_884(sx[0], sy[0], by[i], v0.y);
-                dmma_884(sx[1], sy[1], by[i], v1.y);
-            }
+            const double2 v = *reinterpret_cast<const double2 *>(q);
+            dmma_884(ax[i & 3], ay[i & 3], bx[i], v.x);
+            dmma_884(ax[i & 3], ay[i & 3], by[i], v.y);
         }
-        sx[0] += e0x; sy[0] += e0y; sx[1] += e1x; sy[1] += e1y;
+        sx += (ax[0] + ax[1]) + (ax[2] + ax[3]);
+        sy += (ay[0] + ay[1]) + (ay[2] + ay[3]);
     }
     // ---- GEMM2: S2^T = S^T Tm,  Tm = T (forward) or T^T ----------------------------------------------
-    double px[2], py[2];
+    double px = 0.0, py = 0.0;
     {
         const double *Tm = rec + kRecV + (FORWARD ? 0 : kRecT);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            double ax = 0.0, ay = 0.0;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const double2 tv = *reinterpret_cast<const double2 *>(Tm + (8 * t + 2 * tg) + kLdT * (8 * u + g));
-                dmma_884(ax, ay, sx[t], tv.x);
-                dmma_884(ax, ay, sy[t], tv.y);
-            }
-            px[u] = ax; py[u] = ay;
-        }
+        const double2 tv = *reinterpret_cast<const double2 *>(Tm + 2 * tg + kLdT * g);
+        dmma_884(px, py, sx, tv.x);
+        dmma_884(px, py, sy, tv.y);
     }
     // ---- GEMM3: B^T -= S2^T V^T ----------------------------------------------------------------------
     {
@@ -137,18 +123,16 @@ __device__ __forceinline__ void wy_chain(double (&bx)[16], double (&by)[16], dou
         const double *base = rec + 2 * (((2 * tg) << 6) + (gh ^ ((tg & 1) << 1))) + (g & 1);
         const double *pe_e = base + 8 * hb, *po_e = base - 8 * hb;                  // even column 2tg
         const double *pe_o = base + 128 + 8 * (hb ^ 1), *po_o = base + 128 - 8 * (hb ^ 1);   // odd column 2tg+1
-        const double n0x = -px[0], n0y = -py[0], n1x = -px[1], n1y = -py[1];
+        const double nx = -px, ny = -py;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const double *qe = ((i & 1) ? po_e : pe_e) + 8 * i;
             const double *qo = ((i & 1) ? po_o : pe_o) + 8 * i;
-            dmma_884(bx[i], by[i], n0x, qe[0]);
-            dmma_884(bx[i], by[i], n0y, qo[0]);
-            dmma_884(bx[i], by[i], n1x, qe[1024]);     // columns 8 + 2tg, 8 + 2tg + 1
-            dmma_884(bx[i], by[i], n1y, qo[1024]);
+            dmma_884(bx[i], by[i], nx, qe[0]);
+            dmma_884(bx[i], by[i], ny, qo[0]);
         }
     }
-    sx[0] = px[0]; sy[0] = py[0]; sx[1] = px[1]; sy[1] = py[1];
+    sx = px; sy = py;
 }
 
 // ========================================================================================
@@ -181,7 +165,7 @@ __device__ __forceinline__ void st_user(double *base, size_t idx, double v, int 
 
 // Per-chunk scratch owned by the context.  Index [panel][tile] with panel 0 = U, 1 = V.
 struct TlrWorkspace {
-    double *rec;     // [2][chunk][nblk][N/16][kRecDoubles]  block-reflector records
+    double *rec;     // [2][chunk][nblk][N/8][kRecDoubles]  block-reflector records
     double *G;       // [chunk][m_pad * N]                   G = BU (AV^T BV)^T, ld m_pad
     double *R;       // [2][chunk][N * N]
     double *Y;       // [2][chunk][N * N]            U_r (panel 0) and W (panel 1)
@@ -379,28 +363,23 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
 // ========================================================================================
 // Flat-tree TSQR over 128-row blocks: block 0 is a plain blocked Householder QR (reflectors below
 // the diagonal, R on top); every further block B_j is eliminated against the running R
-// ("triangle on top of a dense block": reflector i = [e_i ; v_i]).  16-column sub-panels with
+// ("triangle on top of a dense block": reflector i = [e_i ; v_i]).  8-column sub-panels with
 // compact-WY T factors.  Columns are processed LEFT-LOOKING in groups of GW = 8 * NW columns
-// (NW warps per CTA, 8 columns per warp, register resident): for every row block the CTA
-//   (1) streams the records of all earlier sub-panels (TMA, double buffered) through wy_chain,
-//   (2) factors its own sub-panels: the owning warps drop the 16 columns into shared memory, all
-//       warps run the Householder steps (one column per 2*NW lanes, one barrier per step), the
-//       resulting record is applied to the group's trailing columns from shared memory and
-//       written to global memory.
-constexpr int kLdPf = kBlockH + 8;     // 136: panel buffer of the factorisation
+// (NW warps per CTA, 8 columns per warp, register resident).  For every row block
+//   (1) the CTA streams the records of all earlier groups (TMA, double buffered) through wy_chain;
+//   (2) inside the group the warps form a pipeline without CTA barriers: warp w applies the
+//       records of warps 0..w-1 (read from per-warp shared-memory slots, handed over with named
+//       barriers), then factors its OWN 128 x 8 sub-panel alone, in registers (warp_factor), and
+//       publishes the record to its slot and to global memory.
+constexpr int kYbuf = kBlockH + 16;    // per warp, per parity: y[128] | ydiag[8] | z[8]
 
 template <int NW>
 struct TsqrSmem {
     static constexpr int kRec0 = 0;
     static constexpr int kRec1 = kRec0 + kRecDoubles;
-    static constexpr int kPf = kRec1 + kRecDoubles;
-    static constexpr int kVbuf = kPf + kPanelW * kLdPf;   // [2][128]
-    static constexpr int kRd = kVbuf + 2 * kBlockH;       // 16 x 16 diagonal block of R, Rd[ii + 16 c]
-    static constexpr int kTs = kRd + 256;                 // T, Ts[k + 16 c]
-    static constexpr int kTau = kTs + 256;                // [16]
-    static constexpr int kZ = kTau + 16;                  // [2][16]
-    static constexpr int kHs = kZ + 32;                   // tau, scal of the current step
-    static constexpr int kBar = kHs + 2;                  // 2 mbarriers
+    static constexpr int kOwn = kRec1 + kRecDoubles;                 // [NW-1] records of the group's own sub-panels
+    static constexpr int kY = kOwn + (NW - 1) * kRecDoubles;         // [NW][2][kYbuf]
+    static constexpr int kBar = kY + NW * 2 * kYbuf;                 // 2 mbarriers
     static constexpr int kTotal = kBar + 2;
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
@@ -444,198 +423,193 @@ __device__ __forceinline__ void warp_allsum_dmma(double (&v)[NV]) {
     for (int q = 0; q < NV; ++q) v[q] = d0[q];
 }
 
-// Column jc of the compact-WY factor (forward columnwise larft), computed by one warp:
-//   T[r][jc] = -tau_jc * sum_{q=r}^{jc-1} T[r][q] z_q ,  z_q = v_q^T v_jc,  r < jc.
-// Fully unrolled and predicated so that all shared-memory loads are issued up front (this sits
-// on the path to the next CTA barrier).
-__device__ __forceinline__ void t_column(double *Ts, const double *zb, const double *taus, int jc, int lane) {
-    const double *z = zb + (jc & 1) * 16;
-    const double mtau = -taus[jc];
-    const int r = lane;
-    if (r < jc) {
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int q = 0; q < kPanelW - 1; ++q) {
-            const bool on = (q >= r) && (q < jc);
-            const double tv = on ? Ts[r + 16 * q] : 0.0, zv = z[q];
-            if (q & 1) a1 = fma(tv, zv, a1);
-            else a0 = fma(tv, zv, a0);
-        }
-        Ts[r + 16 * jc] = mtau * (a0 + a1);
+// Named barriers with LITERAL ids: ptxas reserves (highest id + 1) barriers per CTA out of the 32 an
+// SM has, so a register-held id (which makes it reserve all 16) would cap residency at 2 CTAs/SM.
+// Call these from fully unrolled code so that `id` folds to a constant.
+#define HCORE_BAR_CASE(op, k) case k: asm volatile(op " " #k ", %0;" ::"r"(nthreads) : "memory"); break;
+#define HCORE_BAR_SWITCH(op)                                                                          \
+    switch (id) {                                                                                     \
+        HCORE_BAR_CASE(op, 1) HCORE_BAR_CASE(op, 2) HCORE_BAR_CASE(op, 3) HCORE_BAR_CASE(op, 4)       \
+        HCORE_BAR_CASE(op, 5) HCORE_BAR_CASE(op, 6) HCORE_BAR_CASE(op, 7) HCORE_BAR_CASE(op, 8)       \
+        HCORE_BAR_CASE(op, 9) HCORE_BAR_CASE(op, 10) HCORE_BAR_CASE(op, 11) HCORE_BAR_CASE(op, 12)    \
+        HCORE_BAR_CASE(op, 13) HCORE_BAR_CASE(op, 14) HCORE_BAR_CASE(op, 15)                          \
+        default: break;                                                                               \
     }
-}
+__device__ __forceinline__ void bar_sync_lit(int id, int nthreads) { HCORE_BAR_SWITCH("bar.sync") }
+__device__ __forceinline__ void bar_arrive_lit(int id, int nthreads) { HCORE_BAR_SWITCH("bar.arrive") }   // does not wait
 
-// Householder factorisation of the 128 x 16 sub-panel held in Pf (plain column-major, ld kLdPf).
-// Produces the record (V swizzled, T, T^T) in `rec`, the R entries in Rg and (blocks > 0) uses /
-// updates the 16 x 16 diagonal block of the running R.  All NW warps participate: warp w owns the
-// columns w, w + NW, ... (CPW = 16 / NW of them), lane l owns rows l, l+32, l+64, l+96; every role
-// decision is warp-uniform.
+// Householder factorisation of the warp's own 128 x 8 sub-panel (columns c0 .. c0+7 of the row
+// block), entirely inside the warp: no CTA barrier, one __syncwarp per Householder step.
 //
-// Step ii is split so that the latency-critical scalar work overlaps the dot products:
-//   phase A  the RAW (unscaled) tail y of column ii is already in shared memory; every warp forms
-//            d_c = y^T x_c for its columns (for the owner's own column this IS the squared norm)
-//            and, in block 0, extracts its row-i elements; one DMMA all-reduce; the owner derives
-//            (beta, tau, scal) and publishes them                                   -> barrier
-//   phase B  w_c = tau (r_c + scal d_c),  x_c -= y (scal w_c)  [v = scal y is never formed for the
-//            update], the owner scales its column to v, the NEXT owner publishes its raw updated
-//            column                                                                 -> barrier
-template <int N, int NW, bool BLK0>
-__device__ __forceinline__ void panel_factor(double *smem, double *rec, double *Rg, int c0, int tid) {
-    using SM = TsqrSmem<NW>;
-    constexpr int CPW = kPanelW / NW, RPT = kBlockH / 32;     // columns per warp, rows per lane
-    constexpr int NV = BLK0 ? 2 * CPW : CPW;
-    double *Pf = smem + SM::kPf, *vbuf = smem + SM::kVbuf, *Rd = smem + SM::kRd, *Ts = smem + SM::kTs,
-           *taus = smem + SM::kTau, *zb = smem + SM::kZ, *hs = smem + SM::kHs;
-    const int w = tid >> 5, l = tid & 31;
-    double x[CPW][RPT];
+//   bx/by  the 8 columns in fragment layout (lane (g, tg): column g, rows 8i+2tg, 8i+2tg+1)
+//   rx/ry  the 8 x 8 "diagonal tile" in the same layout (rows c0+2tg, c0+2tg+1 of column c0+g):
+//          blocks > 0: the diagonal block of the running R (reflector j = [e_j ; v_j]);
+//          block 0   : rows c0..c0+7 of the block itself (tile i* = c0/8, taken out of bx/by, whose
+//                      copy of that tile is dead afterwards); the Householder vectors extend into it.
+// Step j:  the owner lanes (g == j) publish the raw tail y of column j (warp-private shared memory);
+//          every lane forms its partial d = y^T x_g, one DMMA sums the four partials of a column
+//          (A = partials, B = ones), a second one broadcasts r_g = row c0+j of column g; d_j and
+//          alpha = r_j reach all lanes by one shuffle each; all lanes derive (beta, tau, scal);
+//          lanes g > j update x_g -= y * scal * w_g,  w_g = tau (r_g + scal d_g).
+// The owner's column is NOT rescaled in registers (v_j = scal_j * y_j is only formed when the record
+// is written), so z_cj = v_c^T v_j = scal_c (r_c + scal_j d_c) for c < j; these feed the forward
+// recurrence of the compact-WY factor, T[r][j] = -tau_j sum_{q=r}^{j-1} T[r][q] z_qj, one column
+// behind the Householder steps (lane group r holds row r of T).
+template <int N, bool BLK0>
+__device__ __forceinline__ void warp_factor(double (&bx)[16], double (&by)[16], double *yb, double *slot,
+                                            double *recg, double *Rg, int c0, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int g = lane >> 2, tg = lane & 3;
+    const int istar = c0 >> 3;
+    double rx, ry;
+    if (BLK0) {
+        rx = bx[0]; ry = by[0];
 #pragma unroll
-    for (int q = 0; q < CPW; ++q)
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) x[q][k] = Pf[(l + 32 * k) + (w + NW * q) * kLdPf];
-    if (!BLK0) {
-        for (int idx = tid; idx < 256; idx += 32 * NW)
-            Rd[idx] = Rg[(size_t)(c0 + (idx & 15)) + (size_t)(c0 + (idx >> 4)) * N];
+        for (int i = 1; i < 16; ++i) { rx = (i == istar) ? bx[i] : rx; ry = (i == istar) ? by[i] : ry; }
+    } else {
+        const double2 rd = *reinterpret_cast<const double2 *>(Rg + (size_t)(c0 + 2 * tg) + (size_t)(c0 + g) * N);
+        rx = rd.x; ry = rd.y;
     }
-    for (int idx = tid; idx < 256; idx += 32 * NW) Ts[idx] = 0.0;
-    if (w == 0) {       // raw tail of column 0
+    double trow[8];
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) vbuf[l + 32 * k] = (BLK0 && l + 32 * k <= c0) ? 0.0 : x[0][k];
-    }
-    __syncthreads();
-    PROF_DECL(tid == 32 * NW - 32)
+    for (int q = 0; q < 8; ++q) trow[q] = 0.0;
+    double myscal = 0.0, zpub = 0.0, tau_prev = 0.0;
+#ifdef HCORE_B200_WFPROBE
+    PROF_DECL(threadIdx.x == 0)
+#define WF_ADD(slot) PROF_ADD(slot)
+#else
+#define WF_ADD(slot)
+#endif
 
-#pragma unroll 1
-    for (int ii = 0; ii < kPanelW; ++ii) {
-        const int i = c0 + ii;                 // global column = diagonal row in block 0
-        const int so = ii / NW;                // slot of column ii in its owner warp
-        const int ki = i >> 5, li = i & 31;    // block 0: row i lives in lane li, register ki
-        const double *vb = vbuf + (ii & 1) * kBlockH;
-        // ---------------- phase A -------------------------------------------------------------------
-        double yb[RPT], vals[NV], rd[CPW];
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) yb[k] = vb[l + 32 * k];
-        if (!BLK0) {
+    for (int j = 0; j <= 8; ++j) {
+        double *yc = yb + (j & 1) * kYbuf;
+        WF_ADD(40);
+        // ---- publish: raw tail of column j, z values of step j-1 ----------------------------------
+        if (j < 8 && g == j) {
 #pragma unroll
-            for (int q = 0; q < CPW; ++q) rd[q] = Rd[ii + 16 * (w + NW * q)];
-        }
-#pragma unroll
-        for (int q = 0; q < CPW; ++q) {
-            double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                if (k & 1) d1 = fma(yb[k], x[q][k], d1);
-                else d0 = fma(yb[k], x[q][k], d0);
+            for (int i = 0; i < 16; ++i) {
+                double y0 = bx[i], y1 = by[i];
+                if (BLK0) { y0 = (i > istar) ? y0 : 0.0; y1 = (i > istar) ? y1 : 0.0; }
+                *reinterpret_cast<double2 *>(yc + 8 * i + 2 * tg) = make_double2(y0, y1);
             }
-            vals[q] = d0 + d1;
-            if (BLK0) {
-                double xs = x[q][0];
-#pragma unroll
-                for (int k = 1; k < RPT; ++k) xs = (k == ki) ? x[q][k] : xs;
-                vals[CPW + q] = (l == li) ? xs : 0.0;
-            }
+            if (BLK0)
+                *reinterpret_cast<double2 *>(yc + kBlockH + 2 * tg) =
+                    make_double2((2 * tg > j) ? rx : 0.0, (2 * tg + 1 > j) ? ry : 0.0);
         }
-        warp_allsum_dmma<NV>(vals);
+        if (j >= 2 && g < j - 1 && tg == 0) yc[kBlockH + 8 + g] = zpub;
+        __syncwarp();
+        WF_ADD(41);
+        // ---- column j-1 of T --------------------------------------------------------------------------
+        if (j >= 1) {
+            const int jc = j - 1;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < jc; ++q) {
+                const double zq = yc[kBlockH + 8 + q];
+                if (q & 1) t1 = fma(trow[q], zq, t1);
+                else t0 = fma(trow[q], zq, t0);
+            }
+            trow[jc] = (g < jc) ? -tau_prev * (t0 + t1) : (g == jc ? tau_prev : 0.0);
+        }
+        if (j == 8) break;
+        WF_ADD(42);
+        // ---- d_g = y^T x_g ----------------------------------------------------------------------------
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double2 y = *reinterpret_cast<const double2 *>(yc + 8 * i + 2 * tg);
+            if (i & 1) { p2 = fma(bx[i], y.x, p2); p3 = fma(by[i], y.y, p3); }
+            else { p0 = fma(bx[i], y.x, p0); p1 = fma(by[i], y.y, p1); }
+        }
         if (BLK0) {
-#pragma unroll
-            for (int q = 0; q < CPW; ++q) rd[q] = vals[CPW + q];
+            const double2 yd = *reinterpret_cast<const double2 *>(yc + kBlockH + 2 * tg);
+            p0 = fma(rx, yd.x, p0);
+            p1 = fma(ry, yd.y, p1);
         }
-        double beta = 0.0;
-        if (w == ii % NW) {                    // owner warp: reflector scalars
-            double s2 = vals[0], alpha = rd[0];
+        WF_ADD(43);
+        double d0 = 0.0, d1 = 0.0, r0 = 0.0, r1 = 0.0;
+        dmma_884(d0, d1, (p0 + p1) + (p2 + p3), 1.0);                            // d_g in all four lanes of the group
+        dmma_884(r0, r1, (tg == (j >> 1)) ? ((j & 1) ? ry : rx) : 0.0, 1.0);     // r_g = tile row j of column g
+        const double dj = __shfl_sync(kFull, d0, 4 * j), alpha = __shfl_sync(kFull, r0, 4 * j);
+        const Householder h = make_householder(alpha, dj);
+        const double zc = fma(h.scal, d0, r0);
+        WF_ADD(44);
+        if (g > j) {
+            const double wv = h.tau * zc, f = h.scal * wv;
 #pragma unroll
-            for (int q = 1; q < CPW; ++q) { s2 = (q == so) ? vals[q] : s2; alpha = (q == so) ? rd[q] : alpha; }
-            const Householder h = make_householder(alpha, s2);
-            beta = h.beta;
-            if (l == 0) {
-                hs[0] = h.tau;
-                hs[1] = h.scal;
-                taus[ii] = h.tau;
-                Ts[ii + 16 * ii] = h.tau;
-                if (!BLK0) Rd[ii + 16 * ii] = h.beta;
+            for (int i = 0; i < 16; ++i) {
+                const double2 y = *reinterpret_cast<const double2 *>(yc + 8 * i + 2 * tg);
+                bx[i] = fma(-y.x, f, bx[i]);
+                by[i] = fma(-y.y, f, by[i]);
             }
-        }
-        // T column ii-1 by the warp that owned it (its z values were published in step ii-1)
-        if (ii > 1 && w == (ii - 1) % NW) t_column(Ts, zb, taus, ii - 1, l);
-        __syncthreads();
-        PROF_ADD(30);
-        // ---------------- phase B -------------------------------------------------------------------
-        const double tau = hs[0], scal = hs[1];
-#pragma unroll
-        for (int q = 0; q < CPW; ++q) {
-            const int cc = w + NW * q;
-            const double zc = fma(scal, vals[q], rd[q]);          // r_c + scal * d_c
-            if (cc > ii) {
-                const double wv = tau * zc, f = scal * wv;
-#pragma unroll
-                for (int k = 0; k < RPT; ++k) {
-                    x[q][k] = fma(-yb[k], f, x[q][k]);
-                    if (BLK0) x[q][k] = (l == li && k == ki) ? x[q][k] - wv : x[q][k];
-                }
-                if (!BLK0 && l == 0) Rd[ii + 16 * cc] = rd[q] - wv;
-            } else if (cc < ii) {
-                if (l == 0) zb[(ii & 1) * 16 + cc] = zc;          // z_c = v_c^T v_ii for the T factor
-            } else {                                              // my column becomes the reflector
-#pragma unroll
-                for (int k = 0; k < RPT; ++k) {
-                    const double v = yb[k] * scal;
-                    if (BLK0) x[q][k] = (l + 32 * k > i) ? v : ((l == li && k == ki) ? beta : x[q][k]);
-                    else x[q][k] = v;
-                }
-            }
-        }
-        if (ii + 1 < kPanelW && w == (ii + 1) % NW) {             // next owner: publish the raw tail
-            const int so2 = (ii + 1) / NW;
-            double *vn = vbuf + ((ii + 1) & 1) * kBlockH;
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                double v = x[0][k];
-#pragma unroll
-                for (int q = 1; q < CPW; ++q) v = (q == so2) ? x[q][k] : v;
-                vn[l + 32 * k] = (BLK0 && l + 32 * k <= i + 1) ? 0.0 : v;
-            }
-        }
-        __syncthreads();
-        PROF_ADD(31);
-    }
-    if (w == (kPanelW - 1) % NW) t_column(Ts, zb, taus, kPanelW - 1, l);          // last T column
-    // ---- outputs: explicit reflector panel (swizzled), R entries ------------------------------------
-#pragma unroll
-    for (int q = 0; q < CPW; ++q) {
-        const int cc = w + NW * q, col = c0 + cc;
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const int row = l + 32 * k;
-            double v = x[q][k];
             if (BLK0) {
-                v = (row > col) ? x[q][k] : (row == col ? 1.0 : 0.0);
-                if (row < N) Rg[(size_t)row + (size_t)col * N] = (row <= col) ? x[q][k] : 0.0;
+                const double2 yd = *reinterpret_cast<const double2 *>(yc + kBlockH + 2 * tg);
+                rx = fma(-yd.x, f, rx);
+                ry = fma(-yd.y, f, ry);
             }
-            rec[vswz(row, cc)] = v;
+            if (tg == (j >> 1)) { if (j & 1) ry -= wv; else rx -= wv; }
+        } else if (g == j) {
+            myscal = h.scal;
+            if (tg == (j >> 1)) { if (j & 1) ry = h.beta; else rx = h.beta; }
+        } else {
+            zpub = myscal * zc;
         }
+        tau_prev = h.tau;
+        WF_ADD(45);
     }
-    __syncthreads();
-    for (int idx = tid; idx < 256; idx += 32 * NW) {
-        const int k = idx & 15, q = idx >> 4;            // T[k][q]
-        const double tv = Ts[idx];
-        rec[kRecV + k + kLdT * q] = tv;                  // T   : B[k][n] = T[k][n]
-        rec[kRecV + kRecT + q + kLdT * k] = tv;          // T^T : B[k][n] = T[n][k]
-        if (!BLK0) Rg[(size_t)(c0 + k) + (size_t)(c0 + q) * N] = (q >= k) ? Rd[k + 16 * q] : 0.0;
+    // ---- outputs: explicit reflector panel (swizzled) + T images -> slot and global record; R entries ---
+    {
+        const int hsw = ((g & 1) << 2) ^ (((g >> 1) & 3) << 1);
+        const int col = c0 + g;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double v0, v1;
+            if (BLK0) {
+                const int row0 = 8 * i + 2 * tg;
+                const double s0 = (i == istar) ? rx : bx[i], s1 = (i == istar) ? ry : by[i];
+                v0 = (row0 > col) ? s0 * myscal : (row0 == col ? 1.0 : 0.0);
+                v1 = (row0 + 1 > col) ? s1 * myscal : (row0 + 1 == col ? 1.0 : 0.0);
+                if (row0 < N)
+                    *reinterpret_cast<double2 *>(Rg + (size_t)row0 + (size_t)col * N) =
+                        make_double2((row0 <= col) ? s0 : 0.0, (row0 + 1 <= col) ? s1 : 0.0);
+            } else {
+                v0 = bx[i] * myscal;
+                v1 = by[i] * myscal;
+            }
+            const int off = 2 * ((g << 6) + ((4 * i + tg) ^ hsw));
+            if (slot) *reinterpret_cast<double2 *>(slot + off) = make_double2(v0, v1);
+            *reinterpret_cast<double2 *>(recg + off) = make_double2(v0, v1);
+        }
+        if (!BLK0)
+            *reinterpret_cast<double2 *>(Rg + (size_t)(c0 + 2 * tg) + (size_t)col * N) = make_double2(rx, ry);
+        // T[g][2tg], T[g][2tg+1]
+        const double ta = (tg == 0) ? trow[0] : (tg == 1) ? trow[2] : (tg == 2) ? trow[4] : trow[6];
+        const double tb = (tg == 0) ? trow[1] : (tg == 1) ? trow[3] : (tg == 2) ? trow[5] : trow[7];
+        const int o0 = kRecV + g + kLdT * (2 * tg);              // T   : B[k][n] = T[k][n] at k + 8 n
+        const int o1 = kRecV + kRecT + 2 * tg + kLdT * g;        // T^T : B[k][n] = T[n][k] at k + 8 n
+        if (slot) {
+            slot[o0] = ta;
+            slot[o0 + kLdT] = tb;
+            *reinterpret_cast<double2 *>(slot + o1) = make_double2(ta, tb);
+        }
+        recg[o0] = ta;
+        recg[o0 + kLdT] = tb;
+        *reinterpret_cast<double2 *>(recg + o1) = make_double2(ta, tb);
     }
-    for (int idx = tid; idx < 2 * (kLdT - 16) * 16; idx += 32 * NW) {   // padding of the T images
-        const int im = idx / ((kLdT - 16) * 16), r = idx % ((kLdT - 16) * 16);
-        rec[kRecV + im * kRecT + 16 + (r % (kLdT - 16)) + kLdT * (r / (kLdT - 16))] = 0.0;
-    }
-    __syncthreads();
+    WF_ADD(46);
 }
 
 // One CTA (NW warps) per panel: blockIdx.x = 2 * tile + panel.
 template <int N, int NW>
 __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, TlrWorkspace ws) {
     using SM = TsqrSmem<NW>;
-    constexpr int GW = 8 * NW, NSP = N / kPanelW, NT = 32 * NW;
+    constexpr int GW = 8 * NW, NSP = N / kSubW, NT = 32 * NW;
+    constexpr int kBarFull = 1, kBarFree = NW;         // named barriers: record of warp s published / consumed
+    static_assert(2 * NW - 2 <= 15, "named barrier ids 1 .. 2 NW - 2");
     extern __shared__ __align__(16) double smem[];
     double *recbuf[2] = {smem + SM::kRec0, smem + SM::kRec1};
-    double *Pf = smem + SM::kPf;
+    double *own = smem + SM::kOwn;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kBar);
 
     const int t = blockIdx.x >> 1, pnl = blockIdx.x & 1;
@@ -649,6 +623,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
     const double *Gt = ws.G + (size_t)t * m_pad * N;
     double *Rg = ws.R + nn_offset(ws, pnl, t, N);
     double *recg = ws.rec + rec_offset(ws, pnl, t, NSP);
+    double *yb = smem + SM::kY + warp * 2 * kYbuf;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -662,13 +637,15 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
 
     for (int gc0 = 0; gc0 < n16; gc0 += GW) {
         const int gcols = (n16 - gc0 < GW) ? (n16 - gc0) : GW;      // multiple of 16
+        const int nsub = gcols / kSubW;                             // sub-panels (= active warps) of the group
         const int lc = 8 * warp;                                    // my first slice column
-        const bool have_cols = lc < gcols;
-        const ColSrc src = panel_column(ar, Gt, m_pad, gt, pnl, gc0 + lc + g, c, n);
-        const int nprev = gc0 / kPanelW;                            // records of earlier sub-panels
+        const bool have_cols = warp < nsub;
+        const int mycol = gc0 + lc + g;
+        const ColSrc src = panel_column(ar, Gt, m_pad, gt, pnl, mycol, c, n);
+        const int nprev = gc0 / kSubW;                              // records of earlier groups
         for (int j = 0; j < ws.nblk; ++j) {
             const bool blk0 = (j == 0);
-            const double *recj = recg + (size_t)j * NSP * kRecDoubles;
+            double *recj = recg + (size_t)j * NSP * kRecDoubles;
             // prefetch the first earlier record while the slice is loaded
             if (nprev > 0 && tid == 0) {
                 mbar_expect_tx(&bars[0], kRecBytes);
@@ -703,67 +680,64 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                 mbar_wait(&bars[b], phase[b]);
                 phase[b] ^= 1;
                 if (have_cols) {
-                    const int pc0 = sp * kPanelW;
-                    double sx[2] = {0.0, 0.0}, sy[2] = {0.0, 0.0};
-                    double *rs = Rg + (size_t)pc0 + 2 * tg + (size_t)(gc0 + lc + g) * N;
-                    if (!blk0) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) { sx[q] = rs[8 * q]; sy[q] = rs[8 * q + 1]; }
-                    }
+                    double sx = 0.0, sy = 0.0;
+                    double *rs = Rg + (size_t)(sp * kSubW + 2 * tg) + (size_t)mycol * N;
+                    double2 r0 = make_double2(0.0, 0.0);
+                    if (!blk0) { r0 = *reinterpret_cast<const double2 *>(rs); sx = r0.x; sy = r0.y; }
                     wy_chain<true>(bx, by, sx, sy, recbuf[b], lane);
-                    if (!blk0) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) { rs[8 * q] -= sx[q]; rs[8 * q + 1] -= sy[q]; }
-                    }
+                    if (!blk0) *reinterpret_cast<double2 *>(rs) = make_double2(r0.x - sx, r0.y - sy);
                 }
             }
             PROF_ADD(1);
-            __syncthreads();     // record buffers free (generic reads done), R strips visible
+            if (nprev > 0) {
+                // the next async-proxy write (TMA) into the record buffers follows these generic reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+            }
             PROF_ADD(2);
 
-            // ---- (2) the group's own sub-panels ---------------------------------------------------------
-            for (int lc0 = 0; lc0 < gcols; lc0 += kPanelW) {
-                const int c0 = gc0 + lc0, s = c0 / kPanelW;
-                double *rec = recbuf[s & 1];
-                if (lc >= lc0 && lc < lc0 + kPanelW) {          // owners: registers -> panel buffer
-                    const int pc = lc - lc0 + g;
+            // ---- (2) the group's own sub-panels: warp pipeline -------------------------------------------
+            if (have_cols) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        *reinterpret_cast<double2 *>(Pf + (8 * i + 2 * tg) + pc * kLdPf) = make_double2(bx[i], by[i]);
+                for (int s = 0; s < NW - 1; ++s) {
+                    if (s < warp) {
+                        const int cnt = 32 * (nsub - s);
+                        bar_sync_lit(kBarFull + s, cnt);                    // record of warp s is in its slot
+                        double sx = 0.0, sy = 0.0;
+                        double *rs = Rg + (size_t)(gc0 + s * kSubW + 2 * tg) + (size_t)mycol * N;
+                        double2 r0 = make_double2(0.0, 0.0);
+                        if (!blk0) { r0 = *reinterpret_cast<const double2 *>(rs); sx = r0.x; sy = r0.y; }
+                        wy_chain<true>(bx, by, sx, sy, own + s * kRecDoubles, lane);
+                        if (!blk0) *reinterpret_cast<double2 *>(rs) = make_double2(r0.x - sx, r0.y - sy);
+                        bar_arrive_lit(kBarFree + s, cnt);                  // done with slot s
+                    }
                 }
-                __syncthreads();
                 PROF_ADD(3);
-                if (blk0) panel_factor<N, NW, true>(smem, rec, Rg, c0, tid);
-                else panel_factor<N, NW, false>(smem, rec, Rg, c0, tid);
+                const bool publish = warp + 1 < nsub;
+                double *slot = publish ? own + warp * kRecDoubles : nullptr;
+                double *rg = recj + (size_t)(nprev + warp) * kRecDoubles;
+                if (blk0) warp_factor<N, true>(bx, by, yb, slot, rg, Rg, gc0 + lc, lane);
+                else warp_factor<N, false>(bx, by, yb, slot, rg, Rg, gc0 + lc, lane);
                 PROF_ADD(4);
-                // record -> global (all threads, coalesced)
-                {
-                    double *dst = recg + ((size_t)j * NSP + s) * kRecDoubles;
-                    for (int idx = tid; idx < kRecDoubles / 2; idx += NT)
-                        reinterpret_cast<double2 *>(dst)[idx] = reinterpret_cast<const double2 *>(rec)[idx];
+                if (publish) {
+                    const int cnt = 32 * (nsub - warp);
+                    __threadfence_block();
+#pragma unroll
+                    for (int w = 0; w < NW - 1; ++w) {
+                        if (w == warp) {
+                            bar_arrive_lit(kBarFull + w, cnt);
+                            bar_sync_lit(kBarFree + w, cnt);                // slot reusable in the next row block
+                        }
+                    }
                 }
                 PROF_ADD(5);
-                // trailing columns of the group
-                if (have_cols && lc >= lc0 + kPanelW) {
-                    double sx[2] = {0.0, 0.0}, sy[2] = {0.0, 0.0};
-                    double *rs = Rg + (size_t)c0 + 2 * tg + (size_t)(gc0 + lc + g) * N;
-                    if (!blk0) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) { sx[q] = rs[8 * q]; sy[q] = rs[8 * q + 1]; }
-                    }
-                    wy_chain<true>(bx, by, sx, sy, rec, lane);
-                    if (!blk0) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) { rs[8 * q] -= sx[q]; rs[8 * q + 1] -= sy[q]; }
-                    }
-                }
-                PROF_ADD(6);
             }
-            // async-proxy writes (TMA) into the record buffers follow generic-proxy accesses
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            PROF_ADD(7);
         }  // row blocks
+        // the records of this group (generic-proxy stores) are streamed by TMA (async proxy) in the next group
+        __threadfence();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) asm volatile("fence.proxy.async.global;" ::: "memory");
     }  // column groups
     // padding columns n16..N-1 of R
     for (int idx = tid; idx < N * (N - n16); idx += NT) Rg[(size_t)n16 * N + idx] = 0.0;
@@ -786,7 +760,7 @@ struct ApplySmem {
 template <int N, int NW>
 __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar, TlrWorkspace ws) {
     using SM = ApplySmem<NW>;
-    constexpr int NSP = N / kPanelW;
+    constexpr int NSP = N / kSubW;
     extern __shared__ __align__(16) double smem[];
     double *recbuf[2] = {smem + SM::kRec0, smem + SM::kRec1};
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kBar);
@@ -799,7 +773,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar,
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
     const int n16 = round_up(ws.ncols[t], kPanelW);
-    const int nsp = n16 / kPanelW;
+    const int nsp = n16 / kSubW;
     const int m = ar.nb;
     const int mycol = col0 + 8 * warp + g;                 // output column of this lane
     const bool warp_on = col0 + 8 * warp < rnew;           // warp has at least one valid column
@@ -849,17 +823,11 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar,
         mbar_wait(&bars[b], phase[b]);
         phase[b] ^= 1;
         if (warp_on) {
-            double sx[2] = {0.0, 0.0}, sy[2] = {0.0, 0.0};
-            double *ys = Yg + s * kPanelW + 2 * tg;
-            if (j > 0 && col_on) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) { sx[q] = ys[8 * q]; sy[q] = ys[8 * q + 1]; }
-            }
+            double sx = 0.0, sy = 0.0;
+            double *ys = Yg + s * kSubW + 2 * tg;
+            if (j > 0 && col_on) { sx = ys[0]; sy = ys[1]; }
             wy_chain<false>(bx, by, sx, sy, recbuf[b], lane);
-            if (j > 0 && col_on) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) { ys[8 * q] -= sx[q]; ys[8 * q + 1] -= sy[q]; }
-            }
+            if (j > 0 && col_on) { ys[0] -= sx; ys[1] -= sy; }
             if (s == 0 && col_on) {      // row block finished -> output
                 const bool v16 = !ar.f32 && (reinterpret_cast<uintptr_t>(outb + outo) & 15) == 0;
 #pragma unroll

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-W = 16      # sub-panel width
+W = 8       # sub-panel width (= the 8 columns a warp owns)
 H = 128     # row-block height
 
 

@@ -12,6 +12,8 @@ import json;d=json.load(open('gpurun_out/quick_$TAG.json'));print(d['value'],{k:
       ncu --set full --clock-control none --import-source on -k regex:tlr_ -s 4 -c 4 -f -o gpurun_out/prof_$TAG python tools/profile_run.py 296 1024 64 2 > gpurun_out/prof_full.log 2>&1; tail -3 gpurun_out/prof_full.log ;;
  quick4) HCORE_B200_TSQR_WARPS=4 timeout 600 python bench.py --tiles 4736 --no-e2e --no-cpu-baseline --steps 2 > gpurun_out/quick4_$TAG.json 2> gpurun_out/quick4_$TAG.err; python -c "
 import json;d=json.load(open('gpurun_out/quick4_$TAG.json'));print(d['value'],{k:round(v['ms'],2) for k,v in d['stages'].items()},d['failed_tiles'],d['mean_new_rank'],d['sample_abs_err_fro'])"; tail -5 gpurun_out/quick4_$TAG.err ;;
+ quickw) for W in 8 4 2; do HCORE_B200_TSQR_WARPS=$W timeout 600 python bench.py --tiles 4736 --no-e2e --no-cpu-baseline --steps 2 > gpurun_out/quickw${W}_$TAG.json 2> gpurun_out/quickw${W}_$TAG.err; python -c "
+import json;d=json.load(open('gpurun_out/quickw${W}_$TAG.json'));print('W=$W',d['value'],{k:round(v['ms'],2) for k,v in d['stages'].items()},d['failed_tiles'],d['mean_new_rank'],d['sample_abs_err_fro'])"; tail -3 gpurun_out/quickw${W}_$TAG.err; done ;;
  ops) timeout 1200 python tools/bench_ops.py gpurun_out/ops_$TAG.json 2>&1 | tail -20 ;;
  sanitize) timeout 900 compute-sanitizer --tool memcheck python tools/profile_run.py 4 256 16 1 2>&1 | tail -30 ;;
 esac

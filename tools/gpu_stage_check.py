@@ -45,8 +45,8 @@ def run_case(nb, k, T, alpha=-1.0, beta=1.0, acc=1e-8, rk=0, verbose=True):
             xu = np.hstack([beta * CU, alpha * AU])
             xv = np.hstack([CV, BU @ (AV.T @ BV).T])
             n = xu.shape[1]
-            nblk, nspf = m_pad // 128, N // 16
-            REC, RECV, LDT = 2816, 2048, 24
+            nblk, nspf = m_pad // 128, N // 8
+            REC, RECV, LDT = 1152, 1024, 8
             if stages == 1:
                 Gd = ctx.debug_fetch(7, t, m_pad * N).reshape(N, m_pad).T
                 Gm = BU @ (AV.T @ BV).T
@@ -55,7 +55,7 @@ def run_case(nb, k, T, alpha=-1.0, beta=1.0, acc=1e-8, rk=0, verbose=True):
                 print(f"  [stage1 t={t}] G: max|dev-model|={e:.2e} padrows={z:.1e}")
                 ok &= e < 1e-12 and z == 0
             if stages == 2:
-                rr, cc = np.meshgrid(np.arange(128), np.arange(16), indexing="ij")
+                rr, cc = np.meshgrid(np.arange(128), np.arange(8), indexing="ij")
                 hh = ((cc & 1) << 2) ^ (((cc >> 1) & 3) << 1)
                 swz = (((cc << 6) + ((rr >> 1) ^ hh)) << 1) + (rr & 1)
                 for w, nm, X in ((2, "Ru", xu), (3, "Rv", xv)):
@@ -68,11 +68,11 @@ def run_case(nb, k, T, alpha=-1.0, beta=1.0, acc=1e-8, rk=0, verbose=True):
                     ev = et = ett = 0.0
                     for j, (lo, hi) in enumerate(f["bounds"]):
                         for s_ in range(len(f["T"][j])):
-                            V = recs[j, s_, :RECV][swz]                       # 128 x 16 explicit reflector panel
+                            V = recs[j, s_, :RECV][swz]                       # 128 x 8 explicit reflector panel
                             Vm = dm._vpanel(f, j, s_)
                             ev = max(ev, np.abs(V[:hi - lo, :Vm.shape[1]] - Vm).max())
-                            Tm_ = recs[j, s_, RECV:RECV + 16 * LDT].reshape(16, LDT)[:, :16].T      # T[k][q] at k + 24 q
-                            Tt_ = recs[j, s_, RECV + 16 * LDT:].reshape(16, LDT)[:, :16]            # T[k][q] at q + 24 k
+                            Tm_ = recs[j, s_, RECV:RECV + 8 * LDT].reshape(8, LDT)[:, :8].T      # T[k][q] at k + 8 q
+                            Tt_ = recs[j, s_, RECV + 8 * LDT:].reshape(8, LDT)[:, :8]            # T[k][q] at q + 8 k
                             pw = f["T"][j][s_].shape[0]
                             et = max(et, np.abs(Tm_[:pw, :pw] - f["T"][j][s_]).max())
                             ett = max(ett, np.abs(Tt_ - Tm_).max())

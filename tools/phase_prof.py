@@ -37,9 +37,10 @@ L.hcore_b200_prof_read(buf, 64, 1)
 run()
 L.hcore_b200_prof_read(buf, 64, 1)
 v = list(buf)
-TSQR = {0: "load columns", 1: "chain: earlier records (TMA wait + DMMA)", 2: "sync after chain", 3: "owners -> panel buffer + sync",
-        4: "panel_factor", 5: "record -> global", 6: "chain: trailing columns", 7: "fence + sync"}
-PF = {30: "panel_factor phase A (dots, all-reduce, scalars, barrier)", 31: "panel_factor phase B (update, publish, barrier)"}
+TSQR = {0: "load columns", 1: "chain: records of earlier groups (TMA wait + DMMA)", 2: "fence + sync after chain",
+        3: "chain: records of the group's earlier warps (wait + DMMA)", 4: "warp_factor (own 128 x 8 sub-panel)",
+        5: "publish + wait until the slot is consumed"}
+PF = {}
 SVD = {10: "core product T'", 11: "column norms", 12: "QRCP", 13: "transpose", 14: "Jacobi", 15: "sigma/sort/truncate",
        16: "U_r scatter", 17: "W products"}
 for name, tab, cnt in (("tlr_tsqr_kernel", TSQR, 9), ("  inside panel_factor", PF, 9), ("tlr_svd_kernel", SVD, 29)):
