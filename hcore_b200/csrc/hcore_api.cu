@@ -66,7 +66,7 @@ struct hcore_b200_context {
     cudaStream_t streams[2] = {nullptr, nullptr};
     // debug / profiling
     int debug_stages = 4;
-    int tsqr_warps = 4;
+    int tsqr_warps = 2;
     bool stage_timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double stage_ms[4] = {0, 0, 0, 0};
@@ -163,7 +163,8 @@ int launch_chunk_n(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspac
     // kernel shapes: warps per QR CTA (8 columns each) and per apply CTA; tunable for experiments
     if (ctx->tsqr_warps == 8) return launch_chunk<N, 8, 4>(ctx, ar, ws, st);
     if (ctx->tsqr_warps == 2) return launch_chunk<N, 2, 4>(ctx, ar, ws, st);
-    return launch_chunk<N, 4, 4>(ctx, ar, ws, st);
+    if (ctx->tsqr_warps == 4) return launch_chunk<N, 4, 4>(ctx, ar, ws, st);
+    return launch_chunk<N, 2, 4>(ctx, ar, ws, st);
 }
 
 // out[i] = base + i * stride_bytes (factor arrays at a fixed stride; element size 8 or 4)

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     using G = Geometry<N>;
     using SM = SvdSmem<N>;
     constexpr int LDL = G::kLdL;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double *L = smem + SM::kL, *vn = smem + SM::kVn, *vvec = smem + SM::kVvec, *sig = smem + SM::kSig,
            *ssort = smem + SM::kSsort;
     int *perm = reinterpret_cast<int *>(smem + SM::kInts);
@@ -256,59 +256,82 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     }
     __syncthreads();
     PROF_ADD(13);
-    const int kq2 = (kq + 1) & ~1;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq2
+    const int kq4 = (kq + 3) & ~3;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq4
 
-    // ---- one-sided Jacobi on the columns of L ---------------------------------------------
-    // 8 lanes per column pair; lane l8 owns rows l8, l8+8, ...  The four pairs of a warp are
-    // taken in the order k, k+2, k+1, k+3 so that the two 8-lane groups of a half-warp read
-    // columns two apart (64-byte segments 16 banks apart: conflict-free with ld = N+4).
-    const int l8 = tid & 7;
-    const int grp = ((tid >> 5) << 2) | ((tid >> 4) & 1) | (((tid >> 3) & 1) << 1);
-    const int npairs = kq2 >> 1;
+    // ---- one-sided Jacobi on the columns of L, in blocks of two columns -----------------------------
+    // A group of 16 lanes owns one PAIR OF BLOCKS (four columns) per step and holds it in registers
+    // (lane l16: row pairs 2 l16 + 32 e, e < N/32): the four cross rotations run as two rounds of two
+    // independent rotations without touching shared memory, the two in-block rotations are added in
+    // the first step of a sweep.  Blocks meet in round-robin order, so a sweep has kq4/2 - 1 barrier
+    // steps instead of kq - 1, and every column pair is rotated exactly once per sweep.
+    constexpr int RP = N / 32;
+    const int l16 = tid & 15, grp = tid >> 4;
+    const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step (<= 32 groups)
     int sweeps = 0;
-    bool converged = (kq2 < 2);
+    bool converged = (kq4 < 4);
+    auto rotate = [&](double2 (&xp)[RP], double2 (&xq)[RP], int &big) {
+        double app = 0.0, aqq = 0.0, apq = 0.0, bpp = 0.0, bqq = 0.0, bpq = 0.0;
+#pragma unroll
+        for (int e = 0; e < RP; ++e) {
+            app = fma(xp[e].x, xp[e].x, app); bpp = fma(xp[e].y, xp[e].y, bpp);
+            aqq = fma(xq[e].x, xq[e].x, aqq); bqq = fma(xq[e].y, xq[e].y, bqq);
+            apq = fma(xp[e].x, xq[e].x, apq); bpq = fma(xp[e].y, xq[e].y, bpq);
+        }
+        app += bpp; aqq += bqq; apq += bpq;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            app += __shfl_xor_sync(0xffffffffu, app, o);
+            aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
+            apq += __shfl_xor_sync(0xffffffffu, apq, o);
+        }
+        // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
+        const double den2 = app * aqq, apq2 = apq * apq;
+        if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
+            if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
+            // d = aqq - app, hyp = sqrt(d^2 + 4 apq^2):  cos^2 = (|d| + hyp) / (2 hyp),
+            // sin = sign(d) apq / (hyp cos)   -- two reciprocal square roots, no division
+            const double dd = aqq - app, h2 = 2.0 * apq;
+            const double rh = rsqrt(fma(dd, dd, h2 * h2));
+            const double u = 0.5 * fma(fabs(dd), rh, 1.0);
+            const double ru = rsqrt(u);
+            const double cs = u * ru;
+            const double sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
+#pragma unroll
+            for (int e = 0; e < RP; ++e) {
+                const double px = xp[e].x, py = xp[e].y, qx = xq[e].x, qy = xq[e].y;
+                xp[e].x = cs * px - sn * qx; xp[e].y = cs * py - sn * qy;
+                xq[e].x = fma(sn, px, cs * qx); xq[e].y = fma(sn, py, cs * qy);
+            }
+        }
+    };
     for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
         int big = 0;
-        for (int step = 0; step < kq2 - 1; ++step) {
-            for (int k = grp; k < npairs; k += (int)(blockDim.x >> 3)) {
+        for (int step = 0; step < nb2 - 1; ++step) {
+            if (grp < nbp) {
                 int p, qq;
-                rr_pair(kq2, step, k, p, qq);
-                double xp[N / 8], xq[N / 8];
-                double app = 0.0, aqq = 0.0, apq = 0.0;
+                rr_pair(nb2, step, grp, p, qq);
+                double *c0p = L + (size_t)(2 * p) * LDL + 2 * l16, *c1p = c0p + LDL;
+                double *c0q = L + (size_t)(2 * qq) * LDL + 2 * l16, *c1q = c0q + LDL;
+                double2 p0[RP], p1[RP], q0[RP], q1[RP];
 #pragma unroll
-                for (int e = 0; e < N / 8; ++e) {
-                    const int rr = l8 + 8 * e;
-                    const bool on = rr < n16;
-                    xp[e] = on ? L[rr + p * LDL] : 0.0;
-                    xq[e] = on ? L[rr + qq * LDL] : 0.0;
-                    app = fma(xp[e], xp[e], app);
-                    aqq = fma(xq[e], xq[e], aqq);
-                    apq = fma(xp[e], xq[e], apq);
+                for (int e = 0; e < RP; ++e) {
+                    const bool on = 2 * l16 + 32 * e < n16;
+                    const double2 z = make_double2(0.0, 0.0);
+                    p0[e] = on ? *reinterpret_cast<const double2 *>(c0p + 32 * e) : z;
+                    p1[e] = on ? *reinterpret_cast<const double2 *>(c1p + 32 * e) : z;
+                    q0[e] = on ? *reinterpret_cast<const double2 *>(c0q + 32 * e) : z;
+                    q1[e] = on ? *reinterpret_cast<const double2 *>(c1q + 32 * e) : z;
                 }
+                if (step == 0) { rotate(p0, p1, big); rotate(q0, q1, big); }
+                rotate(p0, q0, big); rotate(p1, q1, big);
+                rotate(p0, q1, big); rotate(p1, q0, big);
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
-                    app += __shfl_xor_sync(0xffffffffu, app, o);
-                    aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
-                    apq += __shfl_xor_sync(0xffffffffu, apq, o);
-                }
-                // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
-                const double den2 = app * aqq, apq2 = apq * apq;
-                if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
-                    if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
-                    // tan(theta) = sign(d) * 2apq / (|d| + sqrt(d^2 + 4 apq^2)),  d = aqq - app
-                    const double dd = aqq - app, h2 = 2.0 * apq;
-                    const double s2 = fma(dd, dd, h2 * h2);
-                    const double hyp = s2 * rsqrt(s2);
-                    const double tt = (dd >= 0.0 ? h2 : -h2) * __drcp_rn(fabs(dd) + hyp);
-                    const double cs = rsqrt(fma(tt, tt, 1.0));
-                    const double sn = cs * tt;
-#pragma unroll
-                    for (int e = 0; e < N / 8; ++e) {
-                        const int rr = l8 + 8 * e;
-                        if (rr < n16) {
-                            L[rr + p * LDL] = cs * xp[e] - sn * xq[e];
-                            L[rr + qq * LDL] = sn * xp[e] + cs * xq[e];
-                        }
+                for (int e = 0; e < RP; ++e) {
+                    if (2 * l16 + 32 * e < n16) {
+                        *reinterpret_cast<double2 *>(c0p + 32 * e) = p0[e];
+                        *reinterpret_cast<double2 *>(c1p + 32 * e) = p1[e];
+                        *reinterpret_cast<double2 *>(c0q + 32 * e) = q0[e];
+                        *reinterpret_cast<double2 *>(c1q + 32 * e) = q1[e];
                     }
                 }
             }
