@@ -508,9 +508,9 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int kmax8 = HCORE_B200_MAX_STACK;      // ranks up to 128
-    const int m_pad = round_up(nb, 8);
-    const size_t sm_prep = (size_t)HCORE_B200_MAX_STACK * kDenseLdP * sizeof(double);
-    const size_t sm_upd = 2ull * kDenseKc * (kBlockH + 4) * sizeof(double);
+    const int m_pad = round_up(nb, kPgRows);
+    const size_t sm_prep = PgSmem::kBytes;
+    const size_t sm_upd = DenseUpdSmem::kBytes;
     {
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_prep));
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_upd));
@@ -528,8 +528,7 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
         ar.X = (double *)ctx->X.p;
         ar.scale = scale; ar.nb = nb; ar.m_pad = m_pad; ar.kmax8 = kmax8; ar.syrk = syrk;
         dense_prep_kernel<<<cnt, 256, sm_prep, st>>>(ar);
-        const int nbk = (nb + kBlockH - 1) / kBlockH;
-        dense_update_kernel<<<dim3(nbk, nbk, cnt), 256, sm_upd, st>>>(ar);
+        dense_update_kernel<<<dim3((nb + kDuRows - 1) / kDuRows, (nb + kDuCols - 1) / kDuCols, cnt), 256, sm_upd, st>>>(ar);
         ctx->launches += 2;
     }
     CUDA_TRY(ctx, cudaGetLastError());

@@ -224,37 +224,18 @@ __device__ __forceinline__ void pg_stage(double *dst, const double *src, size_t 
     }
 }
 
-template <int N>
-__global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace ws) {
+// G(m_pad x a, ld m_pad) = pscale * BU (AV^T BV)^T for one tile, by the whole CTA (256 threads).
+// AV: m x a (ld lda), BU, BV: m x b (ld ldb); rows m .. m_pad-1 of G are written as zeros.
+__device__ __forceinline__ void pg_body(double *smem, const double *AV, const double *BU, const double *BV, int a, int b,
+                                        int m, int lda, int ldb, int m_pad, int f32, double pscale, double *Gt) {
     using SM = PgSmem;
-    extern __shared__ __align__(16) double smem[];
     double *P = smem + SM::kP;
-    const int t = blockIdx.x, gt = ar.tile0 + t;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
-    const int a = ar.Ark[gt], b = ar.Brk[gt], c = ar.Crk[gt];
-    const int n = a + c, m = ar.nb;
-
-    int st = HCORE_B200_OK;
-    if (a <= 0 || b <= 0 || c <= 0) st = HCORE_B200_ERR_ZERO_RANK;
-    else if (ar.maxrk < n) st = HCORE_B200_ERR_MAXRK;
-    else if (n > N || n > m || b > N) st = HCORE_B200_ERR_UNSUPPORTED;
-    if (tid == 0) {
-        ws.st[t] = st;
-        ws.ncols[t] = n;
-        ws.newrank[t] = c;
-        if (ar.status) ar.status[gt] = st;
-    }
-    if (st != HCORE_B200_OK) return;
-
-    const double *AV = ar.AV[gt], *BU = ar.BU[gt], *BV = ar.BV[gt];
-    const int m_pad = ws.m_pad;
     const int nchunks = (m + kPgRows - 1) / kPgRows, nchunks_pad = m_pad / kPgRows;
-    const int f32 = ar.f32;
-    const bool va = !f32 && ((reinterpret_cast<uintptr_t>(AV) & 15) == 0) && ((ar.lda & 1) == 0);
+    const bool va = !f32 && ((reinterpret_cast<uintptr_t>(AV) & 15) == 0) && ((lda & 1) == 0);
     const bool vb = !f32 && ((reinterpret_cast<uintptr_t>(BV) & 15) == 0) && ((reinterpret_cast<uintptr_t>(BU) & 15) == 0) &&
-                    ((ar.ldb & 1) == 0);
-    double *Gt = ws.G + (size_t)t * m_pad * N;
+                    ((ldb & 1) == 0);
 
     for (int ia = 0; ia < a; ia += kPgKC) {
         const int as = (a - ia < kPgKC) ? (a - ia) : kPgKC, as8 = round_up(as, 8);
@@ -268,15 +249,15 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
                 double acc[8][2];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-                pg_stage(smem, AVs, ia, ar.lda, m, 0, as, as8, va, f32, tid);
-                pg_stage(smem + kPgKC * kPgLd, BVs, jb, ar.ldb, m, 0, bs, bs8, vb, f32, tid);
+                pg_stage(smem, AVs, ia, lda, m, 0, as, as8, va, f32, tid);
+                pg_stage(smem + kPgKC * kPgLd, BVs, jb, ldb, m, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const double *cur = smem + (ch & 1) * SM::kStage;
                     if (ch + 1 < nchunks) {
                         double *nxt = smem + ((ch + 1) & 1) * SM::kStage;
-                        pg_stage(nxt, AVs, ia, ar.lda, m, (ch + 1) * kPgRows, as, as8, va, f32, tid);
-                        pg_stage(nxt + kPgKC * kPgLd, BVs, jb, ar.ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
+                        pg_stage(nxt, AVs, ia, lda, m, (ch + 1) * kPgRows, as, as8, va, f32, tid);
+                        pg_stage(nxt + kPgKC * kPgLd, BVs, jb, ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
                         cp_async_commit();
                         cp_async_wait<1>();
                     } else {
@@ -303,8 +284,8 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if (8 * q < bs8) {
-                            P[(i0 + g) + (8 * q + 2 * tg) * kPgLdP] = acc[q][0];
-                            P[(i0 + g) + (8 * q + 2 * tg + 1) * kPgLdP] = acc[q][1];
+                            P[(i0 + g) + (8 * q + 2 * tg) * kPgLdP] = pscale * acc[q][0];
+                            P[(i0 + g) + (8 * q + 2 * tg + 1) * kPgLdP] = pscale * acc[q][1];
                         }
                     }
                 }
@@ -313,12 +294,12 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
             // ---- G[:, ia..] (+)= BU[:, jb..] P^T: warp -> (8-row strip of the chunk, 4 column tiles) ------
             {
                 const int strip = warp & 3, q0 = 4 * (warp >> 2);
-                pg_stage(smem, BUs, jb, ar.ldb, m, 0, bs, bs8, vb, f32, tid);
+                pg_stage(smem, BUs, jb, ldb, m, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
                 for (int ch = 0; ch < nchunks_pad; ++ch) {
                     const double *cur = smem + (ch & 1) * SM::kStage;
                     if (ch + 1 < nchunks_pad) {
-                        pg_stage(smem + ((ch + 1) & 1) * SM::kStage, BUs, jb, ar.ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
+                        pg_stage(smem + ((ch + 1) & 1) * SM::kStage, BUs, jb, ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
                         cp_async_commit();
                         cp_async_wait<1>();
                     } else {
@@ -356,6 +337,29 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
             }
         }
     }
+}
+
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace ws) {
+    extern __shared__ __align__(16) double smem[];
+    const int t = blockIdx.x, gt = ar.tile0 + t;
+    const int a = ar.Ark[gt], b = ar.Brk[gt], c = ar.Crk[gt];
+    const int n = a + c, m = ar.nb;
+
+    int st = HCORE_B200_OK;
+    if (a <= 0 || b <= 0 || c <= 0) st = HCORE_B200_ERR_ZERO_RANK;
+    else if (ar.maxrk < n) st = HCORE_B200_ERR_MAXRK;
+    else if (n > N || n > m || b > N) st = HCORE_B200_ERR_UNSUPPORTED;
+    if (threadIdx.x == 0) {
+        ws.st[t] = st;
+        ws.ncols[t] = n;
+        ws.newrank[t] = c;
+        if (ar.status) ar.status[gt] = st;
+    }
+    if (st != HCORE_B200_OK) return;
+    pg_body(smem, ar.AV[gt], ar.BU[gt], ar.BV[gt], a, b, m, ar.lda, ar.ldb, ws.m_pad, ar.f32, 1.0,
+            ws.G + (size_t)t * ws.m_pad * N);
 }
 
 // ========================================================================================

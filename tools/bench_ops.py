@@ -35,9 +35,10 @@ def timed(fn, restore, reps=3, warm=2):
 
 
 out = {"hbm_gbs_measured": HBM}
+ONLY = os.environ.get("OPS_ONLY", "")        # "", "sweep", "sz", "dense"
 # ---- dgemm sweep -------------------------------------------------------------------------------------
 sweep = []
-for nb, k, T in [(512, 16, 8192), (512, 32, 8192), (512, 64, 4096), (1024, 16, 8192), (1024, 32, 8192), (1024, 64, 4736),
+for nb, k, T in [] if ONLY not in ("", "sweep") else [(512, 16, 8192), (512, 32, 8192), (512, 64, 4096), (1024, 16, 8192), (1024, 32, 8192), (1024, 64, 4736),
                  (2048, 32, 2368), (2048, 64, 2368)]:
     d = bench.make_device_batch(torch, T, nb, k, dev, seed=3)
     fn = lambda: ctx.dgemm_batched(-1.0, d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], 1.0, d["cu"], d["cv"],
@@ -53,7 +54,7 @@ for nb, k, T in [(512, 16, 8192), (512, 32, 8192), (512, 64, 4096), (1024, 16, 8
 out["dgemm_sweep"] = sweep
 # ---- sgemm / zgemm --------------------------------------------------------------------------------------
 nb, k = 1024, 64
-for name, dt, T, acc in (("sgemm", torch.float32, 4736, 1e-4), ("zgemm", torch.complex128, 592, 1e-8)):
+for name, dt, T, acc in () if ONLY not in ("", "sz") else (("sgemm", torch.float32, 4736, 1e-4), ("zgemm", torch.complex128, 592, 1e-8)):
     d = bench.make_device_batch(torch, T, nb, k, dev, seed=4)
     conv = {}
     for nm in ("au", "av", "bu", "bv", "cu0", "cv0", "cu", "cv"):
@@ -76,7 +77,10 @@ for name, dt, T, acc in (("sgemm", torch.float32, 4736, 1e-4), ("zgemm", torch.c
     del conv, d
     torch.cuda.empty_cache()
 # ---- dense-C updates (config 3) ---------------------------------------------------------------------------
-nb, k, T = 1024, 32, 2048
+nb, k, T = 1024, 32, (2048 if ONLY in ("", "dense") else 0)
+if T == 0:
+    ctx.close()
+    sys.exit(0)
 d = bench.make_device_batch(torch, T, nb, k, dev, seed=5)
 cd = torch.rand((T, nb, nb), dtype=torch.float64, device=dev)
 for name, fn in (("dgemmcd", lambda: ctx.dgemmcd_batched(d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], cd)),

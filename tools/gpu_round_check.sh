@@ -15,6 +15,8 @@ import json;d=json.load(open('gpurun_out/quick4_$TAG.json'));print(d['value'],{k
  quickw) for W in 8 4 2; do HCORE_B200_TSQR_WARPS=$W timeout 600 python bench.py --tiles 4736 --no-e2e --no-cpu-baseline --steps 2 > gpurun_out/quickw${W}_$TAG.json 2> gpurun_out/quickw${W}_$TAG.err; python -c "
 import json;d=json.load(open('gpurun_out/quickw${W}_$TAG.json'));print('W=$W',d['value'],{k:round(v['ms'],2) for k,v in d['stages'].items()},d['failed_tiles'],d['mean_new_rank'],d['sample_abs_err_fro'])"; tail -3 gpurun_out/quickw${W}_$TAG.err; done ;;
  ops) timeout 1200 python tools/bench_ops.py gpurun_out/ops_$TAG.json 2>&1 | tail -20 ;;
+ dense) timeout 600 python -m pytest tests -m gpu -x -q -k "dgemmcd or dsyrk" 2>&1 | tail -8; OPS_ONLY=dense timeout 600 python tools/bench_ops.py gpurun_out/dense_$TAG.json 2>&1 | tail -4
+        ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'dense_' -c 12 --csv --log-file gpurun_out/dense_launches_$TAG.csv env OPS_ONLY=dense python tools/bench_ops.py > /dev/null 2>&1; grep -v "^==" gpurun_out/dense_launches_$TAG.csv | awk -F'","' '{print $5, $(NF)}' | tail -6 ;;
  sanitize) timeout 900 compute-sanitizer --tool memcheck python tools/profile_run.py 4 256 16 1 2>&1 | tail -30 ;;
 esac
 done
