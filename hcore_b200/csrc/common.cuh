@@ -229,8 +229,10 @@ __device__ __forceinline__ void rr_pair(int n, int step, int k, int &p, int &q) 
         a = n - 1;
         b = step;
     } else {
-        a = (step + k) % (n - 1);
-        b = (step - k + n - 1) % (n - 1);
+        a = step + k;                       // 0 <= step < n - 1, 0 < k < n / 2: one conditional
+        a = a >= n - 1 ? a - (n - 1) : a;   // subtraction replaces the modulo
+        b = step - k + n - 1;
+        b = b >= n - 1 ? b - (n - 1) : b;
     }
     p = a < b ? a : b;
     q = a < b ? b : a;

@@ -269,23 +269,37 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step (<= 32 groups)
     int sweeps = 0;
     bool converged = (kq4 < 4);
-    auto rotate = [&](double2 (&xp)[RP], double2 (&xq)[RP], int &big) {
-        double app = 0.0, aqq = 0.0, apq = 0.0, bpp = 0.0, bqq = 0.0, bpq = 0.0;
+    // Two independent rotations A = (ap, aq) and B = (bp, bq) at once.  The six partial sums are reduced
+    // by recursive halving: the lower 8 lanes of the group end up with the three totals of A, the upper
+    // 8 with those of B (12 exchanges instead of 24), each half derives ITS rotation (the scalar chain
+    // runs once for both) and the halves swap (cos, sin).  sin == 0 means "no rotation".
+    const bool hi8 = (l16 & 8) != 0;
+    auto rotate2 = [&](double2 (&ap)[RP], double2 (&aq)[RP], double2 (&bp)[RP], double2 (&bq)[RP], int &big) {
+        double sa[3] = {0.0, 0.0, 0.0}, ta[3] = {0.0, 0.0, 0.0}, sb[3] = {0.0, 0.0, 0.0}, tb[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int e = 0; e < RP; ++e) {
-            app = fma(xp[e].x, xp[e].x, app); bpp = fma(xp[e].y, xp[e].y, bpp);
-            aqq = fma(xq[e].x, xq[e].x, aqq); bqq = fma(xq[e].y, xq[e].y, bqq);
-            apq = fma(xp[e].x, xq[e].x, apq); bpq = fma(xp[e].y, xq[e].y, bpq);
+            sa[0] = fma(ap[e].x, ap[e].x, sa[0]); ta[0] = fma(ap[e].y, ap[e].y, ta[0]);
+            sa[1] = fma(aq[e].x, aq[e].x, sa[1]); ta[1] = fma(aq[e].y, aq[e].y, ta[1]);
+            sa[2] = fma(ap[e].x, aq[e].x, sa[2]); ta[2] = fma(ap[e].y, aq[e].y, ta[2]);
+            sb[0] = fma(bp[e].x, bp[e].x, sb[0]); tb[0] = fma(bp[e].y, bp[e].y, tb[0]);
+            sb[1] = fma(bq[e].x, bq[e].x, sb[1]); tb[1] = fma(bq[e].y, bq[e].y, tb[1]);
+            sb[2] = fma(bp[e].x, bq[e].x, sb[2]); tb[2] = fma(bp[e].y, bq[e].y, tb[2]);
         }
-        app += bpp; aqq += bqq; apq += bpq;
+        double v[3];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            app += __shfl_xor_sync(0xffffffffu, app, o);
-            aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
-            apq += __shfl_xor_sync(0xffffffffu, apq, o);
+        for (int q = 0; q < 3; ++q) {
+            const double a = sa[q] + ta[q], b = sb[q] + tb[q];
+            v[q] = (hi8 ? b : a) + __shfl_xor_sync(0xffffffffu, hi8 ? a : b, 8);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
         }
         // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
+        const double app = v[0], aqq = v[1], apq = v[2];
         const double den2 = app * aqq, apq2 = apq * apq;
+        double cs = 1.0, sn = 0.0;
         if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
             if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
             // d = aqq - app, hyp = sqrt(d^2 + 4 apq^2):  cos^2 = (|d| + hyp) / (2 hyp),
@@ -294,13 +308,25 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
             const double rh = rsqrt(fma(dd, dd, h2 * h2));
             const double u = 0.5 * fma(fabs(dd), rh, 1.0);
             const double ru = rsqrt(u);
-            const double cs = u * ru;
-            const double sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
+            cs = u * ru;
+            sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
+        }
+        const double ocs = __shfl_xor_sync(0xffffffffu, cs, 8), osn = __shfl_xor_sync(0xffffffffu, sn, 8);
+        const double csa = hi8 ? ocs : cs, sna = hi8 ? osn : sn, csb = hi8 ? cs : ocs, snb = hi8 ? sn : osn;
+        if (sna != 0.0) {
 #pragma unroll
             for (int e = 0; e < RP; ++e) {
-                const double px = xp[e].x, py = xp[e].y, qx = xq[e].x, qy = xq[e].y;
-                xp[e].x = cs * px - sn * qx; xp[e].y = cs * py - sn * qy;
-                xq[e].x = fma(sn, px, cs * qx); xq[e].y = fma(sn, py, cs * qy);
+                const double px = ap[e].x, py = ap[e].y, qx = aq[e].x, qy = aq[e].y;
+                ap[e].x = csa * px - sna * qx; ap[e].y = csa * py - sna * qy;
+                aq[e].x = fma(sna, px, csa * qx); aq[e].y = fma(sna, py, csa * qy);
+            }
+        }
+        if (snb != 0.0) {
+#pragma unroll
+            for (int e = 0; e < RP; ++e) {
+                const double px = bp[e].x, py = bp[e].y, qx = bq[e].x, qy = bq[e].y;
+                bp[e].x = csb * px - snb * qx; bp[e].y = csb * py - snb * qy;
+                bq[e].x = fma(snb, px, csb * qx); bq[e].y = fma(snb, py, csb * qy);
             }
         }
     };
@@ -322,9 +348,9 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
                     q0[e] = on ? *reinterpret_cast<const double2 *>(c0q + 32 * e) : z;
                     q1[e] = on ? *reinterpret_cast<const double2 *>(c1q + 32 * e) : z;
                 }
-                if (step == 0) { rotate(p0, p1, big); rotate(q0, q1, big); }
-                rotate(p0, q0, big); rotate(p1, q1, big);
-                rotate(p0, q1, big); rotate(p1, q0, big);
+                if (step == 0) rotate2(p0, p1, q0, q1, big);
+                rotate2(p0, q0, p1, q1, big);
+                rotate2(p0, q1, p1, q0, big);
 #pragma unroll
                 for (int e = 0; e < RP; ++e) {
                     if (2 * l16 + 32 * e < n16) {
