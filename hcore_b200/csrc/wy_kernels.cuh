@@ -658,14 +658,35 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
             // ---- my 8 columns of the row block -> registers -----------------------------------------
             double bx[16], by[16];
             const bool v16 = src.p && !src.f32 && ((reinterpret_cast<uintptr_t>(src.p + src.off) & 15) == 0);
+            if (v16 && (j + 1) * kBlockH <= m) {
+                // whole block in range: sixteen independent 16-byte loads in flight before the first use
+                // (with the bounds checks inside the loop every load was followed by its consumer and
+                // the sixteen DRAM/L2 latencies added up)
+                const double2 *p2 = reinterpret_cast<const double2 *>(src.p + src.off + j * kBlockH + 2 * tg);
+                double2 v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int row = j * kBlockH + 8 * i + 2 * tg;
-                if (v16 && row + 1 < m) {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(src.p + src.off + row));
-                    bx[i] = src.scale * v.x;
-                    by[i] = src.scale * v.y;
-                } else {
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(p2 + 4 * i);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    bx[i] = src.scale * v[i].x;
+                    by[i] = src.scale * v[i].y;
+                }
+            } else if (src.p && src.f32 && (j + 1) * kBlockH <= m &&
+                       ((reinterpret_cast<uintptr_t>(reinterpret_cast<const float *>(src.p) + src.off) & 7) == 0)) {
+                const float2 *p2 = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(src.p) + src.off +
+                                                                    j * kBlockH + 2 * tg);
+                float2 v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(p2 + 4 * i);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    bx[i] = src.scale * (double)v[i].x;
+                    by[i] = src.scale * (double)v[i].y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int row = j * kBlockH + 8 * i + 2 * tg;
                     bx[i] = (src.p && row < m) ? src.scale * ld_user(src.p, src.off + row, src.f32) : 0.0;
                     by[i] = (src.p && row + 1 < m) ? src.scale * ld_user(src.p, src.off + row + 1, src.f32) : 0.0;
                 }
