@@ -342,12 +342,24 @@ def main():
         ach = fl[nm] * T_local / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         stages[nm] = {"ms": ms, "share": ms / max(sum(stage_ms), 1e-9), "model_tflops": ach, "frac_fp64_peak": ach / peak_tflops}
     dom = max(names, key=lambda nm: stages[nm]["ms"])
+    # DRAM bytes of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one
+    # `ncu --set full` capture (per tile, profiles/roofline_traffic.json) x the tiles one launch processes
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        ent = tj.get(f"tlr_{dom}_kernel")
+        if ent and (nb, k) == (tj.get("nb"), tj.get("rank")):
+            traffic = ent["dram_bytes_per_tile"] * (T_local / nchunks)
+            traffic_src = tj.get("source")
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": f"tlr_{dom}_kernel", "achieved": stages[dom]["model_tflops"],
                 "peak": peak_tflops, "unit": "TFLOP/s", "frac": stages[dom]["model_tflops"] / peak_tflops,
-                "traffic": None,
+                "traffic": traffic,
                 "note": "FP64: peak = max(DMMA m8n8k4 micro-benchmark 37.1 TF (profiles/fp64_peak_r1.txt), cuBLAS DGEMM "
                         f"8192^3 measured in this run = {cublas_tflops:.1f} TF); MEASURED_PEAKS.json has no FP64 entry. "
                         "achieved = reference flop model of the stage x tiles / CUDA-event time of the stage's launches",
+                "traffic_source": traffic_src, "launches_per_step": nchunks,
                 "pipeline_frac": value / world * flops_tile / 1e12 / peak_tflops}
 
     line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
@@ -363,40 +375,53 @@ def main():
             "gpu_launches": launches, "stages": stages, "roofline": roofline, "clocks": clocks,
             "wall_s_timed_region": wall}
 
+    # ---- end to end through the C ABI with HOST buffers (H2D + D2H inside the timed region) ----
+    # every rank runs it on its own GPU at the same time; the time is the max over ranks
+    if not args.no_e2e:
+        Te = min(args.e2e_tiles if world == 1 else min(args.e2e_tiles, 1024), T_local)
+        host = {}
+        for nm in ("au", "av", "bu", "bv"):
+            host[nm] = d[nm][:Te].cpu().pin_memory()
+        host["cu"] = torch.zeros((Te, 2 * k, nb), dtype=torch.float64).pin_memory()
+        host["cv"] = torch.zeros((Te, 2 * k, nb), dtype=torch.float64).pin_memory()
+        cu0h, cv0h = d["cu0"][:Te].cpu(), d["cv0"][:Te].cpu()
+        ark = torch.full((Te,), k, dtype=torch.int32).pin_memory()
+        brk = torch.full((Te,), k, dtype=torch.int32).pin_memory()
+        crk = torch.full((Te,), k, dtype=torch.int32).pin_memory()
+        sth = torch.zeros((Te,), dtype=torch.int32).pin_memory()
+        times = []
+        for it in range(args.warmup + args.steps):
+            host["cu"][:, :k].copy_(cu0h)
+            host["cv"][:, :k].copy_(cv0h)
+            crk.fill_(k)
+            barrier()
+            t0 = time.perf_counter()
+            ctx.dgemm_batched_host(-1.0, host["au"], host["av"], ark, host["bu"], host["bv"], brk, 1.0,
+                                   host["cu"], host["cv"], crk, rk=0, maxrk=2 * k, acc=acc, status=sth)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        te = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        nf = torch.tensor([float((sth != 0).sum().item())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nf, op=dist.ReduceOp.SUM)
+        # bytes that actually cross PCIe (the library copies only the columns that carry data: Crk columns of
+        # C in, max new rank of each 512-tile slice out)
+        per_tile_in = (4 * k + 2 * k) * nb * 8
+        out_bytes = 0
+        crk_np = crk.numpy()
+        for s0 in range(0, Te, 512):
+            sl = crk_np[s0:s0 + 512]
+            out_bytes += 2 * len(sl) * nb * int(sl.max()) * 8
+        line["e2e"] = {"value": world * Te / float(te.item()), "unit": "tiles/s",
+                       "h2d_bytes_per_step": world * (Te * per_tile_in + 3 * 4 * Te),
+                       "d2h_bytes_per_step": world * (out_bytes + 2 * 4 * Te),
+                       "tiles_per_step": world * Te, "failed_tiles": int(nf.item()),
+                       "note": "HCORE_dgemm_batched_host on every rank at once: pinned host buffers, sliced "
+                               "H2D/compute/D2H pipeline on two streams; host wall clock, max over ranks"}
+        del host
     if rank == 0 and world == 1:
-        # ---- end to end through the C ABI with HOST buffers (H2D + D2H inside the timed region) ----
-        if not args.no_e2e:
-            Te = min(args.e2e_tiles, T_local)
-            host = {}
-            for nm in ("au", "av", "bu", "bv"):
-                host[nm] = d[nm][:Te].cpu().pin_memory()
-            host["cu"] = torch.zeros((Te, 2 * k, nb), dtype=torch.float64).pin_memory()
-            host["cv"] = torch.zeros((Te, 2 * k, nb), dtype=torch.float64).pin_memory()
-            cu0h, cv0h = d["cu0"][:Te].cpu(), d["cv0"][:Te].cpu()
-            ark = torch.full((Te,), k, dtype=torch.int32).pin_memory()
-            brk = torch.full((Te,), k, dtype=torch.int32).pin_memory()
-            crk = torch.full((Te,), k, dtype=torch.int32).pin_memory()
-            sth = torch.zeros((Te,), dtype=torch.int32).pin_memory()
-            times = []
-            for it in range(args.warmup + args.steps):
-                host["cu"][:, :k].copy_(cu0h)
-                host["cv"][:, :k].copy_(cv0h)
-                crk.fill_(k)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                ctx.dgemm_batched_host(-1.0, host["au"], host["av"], ark, host["bu"], host["bv"], brk, 1.0,
-                                       host["cu"], host["cv"], crk, rk=0, maxrk=2 * k, acc=acc, status=sth)
-                dt = time.perf_counter() - t0
-                if it >= args.warmup:
-                    times.append(dt)
-            per_tile_in = (4 * k + 2 * 2 * k) * nb * 8
-            per_tile_out = 2 * 2 * k * nb * 8
-            line["e2e"] = {"value": Te / float(np.mean(times)), "unit": "tiles/s",
-                           "h2d_bytes_per_step": Te * per_tile_in + 3 * 4 * Te,
-                           "d2h_bytes_per_step": Te * per_tile_out + 2 * 4 * Te,
-                           "tiles_per_step": Te, "failed_tiles": int((sth != 0).sum().item()),
-                           "note": "HCORE_dgemm_batched_host: pinned host buffers, chunked H2D/compute/D2H pipeline"}
-            del host
         # ---- CPU baseline: the reference on the host cores ----
         if not args.no_cpu_baseline:
             try:

@@ -36,8 +36,6 @@ constexpr int kLdT = 8;                            // leading dim of the T image
 constexpr int kRecT = kSubW * kLdT;                // 64
 constexpr int kRecDoubles = kRecV + 2 * kRecT;     // V | T | T^T  = 1152
 constexpr int kRecBytes = kRecDoubles * 8;         // 9 216
-constexpr int kRecFwd = kRecV + kRecT;             // V | T: all the factorisation (forward chain) reads
-constexpr int kRecFwdBytes = kRecFwd * 8;          // 8 704
 
 // Swizzled position of element (row r, column c) of a 128 x 8 reflector panel.  16-byte slots
 // hold row pairs; slot = c*64 + ((r/2) ^ h(c)).  h is chosen so that both access patterns of
@@ -379,16 +377,14 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
 //       publishes the record to its slot and to global memory.
 constexpr int kYbuf = kBlockH + 16;    // per warp, per parity: y[128] | ydiag[8] | z[8]
 
-constexpr int kTsqrRing = 4;           // TMA ring depth: records of earlier groups are fetched 3 ahead
-
 template <int NW>
 struct TsqrSmem {
-    // the forward chain never reads the T^T image: buffers and slots hold V | T only
-    static constexpr int kRec0 = 0;                                  // [kTsqrRing] ring of streamed records
-    static constexpr int kOwn = kRec0 + kTsqrRing * kRecFwd;         // [NW-1] records of the group's own sub-panels
-    static constexpr int kY = kOwn + (NW - 1) * kRecFwd;             // [NW][2][kYbuf]
-    static constexpr int kBar = kY + NW * 2 * kYbuf;                 // kTsqrRing mbarriers
-    static constexpr int kTotal = kBar + kTsqrRing;
+    static constexpr int kRec0 = 0;
+    static constexpr int kRec1 = kRec0 + kRecDoubles;
+    static constexpr int kOwn = kRec1 + kRecDoubles;                 // [NW-1] records of the group's own sub-panels
+    static constexpr int kY = kOwn + (NW - 1) * kRecDoubles;         // [NW][2][kYbuf]
+    static constexpr int kBar = kY + NW * 2 * kYbuf;                 // 2 mbarriers
+    static constexpr int kTotal = kBar + 2;
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
 
@@ -596,9 +592,10 @@ __device__ __forceinline__ void warp_factor(double (&bx)[16], double (&by)[16], 
         const double tb = (tg == 0) ? trow[1] : (tg == 1) ? trow[3] : (tg == 2) ? trow[5] : trow[7];
         const int o0 = kRecV + g + kLdT * (2 * tg);              // T   : B[k][n] = T[k][n] at k + 8 n
         const int o1 = kRecV + kRecT + 2 * tg + kLdT * g;        // T^T : B[k][n] = T[n][k] at k + 8 n
-        if (slot) {                      // slots hold V | T only
+        if (slot) {
             slot[o0] = ta;
             slot[o0 + kLdT] = tb;
+            *reinterpret_cast<double2 *>(slot + o1) = make_double2(ta, tb);
         }
         recg[o0] = ta;
         recg[o0 + kLdT] = tb;
@@ -615,8 +612,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
     constexpr int kBarFull = 1, kBarFree = NW;         // named barriers: record of warp s published / consumed
     static_assert(2 * NW - 2 <= 15, "named barrier ids 1 .. 2 NW - 2");
     extern __shared__ __align__(16) double smem[];
-    constexpr int S = kTsqrRing;
-    double *ring = smem + SM::kRec0;
+    double *recbuf[2] = {smem + SM::kRec0, smem + SM::kRec1};
     double *own = smem + SM::kOwn;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kBar);
 
@@ -634,12 +630,12 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
     double *yb = smem + SM::kY + warp * 2 * kYbuf;
 
     if (tid == 0) {
-#pragma unroll
-        for (int b = 0; b < S; ++b) mbar_init(&bars[b], 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    uint32_t phasebits = 0;                          // bit b: parity of the next completion of bars[b]
+    uint32_t phase[2] = {0, 0};
     PROF_DECL(tid == NT - 32)
     PROF_COUNT(9, 1);
 
@@ -651,21 +647,14 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
         const int mycol = gc0 + lc + g;
         const ColSrc src = panel_column(ar, Gt, m_pad, gt, pnl, mycol, c, n);
         const int nprev = gc0 / kSubW;                              // records of earlier groups
-        // The records of the earlier groups form ONE stream over all row blocks of this group (row block
-        // j, record sp -> q = j nprev + sp), fetched S - 1 records ahead into a ring of S buffers: the
-        // fetch of a record has three records of arithmetic (and the group's own-phase at a block
-        // boundary) to hide behind.
-        const int nstream = ws.nblk * nprev;
-        auto issue = [&](int q) {                                  // one thread
-            const int jj = q / nprev, ss = q - jj * nprev, b = q % S;
-            mbar_expect_tx(&bars[b], kRecFwdBytes);
-            tma_load_1d(ring + b * kRecFwd, recg + ((size_t)jj * NSP + ss) * kRecDoubles, kRecFwdBytes, &bars[b]);
-        };
-        if (tid == 0)
-            for (int q = 0; q < S - 1 && q < nstream; ++q) issue(q);
         for (int j = 0; j < ws.nblk; ++j) {
             const bool blk0 = (j == 0);
             double *recj = recg + (size_t)j * NSP * kRecDoubles;
+            // prefetch the first earlier record while the slice is loaded
+            if (nprev > 0 && tid == 0) {
+                mbar_expect_tx(&bars[0], kRecBytes);
+                tma_load_1d(recbuf[0], recj, kRecBytes, &bars[0]);
+            }
             // ---- my 8 columns of the row block -> registers -----------------------------------------
             double bx[16], by[16];
             const bool v16 = src.p && !src.f32 && ((reinterpret_cast<uintptr_t>(src.p + src.off) & 15) == 0);
@@ -705,17 +694,22 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
             PROF_ADD(0);
             // ---- (1) reflectors of the earlier groups ------------------------------------------------
             for (int sp = 0; sp < nprev; ++sp) {
-                const int q = j * nprev + sp, b = q % S;
-                __syncthreads();                     // everybody is done with record q - 1: its buffer is free
-                if (tid == 0 && q + S - 1 < nstream) issue(q + S - 1);
-                mbar_wait(&bars[b], (phasebits >> b) & 1u);
-                phasebits ^= 1u << b;
+                const int b = sp & 1;
+                if (sp + 1 < nprev) {
+                    __syncthreads();                 // everybody is done with buffer b^1 (record sp-1)
+                    if (tid == 0) {
+                        mbar_expect_tx(&bars[b ^ 1], kRecBytes);
+                        tma_load_1d(recbuf[b ^ 1], recj + (size_t)(sp + 1) * kRecDoubles, kRecBytes, &bars[b ^ 1]);
+                    }
+                }
+                mbar_wait(&bars[b], phase[b]);
+                phase[b] ^= 1;
                 if (have_cols) {
                     double sx = 0.0, sy = 0.0;
                     double *rs = Rg + (size_t)(sp * kSubW + 2 * tg) + (size_t)mycol * N;
                     double2 r0 = make_double2(0.0, 0.0);
                     if (!blk0) { r0 = *reinterpret_cast<const double2 *>(rs); sx = r0.x; sy = r0.y; }
-                    wy_chain<true>(bx, by, sx, sy, ring + b * kRecFwd, lane);
+                    wy_chain<true>(bx, by, sx, sy, recbuf[b], lane);
                     if (!blk0) *reinterpret_cast<double2 *>(rs) = make_double2(r0.x - sx, r0.y - sy);
                 }
             }
@@ -738,14 +732,14 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
                         double *rs = Rg + (size_t)(gc0 + s * kSubW + 2 * tg) + (size_t)mycol * N;
                         double2 r0 = make_double2(0.0, 0.0);
                         if (!blk0) { r0 = *reinterpret_cast<const double2 *>(rs); sx = r0.x; sy = r0.y; }
-                        wy_chain<true>(bx, by, sx, sy, own + s * kRecFwd, lane);
+                        wy_chain<true>(bx, by, sx, sy, own + s * kRecDoubles, lane);
                         if (!blk0) *reinterpret_cast<double2 *>(rs) = make_double2(r0.x - sx, r0.y - sy);
                         bar_arrive_lit(kBarFree + s, cnt);                  // done with slot s
                     }
                 }
                 PROF_ADD(3);
                 const bool publish = warp + 1 < nsub;
-                double *slot = publish ? own + warp * kRecFwd : nullptr;
+                double *slot = publish ? own + warp * kRecDoubles : nullptr;
                 double *rg = recj + (size_t)(nprev + warp) * kRecDoubles;
                 if (blk0) warp_factor<N, true>(bx, by, yb, slot, rg, Rg, gc0 + lc, lane);
                 else warp_factor<N, false>(bx, by, yb, slot, rg, Rg, gc0 + lc, lane);
