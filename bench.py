@@ -244,6 +244,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner out of stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
     nb, k, acc = args.nb, args.rank, args.acc
@@ -407,12 +409,13 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             dist.all_reduce(nf, op=dist.ReduceOp.SUM)
         # bytes that actually cross PCIe (the library copies only the columns that carry data: Crk columns of
-        # C in, max new rank of each 512-tile slice out)
+        # C in, max new rank of each slice out)
         per_tile_in = (4 * k + 2 * k) * nb * 8
         out_bytes = 0
         crk_np = crk.numpy()
-        for s0 in range(0, Te, 512):
-            sl = crk_np[s0:s0 + 512]
+        hc = max(int(torch.cuda.get_device_properties(dev).multi_processor_count), 64)   # the library's slice size
+        for s0 in range(0, Te, hc):
+            sl = crk_np[s0:s0 + hc]
             out_bytes += 2 * len(sl) * nb * int(sl.max()) * 8
         line["e2e"] = {"value": world * Te / float(te.item()), "unit": "tiles/s",
                        "h2d_bytes_per_step": world * (Te * per_tile_in + 3 * 4 * Te),

@@ -381,7 +381,9 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
     // H2D copy of slice i+1 and the D2H copy of slice i-1 overlap the kernels of slice i.
     // The kernels themselves share the context workspace, so they are serialised by an
     // event chain (compute of slice i+1 waits for compute of slice i).
-    const int hc = std::min(ntiles, 512);
+    // Slice = one wave of the SVD kernel (one CTA per SM): the path is PCIe-bound (3.1 MB in, 1.5 MB out per
+    // tile against ~10 us of GPU time), so small slices only shorten the pipeline fill and drain.
+    const int hc = std::min(ntiles, std::max(ctx->num_sms, 64));
     const size_t perA = (size_t)strideA * 8, perB = (size_t)strideB * 8, perC = (size_t)strideC * 8;
     const size_t per_tile = 2 * perA + 2 * perB + 2 * perC;
     for (int s = 0; s < 2; ++s) {
