@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["orth_factor", "make_lr_batch", "make_dense_batch", "TlrBatch"]
+__all__ = ["orth_factor", "make_lr_batch", "make_dense_batch", "make_covariance_batch", "TlrBatch"]
 
 
 def orth_factor(rng: np.random.Generator, nb: int, k: int, dtype=np.float64) -> np.ndarray:
@@ -96,3 +96,56 @@ def make_dense_batch(ntiles, nb, *, base_seed=4321, dtype=np.float64, lower_only
             x = np.triu(x)  # [col, row] storage: keeping col <= row is the lower triangle
         cd[t] = x
     return cd
+
+
+def _morton_points(n, rng):
+    """``n`` jittered points of the unit square in Morton (Z-curve) order, as HiCMA's
+    synthetic covariance problems order them (neighbouring indices = neighbouring points)."""
+    side = int(np.ceil(np.sqrt(n)))
+    ix, iy = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    ix, iy = ix.ravel(), iy.ravel()
+
+    def spread(v):
+        v = v.astype(np.uint64)
+        out = np.zeros_like(v)
+        for bit in range(16):
+            out |= ((v >> np.uint64(bit)) & np.uint64(1)) << np.uint64(2 * bit)
+        return out
+
+    order = np.argsort(spread(ix) | (spread(iy) << np.uint64(1)), kind="stable")[:n]
+    jit = (rng.random((n, 2)) - 0.5) * 0.4
+    return (np.stack([ix[order], iy[order]], axis=1) + 0.5 + jit) / side
+
+
+def compress_tile(a, acc, maxrk):
+    """Dense tile -> (U, V) with orthonormal U and V carrying the singular values, truncated at the
+    absolute accuracy ``acc`` (what the reference's tests do with dgesvd,
+    ``testing/testing_dgemm.c:119-236``).  Returns column-major (r, nb) arrays."""
+    u, s, vt = np.linalg.svd(a, full_matrices=False)
+    r = int(np.searchsorted(-s, -acc))          # first index with s < acc
+    r = max(1, min(r, maxrk))
+    return np.ascontiguousarray(u[:, :r].T), np.ascontiguousarray(vt[:r] * s[:r, None]), r
+
+
+def make_covariance_batch(ntiles, nb, maxrk, *, acc=1e-8, base_seed=99, length=0.4, first_tile=0):
+    """The realistic regime: per problem three tiles cut from ONE squared-exponential
+    covariance matrix ``K(x, y) = exp(-(|x - y| / length)^2)`` (HiCMA's synthetic ``sqexp`` problem) over
+    3*nb Morton-ordered points of the unit square, compressed to accuracy ``acc``: ``A = K[1, 0]``, ``B = K[2, 0]``, ``C = K[2, 1]`` -- the
+    operands of the TLR-Cholesky trailing update ``C <- C - A B^T`` in which the update shares most of
+    its column space with C, so the rank after recompression stays close to the ranks going in.
+    Per-tile ranks differ (ragged batch); factors are zero padded to ``maxrk`` columns."""
+    au = np.zeros((ntiles, maxrk, nb)); av = np.zeros_like(au)
+    bu = np.zeros_like(au); bv = np.zeros_like(au)
+    cu = np.zeros_like(au); cv = np.zeros_like(au)
+    ark = np.zeros(ntiles, np.int32); brk = np.zeros(ntiles, np.int32); crk = np.zeros(ntiles, np.int32)
+    for t in range(ntiles):
+        rng = np.random.default_rng(base_seed + first_tile + t)
+        pts = _morton_points(3 * nb, rng)
+        d = np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1))
+        k = np.exp(-(d / (length * (1.0 + 0.5 * ((first_tile + t) % 3)))) ** 2)
+        blk = lambda i, j: k[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb]
+        # B enters the product transposed: A B^T = K10 (K20)^T
+        for (uu, vv, rr, tile) in ((au, av, ark, blk(1, 0)), (bu, bv, brk, blk(2, 0)), (cu, cv, crk, blk(2, 1))):
+            u, v, r = compress_tile(tile, acc, maxrk // 2)
+            uu[t, :r], vv[t, :r], rr[t] = u, v, r
+    return TlrBatch(nb, maxrk, au, av, bu, bv, cu, cv, ark, brk, crk)

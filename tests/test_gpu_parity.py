@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from hcore_b200 import api
-from hcore_b200.tilegen import make_lr_batch, make_dense_batch
+from hcore_b200.tilegen import make_lr_batch, make_dense_batch, make_covariance_batch
 from oracle import tlr_oracle as orc
 
 torch = pytest.importorskip("torch")
@@ -248,6 +248,27 @@ def test_vs_oracle(ctx, nb, k, alpha, beta, rk, acc):
         r = int(crk[t])
         assert abs(r - r_o) <= (0 if rk else 1)
         dense = b.dense_c(t, alpha, beta)
+        e_o = np.linalg.norm(cu_o.T @ cv_o - dense)
+        e_d = np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense)
+        assert e_d <= max(1.01 * e_o, 256 * EPS * np.linalg.norm(dense)) + (acc if r != r_o else 0.0)
+
+
+@pytest.mark.parametrize("nb,maxrk,acc", [(256, 128, 1e-8), (500, 128, 1e-6)])
+def test_covariance_tiles_vs_oracle(ctx, nb, maxrk, acc):
+    """The realistic regime: A, B, C cut from one exponential-kernel covariance matrix (ragged ranks,
+    update and C share most of their column space, rank after recompression close to the ranks in)."""
+    T = 4
+    b = make_covariance_batch(T, nb, maxrk, acc=acc)
+    cu, cv, crk, st = _run_batch(ctx, b, -1.0, 1.0, 0, maxrk, acc)
+    assert (st == 0).all()
+    for t in range(T):
+        a_, b_, c_ = int(b.ark[t]), int(b.brk[t]), int(b.crk[t])
+        cu_o, cv_o, r_o, sig = orc.tlr_gemm_colmajor(b.au[t, :a_], b.av[t, :a_], b.bu[t, :b_], b.bv[t, :b_], b.cu[t], b.cv[t],
+                                                     c_, alpha=-1.0, beta=1.0, rk=0, maxrk=maxrk, acc=acc)
+        r = int(crk[t])
+        assert abs(r - r_o) <= 1
+        assert r < a_ + c_                                   # the stack really was rank deficient
+        dense = b.dense_c(t, -1.0, 1.0)
         e_o = np.linalg.norm(cu_o.T @ cv_o - dense)
         e_d = np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense)
         assert e_d <= max(1.01 * e_o, 256 * EPS * np.linalg.norm(dense)) + (acc if r != r_o else 0.0)

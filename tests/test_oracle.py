@@ -182,3 +182,25 @@ def test_device_model_rank_deficient_stack():
     D = args[4] @ args[5].T - (au @ args[1].T) @ (args[2] @ args[3].T).T
     assert abs(r - r2) <= 1 and r <= 7
     assert np.linalg.norm(cu @ cv.T - D) < 5e-8
+
+
+@pytest.mark.skipif(not rb.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_covariance_tiles_oracle_vs_live_reference():
+    """The realistic regime (tiles of one squared-exponential covariance matrix, ragged ranks, rank-deficient
+    stack): generator is shard invariant, the oracle agrees with the compiled reference on it."""
+    from hcore_b200.tilegen import make_covariance_batch
+    rb.set_blas_threads(1)
+    nb, maxrk, acc = 160, 96, 1e-8
+    b = make_covariance_batch(3, nb, maxrk, acc=acc)
+    b2 = make_covariance_batch(1, nb, maxrk, acc=acc, first_tile=2)
+    assert np.array_equal(b.cu[2], b2.cu[0]) and np.array_equal(b.av[2], b2.av[0]) and b.brk[2] == b2.brk[0]
+    for t in range(3):
+        a_, b_, c_ = int(b.ark[t]), int(b.brk[t]), int(b.crk[t])
+        cu, cv, r, fl = rb.hcore_gemm(b.au[t, :a_], b.av[t, :a_], b.bu[t, :b_], b.bv[t, :b_], b.cu[t], b.cv[t], c_,
+                                      alpha=-1.0, beta=1.0, rk=0, maxrk=maxrk, acc=acc)
+        cu2, cv2, r2, _ = orc.tlr_gemm_colmajor(b.au[t, :a_], b.av[t, :a_], b.bu[t, :b_], b.bv[t, :b_], b.cu[t], b.cv[t], c_,
+                                                alpha=-1.0, beta=1.0, rk=0, maxrk=maxrk, acc=acc)
+        assert r == r2 and r < a_ + c_
+        dense = b.dense_c(t, -1.0, 1.0)
+        e1, e2 = np.linalg.norm(cu[:r].T @ cv[:r] - dense), np.linalg.norm(cu2.T @ cv2 - dense)
+        assert abs(e1 - e2) <= 1e-3 * e1 + 64 * np.finfo(float).eps * np.linalg.norm(dense)

@@ -76,6 +76,28 @@ for name, dt, T, acc in () if ONLY not in ("", "sz") else (("sgemm", torch.float
     print(name, out[name], flush=True)
     del conv, d
     torch.cuda.empty_cache()
+# ---- the realistic regime: tiles of one squared-exponential covariance matrix -------------------
+if ONLY in ("", "cov"):
+    from hcore_b200.tilegen import make_covariance_batch
+    nb, maxrk, acc, reps = 1024, 128, 1e-8, 296
+    b = make_covariance_batch(8, nb, maxrk, acc=acc)          # 8 distinct problems (CPU SVDs), replicated
+    rep = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev).repeat((reps,) + (1,) * (x.ndim - 1)).contiguous()
+    t = {n: rep(getattr(b, n)) for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
+    cu0, cv0, crk0 = t["cu"].clone(), t["cv"].clone(), t["crk"].clone()
+    T = t["au"].shape[0]
+    status = torch.zeros(T, dtype=torch.int32, device=dev)
+
+    def restore():
+        t["cu"].copy_(cu0); t["cv"].copy_(cv0); t["crk"].copy_(crk0)
+    fn = lambda: ctx.dgemm_batched(-1.0, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], 1.0, t["cu"], t["cv"],
+                                   t["crk"], rk=0, maxrk=maxrk, acc=acc, status=status)
+    ms = timed(fn, restore)
+    out["covariance"] = {"nb": nb, "tiles": T, "acc": acc, "tiles_per_s": T / ms * 1e3,
+                         "ranks_in": [b.ark.tolist(), b.brk.tolist(), b.crk.tolist()],
+                         "mean_new_rank": float(t["crk"].float().mean().item()), "failed": int((status != 0).sum().item())}
+    print("covariance", out["covariance"], flush=True)
+    del t, cu0, cv0
+    torch.cuda.empty_cache()
 # ---- dense-C updates (config 3) ---------------------------------------------------------------------------
 nb, k, T = 1024, 32, (2048 if ONLY in ("", "dense") else 0)
 if T == 0:
