@@ -25,6 +25,9 @@ EXPORTED_SYMBOLS = [
     "hcore_b200_debug_fetch", "hcore_b200_debug_set_stages", "hcore_b200_set_stage_timing",
     "hcore_b200_stage_ms",
     "HCORE_dgemm", "HCORE_dgemmcd", "HCORE_dsyrk",
+    "HCORE_dgemm_qr_svd", "HCORE_dgemm_ormqr",
+    "HCORE_dgemm_batched_qr_svd", "HCORE_dgemm_batched_ormqr",
+    "HCORE_dgemm_batched_qr_svd_strided", "HCORE_dgemm_batched_ormqr_strided",
     "use_trmm", "gemm_print_index", "gemm_print_mat", "hc_nelm_limit", "syrk_print_index",
     "gemmcd_print_index", "gemmcd_print_mat", "gemmcd_use_scratch",
 ]
@@ -72,6 +75,11 @@ def load():
     L.HCORE_dgemm_batched.argtypes = [vp, i, i, d, vp, vp, vp, i, vp, vp, vp, i, d, vp, vp, vp, i, i, i, d, vp, vp]
     L.HCORE_dgemm_batched_strided.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
                                               vp, vp, vp, i, i64, i, i, d, vp, vp]
+    L.HCORE_dgemm_batched_qr_svd.argtypes = [vp, i, i, d, vp, vp, vp, i, vp, vp, vp, i, d, vp, vp, vp, i, i, i, d, vp, vp, vp]
+    L.HCORE_dgemm_batched_ormqr.argtypes = [vp, i, i, vp, vp, vp, i, vp]
+    L.HCORE_dgemm_batched_qr_svd_strided.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
+                                                     vp, vp, vp, i, i64, i, i, d, vp, vp, vp]
+    L.HCORE_dgemm_batched_ormqr_strided.argtypes = [vp, i, i, vp, vp, vp, i, i64, vp]
     f = C.c_float
     L.HCORE_sgemm_batched.argtypes = [vp, i, i, f, vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, i, i, i, f, vp, vp]
     L.HCORE_sgemm_batched_strided.argtypes = [vp, i, i, f, vp, vp, vp, i, i64, vp, vp, vp, i, i64, f,
@@ -91,6 +99,14 @@ def load():
     dp = C.POINTER(C.c_double)
     L.HCORE_dgemm.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, dp, dp, i, d, dp, dp, dp, i, i, i, d, dp, vp]
     L.HCORE_dgemm.restype = None
+    # split-phase legacy symbols (reference src/include/hcore_d.h:190-268): ranks are int*
+    ip, dpp = C.POINTER(C.c_int), C.POINTER(dp)
+    L.HCORE_dgemm_qr_svd.argtypes = [i, i, i, i, d, dp, dp, ip, i, dp, dp, ip, i, d, dp, dp, ip, i, i, i, i, d, dp, vp,
+                                     dpp, dpp, dpp, ip, ip, dpp, ip, dpp, ip, dpp, ip, dpp, ip, dpp, ip, dpp, dpp, ip, dpp]
+    L.HCORE_dgemm_qr_svd.restype = None
+    L.HCORE_dgemm_ormqr.argtypes = [i, i, i, i, d, dp, dp, ip, i, d, dp, dp, ip, i, i, i, i, d, dp, vp,
+                                    dp, dp, i, i, dp, i, dp, i, dp, i, dp, i, dp, i, dp, dp, i, dp]
+    L.HCORE_dgemm_ormqr.restype = None
     fp = C.POINTER(C.c_float)
     # reference src/include/hcore_s.h:25-46
     L.HCORE_sgemm.argtypes = [i, i, i, i, f, fp, fp, fp, i, fp, fp, fp, i, f, fp, fp, fp, i, i, i, f, fp, vp]

@@ -223,6 +223,33 @@ class Context:
             int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))
         self._check(rc)
 
+    # -- split-phase batched update (reference HCORE_dgemm_qr_svd / HCORE_dgemm_ormqr) --
+    def dgemm_batched_qr_svd(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, newrank, *, rk, maxrk, acc,
+                             status=None, stream=None):
+        """First half: stack, QR, SVD, truncation.  Writes the revealed ranks to ``newrank`` (T,) int32 and
+        leaves ``CU, CV, Crk`` untouched; the reflectors stay in the context until ``dgemm_batched_ormqr``."""
+        T, ka, nb = AU.shape
+        for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+            self._dev_f64(x, nm)
+        for nm, x in (("Ark", Ark), ("Brk", Brk), ("Crk", Crk), ("newrank", newrank)):
+            self._dev_i32(x, nm)
+        if status is not None:
+            self._dev_i32(status, "status")
+        kb, kc = BU.shape[1], CU.shape[1]
+        rc = self._L.HCORE_dgemm_batched_qr_svd_strided(
+            self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb,
+            _ptr(BU), _ptr(BV), _ptr(Brk), nb, kb * nb, float(beta), _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
+            int(rk), int(maxrk), float(acc), _ptr(newrank), _ptr(status), self._stream_ptr(stream))
+        self._check(rc)
+
+    def dgemm_batched_ormqr(self, CU, CV, Crk, stream=None):
+        """Second half: forms the new factors in ``CU, CV`` ((T, >= new rank, nb), may be freshly allocated at
+        the exact size) and sets ``Crk``."""
+        T, kc, nb = CU.shape
+        self._dev_f64(CU, "CU"); self._dev_f64(CV, "CV"); self._dev_i32(Crk, "Crk")
+        self._check(self._L.HCORE_dgemm_batched_ormqr_strided(self._h, T, nb, _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
+                                                              self._stream_ptr(stream)))
+
     def sgemm_batched(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc,
                       status=None, stream=None):
         """Batched ``HCORE_sgemm``: as :meth:`dgemm_batched` with float32 factor tensors."""

@@ -73,6 +73,8 @@ struct hcore_b200_context {
     // geometry of the last chunk (for debug_fetch)
     TlrWorkspace last_ws{};
     int last_N = 0;
+    // split-phase state (HCORE_dgemm_batched_qr_svd -> HCORE_dgemm_batched_ormqr)
+    struct { bool pending = false; int ntiles = 0, nb = 0, f32 = 0, maxrk = 0; } split;
 };
 
 namespace {
@@ -123,6 +125,13 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_apply_kernel<N, AW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)ApplySmem<AW>::kBytes));
     }
+    if (ar.phase == 2) {           // split-phase second half: reflector application only
+        dim3 grid((N + 8 * AW - 1) / (8 * AW), 2, ar.ntiles);
+        tlr_apply_kernel<N, AW><<<grid, 32 * AW, ApplySmem<AW>::kBytes, st>>>(ar, ws);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return HCORE_B200_OK;
+    }
     const bool tm = ctx->stage_timing;
     if (tm) cudaEventRecord(ctx->ev[0], st);
     if (ctx->debug_stages >= 1) {
@@ -140,7 +149,7 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[3], st);
-    if (ctx->debug_stages >= 4) {
+    if (ctx->debug_stages >= 4 && ar.phase == 0) {
         dim3 grid((N + 8 * AW - 1) / (8 * AW), 2, ar.ntiles);
         tlr_apply_kernel<N, AW><<<grid, 32 * AW, ApplySmem<AW>::kBytes, st>>>(ar, ws);
         ctx->launches++;
@@ -252,8 +261,10 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
                         const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
                         const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
                         double beta, double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
-                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32) {
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32,
+                        int phase = 0, int32_t *d_newrank = nullptr) {
     if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
+    if (phase == 1 && !d_newrank) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -261,6 +272,13 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
     const int m_pad = round_up(std::max(nb, kBlockH), kBlockH);
     const int nblk = m_pad / kBlockH;
     const int chunk = std::min(ntiles, default_chunk(ctx, N, m_pad, nblk));
+    ctx->split.pending = false;
+    if (phase == 1 && chunk < ntiles) {
+        // the reflectors of every tile have to survive until the second half: one workspace chunk
+        ctx->err = "split-phase batch exceeds the workspace chunk (" + std::to_string(chunk) +
+                   " tiles): split the batch or raise hcore_b200_set_chunk()";
+        return HCORE_B200_ERR_ARG;
+    }
 
     CUDA_TRY(ctx, ctx->rec.reserve(2ull * chunk * nblk * (N / kSubW) * kRecBytes));
     CUDA_TRY(ctx, ctx->G.reserve((size_t)chunk * m_pad * N * 8));
@@ -293,6 +311,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
         ar.nb = nb; ar.lda = lda; ar.ldb = ldb; ar.ldc = ldc;
         ar.alpha = alpha; ar.beta = beta; ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc;
         ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0); ar.f32 = f32;
+        ar.phase = phase; ar.rank_out = (phase == 1) ? d_newrank : d_Crk;
         int rc;
         switch (N) {
             case 32: rc = launch_chunk_n<32>(ctx, ar, ws, st); break;
@@ -301,7 +320,35 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
         }
         if (rc != HCORE_B200_OK) return rc;
     }
+    if (phase == 1) {
+        ctx->split.pending = true; ctx->split.ntiles = ntiles; ctx->split.nb = nb; ctx->split.f32 = f32;
+        ctx->split.maxrk = maxrk;
+    }
     return HCORE_B200_OK;
+}
+
+// Second half of a split-phase update: CU = Q_u [U_r; 0], CV = Q_v [W; 0] written to the caller's (possibly
+// re-allocated) factor arrays, Crk <- new rank.  The reflectors are the ones phase 1 left in the workspace.
+static int tlr_batched_apply(hcore_b200_handle_t ctx, int ntiles, int nb, double *const *d_CU, double *const *d_CV,
+                             int32_t *d_Crk, int ldc, void *stream) {
+    if (!ctx || ldc < nb) return HCORE_B200_ERR_ARG;
+    if (!ctx->split.pending || ctx->split.ntiles != ntiles || ctx->split.nb != nb) {
+        ctx->err = "HCORE_dgemm_batched_ormqr without a matching HCORE_dgemm_batched_qr_svd on this handle";
+        return HCORE_B200_ERR_ARG;
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TlrArgs ar{};
+    ar.CU = d_CU; ar.CV = d_CV; ar.Crk = d_Crk; ar.rank_out = d_Crk; ar.status = nullptr;
+    ar.nb = nb; ar.ldc = ldc; ar.tile0 = 0; ar.ntiles = ntiles; ar.f32 = ctx->split.f32; ar.phase = 2;
+    ar.maxrk = ctx->split.maxrk;
+    int rc;
+    switch (ctx->last_N) {
+        case 32: rc = launch_chunk_n<32>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
+        case 64: rc = launch_chunk_n<64>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
+        default: rc = launch_chunk_n<128>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
+    }
+    ctx->split.pending = false;
+    return rc;
 }
 
 // strided factor arrays -> pointer arrays (on the device), then the pointer-array path
@@ -309,7 +356,8 @@ static int tlr_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, doub
                         const void *d_AU, const void *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
                         const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
                         double beta, void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
-                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32) {
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32,
+                        int phase = 0, int32_t *d_newrank = nullptr) {
     if (!ctx || ntiles < 0) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -327,7 +375,8 @@ static int tlr_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, doub
     CUDA_TRY(ctx, cudaGetLastError());
     return tlr_batched(ctx, ntiles, nb, alpha, pp, pp + ntiles, d_Ark, lda, pp + 2 * (size_t)ntiles,
                        pp + 3 * (size_t)ntiles, d_Brk, ldb, beta, (double *const *)(pp + 4 * (size_t)ntiles),
-                       (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, rk, maxrk, acc, d_status, stream, f32);
+                       (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, rk, maxrk, acc, d_status, stream, f32,
+                       phase, d_newrank);
 }
 
 extern "C" {
@@ -339,6 +388,48 @@ int HCORE_dgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alph
                         int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
     return tlr_batched(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, d_BU, d_BV, d_Brk, ldb, beta, d_CU, d_CV, d_Crk, ldc,
                        rk, maxrk, acc, d_status, stream, 0);
+}
+
+// ---- split-phase update (reference HCORE_dgemm_qr_svd / HCORE_dgemm_ormqr, src/compute/hcore_dgemm.c:1312-1699) ----
+int HCORE_dgemm_batched_qr_svd(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
+                        double beta, const double *const *d_CU, const double *const *d_CV, const int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc, int32_t *d_newrank, int32_t *d_status, void *stream) {
+    return tlr_batched(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, d_BU, d_BV, d_Brk, ldb, beta,
+                       (double *const *)d_CU, (double *const *)d_CV, const_cast<int32_t *>(d_Crk), ldc, rk, maxrk, acc,
+                       d_status, stream, 0, 1, d_newrank);
+}
+
+int HCORE_dgemm_batched_ormqr(hcore_b200_handle_t ctx, int ntiles, int nb, double *const *d_CU, double *const *d_CV,
+                        int32_t *d_Crk, int ldc, void *stream) {
+    return tlr_batched_apply(ctx, ntiles, nb, d_CU, d_CV, d_Crk, ldc, stream);
+}
+
+int HCORE_dgemm_batched_qr_svd_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double beta, const double *d_CU, const double *d_CV, const int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_newrank, int32_t *d_status, void *stream) {
+    return tlr_batched_strided(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, strideA, d_BU, d_BV, d_Brk, ldb, strideB, beta,
+                               const_cast<double *>(d_CU), const_cast<double *>(d_CV), const_cast<int32_t *>(d_Crk), ldc,
+                               strideC, rk, maxrk, acc, d_status, stream, 0, 1, d_newrank);
+}
+
+int HCORE_dgemm_batched_ormqr_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double *d_CU, double *d_CV,
+                        int32_t *d_Crk, int ldc, int64_t strideC, void *stream) {
+    if (!ctx || ntiles <= 0) return ntiles == 0 ? HCORE_B200_OK : HCORE_B200_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // the pointer table of phase 1 is still in ctx->ptrs (6 x ntiles): slots 4 and 5 are re-filled
+    CUDA_TRY(ctx, ctx->ptrs.reserve(6ull * ntiles * sizeof(double *)));
+    const double **pp = (const double **)ctx->ptrs.p;
+    const int thr = 256, blk = (ntiles + thr - 1) / thr;
+    fill_ptrs_kernel<<<blk, thr, 0, st>>>(pp + 4 * (size_t)ntiles, (const char *)d_CU, strideC * 8, ntiles);
+    fill_ptrs_kernel<<<blk, thr, 0, st>>>(pp + 5 * (size_t)ntiles, (const char *)d_CV, strideC * 8, ntiles);
+    ctx->launches += 2;
+    return tlr_batched_apply(ctx, ntiles, nb, (double *const *)(pp + 4 * (size_t)ntiles),
+                             (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, stream);
 }
 
 int HCORE_sgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, float alpha,
@@ -691,6 +782,105 @@ void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha, doub
     const int rnew = legacy_gemm("HCORE_dgemm", 8, M, alpha, AU, AV, a, LDA, BU, BV, b, LDB, beta, CU, CV, c, LDC, rk, maxrk, acc);
     if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
     Crk[0] = (double)rnew;
+}
+
+// ---- split-phase legacy symbols (reference src/compute/hcore_dgemm.c:1312-1597 and :1602-1699) -----------
+// HCORE_dgemm_qr_svd reveals the new rank, the caller may re-size its C factors, HCORE_dgemm_ormqr then
+// forms them.  The reference hands its intermediate host buffers from one call to the other through 19
+// pass-through parameters; here the intermediates (block reflectors, U_r, W) stay on the device in the
+// process-wide context, so the pass-through pointers are returned as NULL / the caller's own CU, CV, and
+// the two calls must be paired (qr_svd, then ormqr for the same tile, no other legacy call in between).
+static struct { bool pending = false; int M = 0, n = 0, rnew = 0, LDC = 0; char *dCU = nullptr, *dCV = nullptr; } g_split;
+
+static uint64_t ormqr_flops(uint64_t m, uint64_t n, uint64_t r) {       // the two dormqr terms of the model
+    return (4 * r * m * n - 2 * r * n * n + 3 * r * n) + (4 * m * r * n - 2 * r * n * n + 2 * r * n + m * n - n * n / 2 + n / 2);
+}
+
+void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha, double *AU, double *AV, int *Ark, int LDA,
+                        double *BU, double *BV, int *Brk, int LDB, double beta, double *CU, double *CV, int *Crk, int LDC,
+                        int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
+                        double **_p_work_new, double **_p__CU, double **_p__CV, int *_p_CU_ncols, int *_p_new_UVrk,
+                        double **_p_newU, int *_p_ld_newU, double **_p_qrtauA, int *_p_CV_ncols, double **_p_newV,
+                        int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
+                        int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
+                        double **_p__CV_save) {
+    (void)transA; (void)transB; (void)N; (void)storage_maxrank;
+    const char *who = "HCORE_dgemm_qr_svd";
+    const int a = Ark[0], b = Brk[0], c = Crk[0];
+    std::lock_guard<std::mutex> lock(g_mu);
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    if (a == 0 || b == 0 || c == 0) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
+    // the split-phase variant accepts Ark + Crk up to 2 * maxrk (reference :1186, :1259)
+    if (2 * maxrk < a + c) legacy_fail(who, "increase maxrank (2 * maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
+    const int cap = std::max(maxrk, a + c);
+    cudaSetDevice(ctx->device);
+    const size_t fa = (size_t)LDA * a * 8, fb = (size_t)LDB * b * 8, fcin = (size_t)LDC * c * 8;
+    const size_t fc = ((size_t)LDC * (a + c) * 8 + 15) / 16 * 16;
+    const size_t fa16 = (fa + 15) / 16 * 16, fb16 = (fb + 15) / 16 * 16;
+    if (ctx->stage[0].reserve(2 * fa16 + 2 * fb16 + 2 * fc) != cudaSuccess ||
+        ctx->stage_ints[0].reserve(8 * sizeof(int)) != cudaSuccess)
+        legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+    char *base = (char *)ctx->stage[0].p;
+    char *dAU = base, *dAV = base + fa16, *dBU = base + 2 * fa16, *dBV = base + 2 * fa16 + fb16,
+         *dCU = base + 2 * fa16 + 2 * fb16, *dCV = base + 2 * fa16 + 2 * fb16 + fc;
+    int *di = (int *)ctx->stage_ints[0].p;
+    int hi[5] = {a, b, c, 0, 0};
+    cudaStream_t st = ctx->streams[0];
+    cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    int rc = tlr_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV, di + 2,
+                                 LDC, 0, rk, cap, acc, di + 3, st, 0, 1, di + 4);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+    cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
+    const int rnew = hi[4];
+    g_split.pending = true; g_split.M = M; g_split.n = a + c; g_split.rnew = rnew; g_split.LDC = LDC;
+    g_split.dCU = dCU; g_split.dCV = dCV;
+    if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew) - ormqr_flops(M, a + c, rnew);
+    *_p_work_new = work; *_p__CU = CU; *_p__CV = CV; *_p_CU_ncols = a + c; *_p_new_UVrk = rnew;
+    *_p_newU = nullptr; *_p_ld_newU = M; *_p_qrtauA = nullptr; *_p_CV_ncols = a + c; *_p_newV = nullptr;
+    *_p_ld_newV = maxrk; *_p_qrtauB = nullptr; *_p_use_CUV_clone = 0; *_p_CUclone = nullptr; *_p_ld_CUclone = M;
+    *_p__CU_save = CU; *_p_CVclone = nullptr; *_p_ld_CVclone = M; *_p__CV_save = CV;
+}
+
+void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha, double *AU, double *AV, int *Ark, int LDA,
+                       double beta, double *CU, double *CV, int *Crk, int LDC, int rk, int storage_maxrank, int maxrk,
+                       double acc, double *work, flop_counter *flops, double *_CU, double *_CV, int CU_ncols,
+                       int new_UVrk, double *newU, int ld_newU, double *qrtauA, int CV_ncols, double *newV, int ld_newV,
+                       double *qrtauB, int use_CUV_clone, double *CUclone, int ld_CUclone, double *_CU_save,
+                       double *CVclone, int ld_CVclone, double *_CV_save) {
+    (void)transA; (void)transB; (void)N; (void)alpha; (void)AU; (void)AV; (void)Ark; (void)LDA; (void)beta; (void)rk;
+    (void)maxrk; (void)acc; (void)work; (void)CU_ncols; (void)newU; (void)ld_newU; (void)qrtauA; (void)CV_ncols; (void)newV;
+    (void)ld_newV; (void)qrtauB; (void)use_CUV_clone; (void)CUclone; (void)ld_CUclone; (void)CVclone; (void)ld_CVclone;
+    (void)_CU; (void)_CV;
+    const char *who = "HCORE_dgemm_ormqr";
+    std::lock_guard<std::mutex> lock(g_mu);
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    if (!g_split.pending || g_split.M != M || g_split.rnew != new_UVrk)
+        legacy_fail(who, "no matching HCORE_dgemm_qr_svd call precedes this one", HCORE_B200_ERR_ARG);
+    if (new_UVrk > storage_maxrank) {                     // reference :1649-1652
+        fprintf(stderr, "%s: Increase storage maxrank %d. Observed rank for U and V is %d\n", who, storage_maxrank, new_UVrk);
+        exit(-1);
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->streams[0];
+    int *di = (int *)ctx->stage_ints[0].p;
+    // the device copies keep the leading dimension of the first call; the host arrays may have a new one
+    int rc = HCORE_dgemm_batched_ormqr_strided(ctx, 1, M, (double *)g_split.dCU, (double *)g_split.dCV, di + 2, g_split.LDC, 0, st);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+    double *outU = _CU_save ? _CU_save : CU, *outV = _CV_save ? _CV_save : CV;
+    cudaMemcpy2DAsync(outU, (size_t)LDC * 8, g_split.dCU, (size_t)g_split.LDC * 8, (size_t)M * 8, new_UVrk, cudaMemcpyDeviceToHost, st);
+    cudaMemcpy2DAsync(outV, (size_t)LDC * 8, g_split.dCV, (size_t)g_split.LDC * 8, (size_t)M * 8, new_UVrk, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    if (flops) flops->update += ormqr_flops(M, g_split.n, new_UVrk);
+    Crk[0] = new_UVrk;
+    g_split.pending = false;
 }
 
 // reference src/compute/hcore_sgemm.c:703 (float clone of HCORE_dgemm; ranks travel as float)

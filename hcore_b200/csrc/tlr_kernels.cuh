@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
         ws.sweeps[t] = sweeps;
         ws.st[t] = st;
         if (ar.status) ar.status[gt] = st;
-        if (st == HCORE_B200_OK) ar.Crk[gt] = rnew;
+        if (st == HCORE_B200_OK) ar.rank_out[gt] = rnew;
     }
     if (st != HCORE_B200_OK) return;
     PROF_ADD(15);

@@ -151,6 +151,9 @@ struct TlrArgs {
     int tile0;            // first tile of this chunk in the user arrays
     int ntiles;           // tiles in this chunk
     int f32;              // 1: the user arrays hold float (HCORE_sgemm); arithmetic stays FP64
+    int *rank_out;        // where the new rank goes: Crk (fused call, phase 2) or the caller's new-rank array (phase 1)
+    int phase;            // 0: whole update; 1: stack + QR + SVD only (HCORE_dgemm_qr_svd); 2: reflector application
+                          //    only, into possibly re-allocated CU/CV (HCORE_dgemm_ormqr)
 };
 
 // User-array element access: the factor arrays are double, or float when ar.f32 is set (the
@@ -793,8 +796,11 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_apply_kernel(TlrArgs ar,
     const int t = blockIdx.z, pnl = blockIdx.y, col0 = blockIdx.x * 8 * NW;
     if (ws.st[t] != HCORE_B200_OK) return;
     const int rnew = ws.newrank[t];
-    if (col0 >= rnew) return;
     const int gt = ar.tile0 + t;
+    // split-phase call: the rank revealed by phase 1 becomes the tile's rank now (reference
+    // HCORE_dgemm_ormqr, src/compute/hcore_dgemm.c:1688, Crk[0] = new_Crk)
+    if (ar.phase == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && ar.rank_out) ar.rank_out[gt] = rnew;
+    if (col0 >= rnew) return;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
     const int n16 = round_up(ws.ncols[t], kPanelW);

@@ -154,6 +154,36 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t handle, int ntiles, int nb,
                         int rk, int maxrk, double acc,
                         int32_t *h_status);
 
+/* ---- split-phase batched update (device pointers) --------------------------------------
+ * Batched form of the reference's HCORE_dgemm_qr_svd / HCORE_dgemm_ormqr pair
+ * (src/compute/hcore_dgemm.c:1312-1597, :1602-1699): phase 1 stacks, factors and truncates every
+ * tile and writes the revealed ranks to d_newrank WITHOUT touching CU, CV or Crk; the caller may
+ * then allocate exact-size factor arrays; phase 2 forms CU = Q_u [U_r; 0], CV = Q_v [W; 0] in the
+ * arrays it is given (any ldc >= nb) and sets Crk.  The block reflectors stay in the handle's
+ * workspace between the two calls, so ntiles must fit one workspace chunk (hcore_b200_set_chunk;
+ * default 16 x #SM tiles) and no other update may run on the handle in between
+ * (HCORE_B200_ERR_ARG otherwise).  The fused call and the pair give bit-identical factors. */
+int HCORE_dgemm_batched_qr_svd(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
+                        double beta,
+                        const double *const *d_CU, const double *const *d_CV, const int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_newrank, int32_t *d_status, void *stream);
+int HCORE_dgemm_batched_ormqr(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc, void *stream);
+int HCORE_dgemm_batched_qr_svd_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double beta,
+                        const double *d_CU, const double *d_CV, const int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_newrank, int32_t *d_status, void *stream);
+int HCORE_dgemm_batched_ormqr_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC, void *stream);
+
 /* ---- batched dense-C updates (device pointers) ---------------------------------------- */
 /* Batched HCORE_dgemmcd (reference src/compute/hcore_dgemmcd.c:36-107):
  *   CD[t] <- CD[t] - (Au Av^T)(Bu Bv^T)^T ; alpha/beta are hard-wired to -1/+1 there. */

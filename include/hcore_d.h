@@ -37,6 +37,32 @@ void HCORE_dsyrk(HCORE_enum uplo, HCORE_enum trans, int N, int K, double alpha,
                  const double *AU, int LDAU, const double *AV, int LDAV,
                  double beta, double *CD, int LDCD, double *work, flop_counter *flops);
 
+/* Split-phase update (reference src/include/hcore_d.h:190-268, src/compute/hcore_dgemm.c:1312-1597 and
+ * :1602-1699): HCORE_dgemm_qr_svd stacks, factors and truncates and returns the new rank in
+ * *_p_new_UVrk so that the caller can re-size CU/CV; HCORE_dgemm_ormqr then writes the new factors (to
+ * _CU_save / _CV_save with leading dimension LDC) and sets Crk[0].  Ranks travel as int here (as in
+ * the reference's split API).  Same prototypes as the reference; the intermediates stay on the device,
+ * so the pass-through pointers come back as NULL (or the caller's CU/CV) and the two calls must be
+ * paired: qr_svd, then ormqr for the same tile, with no other HCORE_* call in between. */
+void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha,
+                        double *AU, double *AV, int *Ark, int LDA,
+                        double *BU, double *BV, int *Brk, int LDB,
+                        double beta, double *CU, double *CV, int *Crk, int LDC,
+                        int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
+                        double **_p_work_new, double **_p__CU, double **_p__CV, int *_p_CU_ncols, int *_p_new_UVrk,
+                        double **_p_newU, int *_p_ld_newU, double **_p_qrtauA, int *_p_CV_ncols, double **_p_newV,
+                        int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
+                        int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
+                        double **_p__CV_save);
+void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha,
+                       double *AU, double *AV, int *Ark, int LDA,
+                       double beta, double *CU, double *CV, int *Crk, int LDC,
+                       int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
+                       double *_CU, double *_CV, int CU_ncols, int new_UVrk, double *newU, int ld_newU,
+                       double *qrtauA, int CV_ncols, double *newV, int ld_newV, double *qrtauB,
+                       int use_CUV_clone, double *CUclone, int ld_CUclone, double *_CU_save,
+                       double *CVclone, int ld_CVclone, double *_CV_save);
+
 /* Link-compatible tunables the reference library defines (reference
  * src/compute/hcore_dgemm.c:37-43, hcore_dsyrk.c:21, hcore_dgemmcd.c:24-26).  They are
  * accepted and ignored: there is no scratch protocol and no printing on the GPU path.

@@ -389,3 +389,75 @@ def test_dgemmcd_dsyrk_batched_vs_oracle(ctx, nb, ka, kb):
         out = c2[i].cpu().numpy().T
         assert np.abs(out - ref).max() < 1000 * EPS * max(1.0, np.abs(ref).max())
         assert np.abs(np.triu(out, 1)).max() == 0.0
+
+
+# ---- (5) split-phase API: rank first, factors into exact-size arrays afterwards ------------------------------
+
+def test_split_phase_batched_equals_fused(ctx):
+    """HCORE_dgemm_batched_qr_svd + HCORE_dgemm_batched_ormqr (reference HCORE_dgemm_qr_svd / _ormqr,
+    src/compute/hcore_dgemm.c:1312-1699) give the fused call's factors bit for bit, written into freshly
+    allocated arrays of exactly max(new rank) columns; phase 1 leaves C untouched."""
+    nb, k, T = 320, 24, 5
+    b = make_lr_batch(T, nb, k, base_seed=77)
+    cu_f, cv_f, crk_f, st_f = _run_batch(ctx, b, -1.0, 1.0, 0, 2 * k, 1e-8)
+    t = _to_dev(b)
+    newrank = torch.zeros(T, dtype=torch.int32, device="cuda:0")
+    status = torch.full((T,), -7, dtype=torch.int32, device="cuda:0")
+    cu_before, crk_before = t["cu"].clone(), t["crk"].clone()
+    ctx.dgemm_batched_qr_svd(-1.0, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], 1.0, t["cu"], t["cv"], t["crk"],
+                             newrank, rk=0, maxrk=2 * k, acc=1e-8, status=status)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    assert torch.equal(t["cu"], cu_before) and torch.equal(t["crk"], crk_before)
+    assert np.array_equal(newrank.cpu().numpy(), crk_f)
+    rmax = int(newrank.max().item())
+    cu_new = torch.zeros((T, rmax, nb), dtype=torch.float64, device="cuda:0")
+    cv_new = torch.zeros_like(cu_new)
+    ctx.dgemm_batched_ormqr(cu_new, cv_new, t["crk"])
+    torch.cuda.synchronize()
+    assert np.array_equal(t["crk"].cpu().numpy(), crk_f)
+    for i in range(T):
+        r = int(crk_f[i])
+        assert np.array_equal(cu_new[i, :r].cpu().numpy(), cu_f[i, :r])
+        assert np.array_equal(cv_new[i, :r].cpu().numpy(), cv_f[i, :r])
+    # a second half without a first half is refused
+    with pytest.raises(Exception):
+        ctx.dgemm_batched_ormqr(cu_new, cv_new, t["crk"])
+
+
+def test_split_phase_legacy_symbols():
+    """HCORE_dgemm_qr_svd / HCORE_dgemm_ormqr with the reference's prototypes (host pointers, int ranks):
+    same factors and flop count as the one-call HCORE_dgemm; the caller re-allocates C in between."""
+    import ctypes as C
+    from hcore_b200 import _lib
+    L = _lib.load()
+    nb, k = 200, 12
+    b = make_lr_batch(1, nb, k, base_seed=5)
+    au, av, bu, bv = (np.ascontiguousarray(x[0]) for x in (b.au, b.av, b.bu, b.bv))
+    cu = np.zeros((2 * k, nb)); cv = np.zeros((2 * k, nb)); cu[:k] = b.cu[0][:k]; cv[:k] = b.cv[0][:k]
+    ref_cu, ref_cv, crk = cu.copy(), cv.copy(), np.array([float(k)])
+    fl1 = api.FlopCounter()
+    api.hcore_dgemm(111, 112, nb, nb, -1.0, au, av, np.array([float(k)]), nb, bu, bv, np.array([float(k)]), nb, 1.0,
+                    ref_cu, ref_cv, crk, nb, 0, 2 * k, 1e-8, flops=fl1)
+    r_ref = int(crk[0])
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    P = lambda x: x.ctypes.data_as(dp)
+    ark, brk, ck = (C.c_int * 1)(k), (C.c_int * 1)(k), (C.c_int * 1)(k)
+    outs_p = [dp() for _ in range(11)]; outs_i = [C.c_int() for _ in range(8)]
+    fl2 = api.FlopCounter()
+    o = outs_p; n = outs_i
+    L.HCORE_dgemm_qr_svd(111, 112, nb, nb, -1.0, P(au), P(av), ark, nb, P(bu), P(bv), brk, nb, 1.0, P(cu), P(cv), ck, nb,
+                         0, 2 * k, 2 * k, 1e-8, None, C.byref(fl2),
+                         C.byref(o[0]), C.byref(o[1]), C.byref(o[2]), C.byref(n[0]), C.byref(n[1]), C.byref(o[3]), C.byref(n[2]),
+                         C.byref(o[4]), C.byref(n[3]), C.byref(o[5]), C.byref(n[4]), C.byref(o[6]), C.byref(n[5]), C.byref(o[7]),
+                         C.byref(n[6]), C.byref(o[8]), C.byref(o[9]), C.byref(n[7]), C.byref(o[10]))
+    rnew = n[1].value
+    assert rnew == r_ref and ck[0] == k and n[0].value == 2 * k
+    # the caller re-allocates C at the revealed rank (leading dimension unchanged) and finishes the update
+    cu2 = np.zeros((rnew, nb)); cv2 = np.zeros((rnew, nb))
+    L.HCORE_dgemm_ormqr(111, 112, nb, nb, -1.0, P(au), P(av), ark, nb, 1.0, P(cu2), P(cv2), ck, nb, 0, 2 * k, 2 * k, 1e-8,
+                        None, C.byref(fl2), o[1], o[2], n[0].value, rnew, o[3], n[2].value, o[4], n[3].value, o[5], n[4].value,
+                        o[6], n[5].value, o[7], n[6].value, P(cu2), o[9], n[7].value, P(cv2))
+    assert ck[0] == rnew
+    assert np.array_equal(cu2, ref_cu[:rnew]) and np.array_equal(cv2, ref_cv[:rnew])
+    assert fl2.update == fl1.update
