@@ -568,9 +568,15 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hco
     ws.sigma = (double *)ctx->zsigma.p;
     ws.ncols = (int *)ctx->zints.p; ws.newrank = ws.ncols + chunk; ws.st = ws.newrank + chunk; ws.sweeps = ws.st + chunk;
     ws.chunk = chunk; ws.N = N;
-    const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = 8ull * nb * sizeof(zc);
+    // apply kernel: W column buffers + 2 reflector buffers of nb complex each; W = 8, 4 or 2 warps
+    int apw = 8;
+    while (apw > 2 && (size_t)(apw + 2) * nb * sizeof(zc) > 227 * 1024) apw >>= 1;
+    const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = (size_t)(apw + 2) * nb * sizeof(zc);
     if (sm_ap > 227 * 1024) { ctx->err = "HCORE_zgemm: nb too large for the apply kernel's shared memory"; return HCORE_B200_ERR_ARG; }
+    const size_t sm_qrb = (2ull * kZB * nb + 16 + 2 * kZB) * sizeof(double);
     CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qr));
+    if (nb <= 32 * kZRows)
+        CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qrb));
     CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ap));
     for (int t0 = 0; t0 < ntiles; t0 += chunk) {
         ZArgs ar{};
@@ -582,9 +588,10 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hco
         ar.alpha = make_double2(alpha.re, alpha.im); ar.beta = make_double2(beta.re, beta.im);
         ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc; ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
         ztlr_stack_kernel<<<ar.ntiles, 256, 0, st>>>(ar, ws);
-        ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
+        if (nb <= 32 * kZRows) ztlr_qr_blocked_kernel<<<2 * ar.ntiles, 256, sm_qrb, st>>>(ar, ws);
+        else ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
         ztlr_svd_kernel<<<ar.ntiles, 512, 0, st>>>(ar, ws);
-        ztlr_apply_kernel<<<dim3((N + 7) / 8, 2, ar.ntiles), 256, sm_ap, st>>>(ar, ws);
+        ztlr_apply_kernel<<<dim3((N + apw - 1) / apw, 2, ar.ntiles), 32 * apw, sm_ap, st>>>(ar, ws);
         ctx->launches += 4;
     }
     CUDA_TRY(ctx, cudaGetLastError());

@@ -16,6 +16,7 @@
 //                      column per warp held in shared memory (replaces LAPACKE_zunmqr, :470-530, :600-620)
 #pragma once
 #include "common.cuh"
+#include "wy_kernels.cuh"
 
 namespace hcore_b200 {
 
@@ -187,6 +188,122 @@ __global__ void __launch_bounds__(512) ztlr_qr_kernel(ZArgs ar, ZWorkspace ws) {
     }
 }
 
+// ---- 2b. blocked Householder QR (nb <= 1024) ----------------------------------------------------------------
+// Same reflectors as ztlr_qr_kernel (zgeqr2 order of operations per column), but the panel is streamed from
+// HBM once per 8-column block instead of once per column: the 8 block columns are factored in shared memory,
+// then every trailing column is loaded into REGISTERS (a warp per column, 32 rows per lane), hit by the 8
+// reflectors in sequence (reflector vectors from shared memory) and written back.  The unblocked kernel
+// moved 268 MB per panel through HBM (66 ms per 592 tiles, HBM-bound); this one moves 33 MB.
+constexpr int kZB = 8;          // block width
+constexpr int kZRows = 32;      // rows per lane of a trailing column: nb - j0 <= 32 * kZRows
+
+__global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspace ws) {
+    extern __shared__ __align__(16) double zsm[];
+    const int t = blockIdx.x >> 1, pnl = blockIdx.x & 1;
+    if (ws.st[t] != HCORE_B200_OK) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int n = ws.ncols[t], m = ar.nb;
+    zc *X = zpanel(ws, pnl, t, m);
+    zc *tau_g = ws.tau + ((size_t)pnl * ws.chunk + t) * ws.N;
+    zc *P = reinterpret_cast<zc *>(zsm);                       // [kZB][m] block columns (row index absolute)
+    double *red = zsm + 2 * (size_t)kZB * m;                   // [8] partial sums, [8..11] tau, scale
+    zc *taus = reinterpret_cast<zc *>(red + 16);               // [kZB]
+    for (int j0 = 0; j0 < n; j0 += kZB) {
+        const int nbk = (n - j0 < kZB) ? (n - j0) : kZB;
+        for (int c = 0; c < nbk; ++c)
+            for (int r = j0 + tid; r < m; r += blockDim.x) P[(size_t)c * m + r] = X[(size_t)(j0 + c) * m + r];
+        __syncthreads();
+        // ---- the block's columns, in shared memory -------------------------------------------------
+        for (int jj = 0; jj < nbk; ++jj) {
+            const int j = j0 + jj;
+            zc *pj = P + (size_t)jj * m;
+            double s = 0.0;
+            for (int r = j + 1 + tid; r < m; r += blockDim.x) s += zabs2(pj[r]);
+            s = warp_sum(s);
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            if (tid == 0) {
+                double xn2 = 0.0;
+                for (int w = 0; w < nwarps; ++w) xn2 += red[w];
+                const zc alpha = pj[j];
+                zc tau = zmake(0.0, 0.0), scale = zmake(0.0, 0.0);
+                if (xn2 != 0.0 || alpha.y != 0.0) {                       // LAPACK zlarfg
+                    const double beta = -copysign(sqrt(zabs2(alpha) + xn2), alpha.x);
+                    tau = zmake((beta - alpha.x) / beta, -alpha.y / beta);
+                    const zc d = zmake(alpha.x - beta, alpha.y);
+                    const double dn = zabs2(d);
+                    scale = zmake(d.x / dn, -d.y / dn);                   // 1 / (alpha - beta)
+                    pj[j] = zmake(beta, 0.0);
+                }
+                tau_g[j] = tau;
+                taus[jj] = tau;
+                red[8] = tau.x; red[9] = tau.y; red[10] = scale.x; red[11] = scale.y;
+            }
+            __syncthreads();
+            const zc tau = zmake(red[8], red[9]), scale = zmake(red[10], red[11]);
+            for (int r = j + 1 + tid; r < m; r += blockDim.x) pj[r] = zmul(pj[r], scale);
+            __syncthreads();
+            if (tau.x != 0.0 || tau.y != 0.0) {
+                const zc ctau = zconj(tau);                                // H^H = I - conj(tau) v v^H
+                for (int c = jj + 1 + warp; c < nbk; c += nwarps) {
+                    zc *pc = P + (size_t)c * m;
+                    zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
+                    int r = j + 1 + lane;
+                    for (; r + 32 < m; r += 64) { d0 = zcfma(pj[r], pc[r], d0); d1 = zcfma(pj[r + 32], pc[r + 32], d1); }
+                    if (r < m) d0 = zcfma(pj[r], pc[r], d0);
+                    zc dot = zwarp_sum(zadd(d0, d1));
+                    dot = zadd(dot, pc[j]);
+                    const zc tw = zmul(ctau, dot), ntw = zmake(-tw.x, -tw.y);
+                    __syncwarp();
+                    if (lane == 0) pc[j] = zsub(pc[j], tw);
+                    for (int q = j + 1 + lane; q < m; q += 32) pc[q] = zfma(ntw, pj[q], pc[q]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- trailing columns: one warp per column, the column in registers ---------------------------
+        for (int c = j0 + nbk + warp; c < n; c += nwarps) {
+            zc *xc = X + (size_t)c * m;
+            zc x[kZRows];
+#pragma unroll
+            for (int i = 0; i < kZRows; ++i) {
+                const int r = j0 + lane + 32 * i;
+                x[i] = (r < m) ? xc[r] : zmake(0.0, 0.0);
+            }
+            for (int jj = 0; jj < nbk; ++jj) {
+                const zc tau = taus[jj];
+                if (tau.x == 0.0 && tau.y == 0.0) continue;
+                const int j = j0 + jj;
+                const zc *pj = P + (size_t)jj * m;
+                zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < kZRows; ++i) {
+                    const int r = j0 + lane + 32 * i;
+                    const zc v = (r > j && r < m) ? pj[r] : zmake(r == j ? 1.0 : 0.0, 0.0);
+                    if (i & 1) d1 = zcfma(v, x[i], d1); else d0 = zcfma(v, x[i], d0);
+                }
+                const zc dot = zwarp_sum(zadd(d0, d1));
+                const zc tw = zmul(zconj(tau), dot), ntw = zmake(-tw.x, -tw.y);
+#pragma unroll
+                for (int i = 0; i < kZRows; ++i) {
+                    const int r = j0 + lane + 32 * i;
+                    const zc v = (r > j && r < m) ? pj[r] : zmake(r == j ? 1.0 : 0.0, 0.0);
+                    x[i] = zfma(ntw, v, x[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kZRows; ++i) {
+                const int r = j0 + lane + 32 * i;
+                if (r < m) xc[r] = x[i];
+            }
+        }
+        // ---- the factored block goes back (reflectors below the diagonal, R on and above) -----------------
+        for (int c = 0; c < nbk; ++c)
+            for (int r = j0 + tid; r < m; r += blockDim.x) X[(size_t)(j0 + c) * m + r] = P[(size_t)c * m + r];
+        __syncthreads();
+    }
+}
+
 // ---- 3. core SVD ------------------------------------------------------------------------------------------
 constexpr double kZTolRot = 1e-15, kZTolStop = 1e-7;
 constexpr int kZMaxSweeps = 60;
@@ -319,40 +436,68 @@ __global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) 
 }
 
 // ---- 4. reflector application --------------------------------------------------------------------------------
-// grid = (ceil(N / 8), 2, tiles), 256 threads: every warp owns one output column, kept in shared
-// memory (m complex per warp), and applies H_{n-1}, ..., H_0 to [y; 0].
+// grid = (ceil(N / W), 2, tiles), W warps: every warp owns one output column, kept in shared memory
+// (m complex per warp), and applies H_{n-1}, ..., H_0 to [y; 0].  The reflector vectors are staged ONCE
+// per CTA through a double-buffered cp.async pipeline (reflector j-1 travels while j is applied) and
+// shared by the W columns; the first version had every warp stream every reflector from L2 with
+// dependent loads (86 ms per 592 tiles at nb = 1024, k = 64).
 __global__ void __launch_bounds__(256) ztlr_apply_kernel(ZArgs ar, ZWorkspace ws) {
     extern __shared__ __align__(16) double zsm[];
     const int t = blockIdx.z, pnl = blockIdx.y;
     if (ws.st[t] != HCORE_B200_OK) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = blockIdx.x * 8 + warp;
+    const int W = blockDim.x >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col = blockIdx.x * W + warp;
     const int rnew = ws.newrank[t];
-    if (col >= rnew) return;
+    if ((int)blockIdx.x * W >= rnew) return;                 // whole CTA idle
+    const bool on = col < rnew;
     const int gt = ar.tile0 + t;
     const int n = ws.ncols[t], m = ar.nb, N = ws.N;
     const zc *X = zpanel(ws, pnl, t, m);
     const zc *tau_g = ws.tau + ((size_t)pnl * ws.chunk + t) * N;
     const zc *y = ws.Y + ((size_t)pnl * ws.chunk + t) * N * N + (size_t)col * N;
     zc *z = reinterpret_cast<zc *>(zsm) + (size_t)warp * m;
+    zc *vbuf = reinterpret_cast<zc *>(zsm) + (size_t)W * m;   // [2][m]
     zc *out = (pnl == 0 ? ar.CU : ar.CV) + (size_t)gt * ar.strideC + (size_t)col * ar.ldc;
-    for (int r = lane; r < m; r += 32) z[r] = (r < n) ? y[r] : zmake(0.0, 0.0);
-    __syncwarp();
-    for (int j = n - 1; j >= 0; --j) {
-        const zc tau = tau_g[j];
-        if (tau.x == 0.0 && tau.y == 0.0) continue;
+    if (on)
+        for (int r = lane; r < m; r += 32) z[r] = (r < n) ? y[r] : zmake(0.0, 0.0);
+    auto stage = [&](int j, int b) {                          // rows j+1 .. m-1 of reflector j -> vbuf[b]
         const zc *v = X + (size_t)j * m;
-        zc dot = zmake(0.0, 0.0);
-        for (int r = j + 1 + lane; r < m; r += 32) dot = zcfma(v[r], z[r], dot);
-        dot = zwarp_sum(dot);
-        dot = zadd(dot, z[j]);
-        const zc tw = zmul(tau, dot), ntw = zmake(-tw.x, -tw.y);
-        __syncwarp();
-        if (lane == 0) z[j] = zsub(z[j], tw);
-        for (int r = j + 1 + lane; r < m; r += 32) z[r] = zfma(ntw, v[r], z[r]);
-        __syncwarp();
+        zc *dst = vbuf + (size_t)b * m;
+        for (int r = j + 1 + tid; r < m; r += blockDim.x) cp_async16(dst + r, v + r);
+        cp_async_commit();
+    };
+    stage(n - 1, 0);
+    for (int j = n - 1; j >= 0; --j) {
+        const int b = (n - 1 - j) & 1;
+        if (j > 0) {
+            stage(j - 1, b ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                      // reflector j is in vbuf[b] for every warp
+        const zc tau = tau_g[j];
+        if (on && (tau.x != 0.0 || tau.y != 0.0)) {
+            const zc *v = vbuf + (size_t)b * m;
+            zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
+            int r = j + 1 + lane;
+            for (; r + 32 < m; r += 64) {
+                d0 = zcfma(v[r], z[r], d0);
+                d1 = zcfma(v[r + 32], z[r + 32], d1);
+            }
+            if (r < m) d0 = zcfma(v[r], z[r], d0);
+            zc dot = zwarp_sum(zadd(d0, d1));
+            dot = zadd(dot, z[j]);
+            const zc tw = zmul(tau, dot), ntw = zmake(-tw.x, -tw.y);
+            __syncwarp();
+            if (lane == 0) z[j] = zsub(z[j], tw);
+            for (int q = j + 1 + lane; q < m; q += 32) z[q] = zfma(ntw, v[q], z[q]);
+        }
+        __syncthreads();                                      // vbuf[b] may be overwritten by the next-but-one stage
     }
-    for (int r = lane; r < m; r += 32) out[r] = z[r];
+    if (on)
+        for (int r = lane; r < m; r += 32) out[r] = z[r];
 }
 
 }  // namespace hcore_b200
