@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     // 8 with those of B (12 exchanges instead of 24), each half derives ITS rotation (the scalar chain
     // runs once for both) and the halves swap (cos, sin).  sin == 0 means "no rotation".
     const bool hi8 = (l16 & 8) != 0;
+    const unsigned hmask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;   // the warp's other 16-lane group may be idle
     auto rotate2 = [&](double2 (&ap)[RP], double2 (&aq)[RP], double2 (&bp)[RP], double2 (&bq)[RP], int &big) {
         double sa[3] = {0.0, 0.0, 0.0}, ta[3] = {0.0, 0.0, 0.0}, sb[3] = {0.0, 0.0, 0.0}, tb[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -289,12 +290,12 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const double a = sa[q] + ta[q], b = sb[q] + tb[q];
-            v[q] = (hi8 ? b : a) + __shfl_xor_sync(0xffffffffu, hi8 ? a : b, 8);
+            v[q] = (hi8 ? b : a) + __shfl_xor_sync(hmask, hi8 ? a : b, 8);
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+            for (int q = 0; q < 3; ++q) v[q] += __shfl_xor_sync(hmask, v[q], o);
         }
         // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
         const double app = v[0], aqq = v[1], apq = v[2];
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
             cs = u * ru;
             sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
         }
-        const double ocs = __shfl_xor_sync(0xffffffffu, cs, 8), osn = __shfl_xor_sync(0xffffffffu, sn, 8);
+        const double ocs = __shfl_xor_sync(hmask, cs, 8), osn = __shfl_xor_sync(hmask, sn, 8);
         const double csa = hi8 ? ocs : cs, sna = hi8 ? osn : sn, csb = hi8 ? cs : ocs, snb = hi8 ? sn : osn;
         if (sna != 0.0) {
 #pragma unroll

@@ -336,23 +336,36 @@ __global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) 
     for (int sweep = 0; sweep < kZMaxSweeps && !converged; ++sweep) {
         int big = 0;
         for (int step = 0; step < n2 - 1; ++step) {
-            for (int k = warp; k < n2 / 2; k += nwarps) {
+            // 16 lanes per column pair (lane l16 owns rows l16, l16 + 16, ...): two pairs per warp, the
+            // 64 pairs of a step at N = 128 in two rounds of the CTA's 32 half-warps
+            const int l16 = lane & 15, hw = (warp << 1) | (lane >> 4), nhw = nwarps << 1;
+            for (int k = hw; k < n2 / 2; k += nhw) {
                 int p, q;
                 rr_pair(n2, step, k, p, q);
                 if (q >= n) continue;
                 zc *cp = T + (size_t)p * N, *cq = T + (size_t)q * N;
-                zc xp[4], xq[4];
+                zc xp[8], xq[8];
                 double app = 0.0, aqq = 0.0;
                 zc apq = zmake(0.0, 0.0);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = lane + 32 * e;
+                for (int e = 0; e < 8; ++e) {
+                    const int r = l16 + 16 * e;
                     xp[e] = (r < n) ? cp[r] : zmake(0.0, 0.0);
                     xq[e] = (r < n) ? cq[r] : zmake(0.0, 0.0);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
                     app += zabs2(xp[e]); aqq += zabs2(xq[e]);
                     apq = zcfma(xp[e], xq[e], apq);                  // p^H q
                 }
-                app = warp_sum(app); aqq = warp_sum(aqq); apq = zwarp_sum(apq);
+                const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;   // the other half-warp may be idle
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {                    // reductions stay inside the half-warp
+                    app += __shfl_xor_sync(hmask, app, o);
+                    aqq += __shfl_xor_sync(hmask, aqq, o);
+                    apq.x += __shfl_xor_sync(hmask, apq.x, o);
+                    apq.y += __shfl_xor_sync(hmask, apq.y, o);
+                }
                 const double den2 = app * aqq, g2 = zabs2(apq);
                 if (den2 > 0.0 && g2 > (kZTolRot * kZTolRot) * den2) {
                     if (g2 > (kZTolStop * kZTolStop) * den2) big = 1;
@@ -362,8 +375,8 @@ __global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) 
                     const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int r = lane + 32 * e;
+                    for (int e = 0; e < 8; ++e) {
+                        const int r = l16 + 16 * e;
                         if (r < n) {
                             const zc qt = zmul(xq[e], ph);
                             cp[r] = zmake(cs * xp[e].x - sn * qt.x, cs * xp[e].y - sn * qt.y);
