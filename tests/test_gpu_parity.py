@@ -371,7 +371,7 @@ def test_host_buffer_path_matches_device_path(ctx):
 
 # ---- dense-C updates (BASELINE.json configs[2]) ----------------------------------------------------------------
 
-@pytest.mark.parametrize("nb,ka,kb", [(1024, 32, 32), (500, 25, 13), (130, 7, 6), (1024, 64, 96)])
+@pytest.mark.parametrize("nb,ka,kb", [(1024, 32, 32), (500, 25, 13), (130, 7, 6), (1024, 64, 96), (257, 9, 5), (129, 3, 40)])
 def test_dgemmcd_dsyrk_batched_vs_oracle(ctx, nb, ka, kb):
     T = 3
     b = make_lr_batch(T, nb, max(ka, kb), base_seed=17, ranks=[(ka, kb, 1)] * T)
