@@ -87,6 +87,30 @@ def make_device_batch(torch, T, nb, k, dev, seed):
     return d
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """One process per GPU: run on (and first-touch the pinned host buffers from) the CPUs of the NUMA node the
+    GPU hangs off, so that the end-to-end path's H2D/D2H traffic does not cross the socket interconnect.
+    Returns the node id, or None when the topology cannot be read."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bus = pr.pci_bus_id
+        if isinstance(bus, int):                                     # torch exposes domain / bus / device as ints
+            bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), bus, getattr(pr, "pci_device_id", 0))
+        base = f"/sys/bus/pci/devices/{bus.lower()}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def restore_c(d, k):
     d["cu"][:, :k].copy_(d["cu0"])
     d["cv"][:, :k].copy_(d["cv0"])
@@ -243,6 +267,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: hcore_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner out of stdout (one JSON line only)
@@ -420,7 +445,7 @@ def main():
         line["e2e"] = {"value": world * Te / float(te.item()), "unit": "tiles/s",
                        "h2d_bytes_per_step": world * (Te * per_tile_in + 3 * 4 * Te),
                        "d2h_bytes_per_step": world * (out_bytes + 2 * 4 * Te),
-                       "tiles_per_step": world * Te, "failed_tiles": int(nf.item()),
+                       "tiles_per_step": world * Te, "failed_tiles": int(nf.item()), "rank0_numa_node": numa,
                        "note": "HCORE_dgemm_batched_host on every rank at once: pinned host buffers, sliced "
                                "H2D/compute/D2H pipeline on two streams; host wall clock, max over ranks"}
         del host
