@@ -110,9 +110,10 @@ int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
     // a few waves of CTAs per launch, bounded to ~6 GiB of workspace
     size_t per = per_tile_ws_bytes(N, m_pad, nblk);
     size_t cap = (6ull << 30) / per;
-    // 15 x #SM tiles = 2220 on B200: whole waves for the SVD kernel (1 CTA/SM) and for the QR kernel
-    // (2 CTAs per tile, 6 resident per SM); measured +0.8 % over 16 x #SM (tools/exp_chunk.py)
-    int c = ctx->num_sms * 15;
+    // 16 x #SM tiles = 2368 on B200 (whole waves for the one-CTA-per-SM SVD kernel).  15 x #SM gives whole waves
+    // for the QR kernel too and is 0.8 % faster on batches that are a multiple of it, but loses 1 % on the
+    // benchmark's 16 384 tiles (a short last chunk): tools/exp_chunk.py, profiles/bench_r2j.json
+    int c = ctx->num_sms * 16;
     if ((size_t)c > cap) c = (int)cap;
     return std::max(c, 1);
 }

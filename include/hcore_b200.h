@@ -161,7 +161,7 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t handle, int ntiles, int nb,
  * then allocate exact-size factor arrays; phase 2 forms CU = Q_u [U_r; 0], CV = Q_v [W; 0] in the
  * arrays it is given (any ldc >= nb) and sets Crk.  The block reflectors stay in the handle's
  * workspace between the two calls, so ntiles must fit one workspace chunk (hcore_b200_set_chunk;
- * default 15 x #SM tiles) and no other update may run on the handle in between
+ * default 16 x #SM tiles) and no other update may run on the handle in between
  * (HCORE_B200_ERR_ARG otherwise).  The fused call and the pair give bit-identical factors. */
 int HCORE_dgemm_batched_qr_svd(hcore_b200_handle_t handle, int ntiles, int nb,
                         double alpha,
