@@ -101,14 +101,38 @@ __global__ void __launch_bounds__(256) ztlr_stack_kernel(ZArgs ar, ZWorkspace ws
             XU[r + (size_t)col * m] = zmul(ar.alpha, AU[r + (size_t)(col - c) * ar.lda]);
         }
     }
-    // P = AV^T BV: one thread per P entry, lanes along i (coalescing comes from the L1: every
-    // thread streams its two columns)
-    for (int idx = tid; idx < a * b; idx += blockDim.x) {
-        const int i = idx % a, j = idx / a;
-        const zc *pa = AV + (size_t)i * ar.lda, *pb = BV + (size_t)j * ar.ldb;
-        zc acc = zmake(0.0, 0.0);
-        for (int k = 0; k < m; ++k) acc = zfma(pa[k], pb[k], acc);
-        P[i + (size_t)j * N] = acc;
+    // P = AV^T BV: a warp per 4 x 4 tile of P, lanes along the contraction index (coalesced reads of the
+    // eight columns), sixteen accumulators per lane, warp reductions at the end
+    {
+        const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+        const int ta = (a + 3) / 4, tb = (b + 3) / 4;
+        for (int tile = warp; tile < ta * tb; tile += nwarps) {
+            const int i0 = 4 * (tile % ta), j0 = 4 * (tile / ta);
+            zc acc[4][4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = zmake(0.0, 0.0);
+            for (int k = lane; k < m; k += 32) {
+                zc av[4], bv[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    av[p] = (i0 + p < a) ? AV[k + (size_t)(i0 + p) * ar.lda] : zmake(0.0, 0.0);
+                    bv[p] = (j0 + p < b) ? BV[k + (size_t)(j0 + p) * ar.ldb] : zmake(0.0, 0.0);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[p][q] = zfma(av[p], bv[q], acc[p][q]);
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const zc v = zwarp_sum(acc[p][q]);
+                    if (lane == 0 && i0 + p < a && j0 + q < b) P[(i0 + p) + (size_t)(j0 + q) * N] = v;
+                }
+        }
     }
     __syncthreads();
     // G = BU P^T -> X_v[:, c : c+a]: one thread per row, 8 outputs at a time
