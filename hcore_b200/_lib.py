@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = [
     "hcore_b200_debug_fetch", "hcore_b200_debug_set_stages", "hcore_b200_set_stage_timing",
     "hcore_b200_stage_ms",
     "HCORE_dgemm", "HCORE_dgemmcd", "HCORE_dsyrk",
-    "HCORE_dgemm_qr_svd", "HCORE_dgemm_ormqr",
+    "HCORE_dgemm_qr_svd", "HCORE_dgemm_ormqr", "HCORE_dgemm_qr_svd_b_dense",
+    "HCORE_dgemm_batched_b_dense", "HCORE_dgemm_batched_qr_svd_b_dense", "HCORE_dgemm_batched_b_dense_strided",
     "HCORE_dgemm_batched_qr_svd", "HCORE_dgemm_batched_ormqr",
     "HCORE_dgemm_batched_qr_svd_strided", "HCORE_dgemm_batched_ormqr_strided",
     "use_trmm", "gemm_print_index", "gemm_print_mat", "hc_nelm_limit", "syrk_print_index",
@@ -80,6 +81,10 @@ def load():
     L.HCORE_dgemm_batched_qr_svd_strided.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, vp, vp, i, i64, d,
                                                      vp, vp, vp, i, i64, i, i, d, vp, vp, vp]
     L.HCORE_dgemm_batched_ormqr_strided.argtypes = [vp, i, i, vp, vp, vp, i, i64, vp]
+    L.HCORE_dgemm_batched_b_dense.argtypes = [vp, i, i, d, vp, vp, vp, i, vp, i, d, vp, vp, vp, i, i, i, d, vp, vp]
+    L.HCORE_dgemm_batched_qr_svd_b_dense.argtypes = [vp, i, i, d, vp, vp, vp, i, vp, i, d, vp, vp, vp, i, i, i, d, vp, vp, vp]
+    L.HCORE_dgemm_batched_b_dense_strided.argtypes = [vp, i, i, d, vp, vp, vp, i, i64, vp, i, i64, d,
+                                                      vp, vp, vp, i, i64, i, i, d, vp, vp]
     f = C.c_float
     L.HCORE_sgemm_batched.argtypes = [vp, i, i, f, vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, i, i, i, f, vp, vp]
     L.HCORE_sgemm_batched_strided.argtypes = [vp, i, i, f, vp, vp, vp, i, i64, vp, vp, vp, i, i64, f,
@@ -104,6 +109,9 @@ def load():
     L.HCORE_dgemm_qr_svd.argtypes = [i, i, i, i, d, dp, dp, ip, i, dp, dp, ip, i, d, dp, dp, ip, i, i, i, i, d, dp, vp,
                                      dpp, dpp, dpp, ip, ip, dpp, ip, dpp, ip, dpp, ip, dpp, ip, dpp, ip, dpp, dpp, ip, dpp]
     L.HCORE_dgemm_qr_svd.restype = None
+    L.HCORE_dgemm_qr_svd_b_dense.argtypes = [i, i, i, i, d, dp, dp, ip, i, dp, i, d, dp, dp, ip, i, i, i, i, d, dp, vp,
+                                             dpp, dpp, dpp, ip, ip, dpp, ip, dpp, ip, dpp, ip, dpp, ip, dpp, ip, dpp, dpp, ip, dpp]
+    L.HCORE_dgemm_qr_svd_b_dense.restype = None
     L.HCORE_dgemm_ormqr.argtypes = [i, i, i, i, d, dp, dp, ip, i, d, dp, dp, ip, i, i, i, i, d, dp, vp,
                                     dp, dp, i, i, dp, i, dp, i, dp, i, dp, i, dp, i, dp, dp, i, dp]
     L.HCORE_dgemm_ormqr.restype = None

@@ -250,6 +250,22 @@ class Context:
         self._check(self._L.HCORE_dgemm_batched_ormqr_strided(self._h, T, nb, _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb,
                                                               self._stream_ptr(stream)))
 
+    def dgemm_batched_b_dense(self, alpha, AU, AV, Ark, B, beta, CU, CV, Crk, *, rk, maxrk, acc, status=None, stream=None):
+        """B-dense variant (reference ``HCORE_dgemm_qr_svd_b_dense`` + ``HCORE_dgemm_ormqr``): ``B`` is (T, nb, nb),
+        tile t the column-major dense nb x nb matrix; ``C <- alpha (AU AV^T) B^T + beta C``."""
+        T, ka, nb = AU.shape
+        for nm, x in (("AU", AU), ("AV", AV), ("B", B), ("CU", CU), ("CV", CV)):
+            self._dev_f64(x, nm)
+        for nm, x in (("Ark", Ark), ("Crk", Crk)):
+            self._dev_i32(x, nm)
+        if status is not None:
+            self._dev_i32(status, "status")
+        kc = CU.shape[1]
+        rc = self._L.HCORE_dgemm_batched_b_dense_strided(
+            self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), nb, ka * nb, _ptr(B), nb, nb * nb, float(beta),
+            _ptr(CU), _ptr(CV), _ptr(Crk), nb, kc * nb, int(rk), int(maxrk), float(acc), _ptr(status), self._stream_ptr(stream))
+        self._check(rc)
+
     def sgemm_batched(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc,
                       status=None, stream=None):
         """Batched ``HCORE_sgemm``: as :meth:`dgemm_batched` with float32 factor tensors."""

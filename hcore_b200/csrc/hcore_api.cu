@@ -138,7 +138,13 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     const bool tm = ctx->stage_timing;
     if (tm) cudaEventRecord(ctx->ev[0], st);
     if (ctx->debug_stages >= 1) {
-        tlr_pg_kernel<N><<<ar.ntiles, 256, PgSmem::kBytes, st>>>(ar, ws);
+        if (ar.Bd) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_gdense_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)GdSmem<N>::kBytes));
+            tlr_gdense_kernel<N><<<dim3(ws.nblk, ar.ntiles), 256, GdSmem<N>::kBytes, st>>>(ar, ws);
+        } else {
+            tlr_pg_kernel<N><<<ar.ntiles, 256, PgSmem::kBytes, st>>>(ar, ws);
+        }
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[1], st);
@@ -265,7 +271,8 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
                         const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
                         double beta, double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
                         int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32,
-                        int phase = 0, int32_t *d_newrank = nullptr) {
+                        int phase = 0, int32_t *d_newrank = nullptr, const double *const *d_Bdense = nullptr) {
+    // d_Bdense != null: B-dense variant, d_BU / d_BV / d_Brk are unused and ldb is the leading dimension of B
     if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
     if (phase == 1 && !d_newrank) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
@@ -315,6 +322,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
         ar.alpha = alpha; ar.beta = beta; ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc;
         ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0); ar.f32 = f32;
         ar.phase = phase; ar.rank_out = (phase == 1) ? d_newrank : d_Crk;
+        ar.Bd = d_Bdense; ar.ldbd = ldb;
         int rc;
         switch (N) {
             case 32: rc = launch_chunk_n<32>(ctx, ar, ws, st); break;
@@ -433,6 +441,52 @@ int HCORE_dgemm_batched_ormqr_strided(hcore_b200_handle_t ctx, int ntiles, int n
     ctx->launches += 2;
     return tlr_batched_apply(ctx, ntiles, nb, (double *const *)(pp + 4 * (size_t)ntiles),
                              (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, stream);
+}
+
+// ---- B-dense variant (reference HCORE_dgemm_qr_svd_b_dense, src/compute/hcore_dgemm.c:1022-1303) ---------
+int HCORE_dgemm_batched_b_dense(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_B, int ldb, double beta,
+                        double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    if (!d_B) return HCORE_B200_ERR_ARG;
+    return tlr_batched(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, nullptr, nullptr, d_Ark, ldb, beta, d_CU, d_CV, d_Crk,
+                       ldc, rk, maxrk, acc, d_status, stream, 0, 0, nullptr, d_B);
+}
+
+int HCORE_dgemm_batched_qr_svd_b_dense(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_B, int ldb, double beta,
+                        const double *const *d_CU, const double *const *d_CV, const int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc, int32_t *d_newrank, int32_t *d_status, void *stream) {
+    if (!d_B) return HCORE_B200_ERR_ARG;
+    return tlr_batched(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, nullptr, nullptr, d_Ark, ldb, beta,
+                       (double *const *)d_CU, (double *const *)d_CV, const_cast<int32_t *>(d_Crk), ldc, rk, maxrk, acc,
+                       d_status, stream, 0, 1, d_newrank, d_B);
+}
+
+int HCORE_dgemm_batched_b_dense_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_B, int ldb, int64_t strideB, double beta,
+                        double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0 || !d_B) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ctx, ctx->ptrs.reserve(6ull * ntiles * sizeof(double *)));
+    const double **pp = (const double **)ctx->ptrs.p;
+    const void *bases[5] = {d_AU, d_AV, d_B, d_CU, d_CV};
+    const int64_t strides[5] = {strideA, strideA, strideB, strideC, strideC};
+    const int thr = 256, blk = (ntiles + thr - 1) / thr;
+    for (int i = 0; i < 5; ++i) {
+        fill_ptrs_kernel<<<blk, thr, 0, st>>>(pp + (size_t)i * ntiles, (const char *)bases[i], strides[i] * 8, ntiles);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_dgemm_batched_b_dense(ctx, ntiles, nb, alpha, pp, pp + ntiles, d_Ark, lda, pp + 2 * (size_t)ntiles, ldb, beta,
+                                       (double *const *)(pp + 3 * (size_t)ntiles), (double *const *)(pp + 4 * (size_t)ntiles),
+                                       d_Crk, ldc, rk, maxrk, acc, d_status, stream);
 }
 
 int HCORE_sgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, float alpha,
@@ -806,25 +860,20 @@ static uint64_t ormqr_flops(uint64_t m, uint64_t n, uint64_t r) {       // the t
     return (4 * r * m * n - 2 * r * n * n + 3 * r * n) + (4 * m * r * n - 2 * r * n * n + 2 * r * n + m * n - n * n / 2 + n / 2);
 }
 
-void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha, double *AU, double *AV, int *Ark, int LDA,
-                        double *BU, double *BV, int *Brk, int LDB, double beta, double *CU, double *CV, int *Crk, int LDC,
-                        int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
-                        double **_p_work_new, double **_p__CU, double **_p__CV, int *_p_CU_ncols, int *_p_new_UVrk,
-                        double **_p_newU, int *_p_ld_newU, double **_p_qrtauA, int *_p_CV_ncols, double **_p_newV,
-                        int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
-                        int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
-                        double **_p__CV_save) {
-    (void)transA; (void)transB; (void)N; (void)storage_maxrank;
-    const char *who = "HCORE_dgemm_qr_svd";
-    const int a = Ark[0], b = Brk[0], c = Crk[0];
+// Shared body of HCORE_dgemm_qr_svd (B = BU BV^T) and HCORE_dgemm_qr_svd_b_dense (B dense, Bd != null).
+static int legacy_qr_svd(const char *who, int M, double alpha, const double *AU, const double *AV, int a, int LDA,
+                         const double *BU, const double *BV, int b, const double *Bd, int LDB, double beta,
+                         const double *CU, const double *CV, int c, int LDC, int rk, int maxrk, double acc,
+                         flop_counter *flops) {
     std::lock_guard<std::mutex> lock(g_mu);
     hcore_b200_handle_t ctx = legacy_ctx(who);
-    if (a == 0 || b == 0 || c == 0) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
+    if (a == 0 || c == 0 || (!Bd && b == 0)) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
     // the split-phase variant accepts Ark + Crk up to 2 * maxrk (reference :1186, :1259)
     if (2 * maxrk < a + c) legacy_fail(who, "increase maxrank (2 * maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
     const int cap = std::max(maxrk, a + c);
     cudaSetDevice(ctx->device);
-    const size_t fa = (size_t)LDA * a * 8, fb = (size_t)LDB * b * 8, fcin = (size_t)LDC * c * 8;
+    const size_t fa = (size_t)LDA * a * 8, fcin = (size_t)LDC * c * 8;
+    const size_t fb = Bd ? (size_t)LDB * M * 8 : (size_t)LDB * b * 8;       // dense B: one M x M array
     const size_t fc = ((size_t)LDC * (a + c) * 8 + 15) / 16 * 16;
     const size_t fa16 = (fa + 15) / 16 * 16, fb16 = (fb + 15) / 16 * 16;
     if (ctx->stage[0].reserve(2 * fa16 + 2 * fb16 + 2 * fc) != cudaSuccess ||
@@ -834,17 +883,32 @@ void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha, doub
     char *dAU = base, *dAV = base + fa16, *dBU = base + 2 * fa16, *dBV = base + 2 * fa16 + fb16,
          *dCU = base + 2 * fa16 + 2 * fb16, *dCV = base + 2 * fa16 + 2 * fb16 + fc;
     int *di = (int *)ctx->stage_ints[0].p;
-    int hi[5] = {a, b, c, 0, 0};
+    int hi[5] = {a, Bd ? a : b, c, 0, 0};
     cudaStream_t st = ctx->streams[0];
     cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
+    if (Bd) {
+        cudaMemcpyAsync(dBU, Bd, fb, cudaMemcpyHostToDevice, st);
+    } else {
+        cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
+    }
     cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
-    int rc = tlr_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV, di + 2,
+    int rc;
+    if (Bd) {
+        // one tile: the pointer "arrays" are single device pointers kept in the context's pointer table
+        if (ctx->ptrs.reserve(6 * sizeof(double *)) != cudaSuccess) legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+        const double *hp[6] = {(double *)dAU, (double *)dAV, (double *)dBU, (double *)dCU, (double *)dCV, nullptr};
+        cudaMemcpyAsync(ctx->ptrs.p, hp, sizeof(hp), cudaMemcpyHostToDevice, st);
+        const double **pp = (const double **)ctx->ptrs.p;
+        rc = HCORE_dgemm_batched_qr_svd_b_dense(ctx, 1, M, alpha, pp, pp + 1, di, LDA, pp + 2, LDB, beta, pp + 3, pp + 4, di + 2,
+                                                LDC, rk, cap, acc, di + 4, di + 3, st);
+    } else {
+        rc = tlr_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV, di + 2,
                                  LDC, 0, rk, cap, acc, di + 3, st, 0, 1, di + 4);
+    }
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
     cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
@@ -852,11 +916,56 @@ void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha, doub
     const int rnew = hi[4];
     g_split.pending = true; g_split.M = M; g_split.n = a + c; g_split.rnew = rnew; g_split.LDC = LDC;
     g_split.dCU = dCU; g_split.dCV = dCV;
-    if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew) - ormqr_flops(M, a + c, rnew);
-    *_p_work_new = work; *_p__CU = CU; *_p__CV = CV; *_p_CU_ncols = a + c; *_p_new_UVrk = rnew;
-    *_p_newU = nullptr; *_p_ld_newU = M; *_p_qrtauA = nullptr; *_p_CV_ncols = a + c; *_p_newV = nullptr;
-    *_p_ld_newV = maxrk; *_p_qrtauB = nullptr; *_p_use_CUV_clone = 0; *_p_CUclone = nullptr; *_p_ld_CUclone = M;
+    if (flops) {
+        if (Bd) {
+            // reference model of the b_dense path: QR of both stacks + the M x Ark x M product (:272) + SVD parts
+            const uint64_t m = M, n = (uint64_t)a + c, r = rnew;
+            auto geqrf = [](uint64_t mm, uint64_t nn) {
+                return 2 * mm * nn * nn - (uint64_t)(2 * nn * nn * nn / 3.0f) + 2 * mm * nn + (uint64_t)(17 * nn / 3.0f);
+            };
+            flops->update += 2 * geqrf(m, n) + 2 * m * (uint64_t)a * m + 22 * n * n * n + r * n;
+        } else {
+            flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew) - ormqr_flops(M, a + c, rnew);
+        }
+    }
+    return rnew;
+}
+
+#define HCORE_SPLIT_OUTS                                                                                          \
+    *_p_work_new = work; *_p__CU = CU; *_p__CV = CV; *_p_CU_ncols = a + c; *_p_new_UVrk = rnew;                   \
+    *_p_newU = nullptr; *_p_ld_newU = M; *_p_qrtauA = nullptr; *_p_CV_ncols = a + c; *_p_newV = nullptr;           \
+    *_p_ld_newV = maxrk; *_p_qrtauB = nullptr; *_p_use_CUV_clone = 0; *_p_CUclone = nullptr; *_p_ld_CUclone = M;   \
     *_p__CU_save = CU; *_p_CVclone = nullptr; *_p_ld_CVclone = M; *_p__CV_save = CV;
+
+void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha, double *AU, double *AV, int *Ark, int LDA,
+                        double *BU, double *BV, int *Brk, int LDB, double beta, double *CU, double *CV, int *Crk, int LDC,
+                        int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
+                        double **_p_work_new, double **_p__CU, double **_p__CV, int *_p_CU_ncols, int *_p_new_UVrk,
+                        double **_p_newU, int *_p_ld_newU, double **_p_qrtauA, int *_p_CV_ncols, double **_p_newV,
+                        int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
+                        int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
+                        double **_p__CV_save) {
+    (void)transA; (void)transB; (void)N; (void)storage_maxrank;
+    const int a = Ark[0], b = Brk[0], c = Crk[0];
+    const int rnew = legacy_qr_svd("HCORE_dgemm_qr_svd", M, alpha, AU, AV, a, LDA, BU, BV, b, nullptr, LDB, beta, CU, CV, c, LDC,
+                                   rk, maxrk, acc, flops);
+    HCORE_SPLIT_OUTS
+}
+
+// reference src/compute/hcore_dgemm.c:1022-1303: B is a dense M x M tile (leading dimension LDB)
+void HCORE_dgemm_qr_svd_b_dense(int transA, int transB, int M, int N, double alpha, double *AU, double *AV, int *Ark, int LDA,
+                        double *B, int LDB, double beta, double *CU, double *CV, int *Crk, int LDC,
+                        int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
+                        double **_p_work_new, double **_p__CU, double **_p__CV, int *_p_CU_ncols, int *_p_new_UVrk,
+                        double **_p_newU, int *_p_ld_newU, double **_p_qrtauA, int *_p_CV_ncols, double **_p_newV,
+                        int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
+                        int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
+                        double **_p__CV_save) {
+    (void)transA; (void)transB; (void)N; (void)storage_maxrank;
+    const int a = Ark[0], c = Crk[0];
+    const int rnew = legacy_qr_svd("HCORE_dgemm_qr_svd_b_dense", M, alpha, AU, AV, a, LDA, nullptr, nullptr, 0, B, LDB, beta, CU,
+                                   CV, c, LDC, rk, maxrk, acc, flops);
+    HCORE_SPLIT_OUTS
 }
 
 void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha, double *AU, double *AV, int *Ark, int LDA,

@@ -151,6 +151,8 @@ struct TlrArgs {
     int tile0;            // first tile of this chunk in the user arrays
     int ntiles;           // tiles in this chunk
     int f32;              // 1: the user arrays hold float (HCORE_sgemm); arithmetic stays FP64
+    const double *const *Bd;   // dense B tiles (nb x nb, ld ldbd) of the B-dense variant, or null
+    int ldbd;
     int *rank_out;        // where the new rank goes: Crk (fused call, phase 2) or the caller's new-rank array (phase 1)
     int phase;            // 0: whole update; 1: stack + QR + SVD only (HCORE_dgemm_qr_svd); 2: reflector application
                           //    only, into possibly re-allocated CU/CV (HCORE_dgemm_ormqr)
@@ -363,6 +365,117 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
     if (st != HCORE_B200_OK) return;
     pg_body(smem, ar.AV[gt], ar.BU[gt], ar.BV[gt], a, b, m, ar.lda, ar.ldb, ws.m_pad, ar.f32, 1.0,
             ws.G + (size_t)t * ws.m_pad * N);
+}
+
+// ---- 1b. G for a DENSE B operand -----------------------------------------------------------------
+// B-dense variant of the update (reference __qrb_b_dense, src/compute/hcore_dgemm.c:236-288): the tile B is a
+// dense nb x nb matrix, C <- alpha (AU AV^T) B^T + beta C, and the stacked V panel is [CV | G] with
+// G = B AV (nb x a).  grid = (128-row blocks, tiles), 256 threads: warp w owns rows 16 w .. 16 w + 15 of the
+// block and all a columns; 32-wide contraction chunks of B (128 x 32) and AV (32 x a) are staged with
+// cp.async, double buffered.
+template <int N>
+struct GdSmem {
+    static constexpr int kLdB = kBlockH + 4;                     // 132
+    static constexpr int kLdA = kPgRows + 4;                     // 36
+    static constexpr int kStage = kPgRows * kLdB + N * kLdA;     // B chunk | AV chunk
+    static constexpr size_t kBytes = 2ull * kStage * sizeof(double);
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, 1) tlr_gdense_kernel(TlrArgs ar, TlrWorkspace ws) {
+    using SM = GdSmem<N>;
+    extern __shared__ __align__(16) double smem[];
+    const int t = blockIdx.y, gt = ar.tile0 + t, i0 = blockIdx.x * kBlockH;
+    const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
+    const int g = lane >> 2, tg = lane & 3;
+    const int a = ar.Ark[gt], c = ar.Crk[gt];
+    const int n = a + c, m = ar.nb;
+    int st = HCORE_B200_OK;
+    if (a <= 0 || c <= 0) st = HCORE_B200_ERR_ZERO_RANK;
+    else if (ar.maxrk < n) st = HCORE_B200_ERR_MAXRK;
+    else if (n > N || n > m) st = HCORE_B200_ERR_UNSUPPORTED;
+    if (blockIdx.x == 0 && tid == 0) {
+        ws.st[t] = st;
+        ws.ncols[t] = n;
+        ws.newrank[t] = c;
+        if (ar.status) ar.status[gt] = st;
+    }
+    if (st != HCORE_B200_OK) return;
+    const double *B = ar.Bd[gt], *AV = ar.AV[gt];
+    const int ldb = ar.ldbd, lda = ar.lda, m_pad = ws.m_pad;
+    double *Gt = ws.G + (size_t)t * m_pad * N;
+    const int a8 = round_up(a, 8);
+    const bool vec = ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(AV)) & 15) == 0 && (ldb & 1) == 0 &&
+                     (lda & 1) == 0 && !ar.f32;
+    auto stage = [&](int k0, int buf) {
+        double *Bs = smem + buf * SM::kStage, *As = Bs + kPgRows * SM::kLdB;
+        const bool full = vec && i0 + kBlockH <= m && k0 + kPgRows <= m;
+        if (full) {
+            for (int idx = tid; idx < (kBlockH / 2) * kPgRows; idx += 256) {        // B(i0 + r, k0 + kk): rows contiguous
+                const int rp = idx & 63, kk = idx >> 6;
+                cp_async16(Bs + 2 * rp + kk * SM::kLdB, B + (size_t)(k0 + kk) * ldb + i0 + 2 * rp);
+            }
+            for (int idx = tid; idx < (kPgRows / 2) * a; idx += 256) {              // AV(k0 + kk, j): k contiguous
+                const int kp = idx & 15, j = idx >> 4;
+                cp_async16(As + 2 * kp + j * SM::kLdA, AV + (size_t)j * lda + k0 + 2 * kp);
+            }
+        } else {
+            for (int idx = tid; idx < kBlockH * kPgRows; idx += 256) {
+                const int r = idx & 127, kk = idx >> 7;
+                Bs[r + kk * SM::kLdB] = (i0 + r < m && k0 + kk < m) ? ld_user(B, (size_t)(k0 + kk) * ldb + i0 + r, ar.f32) : 0.0;
+            }
+            for (int idx = tid; idx < kPgRows * a; idx += 256) {
+                const int kk = idx & 31, j = idx >> 5;
+                As[kk + j * SM::kLdA] = (k0 + kk < m) ? ld_user(AV, (size_t)j * lda + k0 + kk, ar.f32) : 0.0;
+            }
+        }
+        for (int idx = tid; idx < kPgRows * (a8 - a); idx += 256) As[(idx & 31) + (a + (idx >> 5)) * SM::kLdA] = 0.0;
+        cp_async_commit();
+    };
+    double acc[2][N / 8][2];
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx)
+#pragma unroll
+        for (int tt = 0; tt < N / 8; ++tt) acc[sidx][tt][0] = acc[sidx][tt][1] = 0.0;
+    const int nk = (m + kPgRows - 1) / kPgRows;
+    stage(0, 0);
+    for (int ch = 0; ch < nk; ++ch) {
+        if (ch + 1 < nk) {
+            stage((ch + 1) * kPgRows, (ch + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double *Bs = smem + (ch & 1) * SM::kStage, *As = Bs + kPgRows * SM::kLdB;
+        const double *bp = Bs + 16 * warp + g + tg * SM::kLdB;
+        const double *ap = As + tg + g * SM::kLdA;
+#pragma unroll
+        for (int k = 0; k < kPgRows; k += 4) {
+            const double b0 = bp[k * SM::kLdB], b1 = bp[k * SM::kLdB + 8];
+#pragma unroll
+            for (int tt = 0; tt < N / 8; ++tt) {
+                if (8 * tt < a8) {
+                    const double av = ap[k + 8 * tt * SM::kLdA];
+                    dmma_884(acc[0][tt][0], acc[0][tt][1], b0, av);
+                    dmma_884(acc[1][tt][0], acc[1][tt][1], b1, av);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+        const int row = i0 + 16 * warp + 8 * sidx + g;       // < m_pad (i0 + 127 < m_pad)
+#pragma unroll
+        for (int tt = 0; tt < N / 8; ++tt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * tt + 2 * tg + e;
+                if (col < a) Gt[row + (size_t)col * m_pad] = (row < m) ? acc[sidx][tt][e] : 0.0;
+            }
+        }
+    }
 }
 
 // ========================================================================================

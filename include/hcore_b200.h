@@ -184,6 +184,36 @@ int HCORE_dgemm_batched_qr_svd_strided(hcore_b200_handle_t handle, int ntiles, i
 int HCORE_dgemm_batched_ormqr_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC, void *stream);
 
+/* ---- B-dense variant (device pointers) --------------------------------------------------
+ * Reference HCORE_dgemm_qr_svd_b_dense (src/compute/hcore_dgemm.c:1022-1303, __qrb_b_dense :236-288):
+ * the operand B is a DENSE nb x nb tile (leading dimension ldb), C <- alpha (AU AV^T) B^T + beta C; the
+ * stacked V panel is [CV | B AV].  Fused call, its first half (ranks to d_newrank; finish with
+ * HCORE_dgemm_batched_ormqr) and a strided convenience form. */
+int HCORE_dgemm_batched_b_dense(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_B, int ldb,
+                        double beta,
+                        double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_status, void *stream);
+int HCORE_dgemm_batched_qr_svd_b_dense(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark, int lda,
+                        const double *const *d_B, int ldb,
+                        double beta,
+                        const double *const *d_CU, const double *const *d_CV, const int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_newrank, int32_t *d_status, void *stream);
+int HCORE_dgemm_batched_b_dense_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_B, int ldb, int64_t strideB,
+                        double beta,
+                        double *d_CU, double *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_status, void *stream);
+
 /* ---- batched dense-C updates (device pointers) ---------------------------------------- */
 /* Batched HCORE_dgemmcd (reference src/compute/hcore_dgemmcd.c:36-107):
  *   CD[t] <- CD[t] - (Au Av^T)(Bu Bv^T)^T ; alpha/beta are hard-wired to -1/+1 there. */

@@ -54,6 +54,17 @@ void HCORE_dgemm_qr_svd(int transA, int transB, int M, int N, double alpha,
                         int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
                         int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
                         double **_p__CV_save);
+/* B-dense first half (reference src/include/hcore_d.h:146-188): B is a dense M x M tile. */
+void HCORE_dgemm_qr_svd_b_dense(int transA, int transB, int M, int N, double alpha,
+                        double *AU, double *AV, int *Ark, int LDA,
+                        double *B, int LDB,
+                        double beta, double *CU, double *CV, int *Crk, int LDC,
+                        int rk, int storage_maxrank, int maxrk, double acc, double *work, flop_counter *flops,
+                        double **_p_work_new, double **_p__CU, double **_p__CV, int *_p_CU_ncols, int *_p_new_UVrk,
+                        double **_p_newU, int *_p_ld_newU, double **_p_qrtauA, int *_p_CV_ncols, double **_p_newV,
+                        int *_p_ld_newV, double **_p_qrtauB, int *_p_use_CUV_clone, double **_p_CUclone,
+                        int *_p_ld_CUclone, double **_p__CU_save, double **_p_CVclone, int *_p_ld_CVclone,
+                        double **_p__CV_save);
 void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha,
                        double *AU, double *AV, int *Ark, int LDA,
                        double beta, double *CU, double *CV, int *Crk, int LDC,

@@ -461,3 +461,73 @@ def test_split_phase_legacy_symbols():
     assert ck[0] == rnew
     assert np.array_equal(cu2, ref_cu[:rnew]) and np.array_equal(cv2, ref_cv[:rnew])
     assert fl2.update == fl1.update
+
+
+# ---- (6) B-dense variant ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("nb,k", [(256, 16), (200, 12), (1024, 64), (129, 5)])
+def test_b_dense_batched_vs_oracle(ctx, nb, k):
+    """C <- alpha (AU AV^T) B^T + beta C with a DENSE B tile (reference HCORE_dgemm_qr_svd_b_dense + _ormqr,
+    src/compute/hcore_dgemm.c:1022-1303).  Oracle: the same update with B = B * I^T (BU = B, BV = identity)."""
+    T = 2
+    b = make_lr_batch(T, nb, k, base_seed=31 + nb)
+    rng = np.random.default_rng(5)
+    Bd = (rng.random((T, nb, nb)) - 0.5) / np.sqrt(nb)            # [t][col][row]: column-major nb x nb
+    t = _to_dev(b)
+    Bt = torch.from_numpy(Bd).to("cuda:0")
+    status = torch.full((T,), -7, dtype=torch.int32, device="cuda:0")
+    ctx.dgemm_batched_b_dense(-1.0, t["au"], t["av"], t["ark"], Bt, 1.0, t["cu"], t["cv"], t["crk"], rk=0, maxrk=2 * k,
+                              acc=1e-8, status=status)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    cu, cv, crk = t["cu"].cpu().numpy(), t["cv"].cpu().numpy(), t["crk"].cpu().numpy()
+    eye = np.eye(nb)
+    for i in range(T):
+        Bm = Bd[i].T                                              # math orientation
+        cu_o, cv_o, r_o, _ = orc.tlr_gemm(b.au[i].T, b.av[i].T, Bm, eye, b.cu[i][:k].T, b.cv[i][:k].T, alpha=-1.0, beta=1.0,
+                                          rk=0, maxrk=2 * k, acc=1e-8)
+        r = int(crk[i])
+        assert abs(r - r_o) <= 1
+        dense = b.cu[i][:k].T @ b.cv[i][:k] - (b.au[i].T @ b.av[i]) @ Bm.T
+        e_o = np.linalg.norm(cu_o @ cv_o.T - dense)
+        e_d = np.linalg.norm(cu[i, :r].T @ cv[i, :r] - dense)
+        assert e_d <= max(1.01 * e_o, 256 * EPS * np.linalg.norm(dense)) + (1e-8 if r != r_o else 0.0)
+
+
+def test_b_dense_legacy_split_symbols():
+    """HCORE_dgemm_qr_svd_b_dense + HCORE_dgemm_ormqr (host pointers, reference prototypes) equal the batched call."""
+    import ctypes as C
+    from hcore_b200 import _lib
+    L = _lib.load()
+    nb, k = 160, 10
+    b = make_lr_batch(1, nb, k, base_seed=9)
+    rng = np.random.default_rng(2)
+    Bd = np.ascontiguousarray((rng.random((nb, nb)) - 0.5) / np.sqrt(nb))
+    c = api.Context(0)
+    t = _to_dev(b)
+    Bt = torch.from_numpy(Bd[None]).to("cuda:0")
+    c.dgemm_batched_b_dense(-1.0, t["au"], t["av"], t["ark"], Bt, 1.0, t["cu"], t["cv"], t["crk"], rk=0, maxrk=2 * k, acc=1e-8)
+    torch.cuda.synchronize()
+    r_ref = int(t["crk"][0].item())
+    ref_cu, ref_cv = t["cu"][0, :r_ref].cpu().numpy(), t["cv"][0, :r_ref].cpu().numpy()
+    c.close()
+    au, av = np.ascontiguousarray(b.au[0]), np.ascontiguousarray(b.av[0])
+    cu = np.zeros((2 * k, nb)); cv = np.zeros((2 * k, nb)); cu[:k] = b.cu[0][:k]; cv[:k] = b.cv[0][:k]
+    dp = C.POINTER(C.c_double)
+    P = lambda x: x.ctypes.data_as(dp)
+    ark, ck = (C.c_int * 1)(k), (C.c_int * 1)(k)
+    o = [dp() for _ in range(11)]; n = [C.c_int() for _ in range(8)]
+    fl = api.FlopCounter()
+    L.HCORE_dgemm_qr_svd_b_dense(111, 112, nb, nb, -1.0, P(au), P(av), ark, nb, P(Bd), nb, 1.0, P(cu), P(cv), ck, nb,
+                                 0, 2 * k, 2 * k, 1e-8, None, C.byref(fl),
+                                 C.byref(o[0]), C.byref(o[1]), C.byref(o[2]), C.byref(n[0]), C.byref(n[1]), C.byref(o[3]), C.byref(n[2]),
+                                 C.byref(o[4]), C.byref(n[3]), C.byref(o[5]), C.byref(n[4]), C.byref(o[6]), C.byref(n[5]), C.byref(o[7]),
+                                 C.byref(n[6]), C.byref(o[8]), C.byref(o[9]), C.byref(n[7]), C.byref(o[10]))
+    rnew = n[1].value
+    assert rnew == r_ref
+    cu2 = np.zeros((rnew, nb)); cv2 = np.zeros((rnew, nb))
+    L.HCORE_dgemm_ormqr(111, 112, nb, nb, -1.0, P(au), P(av), ark, nb, 1.0, P(cu2), P(cv2), ck, nb, 0, 2 * k, 2 * k, 1e-8,
+                        None, C.byref(fl), o[1], o[2], n[0].value, rnew, o[3], n[2].value, o[4], n[3].value, o[5], n[4].value,
+                        o[6], n[5].value, o[7], n[6].value, P(cu2), o[9], n[7].value, P(cv2))
+    assert ck[0] == rnew and fl.update > 0
+    assert np.array_equal(cu2, ref_cu) and np.array_equal(cv2, ref_cv)
