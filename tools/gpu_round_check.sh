@@ -17,6 +17,6 @@ import json;d=json.load(open('gpurun_out/quickw${W}_$TAG.json'));print('W=$W',d[
  ops) timeout 1200 python tools/bench_ops.py gpurun_out/ops_$TAG.json 2>&1 | tail -20 ;;
  dense) timeout 600 python -m pytest tests -m gpu -x -q -k "dgemmcd or dsyrk" 2>&1 | tail -8; OPS_ONLY=dense timeout 600 python tools/bench_ops.py gpurun_out/dense_$TAG.json 2>&1 | tail -4
         ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'dense_' -c 12 --csv --log-file gpurun_out/dense_launches_$TAG.csv env OPS_ONLY=dense python tools/bench_ops.py > /dev/null 2>&1; grep -v "^==" gpurun_out/dense_launches_$TAG.csv | awk -F'","' '{print $5, $(NF)}' | tail -6 ;;
- sanitize) timeout 900 compute-sanitizer --tool memcheck python tools/profile_run.py 4 256 16 1 2>&1 | tail -30 ;;
+ sanitize) for tool in memcheck racecheck synccheck; do timeout 900 compute-sanitizer --tool $tool --print-limit 10 python tools/sanitize_run.py 2>&1 | tail -4; done ;;
 esac
 done
