@@ -55,7 +55,7 @@ struct hcore_b200_context {
     int64_t launches = 0;
     std::string err;
     // TLR workspace
-    DevBuf rec, G, R, Y, sigma, ints, ptrs;
+    DevBuf rec, G, R, Y, Lcore, sigma, ints, ptrs;
     // dense workspace
     DevBuf X;
     // complex (zgemm) workspace
@@ -88,11 +88,12 @@ namespace {
         }                                                                                    \
     } while (0)
 
-int pick_width(int maxrk) {
-    const int w = std::min(maxrk, HCORE_B200_MAX_STACK);
+int pick_width(int maxrk, int cap = HCORE_B200_MAX_STACK) {
+    const int w = std::min(maxrk, cap);
     if (w <= 32) return 32;
     if (w <= 64) return 64;
-    return 128;
+    if (w <= 128) return 128;
+    return 256;
 }
 
 size_t per_tile_ws_bytes(int N, int m_pad, int nblk) {
@@ -101,6 +102,7 @@ size_t per_tile_ws_bytes(int N, int m_pad, int nblk) {
     b += (size_t)m_pad * N * 8;                 // G
     b += 2ull * N * N * 8;                      // R
     b += 2ull * N * N * 8;                      // Y
+    if (N > 128) b += (size_t)N * (N + 4) * 8;  // L (core matrix outside shared memory)
     b += (size_t)N * 8 + 16;                    // sigma + ints
     return b;
 }
@@ -220,7 +222,7 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
     if (!ctx) return HCORE_B200_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
+    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->Lcore, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -278,7 +280,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = pick_width(maxrk);
+    const int N = pick_width(maxrk, HCORE_B200_MAX_STACK_D);
     const int m_pad = round_up(std::max(nb, kBlockH), kBlockH);
     const int nblk = m_pad / kBlockH;
     const int chunk = std::min(ntiles, default_chunk(ctx, N, m_pad, nblk));
@@ -294,6 +296,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
     CUDA_TRY(ctx, ctx->G.reserve((size_t)chunk * m_pad * N * 8));
     CUDA_TRY(ctx, ctx->R.reserve(2ull * chunk * N * N * 8));
     CUDA_TRY(ctx, ctx->Y.reserve(2ull * chunk * N * N * 8));
+    if (N > 128) CUDA_TRY(ctx, ctx->Lcore.reserve((size_t)chunk * N * (N + 4) * 8));
     CUDA_TRY(ctx, ctx->sigma.reserve((size_t)chunk * N * 8));
     CUDA_TRY(ctx, ctx->ints.reserve((size_t)chunk * 4 * sizeof(int)));
 
@@ -302,6 +305,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
     ws.G = (double *)ctx->G.p;
     ws.R = (double *)ctx->R.p;
     ws.Y = (double *)ctx->Y.p;
+    ws.L = (double *)ctx->Lcore.p;
     ws.sigma = (double *)ctx->sigma.p;
     ws.ncols = (int *)ctx->ints.p;
     ws.newrank = ws.ncols + chunk;
@@ -327,7 +331,8 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
         switch (N) {
             case 32: rc = launch_chunk_n<32>(ctx, ar, ws, st); break;
             case 64: rc = launch_chunk_n<64>(ctx, ar, ws, st); break;
-            default: rc = launch_chunk_n<128>(ctx, ar, ws, st); break;
+            case 128: rc = launch_chunk_n<128>(ctx, ar, ws, st); break;
+            default: rc = launch_chunk_n<256>(ctx, ar, ws, st); break;
         }
         if (rc != HCORE_B200_OK) return rc;
     }
@@ -356,7 +361,8 @@ static int tlr_batched_apply(hcore_b200_handle_t ctx, int ntiles, int nb, double
     switch (ctx->last_N) {
         case 32: rc = launch_chunk_n<32>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
         case 64: rc = launch_chunk_n<64>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
-        default: rc = launch_chunk_n<128>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
+        case 128: rc = launch_chunk_n<128>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
+        default: rc = launch_chunk_n<256>(ctx, ar, ctx->last_ws, (cudaStream_t)stream); break;
     }
     ctx->split.pending = false;
     return rc;

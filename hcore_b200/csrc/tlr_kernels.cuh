@@ -42,11 +42,14 @@ constexpr double kTolRot = 1e-15;
 constexpr double kTolStop = 1e-7;
 constexpr int kMaxSweeps = 30;
 
+// N <= 128: the core matrix lives in shared memory.  N = 256 (ranks up to 128): 256 x 260 doubles do not fit
+// one SM, the same code then works on a per-tile slab of the workspace that stays L2 resident.
 template <int N>
 struct SvdSmem {
     using G = Geometry<N>;
+    static constexpr bool kGlobalL = (N > 128);
     static constexpr int kL = 0;
-    static constexpr int kVn = kL + N * G::kLdL;
+    static constexpr int kVn = kL + (kGlobalL ? 0 : N * G::kLdL);
     static constexpr int kVvec = kVn + N;
     static constexpr int kSig = kVvec + N;
     static constexpr int kSsort = kSig + N;
@@ -62,7 +65,8 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     using SM = SvdSmem<N>;
     constexpr int LDL = G::kLdL;
     extern __shared__ __align__(16) double smem[];
-    double *L = smem + SM::kL, *vn = smem + SM::kVn, *vvec = smem + SM::kVvec, *sig = smem + SM::kSig,
+    double *L = SM::kGlobalL ? ws.L + (size_t)blockIdx.x * N * LDL : smem + SM::kL;
+    double *vn = smem + SM::kVn, *vvec = smem + SM::kVvec, *sig = smem + SM::kSig,
            *ssort = smem + SM::kSsort;
     int *perm = reinterpret_cast<int *>(smem + SM::kInts);
     int *posof = perm + N;
@@ -264,17 +268,20 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     // independent rotations without touching shared memory, the two in-block rotations are added in
     // the first step of a sweep.  Blocks meet in round-robin order, so a sweep has kq4/2 - 1 barrier
     // steps instead of kq - 1, and every column pair is rotated exactly once per sweep.
-    constexpr int RP = N / 32;
-    const int l16 = tid & 15, grp = tid >> 4;
-    const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step (<= 32 groups)
+    constexpr int LG = (N > 128) ? 32 : 16;            // lanes per block pair (N = 256: a whole warp, 8 rows per lane)
+    constexpr int RP = N / (2 * LG);                   // row pairs per lane and column
+    const int l16 = tid & (LG - 1), grp = tid / LG;    // lane l16 of its group: row pairs 2 l16 + 2 LG e
+    const int ngrp = blockDim.x / LG;
+    const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step
     int sweeps = 0;
     bool converged = (kq4 < 4);
     // Two independent rotations A = (ap, aq) and B = (bp, bq) at once.  The six partial sums are reduced
-    // by recursive halving: the lower 8 lanes of the group end up with the three totals of A, the upper
-    // 8 with those of B (12 exchanges instead of 24), each half derives ITS rotation (the scalar chain
+    // by recursive halving: the lower half of the group ends up with the three totals of A, the upper
+    // half with those of B (12 exchanges instead of 24), each half derives ITS rotation (the scalar chain
     // runs once for both) and the halves swap (cos, sin).  sin == 0 means "no rotation".
-    const bool hi8 = (l16 & 8) != 0;
-    const unsigned hmask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;   // the warp's other 16-lane group may be idle
+    const bool hi8 = (l16 & (LG / 2)) != 0;
+    // the warp's other 16-lane group may be idle: shuffles name the lanes of this group only
+    const unsigned hmask = (LG == 32) ? 0xffffffffu : ((tid & 16) ? 0xffff0000u : 0x0000ffffu);
     auto rotate2 = [&](double2 (&ap)[RP], double2 (&aq)[RP], double2 (&bp)[RP], double2 (&bq)[RP], int &big) {
         double sa[3] = {0.0, 0.0, 0.0}, ta[3] = {0.0, 0.0, 0.0}, sb[3] = {0.0, 0.0, 0.0}, tb[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -290,10 +297,10 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const double a = sa[q] + ta[q], b = sb[q] + tb[q];
-            v[q] = (hi8 ? b : a) + __shfl_xor_sync(hmask, hi8 ? a : b, 8);
+            v[q] = (hi8 ? b : a) + __shfl_xor_sync(hmask, hi8 ? a : b, LG / 2);
         }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = LG / 4; o > 0; o >>= 1) {
 #pragma unroll
             for (int q = 0; q < 3; ++q) v[q] += __shfl_xor_sync(hmask, v[q], o);
         }
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
             cs = u * ru;
             sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
         }
-        const double ocs = __shfl_xor_sync(hmask, cs, 8), osn = __shfl_xor_sync(hmask, sn, 8);
+        const double ocs = __shfl_xor_sync(hmask, cs, LG / 2), osn = __shfl_xor_sync(hmask, sn, LG / 2);
         const double csa = hi8 ? ocs : cs, sna = hi8 ? osn : sn, csb = hi8 ? cs : ocs, snb = hi8 ? sn : osn;
         if (sna != 0.0) {
 #pragma unroll
@@ -334,31 +341,31 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
         int big = 0;
         for (int step = 0; step < nb2 - 1; ++step) {
-            if (grp < nbp) {
+            for (int k = grp; k < nbp; k += ngrp) {         // one pass for N <= 128 (32 groups >= nbp)
                 int p, qq;
-                rr_pair(nb2, step, grp, p, qq);
+                rr_pair(nb2, step, k, p, qq);
                 double *c0p = L + (size_t)(2 * p) * LDL + 2 * l16, *c1p = c0p + LDL;
                 double *c0q = L + (size_t)(2 * qq) * LDL + 2 * l16, *c1q = c0q + LDL;
                 double2 p0[RP], p1[RP], q0[RP], q1[RP];
 #pragma unroll
                 for (int e = 0; e < RP; ++e) {
-                    const bool on = 2 * l16 + 32 * e < n16;
+                    const bool on = 2 * l16 + 2 * LG * e < n16;
                     const double2 z = make_double2(0.0, 0.0);
-                    p0[e] = on ? *reinterpret_cast<const double2 *>(c0p + 32 * e) : z;
-                    p1[e] = on ? *reinterpret_cast<const double2 *>(c1p + 32 * e) : z;
-                    q0[e] = on ? *reinterpret_cast<const double2 *>(c0q + 32 * e) : z;
-                    q1[e] = on ? *reinterpret_cast<const double2 *>(c1q + 32 * e) : z;
+                    p0[e] = on ? *reinterpret_cast<const double2 *>(c0p + 2 * LG * e) : z;
+                    p1[e] = on ? *reinterpret_cast<const double2 *>(c1p + 2 * LG * e) : z;
+                    q0[e] = on ? *reinterpret_cast<const double2 *>(c0q + 2 * LG * e) : z;
+                    q1[e] = on ? *reinterpret_cast<const double2 *>(c1q + 2 * LG * e) : z;
                 }
                 if (step == 0) rotate2(p0, p1, q0, q1, big);
                 rotate2(p0, q0, p1, q1, big);
                 rotate2(p0, q1, p1, q0, big);
 #pragma unroll
                 for (int e = 0; e < RP; ++e) {
-                    if (2 * l16 + 32 * e < n16) {
-                        *reinterpret_cast<double2 *>(c0p + 32 * e) = p0[e];
-                        *reinterpret_cast<double2 *>(c1p + 32 * e) = p1[e];
-                        *reinterpret_cast<double2 *>(c0q + 32 * e) = q0[e];
-                        *reinterpret_cast<double2 *>(c1q + 32 * e) = q1[e];
+                    if (2 * l16 + 2 * LG * e < n16) {
+                        *reinterpret_cast<double2 *>(c0p + 2 * LG * e) = p0[e];
+                        *reinterpret_cast<double2 *>(c1p + 2 * LG * e) = p1[e];
+                        *reinterpret_cast<double2 *>(c0q + 2 * LG * e) = q0[e];
+                        *reinterpret_cast<double2 *>(c1q + 2 * LG * e) = q1[e];
                     }
                 }
             }

@@ -174,6 +174,7 @@ struct TlrWorkspace {
     double *G;       // [chunk][m_pad * N]                   G = BU (AV^T BV)^T, ld m_pad
     double *R;       // [2][chunk][N * N]
     double *Y;       // [2][chunk][N * N]            U_r (panel 0) and W (panel 1)
+    double *L;       // [chunk][N * (N + 4)]         core matrix of the SVD kernel, N = 256 only (else in shared memory)
     double *sigma;   // [chunk][N]                   sorted singular values
     int *ncols;      // [chunk]  a + c
     int *newrank;    // [chunk]
@@ -432,12 +433,16 @@ __global__ void __launch_bounds__(256, 1) tlr_gdense_kernel(TlrArgs ar, TlrWorks
         for (int idx = tid; idx < kPgRows * (a8 - a); idx += 256) As[(idx & 31) + (a + (idx >> 5)) * SM::kLdA] = 0.0;
         cp_async_commit();
     };
-    double acc[2][N / 8][2];
+    // column tiles are processed in passes of at most 16 (128 columns): N = 256 re-streams B once when a > 128
+    constexpr int CT = (N / 8 > 16) ? 16 : N / 8;
+    for (int ct0 = 0; 8 * ct0 < a8; ct0 += CT) {
+    double acc[2][CT][2];
 #pragma unroll
     for (int sidx = 0; sidx < 2; ++sidx)
 #pragma unroll
-        for (int tt = 0; tt < N / 8; ++tt) acc[sidx][tt][0] = acc[sidx][tt][1] = 0.0;
+        for (int tt = 0; tt < CT; ++tt) acc[sidx][tt][0] = acc[sidx][tt][1] = 0.0;
     const int nk = (m + kPgRows - 1) / kPgRows;
+    __syncthreads();
     stage(0, 0);
     for (int ch = 0; ch < nk; ++ch) {
         if (ch + 1 < nk) {
@@ -454,9 +459,9 @@ __global__ void __launch_bounds__(256, 1) tlr_gdense_kernel(TlrArgs ar, TlrWorks
         for (int k = 0; k < kPgRows; k += 4) {
             const double b0 = bp[k * SM::kLdB], b1 = bp[k * SM::kLdB + 8];
 #pragma unroll
-            for (int tt = 0; tt < N / 8; ++tt) {
-                if (8 * tt < a8) {
-                    const double av = ap[k + 8 * tt * SM::kLdA];
+            for (int tt = 0; tt < CT; ++tt) {
+                if (8 * (ct0 + tt) < a8) {
+                    const double av = ap[k + 8 * (ct0 + tt) * SM::kLdA];
                     dmma_884(acc[0][tt][0], acc[0][tt][1], b0, av);
                     dmma_884(acc[1][tt][0], acc[1][tt][1], b1, av);
                 }
@@ -468,14 +473,15 @@ __global__ void __launch_bounds__(256, 1) tlr_gdense_kernel(TlrArgs ar, TlrWorks
     for (int sidx = 0; sidx < 2; ++sidx) {
         const int row = i0 + 16 * warp + 8 * sidx + g;       // < m_pad (i0 + 127 < m_pad)
 #pragma unroll
-        for (int tt = 0; tt < N / 8; ++tt) {
+        for (int tt = 0; tt < CT; ++tt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int col = 8 * tt + 2 * tg + e;
+                const int col = 8 * (ct0 + tt) + 2 * tg + e;
                 if (col < a) Gt[row + (size_t)col * m_pad] = (row < m) ? acc[sidx][tt][e] : 0.0;
             }
         }
     }
+    }   // column passes
 }
 
 // ========================================================================================
@@ -580,6 +586,27 @@ __device__ __forceinline__ void warp_factor(double (&bx)[16], double (&by)[16], 
                                             double *recg, double *Rg, int c0, int lane) {
     constexpr unsigned kFull = 0xffffffffu;
     const int g = lane >> 2, tg = lane & 3;
+    if (BLK0 && c0 >= kBlockH) {
+        // Stack wider than the row block (N = 256): these columns have no diagonal inside row block 0.  Rows
+        // kBlockH .. n-1 of R are "virtual" zero rows appended to the panel (they change neither R nor the
+        // physical rows of Q); the sub-panel gets the identity reflector here, its 128 entries ARE rows
+        // 0 .. 127 of R, and its reflectors are born in the next row blocks (triangle-on-top-of-block with a
+        // zero diagonal to start from).
+        const int hsw0 = ((g & 1) << 2) ^ (((g >> 1) & 3) << 1);
+        const int col0 = c0 + g;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int off = 2 * ((g << 6) + ((4 * i + tg) ^ hsw0));
+            if (slot) *reinterpret_cast<double2 *>(slot + off) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2 *>(recg + off) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2 *>(Rg + (size_t)(8 * i + 2 * tg) + (size_t)col0 * N) = make_double2(bx[i], by[i]);
+        }
+        const int o0 = kRecV + g + kLdT * (2 * tg), o1 = kRecV + kRecT + 2 * tg + kLdT * g;
+        if (slot) { slot[o0] = 0.0; slot[o0 + kLdT] = 0.0; *reinterpret_cast<double2 *>(slot + o1) = make_double2(0.0, 0.0); }
+        recg[o0] = 0.0; recg[o0 + kLdT] = 0.0;
+        *reinterpret_cast<double2 *>(recg + o1) = make_double2(0.0, 0.0);
+        return;
+    }
     const int istar = c0 >> 3;
     double rx, ry;
     if (BLK0) {
@@ -752,6 +779,10 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) tlr_tsqr_kernel(TlrArgs ar, 
     }
     __syncthreads();
     uint32_t phase[2] = {0, 0};
+    if constexpr (N > kBlockH) {          // virtual rows kBlockH .. N-1 of R start as zeros (see warp_factor)
+        for (int idx = tid; idx < (N - kBlockH) * N; idx += NT) Rg[(size_t)kBlockH + idx % (N - kBlockH) + (size_t)(idx / (N - kBlockH)) * N] = 0.0;
+        __syncthreads();
+    }
     PROF_DECL(tid == NT - 32)
     PROF_COUNT(9, 1);
 

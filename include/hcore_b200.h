@@ -54,7 +54,8 @@ extern "C" {
 #define HCORE_B200_ERR_ARG         101  /* invalid argument           (function return value only)       */
 
 /* Largest stacked width Ark + Crk the kernels are compiled for. */
-#define HCORE_B200_MAX_STACK       128
+#define HCORE_B200_MAX_STACK       128   /* complex path, dense-C ranks */
+#define HCORE_B200_MAX_STACK_D     256   /* HCORE_dgemm / HCORE_sgemm: Ark + Crk up to 256 (ranks up to 128) */
 
 typedef struct hcore_b200_context *hcore_b200_handle_t;
 

@@ -236,7 +236,9 @@ def test_large_tiles_vs_reference_outputs(ctx, golden_dir, name, nb, k, T):
 @pytest.mark.parametrize("nb,k,alpha,beta,rk,acc", [
     (128, 16, -1.0, 1.0, 0, 1e-8), (130, 9, 1.0, 1.0, 0, 1e-6), (257, 17, 0.3, -2.0, 0, 1e-10),
     (1000, 40, -1.0, 1.0, 0, 1e-8), (384, 64, -1.0, 1.0, 0, 1e-8), (200, 12, -1.0, 1.0, 7, 1e-8),
-    (200, 12, -1.0, 1.0, 100, 1e-8), (64, 3, -1.0, 1.0, 0, 1e-3), (2048, 32, -1.0, 1.0, 0, 1e-8)])
+    (200, 12, -1.0, 1.0, 100, 1e-8), (64, 3, -1.0, 1.0, 0, 1e-3), (2048, 32, -1.0, 1.0, 0, 1e-8),
+    # ranks up to 128: stack width 256, the core matrix of the SVD kernel lives in L2 instead of shared memory
+    (512, 128, -1.0, 1.0, 0, 1e-8), (300, 100, -1.0, 1.0, 0, 1e-8), (1024, 96, -1.0, 1.0, 150, 1e-8)])
 def test_vs_oracle(ctx, nb, k, alpha, beta, rk, acc):
     T = 3
     b = make_lr_batch(T, nb, k, base_seed=7 + nb)

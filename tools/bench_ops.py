@@ -39,7 +39,7 @@ ONLY = os.environ.get("OPS_ONLY", "")        # "", "sweep", "sz", "dense"
 # ---- dgemm sweep -------------------------------------------------------------------------------------
 sweep = []
 for nb, k, T in [] if ONLY not in ("", "sweep") else [(512, 16, 8192), (512, 32, 8192), (512, 64, 4096), (1024, 16, 8192), (1024, 32, 8192), (1024, 64, 4736),
-                 (2048, 32, 2368), (2048, 64, 2368)]:
+                 (2048, 32, 2368), (2048, 64, 2368), (1024, 128, 1184), (2048, 128, 592)]:
     d = bench.make_device_batch(torch, T, nb, k, dev, seed=3)
     fn = lambda: ctx.dgemm_batched(-1.0, d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], 1.0, d["cu"], d["cv"],
                                    d["crk"], rk=0, maxrk=2 * k, acc=1e-8, status=d["status"])

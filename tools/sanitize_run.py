@@ -9,7 +9,7 @@ from hcore_b200 import api
 from hcore_b200.tilegen import make_lr_batch, make_dense_batch
 dev = torch.device("cuda:0")
 ctx = api.Context(0)
-for nb, k in ((200, 12), (257, 9)):
+for nb, k in ((200, 12), (257, 9), (260, 70)):    # the last one: stack width 256 (core matrix in L2)
     b = make_lr_batch(3, nb, k)
     t = {n: torch.from_numpy(np.ascontiguousarray(getattr(b, n))).to(dev) for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
     st = torch.zeros(3, dtype=torch.int32, device=dev)
@@ -31,7 +31,8 @@ for nb, k in ((200, 12), (257, 9)):
     z = {n: torch.complex(torch.from_numpy(getattr(b, n)).to(dev), 0.5 * torch.roll(torch.from_numpy(getattr(b, n)).to(dev), 1, dims=2)).contiguous()
          for n in ("au", "av", "bu", "bv", "cu", "cv")}
     crk = torch.full((3,), k, dtype=torch.int32, device=dev)
-    ctx.zgemm_batched(-1.0, z["au"], z["av"], t["ark"], z["bu"], z["bv"], t["brk"], 1.0, z["cu"], z["cv"], crk, rk=0, maxrk=2 * k, acc=1e-8, status=st)
+    if 2 * k <= 128:
+      ctx.zgemm_batched(-1.0, z["au"], z["av"], t["ark"], z["bu"], z["bv"], t["brk"], 1.0, z["cu"], z["cv"], crk, rk=0, maxrk=2 * k, acc=1e-8, status=st)
     # dense C
     cd = torch.from_numpy(make_dense_batch(3, nb)).to(dev)
     ark = torch.full((3,), k, dtype=torch.int32, device=dev)
