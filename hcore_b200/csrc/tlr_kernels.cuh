@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
     for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
         int big = 0;
         for (int step = 0; step < nb2 - 1; ++step) {
-            for (int k = grp; k < nbp; k += ngrp) {         // one pass for N <= 128 (32 groups >= nbp)
+            auto do_pair = [&](int k) {
                 int p, qq;
                 rr_pair(nb2, step, k, p, qq);
                 double *c0p = L + (size_t)(2 * p) * LDL + 2 * l16, *c1p = c0p + LDL;
@@ -368,6 +368,11 @@ __global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspac
                         *reinterpret_cast<double2 *>(c1q + 2 * LG * e) = q1[e];
                     }
                 }
+            };
+            if constexpr (LG == 16) {                       // N <= 128: 32 groups >= nbp, a single pass
+                if (grp < nbp) do_pair(grp);
+            } else {
+                for (int k = grp; k < nbp; k += ngrp) do_pair(k);
             }
             __syncthreads();
         }

@@ -586,7 +586,7 @@ __device__ __forceinline__ void warp_factor(double (&bx)[16], double (&by)[16], 
                                             double *recg, double *Rg, int c0, int lane) {
     constexpr unsigned kFull = 0xffffffffu;
     const int g = lane >> 2, tg = lane & 3;
-    if (BLK0 && c0 >= kBlockH) {
+    if (BLK0 && N > kBlockH && c0 >= kBlockH) {
         // Stack wider than the row block (N = 256): these columns have no diagonal inside row block 0.  Rows
         // kBlockH .. n-1 of R are "virtual" zero rows appended to the panel (they change neither R nor the
         // physical rows of Q); the sub-panel gets the identity reflector here, its 128 entries ARE rows
