@@ -35,7 +35,10 @@ def tsqr_factor(x, h=H, w=W):
     m, n = x.shape
     assert m >= n
     h0 = min(m, h)
-    assert h0 >= n
+    # n > h0 (stack wider than the row block, device width 256): rows h0 .. n-1 of R are VIRTUAL zero rows
+    # appended to the panel; columns >= h0 get no reflector in block 0 (their h0 entries are rows 0 .. h0-1
+    # of R) and their reflectors are born in the following blocks, starting from a zero diagonal.
+    nd0 = min(n, h0)                      # columns with a diagonal inside block 0
     bounds = [(0, h0)]
     r0 = h0
     while r0 < m:
@@ -53,6 +56,10 @@ def tsqr_factor(x, h=H, w=W):
             taus = np.zeros(pw)
             Tm = np.zeros((w, w))
             Vpan = np.zeros((hi - lo, pw))
+            if j == 0 and c0 >= nd0:
+                # identity reflector panel (tau = 0); nothing to update to the right either
+                Tj.append(Tm)
+                continue
             for ii in range(pw):
                 i = c0 + ii
                 if j == 0:
@@ -116,7 +123,7 @@ def tsqr_factor(x, h=H, w=W):
                     B[:, c1:] -= Vpan @ S2
             Tj.append(Tm)
         if j == 0:
-            R[:, :] = np.triu(B[:n, :n])
+            R[:nd0, :] = np.triu(B[:nd0, :n])
         Vs.append(B)
         Ts.append(Tj)
     return dict(R=R, V=Vs, T=Ts, bounds=bounds, n=n, m=m, w=w)
@@ -129,6 +136,8 @@ def _vpanel(f, j, s):
     B = f["V"][j]
     if j > 0:
         return B[:, c0:c1]
+    if c0 >= B.shape[0]:                  # wide stack: identity reflector in block 0
+        return np.zeros((B.shape[0], c1 - c0))
     Vp = np.tril(B[:, c0:c1], -c0 - 1 + 0)  # strictly below the global diagonal
     # np.tril with k=-c0-1 keeps element (row, cc) when row - cc >= c0 + 1, i.e. row > c0 + cc
     for cc in range(c1 - c0):
@@ -157,7 +166,8 @@ def tsqr_apply(f, y):
         out[lo:hi] = Z
     lo, hi = f["bounds"][0]
     Yf = np.zeros((hi - lo, r))
-    Yf[:n] = Y
+    nd0 = min(n, hi - lo)
+    Yf[:nd0] = Y[:nd0]                    # rows >= nd0 of Y sit on virtual rows: their output is discarded
     for s in range(nsp - 1, -1, -1):
         pw = min(n, s * w + w) - s * w
         Vp = _vpanel(f, 0, s)

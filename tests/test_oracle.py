@@ -204,3 +204,18 @@ def test_covariance_tiles_oracle_vs_live_reference():
         dense = b.dense_c(t, -1.0, 1.0)
         e1, e2 = np.linalg.norm(cu[:r].T @ cv[:r] - dense), np.linalg.norm(cu2.T @ cv2 - dense)
         assert abs(e1 - e2) <= 1e-3 * e1 + 64 * np.finfo(float).eps * np.linalg.norm(dense)
+
+
+def test_device_model_wide_stack_virtual_rows():
+    """Stack wider than the TSQR row block (the device's width-256 case: 128-row blocks, up to 256 columns): rows
+    h .. n-1 of R are virtual zero rows; R^T R = X^T X, Q has orthonormal columns and Q R = X."""
+    rng = np.random.default_rng(3)
+    m, n, h, w = 70, 24, 16, 8
+    x = rng.random((m, n)) - 0.5
+    f = dm.tsqr_factor(x, h=h, w=w)
+    R = f["R"]
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+    assert np.abs(R.T @ R - x.T @ x).max() < 1e-13
+    q = dm.tsqr_apply(f, np.eye(n))
+    assert np.abs(q.T @ q - np.eye(n)).max() < 1e-13
+    assert np.abs(q @ R - x).max() < 1e-13
