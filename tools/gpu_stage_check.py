@@ -18,8 +18,8 @@ from oracle import tlr_oracle as orc  # noqa: E402
 
 
 def pick_width(maxrk):
-    w = min(maxrk, 128)
-    return 32 if w <= 32 else (64 if w <= 64 else 128)
+    w = min(maxrk, 256)
+    return 32 if w <= 32 else (64 if w <= 64 else (128 if w <= 128 else 256))
 
 
 def run_case(nb, k, T, alpha=-1.0, beta=1.0, acc=1e-8, rk=0, verbose=True):
