@@ -47,7 +47,7 @@ extern "C" {
 #define HCORE_B200_OK                0
 #define HCORE_B200_ERR_ZERO_RANK     1  /* Ark, Brk or Crk == 0   (ref hcore_dgemm.c:743-746: exit)      */
 #define HCORE_B200_ERR_MAXRK         2  /* maxrk < Ark + Crk      (ref hcore_dgemm.c:924-927: exit)      */
-#define HCORE_B200_ERR_UNSUPPORTED   3  /* Ark+Crk above the compiled stack width (128) or > nb           */
+#define HCORE_B200_ERR_UNSUPPORTED   3  /* Ark+Crk above the compiled stack width (256; complex 128) or > nb */
 #define HCORE_B200_ERR_NEWRANK       4  /* rank after truncation > maxrk (ref hcore_dgemm.c:465-468)     */
 #define HCORE_B200_ERR_NO_CONVERGE   5  /* Jacobi SVD hit its sweep limit (ref: dgesvd info != 0, :407)  */
 #define HCORE_B200_ERR_CUDA        100  /* a CUDA runtime call failed (function return value only)       */
@@ -64,11 +64,11 @@ typedef struct { double re, im; } hcore_b200_dcomplex;
 
 /* ---- context ------------------------------------------------------------------------- */
 /* Creates a context on CUDA device `device` (-1: current device).  The context owns the
- * workspace (reflector panels, R factors, T factors) and grows it on demand.            */
+ * workspace (block-reflector records, G, R factors, U_r / W) and grows it on demand.    */
 int  hcore_b200_create(hcore_b200_handle_t *handle, int device);
 int  hcore_b200_destroy(hcore_b200_handle_t handle);
-/* Upper bound on the number of tiles processed per kernel wave (workspace = chunk *
- * about 2.8 MiB at nb=1024, stack 128).  0 selects the default.                          */
+/* Upper bound on the number of tiles processed per kernel launch (workspace = chunk *
+ * about 3.9 MiB at nb=1024, stack 128).  0 selects the default (16 x #SM).               */
 int  hcore_b200_set_chunk(hcore_b200_handle_t handle, int tiles_per_chunk);
 const char *hcore_b200_last_error(hcore_b200_handle_t handle);
 const char *hcore_b200_version(void);
