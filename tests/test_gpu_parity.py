@@ -238,7 +238,8 @@ def test_large_tiles_vs_reference_outputs(ctx, golden_dir, name, nb, k, T):
     (1000, 40, -1.0, 1.0, 0, 1e-8), (384, 64, -1.0, 1.0, 0, 1e-8), (200, 12, -1.0, 1.0, 7, 1e-8),
     (200, 12, -1.0, 1.0, 100, 1e-8), (64, 3, -1.0, 1.0, 0, 1e-3), (2048, 32, -1.0, 1.0, 0, 1e-8),
     # ranks up to 128: stack width 256, the core matrix of the SVD kernel lives in L2 instead of shared memory
-    (512, 128, -1.0, 1.0, 0, 1e-8), (300, 100, -1.0, 1.0, 0, 1e-8), (1024, 96, -1.0, 1.0, 150, 1e-8)])
+    (512, 128, -1.0, 1.0, 0, 1e-8), (300, 100, -1.0, 1.0, 0, 1e-8), (1024, 96, -1.0, 1.0, 150, 1e-8),
+    (4096, 24, -1.0, 1.0, 0, 1e-8)])          # 32 row blocks per panel
 def test_vs_oracle(ctx, nb, k, alpha, beta, rk, acc):
     T = 3
     b = make_lr_batch(T, nb, k, base_seed=7 + nb)
@@ -274,6 +275,14 @@ def test_covariance_tiles_vs_oracle(ctx, nb, maxrk, acc):
         e_o = np.linalg.norm(cu_o.T @ cv_o - dense)
         e_d = np.linalg.norm(cu[t, :r].T @ cv[t, :r] - dense)
         assert e_d <= max(1.01 * e_o, 256 * EPS * np.linalg.norm(dense)) + (acc if r != r_o else 0.0)
+
+
+def test_empty_batch_is_a_no_op(ctx):
+    z = torch.zeros((0, 8, 64), dtype=torch.float64, device="cuda:0")
+    zi = torch.zeros((0,), dtype=torch.int32, device="cuda:0")
+    ctx.dgemm_batched(-1.0, z, z, zi, z, z, zi, 1.0, torch.zeros((0, 16, 64), dtype=torch.float64, device="cuda:0"),
+                      torch.zeros((0, 16, 64), dtype=torch.float64, device="cuda:0"), zi, rk=0, maxrk=16, acc=1e-8)
+    torch.cuda.synchronize()
 
 
 def test_ragged_ranks_and_rank_deficient_stack(ctx):
