@@ -156,7 +156,7 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
     }
     if (tm) cudaEventRecord(ctx->ev[2], st);
     if (ctx->debug_stages >= 3) {
-        tlr_svd_kernel<N><<<ar.ntiles, 512, SvdSmem<N>::kBytes, st>>>(ar, ws);
+        tlr_svd_kernel<N><<<ar.ntiles, SvdThreads<N>::value, SvdSmem<N>::kBytes, st>>>(ar, ws);
         ctx->launches++;
     }
     if (tm) cudaEventRecord(ctx->ev[3], st);

@@ -58,9 +58,14 @@ struct SvdSmem {
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
 
-// One CTA (512 threads) per tile.
+// One CTA per tile.  Threads = 4 N (one 16-lane group per Jacobi block pair), capped at 512: the narrow stacks
+// (N = 32, 64: ranks up to 16 / 32) run four / two tiles per SM at a time instead of one mostly idle 512-thread
+// CTA -- their SVD is pure latency (QRCP steps, Jacobi rounds), so co-resident tiles overlap it.
 template <int N>
-__global__ void __launch_bounds__(512, 1) tlr_svd_kernel(TlrArgs ar, TlrWorkspace ws) {
+struct SvdThreads { static constexpr int value = (4 * N < 512) ? 4 * N : 512; };
+
+template <int N>
+__global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::value) tlr_svd_kernel(TlrArgs ar, TlrWorkspace ws) {
     using G = Geometry<N>;
     using SM = SvdSmem<N>;
     constexpr int LDL = G::kLdL;
