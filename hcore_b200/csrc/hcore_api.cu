@@ -123,7 +123,8 @@ int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
 template <int N, int TW, int AW>
 int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
     {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_pg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PgSmem::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_pg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)PgSmemT<PgWidth<N>::value>::kBytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)TsqrSmem<TW>::kBytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_svd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SvdSmem<N>::kBytes));
@@ -145,7 +146,7 @@ int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace 
                                                (int)GdSmem<N>::kBytes));
             tlr_gdense_kernel<N><<<dim3(ws.nblk, ar.ntiles), 256, GdSmem<N>::kBytes, st>>>(ar, ws);
         } else {
-            tlr_pg_kernel<N><<<ar.ntiles, 256, PgSmem::kBytes, st>>>(ar, ws);
+            tlr_pg_kernel<N><<<ar.ntiles, 256, PgSmemT<PgWidth<N>::value>::kBytes, st>>>(ar, ws);
         }
         ctx->launches++;
     }

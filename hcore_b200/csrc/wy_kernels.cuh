@@ -198,15 +198,18 @@ __device__ __forceinline__ size_t rec_offset(const TlrWorkspace &ws, int panel, 
 // handled in 64-column slabs (one extra sweep per slab pair).
 constexpr int kPgRows = 32;
 constexpr int kPgLd = kPgRows + 4;      // 36: conflict-free fragment loads
-constexpr int kPgKC = 64;               // slab width
-constexpr int kPgLdP = kPgKC + 4;       // 68
+// slab width KC: 64, or 32 for the narrow stacks (N <= 64: 46 KB instead of 108 KB of shared memory, four
+// CTAs per SM instead of two -- the kernel is latency-bound there)
 
-struct PgSmem {
-    static constexpr int kStage = 2 * kPgKC * kPgLd;         // one stage: two 32 x 64 operand chunks
-    static constexpr int kP = 2 * kStage;                    // P slab, ld 68
-    static constexpr int kTotal = kP + kPgKC * kPgLdP;
+template <int KC>
+struct PgSmemT {
+    static constexpr int kLdP = KC + 4;
+    static constexpr int kStage = 2 * KC * kPgLd;            // one stage: two 32 x KC operand chunks
+    static constexpr int kP = 2 * kStage;                    // P slab, ld KC + 4
+    static constexpr int kTotal = kP + KC * kLdP;
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
+using PgSmem = PgSmemT<64>;
 
 // rows [r0, r0+32) x ncol columns (padded with zeros to ncol8) of a column-major matrix -> dst (ld kPgLd)
 __device__ __forceinline__ void pg_stage(double *dst, const double *src, size_t col0, int ld, int m, int r0, int ncol,
@@ -232,9 +235,11 @@ __device__ __forceinline__ void pg_stage(double *dst, const double *src, size_t 
 
 // G(m_pad x a, ld m_pad) = pscale * BU (AV^T BV)^T for one tile, by the whole CTA (256 threads).
 // AV: m x a (ld lda), BU, BV: m x b (ld ldb); rows m .. m_pad-1 of G are written as zeros.
+template <int KC = 64>
 __device__ __forceinline__ void pg_body(double *smem, const double *AV, const double *BU, const double *BV, int a, int b,
                                         int m, int lda, int ldb, int m_pad, int f32, double pscale, double *Gt) {
-    using SM = PgSmem;
+    using SM = PgSmemT<KC>;
+    constexpr int kPgKC = KC, kPgLdP = SM::kLdP;
     double *P = smem + SM::kP;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
@@ -252,9 +257,9 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
             {
                 const bool active = 8 * warp < as8;
                 const int i0 = 8 * warp;
-                double acc[8][2];
+                double acc[KC / 8][2];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
+                for (int q = 0; q < KC / 8; ++q) acc[q][0] = acc[q][1] = 0.0;
                 pg_stage(smem, AVs, ia, lda, m, 0, as, as8, va, f32, tid);
                 pg_stage(smem + kPgKC * kPgLd, BVs, jb, ldb, m, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
@@ -276,7 +281,7 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                         for (int k = 0; k < kPgRows; k += 4) {
                             const double av = As[(k + tg) + (i0 + g) * kPgLd];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
+                            for (int q = 0; q < KC / 8; ++q) {
                                 if (8 * q < bs8) {
                                     const double bv = Bs[(k + tg) + (8 * q + g) * kPgLd];
                                     dmma_884(acc[q][0], acc[q][1], av, bv);
@@ -288,7 +293,7 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                 }
                 if (active) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < KC / 8; ++q) {
                         if (8 * q < bs8) {
                             P[(i0 + g) + (8 * q + 2 * tg) * kPgLdP] = pscale * acc[q][0];
                             P[(i0 + g) + (8 * q + 2 * tg + 1) * kPgLdP] = pscale * acc[q][1];
@@ -299,7 +304,8 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
             __syncthreads();
             // ---- G[:, ia..] (+)= BU[:, jb..] P^T: warp -> (8-row strip of the chunk, 4 column tiles) ------
             {
-                const int strip = warp & 3, q0 = 4 * (warp >> 2);
+                constexpr int QW = KC / 16;                   // column tiles per warp: 8 warps = 4 strips x 2 halves
+                const int strip = warp & 3, q0 = QW * (warp >> 2);
                 pg_stage(smem, BUs, jb, ldb, m, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
                 for (int ch = 0; ch < nchunks_pad; ++ch) {
@@ -312,14 +318,14 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                         cp_async_wait<0>();
                     }
                     __syncthreads();
-                    double acc[4][2];
+                    double acc[QW][2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+                    for (int q = 0; q < QW; ++q) acc[q][0] = acc[q][1] = 0.0;
 #pragma unroll 4
                     for (int k = 0; k < bs8; k += 4) {
                         const double av = cur[(8 * strip + g) + (k + tg) * kPgLd];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int q = 0; q < QW; ++q) {
                             if (8 * (q0 + q) < as8) {
                                 const double bv = P[(8 * (q0 + q) + g) + (k + tg) * kPgLdP];
                                 dmma_884(acc[q][0], acc[q][1], av, bv);
@@ -328,7 +334,7 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                     }
                     const int row = ch * kPgRows + 8 * strip + g;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < QW; ++q) {
                         const int col = 8 * (q0 + q) + 2 * tg;
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
@@ -347,7 +353,10 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
 
 
 template <int N>
-__global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace ws) {
+struct PgWidth { static constexpr int value = (N <= 64) ? 32 : 64; };
+
+template <int N>
+__global__ void __launch_bounds__(256, (N <= 64 ? 4 : 2)) tlr_pg_kernel(TlrArgs ar, TlrWorkspace ws) {
     extern __shared__ __align__(16) double smem[];
     const int t = blockIdx.x, gt = ar.tile0 + t;
     const int a = ar.Ark[gt], b = ar.Brk[gt], c = ar.Crk[gt];
@@ -364,8 +373,8 @@ __global__ void __launch_bounds__(256, 2) tlr_pg_kernel(TlrArgs ar, TlrWorkspace
         if (ar.status) ar.status[gt] = st;
     }
     if (st != HCORE_B200_OK) return;
-    pg_body(smem, ar.AV[gt], ar.BU[gt], ar.BV[gt], a, b, m, ar.lda, ar.ldb, ws.m_pad, ar.f32, 1.0,
-            ws.G + (size_t)t * ws.m_pad * N);
+    pg_body<PgWidth<N>::value>(smem, ar.AV[gt], ar.BU[gt], ar.BV[gt], a, b, m, ar.lda, ar.ldb, ws.m_pad, ar.f32, 1.0,
+                               ws.G + (size_t)t * ws.m_pad * N);
 }
 
 // ---- 1b. G for a DENSE B operand -----------------------------------------------------------------
