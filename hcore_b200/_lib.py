@@ -31,6 +31,11 @@ EXPORTED_SYMBOLS = [
     "HCORE_dgemm_batched_qr_svd_strided", "HCORE_dgemm_batched_ormqr_strided",
     "use_trmm", "gemm_print_index", "gemm_print_mat", "hc_nelm_limit", "syrk_print_index",
     "gemmcd_print_index", "gemmcd_print_mat", "gemmcd_use_scratch",
+    # the remaining tile kernels of one TLR-Cholesky step + HCORE_dgemm_fast
+    "HCORE_dgemm_fast", "HCORE_dtrsm", "HCORE_dpotrf", "HCORE_dgemmbdcd", "HCORE_duncompress", "HCORE_zuncompress",
+    "HCORE_dtrsm_batched_strided", "HCORE_dpotrf_batched_strided", "HCORE_dgemmbdcd_batched_strided",
+    "HCORE_duncompress_batched_strided", "HCORE_zuncompress_batched_strided",
+    "gemmbdcd_print_index", "gemmbdcd_print_mat", "gemmfrk_print_index", "gemmfrk_print_mat",
 ]
 
 _lib = None
@@ -126,5 +131,23 @@ def load():
     L.HCORE_dgemmcd.restype = None
     L.HCORE_dsyrk.argtypes = [i, i, i, i, d, dp, i, dp, i, d, dp, i, dp, vp]
     L.HCORE_dsyrk.restype = None
+    # reference src/include/hcore_d.h:47-67, 87-106, 117-138; hcore_z.h:76-88
+    L.HCORE_dgemm_fast.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, dp, dp, i, d, dp, dp, dp, i, i, i, d, dp]
+    L.HCORE_dgemm_fast.restype = None
+    L.HCORE_dtrsm.argtypes = [i, i, i, i, i, i, d, dp, i, dp, i, vp]
+    L.HCORE_dtrsm.restype = None
+    L.HCORE_dpotrf.argtypes = [i, i, dp, i, ip, vp]
+    L.HCORE_dpotrf.restype = None
+    L.HCORE_dgemmbdcd.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, i, d, dp, i, dp, vp]
+    L.HCORE_dgemmbdcd.restype = None
+    L.HCORE_duncompress.argtypes = [i, i, i, i, d, dp, dp, i, dp, dp, i, d, dp, i]
+    L.HCORE_duncompress.restype = None
+    L.HCORE_zuncompress.argtypes = [i, i, i, i, DComplex, vp, dp, i, vp, dp, i, DComplex, vp, i]
+    L.HCORE_zuncompress.restype = None
+    L.HCORE_dgemmbdcd_batched_strided.argtypes = [vp, i, i, i, d, vp, vp, vp, i, i64, vp, i, i64, d, vp, i, i64, vp]
+    L.HCORE_duncompress_batched_strided.argtypes = [vp, i, i, i, vp, vp, i, i64, vp, vp, i, i64, vp, i, i64, vp, vp]
+    L.HCORE_zuncompress_batched_strided.argtypes = [vp, i, i, i, vp, vp, i, i64, vp, vp, i, i64, vp, i, i64, vp, vp]
+    L.HCORE_dtrsm_batched_strided.argtypes = [vp, i, i, i, i, i, i, i, d, vp, i, i64, vp, vp, i, i64, vp]
+    L.HCORE_dpotrf_batched_strided.argtypes = [vp, i, i, i, vp, i, i64, vp, vp]
     _lib = L
     return L

@@ -15,9 +15,11 @@ import numpy as np
 from . import _lib
 
 HCORE_NoTrans, HCORE_Trans = 111, 112
-HCORE_Lower = 122
+HCORE_Upper, HCORE_Lower = 121, 122
+HCORE_NonUnit, HCORE_Unit = 131, 132
+HCORE_Left, HCORE_Right = 141, 142
 
-STATUS_NAMES = {0: "OK", 1: "ZERO_RANK", 2: "MAXRK", 3: "UNSUPPORTED", 4: "NEWRANK", 5: "NO_CONVERGE"}
+STATUS_NAMES = {0: "OK", 1: "ZERO_RANK", 2: "MAXRK", 3: "UNSUPPORTED", 4: "NEWRANK", 5: "NO_CONVERGE", 6: "RANK_MISMATCH"}
 
 
 class FlopCounter(C.Structure):
@@ -108,6 +110,69 @@ def hcore_dsyrk(uplo, trans, N, K, alpha, AU, LDAU, AV, LDAV, beta, CD, LDCD, wo
         _check_colmajor(x, nm)
     L.HCORE_dsyrk(int(uplo), int(trans), int(N), int(K), float(alpha), _dp(AU), int(LDAU), _dp(AV), int(LDAV),
                   float(beta), _dp(CD), int(LDCD), None, C.byref(flops) if flops is not None else None)
+
+
+def hcore_dgemm_fast(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BU, BV, Brk, LDB, beta, CU, CV, Crk, LDC,
+                     rk, maxrk, acc, work=None):
+    """``HCORE_dgemm_fast`` (reference src/compute/hcore_dgemm_fast.c:59-426): arguments of :func:`hcore_dgemm`
+    without the flop counter; needs the library global ``use_trmm`` set to 1 (reference :82)."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("AV", AV), ("BU", BU), ("BV", BV), ("CU", CU), ("CV", CV)):
+        _check_colmajor(x, nm)
+    L.HCORE_dgemm_fast(int(transA), int(transB), int(M), int(N), float(alpha), _dp(AU), _dp(AV), _dp(Ark), int(LDA),
+                       _dp(BU), _dp(BV), _dp(Brk), int(LDB), float(beta), _dp(CU), _dp(CV), _dp(Crk), int(LDC),
+                       int(rk), int(maxrk), float(acc), None)
+
+
+def set_global(name, value):
+    """Sets one of the reference's link-level tunables (``use_trmm`` ...) in the loaded library."""
+    C.c_int.in_dll(_lib.load(), name).value = int(value)
+
+
+def hcore_dtrsm(side, uplo, transA, diag, M, Brank, alpha, A, LDA, BV, LDBV, flops=None):
+    """``HCORE_dtrsm`` (reference src/compute/hcore_dtrsm.c:24-48): ``BV`` (Brank, LDBV) column-major M x Brank, in place."""
+    L = _lib.load()
+    _check_colmajor(A, "A"); _check_colmajor(BV, "BV")
+    L.HCORE_dtrsm(int(side), int(uplo), int(transA), int(diag), int(M), int(Brank), float(alpha), _dp(A), int(LDA),
+                  _dp(BV), int(LDBV), C.byref(flops) if flops is not None else None)
+
+
+def hcore_dpotrf(uplo, N, A, LDA, flops=None):
+    """``HCORE_dpotrf`` (reference src/compute/hcore_dpotrf.c:23-35): factors ``A`` in place, returns ``info``."""
+    L = _lib.load()
+    _check_colmajor(A, "A")
+    info = C.c_int(-1)
+    L.HCORE_dpotrf(int(uplo), int(N), _dp(A), int(LDA), C.byref(info), C.byref(flops) if flops is not None else None)
+    return info.value
+
+
+def hcore_dgemmbdcd(transA, transB, M, N, alpha, AU, AV, Ark, LDA, BD, LDB, beta, CD, LDC, work=None, flops=None):
+    """``HCORE_dgemmbdcd`` (reference src/compute/hcore_dgemmbdcd.c:35-122): ``CD <- alpha AU (AV^T BD) + beta CD``."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("AV", AV), ("BD", BD), ("CD", CD)):
+        _check_colmajor(x, nm)
+    L.HCORE_dgemmbdcd(int(transA), int(transB), int(M), int(N), float(alpha), _dp(AU), _dp(AV), _dp(Ark), int(LDA),
+                      _dp(BD), int(LDB), float(beta), _dp(CD), int(LDC), None, C.byref(flops) if flops is not None else None)
+
+
+def hcore_duncompress(transA, transB, M, N, alpha, AU, Ark, LDA, BV, Brk, LDB, beta, CD, LDC):
+    """``HCORE_duncompress`` (reference src/compute/hcore_duncompress.c:33-85): ``CD <- AU BV^T``."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("BV", BV), ("CD", CD)):
+        _check_colmajor(x, nm)
+    L.HCORE_duncompress(int(transA), int(transB), int(M), int(N), float(alpha), _dp(AU), _dp(Ark), int(LDA), _dp(BV), _dp(Brk),
+                        int(LDB), float(beta), _dp(CD), int(LDC))
+
+
+def hcore_zuncompress(transA, transB, M, N, alpha, AU, Ark, LDA, BV, Brk, LDB, beta, CD, LDC):
+    """``HCORE_zuncompress`` (reference src/compute/hcore_zuncompress.c:35-95): complex128 arrays, plain transpose."""
+    L = _lib.load()
+    for nm, x in (("AU", AU), ("BV", BV), ("CD", CD)):
+        if x.dtype != np.complex128 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{nm}: need a C-contiguous complex128 array")
+    vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    L.HCORE_zuncompress(int(transA), int(transB), int(M), int(N), _lib.DComplex.of(alpha), vp(AU), _dp(Ark), int(LDA), vp(BV),
+                        _dp(Brk), int(LDB), _lib.DComplex.of(beta), vp(CD), int(LDC))
 
 
 def gemm_flops(m, a, b, c, r):
@@ -336,4 +401,51 @@ class Context:
             self._dev_f64(x, nm)
         rc = self._L.HCORE_dsyrk_batched_strided(self._h, T, nb, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark),
                                                  ka * nb, _ptr(CD), nb * nb, self._stream_ptr(stream))
+        self._check(rc)
+
+    # -- the remaining tile kernels of one TLR-Cholesky step --
+    def dtrsm_batched(self, side, uplo, transA, diag, alpha, A, BV, Brk=None, stream=None):
+        """Batched ``HCORE_dtrsm``: ``A`` (T or 1, n, n) triangular tiles (one shared tile when its first dimension
+        is 1), ``BV`` (T, kmax, M) in place; ``Brk`` optional (T,) int32 ranks."""
+        T, kb, M = BV.shape
+        self._dev_f64(A, "A"); self._dev_f64(BV, "BV")
+        if Brk is not None:
+            self._dev_i32(Brk, "Brk")
+        na = A.shape[-1]
+        strideA = 0 if A.shape[0] == 1 else na * na
+        rc = self._L.HCORE_dtrsm_batched_strided(self._h, T, int(side), int(uplo), int(transA), int(diag), M, kb, float(alpha),
+                                                 _ptr(A), na, strideA, _ptr(BV), _ptr(Brk), M, kb * M, self._stream_ptr(stream))
+        self._check(rc)
+
+    def dpotrf_batched(self, uplo, A, info, stream=None):
+        """Batched ``HCORE_dpotrf``: ``A`` (T, N, N) column-major tiles in place, ``info`` (T,) int32 out."""
+        T, N, _ = A.shape
+        self._dev_f64(A, "A"); self._dev_i32(info, "info")
+        self._check(self._L.HCORE_dpotrf_batched_strided(self._h, T, int(uplo), N, _ptr(A), N, N * N, _ptr(info),
+                                                         self._stream_ptr(stream)))
+
+    def dgemmbdcd_batched(self, alpha, AU, AV, Ark, BD, beta, CD, stream=None):
+        """Batched ``HCORE_dgemmbdcd``: ``CD[t] <- alpha AU (AV^T BD) + beta CD``; ``BD``, ``CD``: (T, N, M) column-major M x N."""
+        T, ka, M = AU.shape
+        N = BD.shape[1]
+        for nm, x in (("AU", AU), ("AV", AV), ("BD", BD), ("CD", CD)):
+            self._dev_f64(x, nm)
+        self._dev_i32(Ark, "Ark")
+        rc = self._L.HCORE_dgemmbdcd_batched_strided(self._h, T, M, N, float(alpha), _ptr(AU), _ptr(AV), _ptr(Ark), M, ka * M,
+                                                     _ptr(BD), M, N * M, float(beta), _ptr(CD), M, N * M, self._stream_ptr(stream))
+        self._check(rc)
+
+    def uncompress_batched(self, AU, Ark, BV, Brk, CD, status=None, stream=None):
+        """Batched ``HCORE_duncompress`` / ``HCORE_zuncompress`` (by dtype): ``CD[t] <- AU BV^T``;
+        ``AU`` (T, k, M), ``BV`` (T, k, N), ``CD`` (T, N, M)."""
+        import torch
+        T, ka, M = AU.shape
+        kb, N = BV.shape[1], BV.shape[2]
+        fn = self._L.HCORE_zuncompress_batched_strided if AU.dtype == torch.complex128 else self._L.HCORE_duncompress_batched_strided
+        for nm, x in (("AU", AU), ("BV", BV), ("CD", CD)):
+            if x.dtype != AU.dtype or not x.is_cuda or not x.is_contiguous():
+                raise TypeError(f"{nm}: need a contiguous CUDA tensor of the same dtype")
+        self._dev_i32(Ark, "Ark"); self._dev_i32(Brk, "Brk")
+        rc = fn(self._h, T, M, N, _ptr(AU), _ptr(Ark), M, ka * M, _ptr(BV), _ptr(Brk), N, kb * N, _ptr(CD), M, N * M,
+                _ptr(status), self._stream_ptr(stream))
         self._check(rc)

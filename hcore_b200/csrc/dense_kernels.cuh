@@ -1,11 +1,16 @@
-// Dense-C updates of the TLR Cholesky trailing update (FP64, sm_100a):
-//   HCORE_dgemmcd  CD <- CD - (Au Av^T)(Bu Bv^T)^T      reference src/compute/hcore_dgemmcd.c:36-107
-//   HCORE_dsyrk    CD <- CD + alpha (AU AV^T)(AU AV^T)^T, strict upper triangle zeroed
-//                                                         reference src/compute/hcore_dsyrk.c:47-189
-// Both are a rank-k update that streams the dense nb x nb tile once: HBM-bound
-// (2 * 8 * nb^2 bytes per tile).  Two kernels:
-//   dense_prep_kernel    X = s * Au * (Av^T Bv)   (nb x b, tiny) into the context workspace
-//   dense_update_kernel  CD[I, J] += X[I, :] * Bu[J, :]^T   per 128 x 64 block of CD (TMA in / out)
+// Dense-C kernels of the TLR Cholesky step (FP64, sm_100a):
+//   HCORE_dgemmcd     CD <- CD - (Au Av^T)(Bu Bv^T)^T      reference src/compute/hcore_dgemmcd.c:36-107
+//   HCORE_dsyrk       CD <- CD + alpha (AU AV^T)(AU AV^T)^T, strict upper triangle zeroed
+//                                                            reference src/compute/hcore_dsyrk.c:47-189
+//   HCORE_dgemmbdcd   CD <- alpha AU (AV^T BD) + beta CD    reference src/compute/hcore_dgemmbdcd.c:35-122
+//   HCORE_duncompress CD <- AU BV^T                         reference src/compute/hcore_duncompress.c:33-85
+//   HCORE_zuncompress the same in complex double            reference src/compute/hcore_zuncompress.c:35-95
+// All of them are a rank-k update  CD <- beta CD + s X Y^T  that streams the dense tile once: HBM-bound
+// (8 * m * n bytes read unless beta = 0, and written).  Kernels:
+//   dense_prep_kernel    X = s * Au * (Av^T Bv)   (m x b, tiny) into the context workspace   (gemmcd, syrk)
+//   dense_bdtav_kernel   Y = BD^T AV              (n x a)       into the context workspace   (gemmbdcd)
+//   dense_update_kernel  CD[I, J] = beta CD[I, J] + s X[I, :] Y[J, :]^T   per 128 x 64 block of CD (TMA in / out)
+//   zdense_update_kernel the complex product (four real DMMAs per tile product), write only
 #pragma once
 #include "common.cuh"
 #include "wy_kernels.cuh"
@@ -13,13 +18,23 @@
 namespace hcore_b200 {
 
 struct DenseArgs {
-    const double *AU, *AV, *BU, *BV;   // strided factor arrays (BU/BV == AU/AV for syrk)
+    // ---- prep: X = scale * AU (AV^T BV) --------------------------------------------------------------------
+    const double *AU, *AV, *BV;          // strided factor arrays (BV == AV for syrk)
     const int *Ark, *Brk;
-    long strideA, strideB, strideC;
-    double *CD;
-    double *X;                           // workspace [ntiles][m_pad * kmax8]
+    long strideA, strideB;
+    int lda, ldb;                        // leading dimensions of the A and B factor arrays
+    int mc;                              // contraction length of AV^T BV (rows); dsyrk's reference uses LDAU (hcore_dsyrk.c:57)
+    double *X;                           // workspace [ntiles][m_pad * kcap]
     double scale;                        // -1 for gemmcd, alpha for syrk
-    int nb, m_pad, kmax8;
+    int m_pad, kcap;
+    // ---- update: CD = beta CD + su * Xop Yop^T -------------------------------------------------------------
+    const double *Xop, *Yop;             // m x k (ld ldx) and n x k (ld ldy) per tile
+    long strideX, strideY, strideC;
+    int ldx, ldy, ldc;
+    const int *Krk;                      // contraction length per tile
+    double *CD;
+    int nb, ncols;                       // rows and columns of CD
+    double su, beta;                     // beta == 0: CD is not read
     int syrk;                            // 1: lower triangle only + zero strict upper
 };
 
@@ -30,10 +45,62 @@ __global__ void __launch_bounds__(256, 2) dense_prep_kernel(DenseArgs ar) {
     extern __shared__ __align__(16) double smem[];
     const int t = blockIdx.x;
     const int a = ar.Ark[t], b = ar.Brk[t], m = ar.nb;
-    if (a <= 0 || b <= 0) return;
+    if (b <= 0) return;                    // the update kernel sees a zero contraction length
+    if (a <= 0) {                          // empty A: X = 0 (never stale workspace contents)
+        double *X = ar.X + (size_t)t * ar.m_pad * ar.kcap;
+        for (int idx = threadIdx.x; idx < ar.m_pad * b; idx += blockDim.x) X[idx] = 0.0;
+        return;
+    }
     const double *AU = ar.AU + (size_t)t * ar.strideA, *AV = ar.AV + (size_t)t * ar.strideA;
     const double *BV = ar.BV + (size_t)t * ar.strideB;
-    pg_body(smem, BV, AU, AV, b, a, m, m, m, ar.m_pad, 0, ar.scale, ar.X + (size_t)t * ar.m_pad * ar.kmax8);
+    pg_body(smem, BV, AU, AV, b, a, m, ar.ldb, ar.lda, ar.m_pad, 0, ar.scale, ar.X + (size_t)t * ar.m_pad * ar.kcap, ar.mc);
+}
+
+// Y = BD^T AV (n x a, ld n_pad) for HCORE_dgemmbdcd (reference hcore_dgemmbdcd.c:78-84 / :100-106 computes its
+// transpose AV^T BD).  grid = (64-row blocks of Y, tiles), 256 threads; warp w owns rows 8 w .. 8 w + 7 of the block.
+// BD is read once (k-contiguous 32-byte segments per lane quad), AV comes out of L1/L2.
+struct BdtAvArgs {
+    const double *AV, *BD;
+    const int *Ark;
+    long strideA, strideB;
+    int lda, ldb, mc, ncols;             // contraction length (rows of AV and BD), columns of BD
+    double *Y;                           // [ntiles][n_pad * kcap]
+    int n_pad, kcap;
+};
+__global__ void __launch_bounds__(256) dense_bdtav_kernel(BdtAvArgs ar) {
+    const int t = blockIdx.y, a = ar.Ark[t];
+    if (a <= 0) return;
+    const int warp = warp_id(), lane = lane_id(), g = lane >> 2, tg = lane & 3;
+    const int i0 = blockIdx.x * 64 + 8 * warp;                     // row of Y = column of BD
+    if (i0 >= ar.n_pad) return;
+    const double *AV = ar.AV + (size_t)t * ar.strideA, *BD = ar.BD + (size_t)t * ar.strideB;
+    double *Y = ar.Y + (size_t)t * ar.n_pad * ar.kcap;
+    const bool ron = i0 + g < ar.ncols;
+    const double *bp = BD + (size_t)(i0 + g) * ar.ldb + tg;
+    for (int q0 = 0; q0 < a; q0 += 64) {                            // 8 column tiles of Y at a time
+        double acc[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
+        for (int k = 0; k < ar.mc; k += 4) {
+            const double bv = (ron && k + tg < ar.mc) ? __ldg(bp + k) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = q0 + 8 * q + g;
+                if (q0 + 8 * q < a) {
+                    const double av = (col < a && k + tg < ar.mc) ? __ldg(AV + (size_t)col * ar.lda + k + tg) : 0.0;
+                    dmma_884(acc[q][0], acc[q][1], bv, av);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = q0 + 8 * q + 2 * tg + e;
+                if (col < a) Y[(i0 + g) + (size_t)col * ar.n_pad] = acc[q][e];
+            }
+        }
+    }
 }
 
 // CD[I, J] += X[I, :] * Bu[J, :]^T per 128 x 64 block of CD (reference hcore_dgemmcd.c:81-85,
@@ -64,24 +131,26 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
     using SM = DenseUpdSmem;
     extern __shared__ __align__(16) double smem[];
     double *Cs = smem + SM::kC, *Bs = smem + SM::kB;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kBar);      // [0] block of CD, [1] Bu chunk
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kBar);      // [0] block of CD, [1] Y chunk
     const int t = blockIdx.z, i0 = blockIdx.x * kDuRows, j0 = blockIdx.y * kDuCols;
-    const int m = ar.nb;
-    const int rows = (m - i0 < kDuRows) ? (m - i0) : kDuRows, cols = (m - j0 < kDuCols) ? (m - j0) : kDuCols;
-    double *CD = ar.CD + (size_t)t * ar.strideC + i0 + (size_t)j0 * m;     // block origin, ld m
-    const double *BU = ar.BU + (size_t)t * ar.strideB + j0;
+    if (ar.Krk[t] < 0) return;                 // tile flagged by the caller (uncompress with mismatched ranks): untouched
+    const int m = ar.nb, nn = ar.ncols, ldc = ar.ldc, ldy = ar.ldy;
+    const int rows = (m - i0 < kDuRows) ? (m - i0) : kDuRows, cols = (nn - j0 < kDuCols) ? (nn - j0) : kDuCols;
+    double *CD = ar.CD + (size_t)t * ar.strideC + i0 + (size_t)j0 * ldc;   // block origin
+    const double *BU = ar.Yop + (size_t)t * ar.strideY + j0;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
-    const bool bulk_ok = ((m & 1) == 0) && ((reinterpret_cast<uintptr_t>(CD) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(BU) & 15) == 0);
+    const bool cd_bulk = ((m & 1) == 0) && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(CD) & 15) == 0);
+    const bool bulk_ok = cd_bulk && ((nn & 1) == 0) && ((ldy & 1) == 0) && ((reinterpret_cast<uintptr_t>(BU) & 15) == 0);
+    const bool readc = ar.beta != 0.0;
 
     if (ar.syrk && j0 > i0 + rows - 1) {      // every entry is strictly above the diagonal: the reference zeroes it
-        if (((m & 1) == 0) && ((reinterpret_cast<uintptr_t>(CD) & 15) == 0)) {
+        if (cd_bulk) {
             const int rp = rows >> 1;
             for (int idx = tid; idx < rp * cols; idx += 256)
-                *reinterpret_cast<double2 *>(CD + 2 * (idx % rp) + (size_t)(idx / rp) * m) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2 *>(CD + 2 * (idx % rp) + (size_t)(idx / rp) * ldc) = make_double2(0.0, 0.0);
         } else {
-            for (int idx = tid; idx < rows * cols; idx += 256) CD[(idx % rows) + (size_t)(idx / rows) * m] = 0.0;
+            for (int idx = tid; idx < rows * cols; idx += 256) CD[(idx % rows) + (size_t)(idx / rows) * ldc] = 0.0;
         }
         return;
     }
@@ -93,20 +162,20 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
             fence_mbar_init();
         }
         __syncthreads();
-        if (warp == 0) {
+        if (warp == 0 && readc) {
             if (lane == 0) mbar_expect_tx(&bars[0], (uint32_t)(rows * cols * 8));
             __syncwarp();
-            for (int c = lane; c < cols; c += 32) tma_load_1d(Cs + c * kDuLdC, CD + (size_t)c * m, (uint32_t)(rows * 8), &bars[0]);
+            for (int c = lane; c < cols; c += 32) tma_load_1d(Cs + c * kDuLdC, CD + (size_t)c * ldc, (uint32_t)(rows * 8), &bars[0]);
         }
-    } else {
+    } else if (readc) {
         for (int idx = tid; idx < rows * cols; idx += 256) {
             const int rr = idx % rows, cc = idx / rows;
-            Cs[rr + cc * kDuLdC] = CD[rr + (size_t)cc * m];
+            Cs[rr + cc * kDuLdC] = CD[rr + (size_t)cc * ldc];
         }
     }
     // ---- product^T: warp w owns rows 16 w .. 16 w + 15 of the block (two row tiles) x 64 columns ----------
-    const int b = ar.Brk[t], b8 = round_up(b, 8);
-    const double *X = ar.X + (size_t)t * ar.m_pad * ar.kmax8 + i0 + 16 * warp + g;
+    const int b = ar.Krk[t] > 0 ? ar.Krk[t] : 0, b8 = round_up(b, 8);
+    const double *X = ar.Xop + (size_t)t * ar.strideX + i0 + 16 * warp + g;
     const bool r0on = 16 * warp + g < rows, r1on = 16 * warp + 8 + g < rows;
     double acc[8][2][2];      // [column tile][row tile][row 2 tg + h]
 #pragma unroll
@@ -114,33 +183,36 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
     uint32_t bphase = 0;
     for (int k0 = 0; k0 < b8; k0 += kDuKc) {
         const int kc = (b8 - k0 < kDuKc) ? (b8 - k0) : kDuKc;          // multiple of 8
-        const int kv = (b - k0 < kc) ? (b - k0) : kc;                  // columns that exist in Bu
+        const int kv = (b - k0 < kc) ? (b - k0) : kc;                  // columns that exist in Y
         if (k0 > 0) __syncthreads();                                   // every warp is done with the previous chunk
         if (bulk_ok) {
             if (warp == 0) {
                 if (lane == 0) mbar_expect_tx(&bars[1], (uint32_t)(kv * cols * 8));
                 __syncwarp();
                 for (int kk = lane; kk < kv; kk += 32)
-                    tma_load_1d(Bs + kk * kDuLdB, BU + (size_t)(k0 + kk) * m, (uint32_t)(cols * 8), &bars[1]);
+                    tma_load_1d(Bs + kk * kDuLdB, BU + (size_t)(k0 + kk) * ldy, (uint32_t)(cols * 8), &bars[1]);
             }
             for (int idx = tid; idx < kDuCols * (kc - kv); idx += 256) Bs[(idx & 63) + (kv + (idx >> 6)) * kDuLdB] = 0.0;
+            if (cols < kDuCols)                                        // ragged last column block: rows of Y that do not exist
+                for (int idx = tid; idx < (kDuCols - cols) * kv; idx += 256)
+                    Bs[cols + idx % (kDuCols - cols) + (idx / (kDuCols - cols)) * kDuLdB] = 0.0;
         } else {
             for (int idx = tid; idx < kDuCols * kc; idx += 256) {
                 const int rr = idx & (kDuCols - 1), kk = idx >> 6;
-                Bs[rr + kk * kDuLdB] = (rr < cols && kk < kv) ? __ldg(BU + rr + (size_t)(k0 + kk) * m) : 0.0;
+                Bs[rr + kk * kDuLdB] = (rr < cols && kk < kv) ? __ldg(BU + rr + (size_t)(k0 + kk) * ldy) : 0.0;
             }
         }
         // X fragments of this chunk: rows 16 w + g and 16 w + 8 + g, columns k0 + 4 ks + tg
         double xa[kDuKc / 4], xb[kDuKc / 4];
 #pragma unroll
         for (int ks = 0; ks < kDuKc / 4; ++ks) {
-            const bool kon = 4 * ks < kc;
-            const double *xp = X + (size_t)(k0 + 4 * ks + tg) * ar.m_pad;
+            const bool kon = k0 + 4 * ks + tg < b;
+            const double *xp = X + (size_t)(k0 + 4 * ks + tg) * ar.ldx;
             xa[ks] = (kon && r0on) ? __ldg(xp) : 0.0;
             xb[ks] = (kon && r1on) ? __ldg(xp + 8) : 0.0;
         }
         if (bulk_ok) {
-            if (kc > kv) __syncthreads();
+            if (kc > kv || cols < kDuCols) __syncthreads();
             mbar_wait(&bars[1], bphase);
             bphase ^= 1;
         } else {
@@ -160,8 +232,9 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
         }
     }
     // ---- update in shared memory, write back -----------------------------------------------------------
-    if (bulk_ok) mbar_wait(&bars[0], 0);
+    if (bulk_ok && readc) mbar_wait(&bars[0], 0);
     else __syncthreads();
+    const double su = ar.su, beta = ar.beta;
     const bool plain = (rows == kDuRows) && (cols == kDuCols) && !(ar.syrk && j0 + cols - 1 > i0);
     if (plain) {
 #pragma unroll
@@ -169,9 +242,9 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
 #pragma unroll
             for (int rt = 0; rt < 2; ++rt) {
                 double2 *p = reinterpret_cast<double2 *>(Cs + 16 * warp + 8 * rt + 2 * tg + (8 * tt + g) * kDuLdC);
-                double2 v = *p;
-                v.x += acc[tt][rt][0];
-                v.y += acc[tt][rt][1];
+                double2 v = readc ? *p : make_double2(0.0, 0.0);
+                v.x = fma(su, acc[tt][rt][0], beta * v.x);
+                v.y = fma(su, acc[tt][rt][1], beta * v.y);
                 *p = v;
             }
         }
@@ -185,7 +258,8 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
                     const int rr = 16 * warp + 8 * rt + 2 * tg + h, cc = 8 * tt + g;
                     if (rr < rows && cc < cols) {
                         double *p = Cs + rr + cc * kDuLdC;
-                        *p = (ar.syrk && j0 + cc > i0 + rr) ? 0.0 : *p + acc[tt][rt][h];
+                        const double old = readc ? *p : 0.0;
+                        *p = (ar.syrk && j0 + cc > i0 + rr) ? 0.0 : fma(su, acc[tt][rt][h], beta * old);
                     }
                 }
             }
@@ -195,7 +269,7 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> visible to the bulk stores
         __syncthreads();
         if (warp == 0) {
-            for (int c = lane; c < cols; c += 32) tma_store_1d(CD + (size_t)c * m, Cs + c * kDuLdC, (uint32_t)(rows * 8));
+            for (int c = lane; c < cols; c += 32) tma_store_1d(CD + (size_t)c * ldc, Cs + c * kDuLdC, (uint32_t)(rows * 8));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
         }
@@ -203,7 +277,68 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
         __syncthreads();
         for (int idx = tid; idx < rows * cols; idx += 256) {
             const int rr = idx % rows, cc = idx / rows;
-            CD[rr + (size_t)cc * m] = Cs[rr + cc * kDuLdC];
+            CD[rr + (size_t)cc * ldc] = Cs[rr + cc * kDuLdC];
+        }
+    }
+}
+
+// ---- complex uncompress: CD = AU BV^T (plain transpose), m x n, contraction Ark -------------------------------
+// reference src/compute/hcore_zuncompress.c:35-95 (cblas_zgemm NoTrans / Trans with alpha = 1, beta = 0: the caller's
+// alpha and beta are ignored).  grid = (64-row blocks, 64-column blocks, tiles), 256 threads; warp w owns rows
+// 8 w .. 8 w + 7 of the block and all 64 columns; the real and imaginary planes of the BV block sit in shared memory.
+struct ZUncArgs {
+    const double2 *AU, *BV;
+    const int *Ark;
+    long strideA, strideB, strideC;
+    int lda, ldb, ldc, m, n;
+    double2 *CD;
+};
+constexpr int kZuK = 32, kZuLd = 64 + 4;
+__global__ void __launch_bounds__(256, 2) zdense_update_kernel(ZUncArgs ar) {
+    __shared__ __align__(16) double Br[kZuK * kZuLd], Bi[kZuK * kZuLd];
+    const int t = blockIdx.z, i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    const int tid = threadIdx.x, warp = warp_id(), lane = lane_id(), g = lane >> 2, tg = lane & 3;
+    if (ar.Ark[t] < 0) return;                 // mismatched ranks: tile left untouched
+    const int k = ar.Ark[t];
+    const double2 *AU = ar.AU + (size_t)t * ar.strideA, *BV = ar.BV + (size_t)t * ar.strideB;
+    double2 *CD = ar.CD + (size_t)t * ar.strideC;
+    const int row = i0 + 8 * warp + g;
+    double cr[8][2], ci[8][2];
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) cr[tt][0] = cr[tt][1] = ci[tt][0] = ci[tt][1] = 0.0;
+    for (int k0 = 0; k0 < k; k0 += kZuK) {
+        __syncthreads();
+        for (int idx = tid; idx < 64 * kZuK; idx += 256) {
+            const int c = idx & 63, kk = idx >> 6;
+            double2 v = make_double2(0.0, 0.0);
+            if (j0 + c < ar.n && k0 + kk < k) v = __ldg(BV + (j0 + c) + (size_t)(k0 + kk) * ar.ldb);
+            Br[c + kk * kZuLd] = v.x;
+            Bi[c + kk * kZuLd] = v.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < kZuK / 4; ++ks) {
+            double2 a = make_double2(0.0, 0.0);
+            if (row < ar.m && k0 + 4 * ks + tg < k) a = __ldg(AU + row + (size_t)(k0 + 4 * ks + tg) * ar.lda);
+            const double nai = -a.y;
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+                const double br = Br[8 * tt + g + (4 * ks + tg) * kZuLd], bi = Bi[8 * tt + g + (4 * ks + tg) * kZuLd];
+                dmma_884(cr[tt][0], cr[tt][1], a.x, br);
+                dmma_884(cr[tt][0], cr[tt][1], nai, bi);
+                dmma_884(ci[tt][0], ci[tt][1], a.x, bi);
+                dmma_884(ci[tt][0], ci[tt][1], a.y, br);
+            }
+        }
+    }
+    if (row < ar.m) {
+#pragma unroll
+        for (int tt = 0; tt < 8; ++tt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = j0 + 8 * tt + 2 * tg + e;
+                if (col < ar.n) CD[row + (size_t)col * ar.ldc] = make_double2(cr[tt][e], ci[tt][e]);
+            }
         }
     }
 }

@@ -11,6 +11,7 @@
 
 #include "tlr_kernels.cuh"
 #include "dense_kernels.cuh"
+#include "chol_kernels.cuh"
 #include "zgemm_kernels.cuh"
 #include "../../include/hcore_d.h"
 #include "../../include/hcore_s.h"
@@ -23,6 +24,10 @@ extern "C" {
 int use_trmm = 0, gemm_print_index = 0, gemm_print_mat = 0, hc_nelm_limit = 512;
 int syrk_print_index = 0, gemmcd_print_index = 0, gemmcd_print_mat = 0, gemmcd_use_scratch = 0;
 int sgemm_use_trmm = 0, sgemm_print_index = 0, sgemm_print_mat = 0;
+int gemmbdcd_print_index = 0, gemmbdcd_print_mat = 0, gemmfrk_print_index = 0, gemmfrk_print_mat = 0;
+// `use_scratch` is DECLARED by the reference library and DEFINED by the application (reference
+// src/compute/hcore_dgemm.c:38, testing/testing_dgemm.c:26): a weak reference keeps both kinds of callers linking.
+extern int use_scratch __attribute__((weak));
 }
 
 namespace {
@@ -57,7 +62,10 @@ struct hcore_b200_context {
     // TLR workspace
     DevBuf rec, G, R, Y, Lcore, sigma, ints, ptrs;
     // dense workspace
-    DevBuf X;
+    DevBuf X, Ywork;
+    // trsm / potrf workspace (inverses of the 64 x 64 diagonal blocks, per-tile info)
+    DevBuf Winv, info;
+    bool attr_done[8] = {false, false, false, false, false, false, false, false};
     // complex (zgemm) workspace
     DevBuf zpanel, ztau, zT, zY, zsigma, zints;
     // host-staging (HCORE_dgemm_batched_host and the legacy wrappers)
@@ -108,7 +116,7 @@ size_t per_tile_ws_bytes(int N, int m_pad, int nblk) {
 }
 
 int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
-    if (ctx->chunk_limit > 0) return ctx->chunk_limit;
+    if (ctx->chunk_limit > 0) return std::min(ctx->chunk_limit, 65535);
     // a few waves of CTAs per launch, bounded to ~6 GiB of workspace
     size_t per = per_tile_ws_bytes(N, m_pad, nblk);
     size_t cap = (6ull << 30) / per;
@@ -117,12 +125,14 @@ int default_chunk(const hcore_b200_context *ctx, int N, int m_pad, int nblk) {
     // benchmark's 16 384 tiles (a short last chunk): tools/exp_chunk.py, profiles/bench_r2j.json
     int c = ctx->num_sms * 16;
     if ((size_t)c > cap) c = (int)cap;
-    return std::max(c, 1);
+    return std::min(std::max(c, 1), 65535);          // the apply kernel's tile index is gridDim.z
 }
 
 template <int N, int TW, int AW>
 int launch_chunk(hcore_b200_context *ctx, const TlrArgs &ar, const TlrWorkspace &ws, cudaStream_t st) {
-    {
+    constexpr int kSlot = (N == 32) ? 0 : (N == 64) ? 1 : (N == 128) ? 2 : 3;
+    if (!ctx->attr_done[kSlot]) {
+        ctx->attr_done[kSlot] = true;
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_pg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)PgSmemT<PgWidth<N>::value>::kBytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(tlr_tsqr_kernel<N, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -223,7 +233,7 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
     if (!ctx) return HCORE_B200_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->Lcore, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
+    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->Lcore, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->Ywork, &ctx->Winv, &ctx->info, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -274,7 +284,8 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
                         const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk, int ldb,
                         double beta, double *const *d_CU, double *const *d_CV, int32_t *d_Crk, int ldc,
                         int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32,
-                        int phase = 0, int32_t *d_newrank = nullptr, const double *const *d_Bdense = nullptr) {
+                        int phase = 0, int32_t *d_newrank = nullptr, const double *const *d_Bdense = nullptr,
+                        int scan_from = 1) {
     // d_Bdense != null: B-dense variant, d_BU / d_BV / d_Brk are unused and ldb is the leading dimension of B
     if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
     if (phase == 1 && !d_newrank) return HCORE_B200_ERR_ARG;
@@ -327,7 +338,7 @@ static int tlr_batched(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha
         ar.alpha = alpha; ar.beta = beta; ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc;
         ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0); ar.f32 = f32;
         ar.phase = phase; ar.rank_out = (phase == 1) ? d_newrank : d_Crk;
-        ar.Bd = d_Bdense; ar.ldbd = ldb;
+        ar.Bd = d_Bdense; ar.ldbd = ldb; ar.scan_from = scan_from;
         int rc;
         switch (N) {
             case 32: rc = launch_chunk_n<32>(ctx, ar, ws, st); break;
@@ -375,7 +386,7 @@ static int tlr_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, doub
                         const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
                         double beta, void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
                         int rk, int maxrk, double acc, int32_t *d_status, void *stream, int f32,
-                        int phase = 0, int32_t *d_newrank = nullptr) {
+                        int phase = 0, int32_t *d_newrank = nullptr, int scan_from = 1) {
     if (!ctx || ntiles < 0) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -394,7 +405,7 @@ static int tlr_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, doub
     return tlr_batched(ctx, ntiles, nb, alpha, pp, pp + ntiles, d_Ark, lda, pp + 2 * (size_t)ntiles,
                        pp + 3 * (size_t)ntiles, d_Brk, ldb, beta, (double *const *)(pp + 4 * (size_t)ntiles),
                        (double *const *)(pp + 5 * (size_t)ntiles), d_Crk, ldc, rk, maxrk, acc, d_status, stream, f32,
-                       phase, d_newrank);
+                       phase, d_newrank, nullptr, scan_from);
 }
 
 extern "C" {
@@ -545,6 +556,8 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
         CUDA_TRY(ctx, ctx->stage[s].reserve(per_tile * hc));
         CUDA_TRY(ctx, ctx->stage_ints[s].reserve((size_t)hc * 4 * sizeof(int)));
     }
+    cudaError_t first_err = cudaSuccess;
+    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && first_err == cudaSuccess) first_err = e; };
     cudaEvent_t done[2];
     for (auto &e : done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int rc = HCORE_B200_OK;
@@ -558,8 +571,8 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
         int rmax = 1;
         for (int t = 0; t < p.cnt; ++t) rmax = std::max(rmax, (int)h_Crk[p.t0 + t]);
         const size_t wout = std::min(perC, (size_t)ldc * rmax * 8);
-        cudaMemcpy2DAsync(h_CU + (size_t)p.t0 * strideC, perC, p.dCU, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st);
-        cudaMemcpy2DAsync(h_CV + (size_t)p.t0 * strideC, perC, p.dCV, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st);
+        ck(cudaMemcpy2DAsync(h_CU + (size_t)p.t0 * strideC, perC, p.dCU, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st));
+        ck(cudaMemcpy2DAsync(h_CV + (size_t)p.t0 * strideC, perC, p.dCV, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st));
         p.cnt = 0;
     };
     for (int t0 = 0; t0 < ntiles && rc == HCORE_B200_OK; t0 += hc, ++slice) {
@@ -573,25 +586,25 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
         double *dCV = (double *)(base + 2 * perA * hc + 2 * perB * hc + perC * hc);
         int *di = (int *)ctx->stage_ints[s].p;
         int *dArk = di, *dBrk = di + hc, *dCrk = di + 2 * hc, *dSt = di + 3 * hc;
-        cudaMemcpyAsync(dAU, h_AU + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dAV, h_AV + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dBU, h_BU + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dBV, h_BV + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st);
+        ck(cudaMemcpyAsync(dAU, h_AU + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpyAsync(dAV, h_AV + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpyAsync(dBU, h_BU + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpyAsync(dBV, h_BV + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st));
         // Only the columns that carry data cross PCIe: the first max(Crk) columns of CU/CV go in,
         // the first max(new Crk) columns come back (2-D copies, one row per tile).
         int cmax = 1;
         for (int t = 0; t < cnt; ++t) cmax = std::max(cmax, (int)h_Crk[t0 + t]);
         const size_t win = std::min(perC, (size_t)ldc * cmax * 8);
-        cudaMemcpy2DAsync(dCU, perC, h_CU + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpy2DAsync(dCV, perC, h_CV + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dArk, h_Ark + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dBrk, h_Brk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dCrk, h_Crk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st);
+        ck(cudaMemcpy2DAsync(dCU, perC, h_CU + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpy2DAsync(dCV, perC, h_CV + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpyAsync(dArk, h_Ark + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpyAsync(dBrk, h_Brk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
+        ck(cudaMemcpyAsync(dCrk, h_Crk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
         if (slice > 0) cudaStreamWaitEvent(st, done[s ^ 1], 0);   // workspace is shared
         rc = HCORE_dgemm_batched_strided(ctx, cnt, nb, alpha, dAU, dAV, dArk, lda, strideA, dBU, dBV, dBrk, ldb,
                                          strideB, beta, dCU, dCV, dCrk, ldc, strideC, rk, maxrk, acc, dSt, st);
         cudaEventRecord(done[s], st);
-        cudaMemcpyAsync(h_Crk + t0, dCrk, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
+        ck(cudaMemcpyAsync(h_Crk + t0, dCrk, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
         if (h_status) cudaMemcpyAsync(h_status + t0, dSt, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
         pending[s] = {t0, cnt, dCU, dCV};
         // while slice `slice` computes, finish the previous one: its new ranks are known once its
@@ -603,6 +616,7 @@ int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double
     cudaStreamSynchronize(ctx->streams[1]);
     for (auto &e : done) cudaEventDestroy(e);
     if (rc != HCORE_B200_OK) return rc;
+    CUDA_TRY(ctx, first_err);
     CUDA_TRY(ctx, cudaGetLastError());
     return HCORE_B200_OK;
 }
@@ -663,34 +677,40 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hco
 }
 
 // ---- dense-C updates ----------------------------------------------------------------------
+// kcap = upper bound of the B-side rank (columns of the X workspace).  mc = rows contracted by AV^T BV.
 static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scale, int syrk,
-                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
-                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB,
-                        double *d_CD, int64_t strideC, void *stream) {
-    if (!ctx || ntiles < 0 || nb <= 0) return HCORE_B200_ERR_ARG;
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA, int lda,
+                        const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB, int ldb, int mc,
+                        double *d_CD, int64_t strideC, int ldc, int kcap, void *stream) {
+    if (!ctx || ntiles < 0 || nb <= 0 || lda < nb || ldb < nb || ldc < nb || kcap <= 0) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int kmax8 = HCORE_B200_MAX_STACK;      // ranks up to 128
+    const int kc8 = round_up(kcap, 8);
     const int m_pad = round_up(nb, kPgRows);
     const size_t sm_prep = PgSmem::kBytes;
     const size_t sm_upd = DenseUpdSmem::kBytes;
-    {
+    if (!ctx->attr_done[4]) {
+        ctx->attr_done[4] = true;
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_prep));
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_upd));
     }
-    const int chunk = std::min(ntiles, 4096);
-    CUDA_TRY(ctx, ctx->X.reserve((size_t)chunk * m_pad * kmax8 * 8));
+    const size_t per = (size_t)m_pad * kc8 * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)ntiles, (size_t)4096, (4ull << 30) / per}));
+    CUDA_TRY(ctx, ctx->X.reserve((size_t)chunk * per));
     for (int t0 = 0; t0 < ntiles; t0 += chunk) {
         const int cnt = std::min(chunk, ntiles - t0);
         DenseArgs ar{};
         ar.AU = d_AU + (size_t)t0 * strideA; ar.AV = d_AV + (size_t)t0 * strideA;
-        ar.BU = d_BU + (size_t)t0 * strideB; ar.BV = d_BV + (size_t)t0 * strideB;
+        ar.BV = d_BV + (size_t)t0 * strideB;
         ar.Ark = d_Ark + t0; ar.Brk = d_Brk + t0;
-        ar.strideA = strideA; ar.strideB = strideB; ar.strideC = strideC;
-        ar.CD = d_CD + (size_t)t0 * strideC;
-        ar.X = (double *)ctx->X.p;
-        ar.scale = scale; ar.nb = nb; ar.m_pad = m_pad; ar.kmax8 = kmax8; ar.syrk = syrk;
+        ar.strideA = strideA; ar.strideB = strideB; ar.lda = lda; ar.ldb = ldb; ar.mc = mc;
+        ar.X = (double *)ctx->X.p; ar.scale = scale; ar.m_pad = m_pad; ar.kcap = kc8;
+        ar.Xop = ar.X; ar.strideX = (long)m_pad * kc8; ar.ldx = m_pad;
+        ar.Yop = d_BU + (size_t)t0 * strideB; ar.strideY = strideB; ar.ldy = ldb;
+        ar.Krk = d_Brk + t0;
+        ar.CD = d_CD + (size_t)t0 * strideC; ar.strideC = strideC; ar.ldc = ldc;
+        ar.nb = nb; ar.ncols = nb; ar.su = 1.0; ar.beta = 1.0; ar.syrk = syrk;
         dense_prep_kernel<<<cnt, 256, sm_prep, st>>>(ar);
         dense_update_kernel<<<dim3((nb + kDuRows - 1) / kDuRows, (nb + kDuCols - 1) / kDuCols, cnt), 256, sm_upd, st>>>(ar);
         ctx->launches += 2;
@@ -699,19 +719,236 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
     return HCORE_B200_OK;
 }
 
+// CD (m x n, ld ldc) = beta CD + su * X (m x k, ld ldx) Y^T (n x k, ld ldy): the update kernel alone
+static int dense_xyt(hcore_b200_handle_t ctx, int ntiles, int m, int n, double su, const double *d_X, int ldx, int64_t strideX,
+                     const double *d_Y, int ldy, int64_t strideY, const int32_t *d_K, double beta, double *d_CD, int ldc,
+                     int64_t strideC, cudaStream_t st) {
+    if (!ctx->attr_done[4]) {
+        ctx->attr_done[4] = true;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(dense_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PgSmem::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(dense_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DenseUpdSmem::kBytes));
+    }
+    for (int t0 = 0; t0 < ntiles; t0 += 32768) {
+        const int cnt = std::min(32768, ntiles - t0);
+        DenseArgs ar{};
+        ar.Xop = d_X + (size_t)t0 * strideX; ar.strideX = strideX; ar.ldx = ldx;
+        ar.Yop = d_Y + (size_t)t0 * strideY; ar.strideY = strideY; ar.ldy = ldy;
+        ar.Krk = d_K + t0;
+        ar.CD = d_CD + (size_t)t0 * strideC; ar.strideC = strideC; ar.ldc = ldc;
+        ar.nb = m; ar.ncols = n; ar.su = su; ar.beta = beta; ar.syrk = 0;
+        dense_update_kernel<<<dim3((m + kDuRows - 1) / kDuRows, (n + kDuCols - 1) / kDuCols, cnt), 256, DenseUpdSmem::kBytes, st>>>(ar);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+static int rank_cap(int64_t stride, int ld, int fallback) {      // columns a strided factor array can hold
+    return stride > 0 ? (int)std::max<int64_t>(1, stride / ld) : fallback;
+}
+
 int HCORE_dgemmcd_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
                         const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB,
                         double *d_CD, int64_t strideC, void *stream) {
-    return dense_launch(ctx, ntiles, nb, -1.0, 0, d_AU, d_AV, d_Ark, strideA, d_BU, d_BV, d_Brk, strideB, d_CD,
-                        strideC, stream);
+    return dense_launch(ctx, ntiles, nb, -1.0, 0, d_AU, d_AV, d_Ark, strideA, nb, d_BU, d_BV, d_Brk, strideB, nb, nb, d_CD,
+                        strideC, nb, rank_cap(strideB, nb, HCORE_B200_MAX_STACK), stream);
 }
 
 int HCORE_dsyrk_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
                         double *d_CD, int64_t strideC, void *stream) {
-    return dense_launch(ctx, ntiles, nb, alpha, 1, d_AU, d_AV, d_Ark, strideA, d_AU, d_AV, d_Ark, strideA, d_CD,
-                        strideC, stream);
+    return dense_launch(ctx, ntiles, nb, alpha, 1, d_AU, d_AV, d_Ark, strideA, nb, d_AU, d_AV, d_Ark, strideA, nb, nb, d_CD,
+                        strideC, nb, rank_cap(strideA, nb, HCORE_B200_MAX_STACK), stream);
+}
+
+// ---- HCORE_dgemmbdcd / HCORE_duncompress / HCORE_zuncompress (device pointers) -------------------------------------
+// reference src/compute/hcore_dgemmbdcd.c:35-122: CD (M x N) <- alpha AU (AV^T BD) + beta CD, BD dense (rows x N).
+static int gemmbdcd_launch(hcore_b200_handle_t ctx, int ntiles, int M, int mc, int N, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BD, int ldb, int64_t strideB, double beta,
+                        double *d_CD, int ldc, int64_t strideC, void *stream, int kcap_in = 0) {
+    if (!ctx || ntiles < 0 || M <= 0 || N <= 0 || mc <= 0 || lda < M || lda < mc || ldb < mc || ldc < M) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kcap = round_up(kcap_in > 0 ? kcap_in : rank_cap(strideA, lda, HCORE_B200_MAX_STACK_D), 8), n_pad = round_up(N, 64);
+    const size_t per = (size_t)n_pad * kcap * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)ntiles, (size_t)8192, (4ull << 30) / per}));
+    CUDA_TRY(ctx, ctx->Ywork.reserve((size_t)chunk * per));
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        const int cnt = std::min(chunk, ntiles - t0);
+        BdtAvArgs pa{};
+        pa.AV = d_AV + (size_t)t0 * strideA; pa.BD = d_BD + (size_t)t0 * strideB; pa.Ark = d_Ark + t0;
+        pa.strideA = strideA; pa.strideB = strideB; pa.lda = lda; pa.ldb = ldb; pa.mc = mc; pa.ncols = N;
+        pa.Y = (double *)ctx->Ywork.p; pa.n_pad = n_pad; pa.kcap = kcap;
+        dense_bdtav_kernel<<<dim3(n_pad / 64, cnt), 256, 0, st>>>(pa);
+        ctx->launches++;
+        int rc = dense_xyt(ctx, cnt, M, N, alpha, d_AU + (size_t)t0 * strideA, lda, strideA, (const double *)ctx->Ywork.p, n_pad,
+                           (int64_t)n_pad * kcap, d_Ark + t0, beta, d_CD + (size_t)t0 * strideC, ldc, strideC, st);
+        if (rc != HCORE_B200_OK) return rc;
+    }
+    return HCORE_B200_OK;
+}
+
+int HCORE_dgemmbdcd_batched_strided(hcore_b200_handle_t ctx, int ntiles, int M, int N, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BD, int ldb, int64_t strideB, double beta,
+                        double *d_CD, int ldc, int64_t strideC, void *stream) {
+    return gemmbdcd_launch(ctx, ntiles, M, M, N, alpha, d_AU, d_AV, d_Ark, lda, strideA, d_BD, ldb, strideB, beta, d_CD, ldc,
+                           strideC, stream);
+}
+
+// reference src/compute/hcore_duncompress.c:33-85: CD (M x N) <- AU BV^T with Ark == Brk columns (its alpha / beta
+// arguments are ignored: cblas_dgemm is called with one / zero).  A tile whose two ranks differ gets
+// HCORE_B200_ERR_RANK_MISMATCH (the reference asserts) and is left untouched.
+__global__ void uncompress_check_kernel(const int *Ark, const int *Brk, int *K, int *status, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool ok = Ark[i] == Brk[i];
+    K[i] = ok ? Ark[i] : -1;
+    if (status) status[i] = ok ? HCORE_B200_OK : HCORE_B200_ERR_RANK_MISMATCH;
+}
+
+int HCORE_duncompress_batched_strided(hcore_b200_handle_t ctx, int ntiles, int M, int N,
+                        const double *d_AU, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double *d_CD, int ldc, int64_t strideC, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0 || M <= 0 || N <= 0 || lda < M || ldb < N || ldc < M) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ctx, ctx->info.reserve((size_t)ntiles * sizeof(int)));
+    int *K = (int *)ctx->info.p;
+    uncompress_check_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_Ark, d_Brk, K, d_status, ntiles);
+    ctx->launches++;
+    // a mismatched tile carries K = -1: the update kernel skips it (see dense_update_kernel)
+    return dense_xyt(ctx, ntiles, M, N, 1.0, d_AU, lda, strideA, d_BV, ldb, strideB, K, 0.0, d_CD, ldc, strideC, st);
+}
+
+int HCORE_zuncompress_batched_strided(hcore_b200_handle_t ctx, int ntiles, int M, int N,
+                        const void *d_AU, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        void *d_CD, int ldc, int64_t strideC, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0 || M <= 0 || N <= 0 || lda < M || ldb < N || ldc < M) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ctx, ctx->info.reserve((size_t)ntiles * sizeof(int)));
+    int *K = (int *)ctx->info.p;
+    uncompress_check_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_Ark, d_Brk, K, d_status, ntiles);
+    for (int t0 = 0; t0 < ntiles; t0 += 32768) {
+        const int cnt = std::min(32768, ntiles - t0);
+        ZUncArgs ar{};
+        ar.AU = (const double2 *)d_AU + (size_t)t0 * strideA; ar.BV = (const double2 *)d_BV + (size_t)t0 * strideB;
+        ar.Ark = K + t0; ar.strideA = strideA; ar.strideB = strideB; ar.strideC = strideC;
+        ar.lda = lda; ar.ldb = ldb; ar.ldc = ldc; ar.m = M; ar.n = N;
+        ar.CD = (double2 *)d_CD + (size_t)t0 * strideC;
+        zdense_update_kernel<<<dim3((M + 63) / 64, (N + 63) / 64, cnt), 256, 0, st>>>(ar);
+        ctx->launches++;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+// ---- HCORE_dtrsm / HCORE_dpotrf (device pointers) ---------------------------------------------------------------
+// reference src/compute/hcore_dtrsm.c:24-48 (cblas_dtrsm): B (M x Brank) <- alpha op(A)^-1 B (side = Left, A is M x M)
+// or alpha B op(A)^-1 (side = Right, A is Brank x Brank).  strideA = 0: one triangular tile for the whole batch.
+int HCORE_dtrsm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int side, int uplo, int transA, int diag, int M, int Brank,
+                        double alpha, const double *d_A, int lda, int64_t strideA,
+                        double *d_BV, const int32_t *d_Brk, int ldbv, int64_t strideB, void *stream) {
+    if (!ctx || ntiles < 0 || M <= 0 || Brank <= 0 || ldbv < M) return HCORE_B200_ERR_ARG;
+    if ((side != 141 && side != 142) || (uplo != 121 && uplo != 122) || (transA < 111 || transA > 113) || (diag != 131 && diag != 132))
+        return HCORE_B200_ERR_ARG;
+    const bool right = side == 142, tr = transA != 111;
+    if (lda < (right ? Brank : M)) return HCORE_B200_ERR_ARG;
+    if (right && d_Brk && strideA == 0 && ntiles > 1) { ctx->err = "HCORE_dtrsm_batched: side = Right with per-tile ranks needs one A per tile"; return HCORE_B200_ERR_ARG; }
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int msz_max = right ? Brank : M;
+    const int nblk = (msz_max + kTb - 1) / kTb, msz_pad = nblk * kTb;
+    const int tilesA = strideA ? ntiles : 1;
+    CUDA_TRY(ctx, ctx->Winv.reserve((size_t)tilesA * nblk * kTb * kTb * 8));
+    TrsmArgs ar{};
+    // op(A)(i, j): strides (1, lda) or transposed (lda, 1); op(A) is lower iff (uplo == Lower) xor trans
+    long si = tr ? lda : 1, sj = tr ? 1 : lda;
+    bool lower = (uplo == 122) != tr;
+    long bi = 1, bj = ldbv;
+    if (right) {                       // X op(A) = alpha B  <=>  op(A)^T X^T = alpha B^T
+        std::swap(si, sj);
+        lower = !lower;
+        std::swap(bi, bj);
+    }
+    if (!lower) { si = -si; sj = -sj; bi = -bi; }     // backward substitution = forward on the reversed index
+    ar.A = d_A; ar.strideA = strideA; ar.a_si = si; ar.a_sj = sj; ar.a_off = 0;
+    ar.B = d_BV; ar.strideB = strideB; ar.b_si = bi; ar.b_sj = bj; ar.b_off = 0;
+    ar.Brk = d_Brk; ar.rank = Brank; ar.M = M; ar.side_right = right; ar.unit_diag = (diag == 132); ar.alpha = alpha;
+    ar.Winv = (double *)ctx->Winv.p; ar.nblk_max = nblk;
+    if (!ctx->attr_done[5]) {
+        ctx->attr_done[5] = true;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+    }
+    trsm_inv_kernel<<<dim3(nblk, tilesA), 256, kCholSmemBytes, st>>>(ar);
+    const int nrhs_max = right ? M : Brank;
+    size_t sm16 = (size_t)trsm_ldx(msz_pad) * 16 * 8, sm8 = (size_t)trsm_ldx(msz_pad) * 8 * 8;
+    if (sm16 <= 200 * 1024) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+        trsm_solve_kernel<16><<<dim3((nrhs_max + 15) / 16, ntiles), 256, sm16, st>>>(ar, msz_pad);
+    } else if (sm8 <= 227 * 1024) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
+        trsm_solve_kernel<8><<<dim3((nrhs_max + 7) / 8, ntiles), 256, sm8, st>>>(ar, msz_pad);
+    } else {
+        ctx->err = "HCORE_dtrsm_batched: triangular dimension above 3584 is not supported";
+        return HCORE_B200_ERR_ARG;
+    }
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+// reference src/compute/hcore_dpotrf.c:23-35 (LAPACKE_dpotrf_work): A = L L^T (uplo = Lower) or U^T U (Upper) in place,
+// d_info[t] = 0 or the order of the first leading minor that is not positive definite.
+int HCORE_dpotrf_batched_strided(hcore_b200_handle_t ctx, int ntiles, int uplo, int N, double *d_A, int lda, int64_t strideA,
+                        int32_t *d_info, void *stream) {
+    if (!ctx || ntiles < 0 || N <= 0 || lda < N || !d_info || (uplo != 121 && uplo != 122)) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ctx, ctx->Winv.reserve((size_t)ntiles * kTb * kTb * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_info, 0, (size_t)ntiles * sizeof(int), st));
+    if (!ctx->attr_done[5]) {
+        ctx->attr_done[5] = true;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmemBytes));
+    }
+    PotrfArgs ar{};
+    ar.A = d_A; ar.strideA = strideA; ar.n = N; ar.info = d_info; ar.Winv = (double *)ctx->Winv.p;
+    ar.si = (uplo == 122) ? 1 : lda; ar.sj = (uplo == 122) ? lda : 1;
+    const int nblk = (N + kTb - 1) / kTb;
+    for (int t0 = 0; t0 < ntiles; t0 += 32768) {
+        const int cnt = std::min(32768, ntiles - t0);
+        PotrfArgs a2 = ar;
+        a2.A = d_A + (size_t)t0 * strideA; a2.info = d_info + t0;
+        for (int jb = 0; jb < nblk; ++jb) {
+            const int j0 = jb * kTb, rem = nblk - jb - 1;
+            potrf_diag_kernel<<<cnt, 256, kCholSmemBytes, st>>>(a2, j0);
+            ctx->launches++;
+            if (rem > 0) {
+                potrf_panel_kernel<<<dim3(rem, cnt), 256, kCholSmemBytes, st>>>(a2, j0);
+                potrf_trail_kernel<<<dim3(rem * (rem + 1) / 2, cnt), 256, kCholSmemBytes, st>>>(a2, j0);
+                ctx->launches += 2;
+            }
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
 }
 
 // ---- debug / profiling -------------------------------------------------------------------------
@@ -778,21 +1015,27 @@ int hcore_b200_debug_fetch(hcore_b200_handle_t ctx, int what, int tile, double *
 }
 
 // ==================================================================================================
-// Legacy single-tile drop-in symbols (host pointers).  A process-wide context is created on
-// first use; calls are serialised by a mutex (the reference is re-entrant only with
-// use_scratch = 0; HiCMA calls it from one worker thread per core).
+// Legacy single-tile drop-in symbols (host pointers).  Re-entrant like the reference with use_scratch = 0
+// (reference src/compute/hcore_dgemm.c:761-923): every calling thread owns its context.
 // ==================================================================================================
-static hcore_b200_handle_t g_ctx = nullptr;
-static std::mutex g_mu;
+// One context (workspace, staging buffers, stream) PER CALLING THREAD: a task runtime with one worker thread per core
+// (HiCMA over StarPU / PaRSEC) gets as many independent streams as it has workers and their single-tile updates
+// overlap on the GPU; nothing is shared between threads, so the split-phase pair of one thread cannot be disturbed
+// by another thread.  Contexts are released when their thread exits.
+struct LegacySlot {
+    hcore_b200_handle_t ctx = nullptr;
+    ~LegacySlot() { if (ctx) hcore_b200_destroy(ctx); }
+};
+static thread_local LegacySlot tl_slot;
 
 static hcore_b200_handle_t legacy_ctx(const char *who) {
-    if (!g_ctx) {
-        if (hcore_b200_create(&g_ctx, -1) != HCORE_B200_OK) {
+    if (!tl_slot.ctx) {
+        if (hcore_b200_create(&tl_slot.ctx, -1) != HCORE_B200_OK) {
             fprintf(stderr, "%s: cannot create a CUDA context (no GPU?). hcore_b200 has no CPU path.\n", who);
             exit(-1);
         }
     }
-    return g_ctx;
+    return tl_slot.ctx;
 }
 
 static void legacy_fail(const char *who, const char *what, int code) {
@@ -800,12 +1043,14 @@ static void legacy_fail(const char *who, const char *what, int code) {
     fprintf(stderr, "%s: %s (code %d)\n", who, what, code);
     exit(-1);
 }
+static inline void lchk(const char *who, cudaError_t e) {          // every staging copy is checked
+    if (e != cudaSuccess) legacy_fail(who, cudaGetErrorString(e), HCORE_B200_ERR_CUDA);
+}
 
 // Shared body of the legacy HCORE_dgemm / HCORE_sgemm: host arrays of element size `es`.
 static int legacy_gemm(const char *who, int es, int M, double alpha, const void *AU, const void *AV, int a, int LDA,
                        const void *BU, const void *BV, int b, int LDB, double beta, void *CU, void *CV, int c, int LDC,
-                       int rk, int maxrk, double acc) {
-    std::lock_guard<std::mutex> lock(g_mu);
+                       int rk, int maxrk, double acc, int scan_from = 1) {
     hcore_b200_handle_t ctx = legacy_ctx(who);
     if (a == 0 || b == 0 || c == 0) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
     if (maxrk < a + c) legacy_fail(who, "increase maxrank (maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
@@ -825,22 +1070,22 @@ static int legacy_gemm(const char *who, int es, int M, double alpha, const void 
     int *di = (int *)ctx->stage_ints[0].p;
     int hi[4] = {a, b, c, 0};
     cudaStream_t st = ctx->streams[0];
-    cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    lchk(who, cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
     int rc = tlr_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV, di + 2,
-                                 LDC, 0, rk, maxrk, acc, di + 3, st, es == 4);
+                                 LDC, 0, rk, maxrk, acc, di + 3, st, es == 4, 0, nullptr, scan_from);
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
-    cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
     const int rnew = hi[2];
-    cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st));
+    lchk(who, cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     return rnew;
 }
@@ -861,7 +1106,9 @@ void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha, doub
 // pass-through parameters; here the intermediates (block reflectors, U_r, W) stay on the device in the
 // process-wide context, so the pass-through pointers are returned as NULL / the caller's own CU, CV, and
 // the two calls must be paired (qr_svd, then ormqr for the same tile, no other legacy call in between).
-static struct { bool pending = false; int M = 0, n = 0, rnew = 0, LDC = 0; char *dCU = nullptr, *dCV = nullptr; } g_split;
+struct SplitState { bool pending = false; int M = 0, n = 0, rnew = 0, LDC = 0; char *dCU = nullptr, *dCV = nullptr;
+                    const double *hCU = nullptr, *hCV = nullptr; };
+static thread_local SplitState g_split;     // per thread, and checked against the caller's CU / CV pointers
 
 static uint64_t ormqr_flops(uint64_t m, uint64_t n, uint64_t r) {       // the two dormqr terms of the model
     return (4 * r * m * n - 2 * r * n * n + 3 * r * n) + (4 * m * r * n - 2 * r * n * n + 2 * r * n + m * n - n * n / 2 + n / 2);
@@ -872,7 +1119,6 @@ static int legacy_qr_svd(const char *who, int M, double alpha, const double *AU,
                          const double *BU, const double *BV, int b, const double *Bd, int LDB, double beta,
                          const double *CU, const double *CV, int c, int LDC, int rk, int maxrk, double acc,
                          flop_counter *flops) {
-    std::lock_guard<std::mutex> lock(g_mu);
     hcore_b200_handle_t ctx = legacy_ctx(who);
     if (a == 0 || c == 0 || (!Bd && b == 0)) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
     // the split-phase variant accepts Ark + Crk up to 2 * maxrk (reference :1186, :1259)
@@ -892,23 +1138,23 @@ static int legacy_qr_svd(const char *who, int M, double alpha, const double *AU,
     int *di = (int *)ctx->stage_ints[0].p;
     int hi[5] = {a, Bd ? a : b, c, 0, 0};
     cudaStream_t st = ctx->streams[0];
-    cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
+    lchk(who, cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st));
     if (Bd) {
-        cudaMemcpyAsync(dBU, Bd, fb, cudaMemcpyHostToDevice, st);
+        lchk(who, cudaMemcpyAsync(dBU, Bd, fb, cudaMemcpyHostToDevice, st));
     } else {
-        cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
+        lchk(who, cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st));
     }
-    cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    lchk(who, cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
     int rc;
     if (Bd) {
         // one tile: the pointer "arrays" are single device pointers kept in the context's pointer table
         if (ctx->ptrs.reserve(6 * sizeof(double *)) != cudaSuccess) legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
         const double *hp[6] = {(double *)dAU, (double *)dAV, (double *)dBU, (double *)dCU, (double *)dCV, nullptr};
-        cudaMemcpyAsync(ctx->ptrs.p, hp, sizeof(hp), cudaMemcpyHostToDevice, st);
+        lchk(who, cudaMemcpyAsync(ctx->ptrs.p, hp, sizeof(hp), cudaMemcpyHostToDevice, st));
         const double **pp = (const double **)ctx->ptrs.p;
         rc = HCORE_dgemm_batched_qr_svd_b_dense(ctx, 1, M, alpha, pp, pp + 1, di, LDA, pp + 2, LDB, beta, pp + 3, pp + 4, di + 2,
                                                 LDC, rk, cap, acc, di + 4, di + 3, st);
@@ -917,12 +1163,12 @@ static int legacy_qr_svd(const char *who, int M, double alpha, const double *AU,
                                  LDC, 0, rk, cap, acc, di + 3, st, 0, 1, di + 4);
     }
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
-    cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
     const int rnew = hi[4];
     g_split.pending = true; g_split.M = M; g_split.n = a + c; g_split.rnew = rnew; g_split.LDC = LDC;
-    g_split.dCU = dCU; g_split.dCV = dCV;
+    g_split.dCU = dCU; g_split.dCV = dCV; g_split.hCU = CU; g_split.hCV = CV;
     if (flops) {
         if (Bd) {
             // reference model of the b_dense path: QR of both stacks + the M x Ark x M product (:272) + SVD parts
@@ -984,12 +1230,12 @@ void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha, doubl
     (void)transA; (void)transB; (void)N; (void)alpha; (void)AU; (void)AV; (void)Ark; (void)LDA; (void)beta; (void)rk;
     (void)maxrk; (void)acc; (void)work; (void)CU_ncols; (void)newU; (void)ld_newU; (void)qrtauA; (void)CV_ncols; (void)newV;
     (void)ld_newV; (void)qrtauB; (void)use_CUV_clone; (void)CUclone; (void)ld_CUclone; (void)CVclone; (void)ld_CVclone;
-    (void)_CU; (void)_CV;
     const char *who = "HCORE_dgemm_ormqr";
-    std::lock_guard<std::mutex> lock(g_mu);
     hcore_b200_handle_t ctx = legacy_ctx(who);
-    if (!g_split.pending || g_split.M != M || g_split.rnew != new_UVrk)
-        legacy_fail(who, "no matching HCORE_dgemm_qr_svd call precedes this one", HCORE_B200_ERR_ARG);
+    // the pair is matched on the calling thread, the tile size, the revealed rank and the identity of the C factors
+    // the first half handed back through *_p__CU / *_p__CV (the reference passes its state the same way)
+    if (!g_split.pending || g_split.M != M || g_split.rnew != new_UVrk || (_CU && _CU != g_split.hCU) || (_CV && _CV != g_split.hCV))
+        legacy_fail(who, "no matching HCORE_dgemm_qr_svd call precedes this one on this thread", HCORE_B200_ERR_ARG);
     if (new_UVrk > storage_maxrank) {                     // reference :1649-1652
         fprintf(stderr, "%s: Increase storage maxrank %d. Observed rank for U and V is %d\n", who, storage_maxrank, new_UVrk);
         exit(-1);
@@ -1001,8 +1247,8 @@ void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha, doubl
     int rc = HCORE_dgemm_batched_ormqr_strided(ctx, 1, M, (double *)g_split.dCU, (double *)g_split.dCV, di + 2, g_split.LDC, 0, st);
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
     double *outU = _CU_save ? _CU_save : CU, *outV = _CV_save ? _CV_save : CV;
-    cudaMemcpy2DAsync(outU, (size_t)LDC * 8, g_split.dCU, (size_t)g_split.LDC * 8, (size_t)M * 8, new_UVrk, cudaMemcpyDeviceToHost, st);
-    cudaMemcpy2DAsync(outV, (size_t)LDC * 8, g_split.dCV, (size_t)g_split.LDC * 8, (size_t)M * 8, new_UVrk, cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpy2DAsync(outU, (size_t)LDC * 8, g_split.dCU, (size_t)g_split.LDC * 8, (size_t)M * 8, new_UVrk, cudaMemcpyDeviceToHost, st));
+    lchk(who, cudaMemcpy2DAsync(outV, (size_t)LDC * 8, g_split.dCV, (size_t)g_split.LDC * 8, (size_t)M * 8, new_UVrk, cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     if (flops) flops->update += ormqr_flops(M, g_split.n, new_UVrk);
     Crk[0] = new_UVrk;
@@ -1028,7 +1274,6 @@ void HCORE_zgemm(HCORE_enum transA, int transB, int M, int N, hcore_b200_dcomple
     (void)transA; (void)transB; (void)N; (void)work;
     const char *who = "HCORE_zgemm";
     const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
-    std::lock_guard<std::mutex> lock(g_mu);
     hcore_b200_handle_t ctx = legacy_ctx(who);
     if (a == 0 || b == 0 || c == 0) legacy_fail(who, "rank values should not be zero", HCORE_B200_ERR_ZERO_RANK);
     if (maxrk < a + c) legacy_fail(who, "increase maxrank (maxrk < Ark + Crk)", HCORE_B200_ERR_MAXRK);
@@ -1043,75 +1288,265 @@ void HCORE_zgemm(HCORE_enum transA, int transB, int M, int N, hcore_b200_dcomple
     int *di = (int *)ctx->stage_ints[0].p;
     int hi[4] = {a, b, c, 0};
     cudaStream_t st = ctx->streams[0];
-    cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
+    lchk(who, cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
     int rc = HCORE_zgemm_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV,
                                          di + 2, LDC, 0, rk, maxrk, acc, di + 3, st);
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
-    cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
     const int rnew = hi[2];
-    cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st));
+    lchk(who, cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     if (flops) flops->update += hcore_b200_gemm_flops(M, a, b, c, rnew);
     Crk[0] = (double)rnew;
 }
 
-static void legacy_dense(const char *who, int syrk, int M, double scale, const double *Au, const double *Av, int a,
-                         const double *Bu, const double *Bv, int b, double *CD) {
-    std::lock_guard<std::mutex> lock(g_mu);
+// Shared body of the legacy HCORE_dgemmcd / HCORE_dsyrk.  lda / ldb / ldc are the leading dimensions the REFERENCE
+// uses for the arrays (dgemmcd: always M, hcore_dgemmcd.c:66-99; dsyrk: LDAU for AU and AV, LDCD for CD,
+// hcore_dsyrk.c:57-58,:103,:144,:165-181), rows_av = rows of AV the reference contracts over.
+static void legacy_dense(const char *who, int syrk, int M, double scale, const double *Au, const double *Av, int a, int lda,
+                         int rows_av, const double *Bu, const double *Bv, int b, int ldb, double *CD, int ldc) {
     hcore_b200_handle_t ctx = legacy_ctx(who);
     cudaSetDevice(ctx->device);
-    const size_t fa = (size_t)M * a * 8, fb = (size_t)M * b * 8, fc = (size_t)M * M * 8;
-    if (ctx->stage[0].reserve(2 * fa + 2 * fb + fc) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
+    if (lda < M || ldb < M || ldc < M || rows_av > lda) legacy_fail(who, "leading dimension smaller than the tile", HCORE_B200_ERR_ARG);
+    const size_t fa = (size_t)lda * a * 8, fb = (size_t)ldb * b * 8, fc = (size_t)ldc * M * 8;
+    const size_t fa16 = (fa + 15) / 16 * 16, fb16 = (fb + 15) / 16 * 16;
+    if (ctx->stage[0].reserve(2 * fa16 + 2 * fb16 + fc) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
         legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
     char *base = (char *)ctx->stage[0].p;
-    double *dAu = (double *)base, *dAv = (double *)(base + fa), *dBu = (double *)(base + 2 * fa),
-           *dBv = (double *)(base + 2 * fa + fb), *dC = (double *)(base + 2 * fa + 2 * fb);
+    double *dAu = (double *)base, *dAv = (double *)(base + fa16), *dBu = (double *)(base + 2 * fa16),
+           *dBv = (double *)(base + 2 * fa16 + fb16), *dC = (double *)(base + 2 * fa16 + 2 * fb16);
     int *di = (int *)ctx->stage_ints[0].p;
     int hi[2] = {a, b};
     cudaStream_t st = ctx->streams[0];
-    cudaMemcpyAsync(dAu, Au, fa, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dAv, Av, fa, cudaMemcpyHostToDevice, st);
+    // the arrays are copied with their padding rows: ld * (cols - 1) + rows elements each
+    lchk(who, cudaMemcpyAsync(dAu, Au, ((size_t)lda * (a - 1) + M) * 8, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(dAv, Av, ((size_t)lda * (a - 1) + rows_av) * 8, cudaMemcpyHostToDevice, st));
     if (!syrk) {
-        cudaMemcpyAsync(dBu, Bu, fb, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dBv, Bv, fb, cudaMemcpyHostToDevice, st);
+        lchk(who, cudaMemcpyAsync(dBu, Bu, ((size_t)ldb * (b - 1) + M) * 8, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(dBv, Bv, ((size_t)ldb * (b - 1) + M) * 8, cudaMemcpyHostToDevice, st));
     }
-    cudaMemcpyAsync(dC, CD, fc, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st);
-    int rc = syrk ? dense_launch(ctx, 1, M, scale, 1, dAu, dAv, di, 0, dAu, dAv, di, 0, dC, 0, st)
-                  : dense_launch(ctx, 1, M, scale, 0, dAu, dAv, di, 0, dBu, dBv, di + 1, 0, dC, 0, st);
+    lchk(who, cudaMemcpy2DAsync(dC, (size_t)ldc * 8, CD, (size_t)ldc * 8, (size_t)M * 8, M, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
+    int rc = syrk ? dense_launch(ctx, 1, M, scale, 1, dAu, dAv, di, 0, lda, dAu, dAv, di, 0, lda, rows_av, dC, 0, ldc, a, st)
+                  : dense_launch(ctx, 1, M, scale, 0, dAu, dAv, di, 0, lda, dBu, dBv, di + 1, 0, ldb, M, dC, 0, ldc, b, st);
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
-    cudaMemcpyAsync(CD, dC, fc, cudaMemcpyDeviceToHost, st);
+    lchk(who, cudaMemcpy2DAsync(CD, (size_t)ldc * 8, dC, (size_t)ldc * 8, (size_t)M * 8, M, cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
 }
 
 void HCORE_dgemmcd(HCORE_enum transA, HCORE_enum transB, int M, double alpha, double *Au, double *Av, int Arank,
                    int LDA, double *Bu, double *Bv, int Brank, int LDB, double beta, double *CD, int LDC, int maxrank,
                    double *work, flop_counter *flops) {
-    // alpha, beta and the leading dimensions are ignored by the reference too (-1/+1 and M,
-    // src/compute/hcore_dgemmcd.c:66-99); flops is never touched there.
+    // alpha, beta and the leading dimensions are ignored by the reference too: -1/+1 and ld = M for every array
+    // (src/compute/hcore_dgemmcd.c:66-99); flops is never touched there.
     (void)transA; (void)transB; (void)alpha; (void)LDA; (void)LDB; (void)beta; (void)LDC; (void)maxrank;
     (void)work; (void)flops;
-    legacy_dense("HCORE_dgemmcd", 0, M, -1.0, Au, Av, Arank, Bu, Bv, Brank, CD);
+    if (Arank <= 0 || Brank <= 0) return;              // k = 0 products: CD unchanged (cblas_dgemm with beta = 1)
+    legacy_dense("HCORE_dgemmcd", 0, M, -1.0, Au, Av, Arank, M, M, Bu, Bv, Brank, M, CD, M);
 }
 
 void HCORE_dsyrk(HCORE_enum uplo, HCORE_enum trans, int N, int K, double alpha, const double *AU, int LDAU,
                  const double *AV, int LDAV, double beta, double *CD, int LDCD, double *work, flop_counter *flops) {
-    // uplo, trans, beta and LDAV are ignored by the reference (src/compute/hcore_dsyrk.c:47-189).
-    (void)uplo; (void)trans; (void)LDAV; (void)beta; (void)LDAU; (void)LDCD; (void)work;
-    legacy_dense("HCORE_dsyrk", 1, N, alpha, AU, AV, K, AU, AV, K, CD);
+    // uplo, trans, beta and LDAV are ignored by the reference (src/compute/hcore_dsyrk.c:47-189).  LDAU is the leading
+    // dimension of BOTH factor arrays and the contraction length of AV^T AV (:57-58,:103), LDCD the one of CD
+    // (:165-181): honoured here, so padded tiles (LDAU, LDCD > N) give the reference's result.
+    (void)uplo; (void)trans; (void)LDAV; (void)beta; (void)work;
+    legacy_dense("HCORE_dsyrk", 1, N, alpha, AU, AV, K, LDAU, LDAU, AU, AV, K, LDAU, CD, LDCD);
     if (flops) {   // reference hcore_dsyrk.c:104,145,172,188 with its contraction length N = LDAU
         const unsigned long n = (unsigned long)LDAU, k = (unsigned long)K, m = (unsigned long)N;
         flops->syrk += 2 * k * k * n + 2 * m * k * k + 2 * m * m * k;
     }
+}
+
+// ---- HCORE_dgemm_fast (reference src/compute/hcore_dgemm_fast.c:59-426) -----------------------------------------
+// The same update as HCORE_dgemm with a leaner data flow on the CPU (triangular core product, no clones when the
+// stack fits C's storage).  Observable differences, reproduced here: it asserts use_trmm == 1 and use_scratch == 1
+// (:82-83), has no flop counter, no "new rank > maxrk" check, and its truncation scan starts at index 2 (:314).
+void HCORE_dgemm_fast(HCORE_enum transA, int transB, int M, int N, double alpha, double *AU, double *AV, double *Ark,
+                      int LDA, double *BU, double *BV, double *Brk, int LDB, double beta, double *CU, double *CV,
+                      double *Crk, int LDC, int rk, int maxrk, double acc, double *work) {
+    (void)transA; (void)transB; (void)N; (void)work;
+    if (use_trmm != 1 || (&use_scratch != nullptr && use_scratch != 1)) {
+        fprintf(stderr, "HCORE_dgemm_fast: Assertion `use_trmm == 1 && use_scratch == 1' failed.\n");   // reference :82-83
+        abort();
+    }
+    const int a = (int)Ark[0], b = (int)Brk[0], c = (int)Crk[0];
+    const int rnew = legacy_gemm("HCORE_dgemm_fast", 8, M, alpha, AU, AV, a, LDA, BU, BV, b, LDB, beta, CU, CV, c, LDC, rk,
+                                 std::max(maxrk, a + c), acc, 2);
+    Crk[0] = (double)rnew;
+}
+
+// ---- HCORE_dtrsm / HCORE_dpotrf / HCORE_dgemmbdcd / HCORE_duncompress / HCORE_zuncompress (host pointers) ------------
+// reference src/compute/hcore_dtrsm.c:24-48
+void HCORE_dtrsm(HCORE_enum side, HCORE_enum uplo, HCORE_enum transA, HCORE_enum diag, int M, int Brank, double alpha,
+                 double *A, int LDA, double *BV, int LDBV, flop_counter *flops) {
+    const char *who = "HCORE_dtrsm";
+    if (side != 141 && side != 142) {                   // reference :47: assert(0 == "side is not CblasLeft or CblasRight")
+        fprintf(stderr, "%s: side is not CblasLeft or CblasRight\n", who);
+        abort();
+    }
+    if (M > 0 && Brank > 0) {
+        hcore_b200_handle_t ctx = legacy_ctx(who);
+        cudaSetDevice(ctx->device);
+        const int na = (side == 141) ? M : Brank;
+        const size_t fa = ((size_t)LDA * na * 8 + 15) / 16 * 16, fb = (size_t)LDBV * Brank * 8;
+        if (ctx->stage[0].reserve(fa + fb) != cudaSuccess) legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+        double *dA = (double *)ctx->stage[0].p, *dB = (double *)((char *)ctx->stage[0].p + fa);
+        cudaStream_t st = ctx->streams[0];
+        lchk(who, cudaMemcpy2DAsync(dA, (size_t)LDA * 8, A, (size_t)LDA * 8, (size_t)na * 8, na, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpy2DAsync(dB, (size_t)LDBV * 8, BV, (size_t)LDBV * 8, (size_t)M * 8, Brank, cudaMemcpyHostToDevice, st));
+        int rc = HCORE_dtrsm_batched_strided(ctx, 1, side, uplo, transA, diag, M, Brank, alpha, dA, LDA, 0, dB, nullptr, LDBV, 0, st);
+        if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+        lchk(who, cudaMemcpy2DAsync(BV, (size_t)LDBV * 8, dB, (size_t)LDBV * 8, (size_t)M * 8, Brank, cudaMemcpyDeviceToHost, st));
+        if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    }
+    if (flops) {                                        // reference :42-45 with flop_counts('t', ...)
+        const unsigned long m = (unsigned long)M, n = (unsigned long)Brank;
+        flops->trsm += (side == 141) ? n * m * m : m * n * n;
+    }
+}
+
+// reference src/compute/hcore_dpotrf.c:23-35
+void HCORE_dpotrf(HCORE_enum uplo, int N, double *A, int LDA, int *info, flop_counter *flops) {
+    const char *who = "HCORE_dpotrf";
+    *info = 0;
+    // The reference forwards `uplo` unchanged to LAPACKE's `char uplo` (:29-32), so its working callers pass the
+    // CHARACTER codes 'L' / 'U'; the HCORE_enum values are accepted here as well.  Anything else is rejected the way
+    // LAPACKE_dpotrf_work rejects it: message, info = -2, matrix untouched.
+    if (uplo == 'L' || uplo == 'l') uplo = HCORE_Lower;
+    else if (uplo == 'U' || uplo == 'u') uplo = HCORE_Upper;
+    if (uplo != HCORE_Lower && uplo != HCORE_Upper) {
+        fprintf(stderr, " ** On entry to DPOTRF parameter number  1 had an illegal value\n");
+        *info = -2;
+    } else if (N > 0) {
+        hcore_b200_handle_t ctx = legacy_ctx(who);
+        cudaSetDevice(ctx->device);
+        if (ctx->stage[0].reserve((size_t)LDA * N * 8) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
+            legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+        double *dA = (double *)ctx->stage[0].p;
+        int *di = (int *)ctx->stage_ints[0].p;
+        cudaStream_t st = ctx->streams[0];
+        lchk(who, cudaMemcpy2DAsync(dA, (size_t)LDA * 8, A, (size_t)LDA * 8, (size_t)N * 8, N, cudaMemcpyHostToDevice, st));
+        int rc = HCORE_dpotrf_batched_strided(ctx, 1, uplo, N, dA, LDA, 0, di, st);
+        if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+        lchk(who, cudaMemcpy2DAsync(A, (size_t)LDA * 8, dA, (size_t)LDA * 8, (size_t)N * 8, N, cudaMemcpyDeviceToHost, st));
+        lchk(who, cudaMemcpyAsync(info, di, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    }
+    if (flops) {                                        // flop_counts('c', N): n^3/3 - n^2/2.0 + n/6 in the reference's integer/double mix
+        const unsigned long n = (unsigned long)N;
+        flops->potrf += (unsigned long)(n * n * n / 3 - n * n / 2.0 + n / 6);
+    }
+}
+
+// reference src/compute/hcore_dgemmbdcd.c:35-122
+void HCORE_dgemmbdcd(HCORE_enum transA, HCORE_enum transB, int M, int N, double alpha, double *AU, double *AV, double *Ark,
+                     int LDA, double *BD, int LDB, double beta, double *CD, int LDC, double *work, flop_counter *flops) {
+    (void)transB; (void)work;
+    const char *who = "HCORE_dgemmbdcd";
+    const int a = (int)Ark[0];
+    // the two branches of the reference differ only in which size they take for the contraction and for the rows of
+    // CD: (M, LDA) when transA == Trans (:74-93), (LDB, M) otherwise (:95-114)
+    const int mc = (transA == HCORE_Trans) ? M : LDB, rows = (transA == HCORE_Trans) ? LDA : M;
+    if (a > 0 && rows > 0 && N > 0) {
+        hcore_b200_handle_t ctx = legacy_ctx(who);
+        cudaSetDevice(ctx->device);
+        if (LDA < rows || LDA < mc || LDB < mc || LDC < rows) legacy_fail(who, "leading dimension smaller than the tile", HCORE_B200_ERR_ARG);
+        const size_t fa = ((size_t)LDA * a * 8 + 15) / 16 * 16, fb = ((size_t)LDB * N * 8 + 15) / 16 * 16, fc = (size_t)LDC * N * 8;
+        if (ctx->stage[0].reserve(2 * fa + fb + fc) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
+            legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+        char *base = (char *)ctx->stage[0].p;
+        double *dAU = (double *)base, *dAV = (double *)(base + fa), *dBD = (double *)(base + 2 * fa), *dC = (double *)(base + 2 * fa + fb);
+        int *di = (int *)ctx->stage_ints[0].p;
+        cudaStream_t st = ctx->streams[0];
+        lchk(who, cudaMemcpyAsync(dAU, AU, ((size_t)LDA * (a - 1) + rows) * 8, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(dAV, AV, ((size_t)LDA * (a - 1) + mc) * 8, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(dBD, BD, ((size_t)LDB * (N - 1) + mc) * 8, cudaMemcpyHostToDevice, st));
+        if (beta != 0.0)
+            lchk(who, cudaMemcpy2DAsync(dC, (size_t)LDC * 8, CD, (size_t)LDC * 8, (size_t)rows * 8, N, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(di, &a, sizeof(int), cudaMemcpyHostToDevice, st));
+        int rc = gemmbdcd_launch(ctx, 1, rows, mc, N, alpha, dAU, dAV, di, LDA, 0, dBD, LDB, 0, beta, dC, LDC, 0, st, a);
+        if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+        lchk(who, cudaMemcpy2DAsync(CD, (size_t)LDC * 8, dC, (size_t)LDC * 8, (size_t)rows * 8, N, cudaMemcpyDeviceToHost, st));
+        if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    }
+    if (flops) {                                        // reference :91-92 / :112-113
+        const unsigned long k = (unsigned long)a, n = (unsigned long)N;
+        flops->update += k * n * (unsigned long)mc * 2 + (unsigned long)rows * n * k * 2;
+    }
+}
+
+// reference src/compute/hcore_duncompress.c:33-85
+void HCORE_duncompress(HCORE_enum transA, HCORE_enum transB, int M, int N, double alpha, double *AU, double *Ark, int LDA,
+                       double *BV, double *Brk, int LDB, double beta, double *CD, int LDC) {
+    (void)transA; (void)transB; (void)alpha; (void)beta;      // never read by the reference: the product is formed with 1 / 0
+    const char *who = "HCORE_duncompress";
+    const int a = (int)Ark[0], b = (int)Brk[0];
+    if (a != b) {                                       // reference :69: assert(_Ark == _Brk)
+        fprintf(stderr, "%s: Assertion `_Ark == _Brk' failed.\n", who);
+        abort();
+    }
+    if (M <= 0 || N <= 0) return;
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    cudaSetDevice(ctx->device);
+    const size_t fa = ((size_t)LDA * std::max(a, 1) * 8 + 15) / 16 * 16, fb = ((size_t)LDB * std::max(a, 1) * 8 + 15) / 16 * 16, fc = (size_t)LDC * N * 8;
+    if (ctx->stage[0].reserve(fa + fb + fc) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
+        legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+    char *base = (char *)ctx->stage[0].p;
+    double *dAU = (double *)base, *dBV = (double *)(base + fa), *dC = (double *)(base + fa + fb);
+    int *di = (int *)ctx->stage_ints[0].p;
+    int hi[2] = {a, b};
+    cudaStream_t st = ctx->streams[0];
+    if (a > 0) {
+        lchk(who, cudaMemcpyAsync(dAU, AU, ((size_t)LDA * (a - 1) + M) * 8, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(dBV, BV, ((size_t)LDB * (a - 1) + N) * 8, cudaMemcpyHostToDevice, st));
+    }
+    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
+    int rc = HCORE_duncompress_batched_strided(ctx, 1, M, N, dAU, di, LDA, 0, dBV, di + 1, LDB, 0, dC, LDC, 0, nullptr, st);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+    lchk(who, cudaMemcpy2DAsync(CD, (size_t)LDC * 8, dC, (size_t)LDC * 8, (size_t)M * 8, N, cudaMemcpyDeviceToHost, st));
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+}
+
+// reference src/compute/hcore_zuncompress.c:35-95
+void HCORE_zuncompress(HCORE_enum transA, HCORE_enum transB, int M, int N, hcore_b200_dcomplex alpha, void *AU, double *Ark,
+                       int LDA, void *BV, double *Brk, int LDB, hcore_b200_dcomplex beta, void *CD, int LDC) {
+    (void)transA; (void)transB; (void)alpha; (void)beta;
+    const char *who = "HCORE_zuncompress";
+    const int a = (int)Ark[0], b = (int)Brk[0];
+    if (a != b) {                                       // reference :77: assert(_Ark == _Brk)
+        fprintf(stderr, "%s: Assertion `_Ark == _Brk' failed.\n", who);
+        abort();
+    }
+    if (M <= 0 || N <= 0) return;
+    hcore_b200_handle_t ctx = legacy_ctx(who);
+    cudaSetDevice(ctx->device);
+    const size_t fa = (size_t)LDA * std::max(a, 1) * 16, fb = (size_t)LDB * std::max(a, 1) * 16, fc = (size_t)LDC * N * 16;
+    if (ctx->stage[0].reserve(fa + fb + fc) != cudaSuccess || ctx->stage_ints[0].reserve(16) != cudaSuccess)
+        legacy_fail(who, "device allocation failed", HCORE_B200_ERR_CUDA);
+    char *base = (char *)ctx->stage[0].p;
+    void *dAU = base, *dBV = base + fa, *dC = base + fa + fb;
+    int *di = (int *)ctx->stage_ints[0].p;
+    int hi[2] = {a, b};
+    cudaStream_t st = ctx->streams[0];
+    if (a > 0) {
+        lchk(who, cudaMemcpyAsync(dAU, AU, ((size_t)LDA * (a - 1) + M) * 16, cudaMemcpyHostToDevice, st));
+        lchk(who, cudaMemcpyAsync(dBV, BV, ((size_t)LDB * (a - 1) + N) * 16, cudaMemcpyHostToDevice, st));
+    }
+    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
+    int rc = HCORE_zuncompress_batched_strided(ctx, 1, M, N, dAU, di, LDA, 0, dBV, di + 1, LDB, 0, dC, LDC, 0, nullptr, st);
+    if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
+    lchk(who, cudaMemcpy2DAsync(CD, (size_t)LDC * 16, dC, (size_t)LDC * 16, (size_t)M * 16, N, cudaMemcpyDeviceToHost, st));
+    if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
 }
 
 }  // extern "C"

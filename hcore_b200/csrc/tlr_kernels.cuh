@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     // reference src/compute/hcore_dgemm.c:444-464: fixed rank if rk != 0, else the first
     // index i >= 1 with sigma_i < acc (absolute); sigma has n = a + c entries.
     if (ar.rk == 0) {
-        if (tid >= 1 && tid < n && ssort[tid] < ar.acc) atomicMin(&misc[1], tid);
+        if (tid >= ar.scan_from && tid < n && ssort[tid] < ar.acc) atomicMin(&misc[1], tid);
     } else if (tid == 0) {
         misc[1] = ar.rk < n ? ar.rk : n;
     }

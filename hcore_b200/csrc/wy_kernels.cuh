@@ -154,6 +154,8 @@ struct TlrArgs {
     const double *const *Bd;   // dense B tiles (nb x nb, ld ldbd) of the B-dense variant, or null
     int ldbd;
     int *rank_out;        // where the new rank goes: Crk (fused call, phase 2) or the caller's new-rank array (phase 1)
+    int scan_from;        // first index the accuracy truncation scan looks at: 1 (HCORE_dgemm, reference hcore_dgemm.c:454) or
+                          //    2 (HCORE_dgemm_fast, reference hcore_dgemm_fast.c:314)
     int phase;            // 0: whole update; 1: stack + QR + SVD only (HCORE_dgemm_qr_svd); 2: reflector application
                           //    only, into possibly re-allocated CU/CV (HCORE_dgemm_ormqr)
 };
@@ -235,15 +237,18 @@ __device__ __forceinline__ void pg_stage(double *dst, const double *src, size_t 
 
 // G(m_pad x a, ld m_pad) = pscale * BU (AV^T BV)^T for one tile, by the whole CTA (256 threads).
 // AV: m x a (ld lda), BU, BV: m x b (ld ldb); rows m .. m_pad-1 of G are written as zeros.
+// mc: contraction length of the P product when it differs from the row count m of BU / G (HCORE_dsyrk contracts over
+// its leading dimension, reference src/compute/hcore_dsyrk.c:57,:103); -1 = m.
 template <int KC = 64>
 __device__ __forceinline__ void pg_body(double *smem, const double *AV, const double *BU, const double *BV, int a, int b,
-                                        int m, int lda, int ldb, int m_pad, int f32, double pscale, double *Gt) {
+                                        int m, int lda, int ldb, int m_pad, int f32, double pscale, double *Gt, int mc = -1) {
     using SM = PgSmemT<KC>;
     constexpr int kPgKC = KC, kPgLdP = SM::kLdP;
     double *P = smem + SM::kP;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
-    const int nchunks = (m + kPgRows - 1) / kPgRows, nchunks_pad = m_pad / kPgRows;
+    const int mp = mc < 0 ? m : mc;                                  // rows contracted by the P product
+    const int nchunks = (mp + kPgRows - 1) / kPgRows, nchunks_pad = m_pad / kPgRows;
     const bool va = !f32 && ((reinterpret_cast<uintptr_t>(AV) & 15) == 0) && ((lda & 1) == 0);
     const bool vb = !f32 && ((reinterpret_cast<uintptr_t>(BV) & 15) == 0) && ((reinterpret_cast<uintptr_t>(BU) & 15) == 0) &&
                     ((ldb & 1) == 0);
@@ -260,15 +265,15 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                 double acc[KC / 8][2];
 #pragma unroll
                 for (int q = 0; q < KC / 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-                pg_stage(smem, AVs, ia, lda, m, 0, as, as8, va, f32, tid);
-                pg_stage(smem + kPgKC * kPgLd, BVs, jb, ldb, m, 0, bs, bs8, vb, f32, tid);
+                pg_stage(smem, AVs, ia, lda, mp, 0, as, as8, va, f32, tid);
+                pg_stage(smem + kPgKC * kPgLd, BVs, jb, ldb, mp, 0, bs, bs8, vb, f32, tid);
                 cp_async_commit();
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const double *cur = smem + (ch & 1) * SM::kStage;
                     if (ch + 1 < nchunks) {
                         double *nxt = smem + ((ch + 1) & 1) * SM::kStage;
-                        pg_stage(nxt, AVs, ia, lda, m, (ch + 1) * kPgRows, as, as8, va, f32, tid);
-                        pg_stage(nxt + kPgKC * kPgLd, BVs, jb, ldb, m, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
+                        pg_stage(nxt, AVs, ia, lda, mp, (ch + 1) * kPgRows, as, as8, va, f32, tid);
+                        pg_stage(nxt + kPgKC * kPgLd, BVs, jb, ldb, mp, (ch + 1) * kPgRows, bs, bs8, vb, f32, tid);
                         cp_async_commit();
                         cp_async_wait<1>();
                     } else {

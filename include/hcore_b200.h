@@ -50,6 +50,7 @@ extern "C" {
 #define HCORE_B200_ERR_UNSUPPORTED   3  /* Ark+Crk above the compiled stack width (256; complex 128) or > nb */
 #define HCORE_B200_ERR_NEWRANK       4  /* rank after truncation > maxrk (ref hcore_dgemm.c:465-468)     */
 #define HCORE_B200_ERR_NO_CONVERGE   5  /* Jacobi SVD hit its sweep limit (ref: dgesvd info != 0, :407)  */
+#define HCORE_B200_ERR_RANK_MISMATCH 6  /* uncompress: Ark != Brk (ref hcore_duncompress.c:69: assert)    */
 #define HCORE_B200_ERR_CUDA        100  /* a CUDA runtime call failed (function return value only)       */
 #define HCORE_B200_ERR_ARG         101  /* invalid argument           (function return value only)       */
 
@@ -229,6 +230,44 @@ int HCORE_dsyrk_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         double alpha,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
                         double *d_CD, int64_t strideC, void *stream);
+
+/* ---- the remaining tile kernels of one TLR-Cholesky step (device pointers) ------------ */
+/* Batched HCORE_dgemmbdcd (reference src/compute/hcore_dgemmbdcd.c:35-122):
+ *   CD[t] (M x N, ld ldc) <- alpha AU[t] (AV[t]^T BD[t]) + beta CD[t];  AU, AV: M x Ark[t] (ld lda), BD dense M x N (ld ldb).
+ *   beta == 0: CD is not read. */
+int HCORE_dgemmbdcd_batched_strided(hcore_b200_handle_t handle, int ntiles, int M, int N, double alpha,
+                        const double *d_AU, const double *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BD, int ldb, int64_t strideB, double beta,
+                        double *d_CD, int ldc, int64_t strideC, void *stream);
+
+/* Batched HCORE_duncompress / HCORE_zuncompress (reference src/compute/hcore_duncompress.c:33-85,
+ * hcore_zuncompress.c:35-95): CD[t] (M x N) <- AU[t] BV[t]^T (plain transpose), AU: M x Ark[t], BV: N x Brk[t].
+ * A tile with Ark[t] != Brk[t] (the reference asserts) gets HCORE_B200_ERR_RANK_MISMATCH in d_status (may be NULL)
+ * and its CD is left untouched.  Complex arrays are interleaved re/im (C99 double _Complex), strides in elements. */
+int HCORE_duncompress_batched_strided(hcore_b200_handle_t handle, int ntiles, int M, int N,
+                        const double *d_AU, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const double *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        double *d_CD, int ldc, int64_t strideC, int32_t *d_status, void *stream);
+int HCORE_zuncompress_batched_strided(hcore_b200_handle_t handle, int ntiles, int M, int N,
+                        const void *d_AU, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        void *d_CD, int ldc, int64_t strideC, int32_t *d_status, void *stream);
+
+/* Batched HCORE_dtrsm (reference src/compute/hcore_dtrsm.c:24-48, cblas_dtrsm semantics, HCORE_enum values):
+ *   side = HCORE_Left : BV[t] (M x Brk[t]) <- alpha op(A[t])^-1 BV[t],  A[t] is M x M
+ *   side = HCORE_Right: BV[t] (M x Brk[t]) <- alpha BV[t] op(A[t])^-1,  A[t] is Brk[t] x Brk[t]
+ * strideA == 0: ONE triangular tile for the whole batch (the diagonal tile of a Cholesky step).
+ * d_Brk may be NULL (every tile has Brank columns); otherwise Brank is the largest rank. */
+int HCORE_dtrsm_batched_strided(hcore_b200_handle_t handle, int ntiles, int side, int uplo, int transA, int diag,
+                        int M, int Brank, double alpha,
+                        const double *d_A, int lda, int64_t strideA,
+                        double *d_BV, const int32_t *d_Brk, int ldbv, int64_t strideB, void *stream);
+
+/* Batched HCORE_dpotrf (reference src/compute/hcore_dpotrf.c:23-35, LAPACK dpotrf semantics): A[t] = L L^T
+ * (uplo = HCORE_Lower) or U^T U (HCORE_Upper) in place; d_info[t] = 0 or the order of the first leading minor that is
+ * not positive definite.  Three launches per 64-column panel: a single tile uses the whole GPU. */
+int HCORE_dpotrf_batched_strided(hcore_b200_handle_t handle, int ntiles, int uplo, int N,
+                        double *d_A, int lda, int64_t strideA, int32_t *d_info, void *stream);
 
 /* ---- flop model ------------------------------------------------------------------------ */
 /* The reference's own accounting of one HCORE_dgemm call (flops->update; reference

@@ -1,11 +1,16 @@
 /*
- * Drop-in replacement for the hot-path part of the reference's src/include/hcore_d.h.
- * Only the three double-precision kernels on the TLR update path are provided
- * (SURVEY.md section 8, rows a1, a11, a12); the prototypes are identical to the
- * reference's so existing callers compile and link unchanged:
- *     HCORE_dgemm    reference src/include/hcore_d.h:25-46
- *     HCORE_dgemmcd  reference src/include/hcore_d.h:68-86
- *     HCORE_dsyrk    reference src/include/hcore_d.h:107-116
+ * Drop-in replacement for the reference's src/include/hcore_d.h: the double-precision kernels of the TLR update
+ * path and the remaining tile kernels of one TLR-Cholesky step
+ * (row f3); the prototypes are identical to the reference's so existing callers compile and link unchanged:
+ *     HCORE_dgemm        reference src/include/hcore_d.h:25-46
+ *     HCORE_dgemm_fast   reference src/include/hcore_d.h:47-67
+ *     HCORE_dgemmcd      reference src/include/hcore_d.h:68-86
+ *     HCORE_dgemmbdcd    reference src/include/hcore_d.h:87-101
+ *     HCORE_dpotrf       reference src/include/hcore_d.h:102-106
+ *     HCORE_dsyrk        reference src/include/hcore_d.h:107-116
+ *     HCORE_dtrsm        reference src/include/hcore_d.h:117-125
+ *     HCORE_duncompress  reference src/include/hcore_d.h:126-138
+ *     HCORE_dgemm_qr_svd_b_dense / HCORE_dgemm_qr_svd / HCORE_dgemm_ormqr   reference :146-268
  * All pointers are HOST pointers, exactly as in the reference; each call runs as a batch
  * of one on the GPU (see include/hcore_b200.h for the batched device-pointer API).
  */
@@ -25,6 +30,15 @@ void HCORE_dgemm(HCORE_enum transA, int transB, int M, int N, double alpha,
                  double *CU, double *CV, double *Crk, int LDC,
                  int rk, int maxrk, double acc, double *work, flop_counter *flops);
 
+/* Same update with the reference's "fast" data flow (definition src/compute/hcore_dgemm_fast.c:59-426): requires the
+ * globals use_trmm == 1 and use_scratch == 1 (asserted, :82-83), no flop counter, truncation scan from index 2 (:314). */
+void HCORE_dgemm_fast(HCORE_enum transA, int transB, int M, int N, double alpha,
+                      double *AU, double *AV, double *Ark, int LDA,
+                      double *BU, double *BV, double *Brk, int LDB,
+                      double beta,
+                      double *CU, double *CV, double *Crk, int LDC,
+                      int rk, int maxrk, double acc, double *work);
+
 /* CD <- CD - (Au Av^T)(Bu Bv^T)^T, CD dense M x M. */
 void HCORE_dgemmcd(HCORE_enum transA, HCORE_enum transB, int M, double alpha,
                    double *Au, double *Av, int Arank, int LDA,
@@ -32,10 +46,31 @@ void HCORE_dgemmcd(HCORE_enum transA, HCORE_enum transB, int M, double alpha,
                    double beta, double *CD, int LDC, int maxrank,
                    double *work, flop_counter *flops);
 
+/* CD (M x N) <- alpha * AU (AV^T BD) + beta * CD with a dense BD (definition src/compute/hcore_dgemmbdcd.c:35-122). */
+void HCORE_dgemmbdcd(HCORE_enum transA, HCORE_enum transB, int M, int N, double alpha,
+                     double *AU, double *AV, double *Ark, int LDA,
+                     double *BD, int LDB,
+                     double beta, double *CD, int LDC, double *work, flop_counter *flops);
+
+/* Cholesky factorisation of a dense tile, LAPACK dpotrf semantics (definition src/compute/hcore_dpotrf.c:23-35). */
+void HCORE_dpotrf(HCORE_enum uplo, int N, double *A, int LDA, int *info, flop_counter *flops);
+
 /* CD <- CD + alpha * (AU AV^T)(AU AV^T)^T, strict upper triangle of CD zeroed. */
 void HCORE_dsyrk(HCORE_enum uplo, HCORE_enum trans, int N, int K, double alpha,
                  const double *AU, int LDAU, const double *AV, int LDAV,
                  double beta, double *CD, int LDCD, double *work, flop_counter *flops);
+
+/* Triangular solve on a tile factor, cblas_dtrsm semantics (definition src/compute/hcore_dtrsm.c:24-48):
+ * BV (M x Brank) <- alpha op(A)^-1 BV (side = HCORE_Left) or alpha BV op(A)^-1 (HCORE_Right). */
+void HCORE_dtrsm(HCORE_enum side, HCORE_enum uplo, HCORE_enum transA, HCORE_enum diag, int M, int Brank, double alpha,
+                 double *A, int LDA, double *BV, int LDBV, flop_counter *flops);
+
+/* CD (M x N) <- AU BV^T; Ark[0] must equal Brk[0]; alpha and beta are ignored as in the reference
+ * (definition src/compute/hcore_duncompress.c:33-85). */
+void HCORE_duncompress(HCORE_enum transA, HCORE_enum transB, int M, int N, double alpha,
+                       double *AU, double *Ark, int LDA,
+                       double *BV, double *Brk, int LDB,
+                       double beta, double *CD, int LDC);
 
 /* Split-phase update (reference src/include/hcore_d.h:190-268, src/compute/hcore_dgemm.c:1312-1597 and
  * :1602-1699): HCORE_dgemm_qr_svd stacks, factors and truncates and returns the new rank in
@@ -77,10 +112,11 @@ void HCORE_dgemm_ormqr(int transA, int transB, int M, int N, double alpha,
 /* Link-compatible tunables the reference library defines (reference
  * src/compute/hcore_dgemm.c:37-43, hcore_dsyrk.c:21, hcore_dgemmcd.c:24-26).  They are
  * accepted and ignored: there is no scratch protocol and no printing on the GPU path.
- * `use_scratch` stays an application-defined symbol in the reference and is not
- * referenced by this library at all. */
+ * `use_scratch` stays an application-defined symbol as in the reference (src/compute/hcore_dgemm.c:38); this library
+ * only holds a WEAK reference to it (HCORE_dgemm_fast checks it when the application defines it). */
 extern int use_trmm, gemm_print_index, gemm_print_mat, hc_nelm_limit;
 extern int syrk_print_index, gemmcd_print_index, gemmcd_print_mat, gemmcd_use_scratch;
+extern int gemmbdcd_print_index, gemmbdcd_print_mat, gemmfrk_print_index, gemmfrk_print_mat;
 
 #ifdef __cplusplus
 }

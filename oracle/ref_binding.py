@@ -65,6 +65,19 @@ def lib():
         L.HCORE_dgemmcd.restype = None
         L.HCORE_dsyrk.argtypes = [i, i, i, i, d, dp, i, dp, i, d, dp, i, dp, fl]
         L.HCORE_dsyrk.restype = None
+        # reference src/include/hcore_d.h:47-67, 87-106, 117-138; src/include/hcore_z.h:76-88
+        L.HCORE_dgemm_fast.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, dp, dp, i, d, dp, dp, dp, i, i, i, d, dp]
+        L.HCORE_dgemm_fast.restype = None
+        L.HCORE_dtrsm.argtypes = [i, i, i, i, i, i, d, dp, i, dp, i, fl]
+        L.HCORE_dtrsm.restype = None
+        L.HCORE_dpotrf.argtypes = [i, i, dp, i, C.POINTER(C.c_int), fl]
+        L.HCORE_dpotrf.restype = None
+        L.HCORE_dgemmbdcd.argtypes = [i, i, i, i, d, dp, dp, dp, i, dp, i, d, dp, i, dp, fl]
+        L.HCORE_dgemmbdcd.restype = None
+        L.HCORE_duncompress.argtypes = [i, i, i, i, d, dp, dp, i, dp, dp, i, d, dp, i]
+        L.HCORE_duncompress.restype = None
+        L.HCORE_zuncompress.argtypes = [i, i, i, i, d, d, vp, dp, i, vp, dp, i, d, d, vp, i]
+        L.HCORE_zuncompress.restype = None
         L.oracle_ref_set_blas_threads.argtypes = [i]
         L.oracle_ref_blas_config.restype = C.c_char_p
         _lib = L
@@ -148,3 +161,84 @@ def hcore_dsyrk(au, av, cd, alpha=-1.0):
     L.HCORE_dsyrk(HCORE_Lower, CblasNoTrans, nb, k, float(alpha), _p(au, C.c_double), nb,
                   _p(av, C.c_double), nb, 1.0, _p(out, C.c_double), nb, None, C.byref(fl))
     return out, int(fl.syrk)
+
+
+# ---- the remaining tile kernels of one TLR-Cholesky step + HCORE_dgemm_fast ----------------
+
+def hcore_dgemm_fast(au, av, bu, bv, cu, cv, crk, *, alpha, beta, rk, maxrk, acc):
+    """Reference ``HCORE_dgemm_fast`` on ONE tile (needs the globals use_trmm = use_scratch = 1, which this sets and
+    restores, and a scratch array: reference src/compute/hcore_dgemm_fast.c:82-83, :117-300)."""
+    L = lib()
+    nb, a, b = au.shape[1], au.shape[0], bu.shape[0]
+    n = a + crk
+    cu2 = np.zeros((max(2 * maxrk, cu.shape[0], n), nb)); cu2[:crk] = cu[:crk]
+    cv2 = np.zeros_like(cu2); cv2[:crk] = cv[:crk]
+    au, av, bu, bv = (np.ascontiguousarray(x, np.float64) for x in (au, av, bu, bv))
+    work = np.zeros(4 * nb * 2 * maxrk + 2 * nb + maxrk * maxrk + 3 * n * n + 2 * nb * n + n + 64 * n + 4096)
+    rks = [np.array([float(x)]) for x in (a, b, crk)]
+    trmm, scr = C.c_int.in_dll(L, "use_trmm"), C.c_int.in_dll(L, "use_scratch")
+    old = trmm.value, scr.value
+    trmm.value, scr.value = 1, 1
+    try:
+        L.HCORE_dgemm_fast(CblasNoTrans, CblasTrans, nb, nb, float(alpha), _p(au, C.c_double), _p(av, C.c_double),
+                           _p(rks[0], C.c_double), nb, _p(bu, C.c_double), _p(bv, C.c_double), _p(rks[1], C.c_double), nb,
+                           float(beta), _p(cu2, C.c_double), _p(cv2, C.c_double), _p(rks[2], C.c_double), nb,
+                           int(rk), int(maxrk), float(acc), _p(work, C.c_double))
+    finally:
+        trmm.value, scr.value = old
+    return cu2, cv2, int(rks[2][0])
+
+
+def hcore_dtrsm(side, uplo, trans, diag, alpha, a, bv):
+    """Reference ``HCORE_dtrsm``; ``a`` (n, n) and ``bv`` (Brank, M) column-major arrays. Returns ``(bv_out, flops_trsm)``."""
+    L = lib()
+    brank, m = bv.shape
+    a = np.ascontiguousarray(a, np.float64)
+    out = np.array(bv, dtype=np.float64, order="C", copy=True)
+    fl = FlopCounter()
+    L.HCORE_dtrsm(int(side), int(uplo), int(trans), int(diag), m, brank, float(alpha), _p(a, C.c_double), a.shape[1],
+                  _p(out, C.c_double), m, C.byref(fl))
+    return out, int(fl.trsm)
+
+
+def hcore_dpotrf(uplo, a):
+    """Reference ``HCORE_dpotrf``; ``a`` (N, N) column-major. Returns ``(a_out, info, flops_potrf)``."""
+    L = lib()
+    n = a.shape[0]
+    out = np.array(a, dtype=np.float64, order="C", copy=True)
+    info = C.c_int(-1)
+    fl = FlopCounter()
+    L.HCORE_dpotrf(int(uplo), n, _p(out, C.c_double), n, C.byref(info), C.byref(fl))
+    return out, info.value, int(fl.potrf)
+
+
+def hcore_dgemmbdcd(trans_a, alpha, au, av, bd, beta, cd):
+    """Reference ``HCORE_dgemmbdcd``; ``au, av`` (a, M), ``bd``, ``cd`` (N, M) column-major. Returns ``(cd_out, flops_update)``."""
+    L = lib()
+    a, m = au.shape
+    n = bd.shape[0]
+    au, av, bd = (np.ascontiguousarray(x, np.float64) for x in (au, av, bd))
+    out = np.array(cd, dtype=np.float64, order="C", copy=True)
+    ark = np.array([float(a)])
+    fl = FlopCounter()
+    L.HCORE_dgemmbdcd(int(trans_a), CblasNoTrans, m, n, float(alpha), _p(au, C.c_double), _p(av, C.c_double),
+                      _p(ark, C.c_double), m, _p(bd, C.c_double), m, float(beta), _p(out, C.c_double), m, None, C.byref(fl))
+    return out, int(fl.update)
+
+
+def hcore_uncompress(au, bv):
+    """Reference ``HCORE_duncompress`` / ``HCORE_zuncompress`` (by dtype); ``au`` (k, M), ``bv`` (k, N). Returns CD (N, M)."""
+    L = lib()
+    k, m = au.shape
+    n = bv.shape[1]
+    dt = au.dtype
+    au, bv = np.ascontiguousarray(au), np.ascontiguousarray(bv)
+    out = np.full((n, m), np.nan, dt)
+    rk = np.array([float(k)]), np.array([float(k)])
+    if dt == np.float64:
+        L.HCORE_duncompress(CblasNoTrans, CblasTrans, m, n, 7.0, _p(au, C.c_double), _p(rk[0], C.c_double), m,
+                            _p(bv, C.c_double), _p(rk[1], C.c_double), n, 3.0, _p(out, C.c_double), m)
+    else:
+        L.HCORE_zuncompress(CblasNoTrans, CblasTrans, m, n, 7.0, 1.0, au.ctypes.data, _p(rk[0], C.c_double), m,
+                            bv.ctypes.data, _p(rk[1], C.c_double), n, 3.0, -1.0, out.ctypes.data, m)
+    return out

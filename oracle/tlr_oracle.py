@@ -26,7 +26,8 @@ import numpy as np
 from scipy.linalg import lapack
 
 __all__ = ["qra", "qrb", "core_svd", "newu", "newv", "tlr_gemm", "tlr_gemm_colmajor",
-           "gemmcd", "syrk", "flop_model", "truncation_rank"]
+           "gemmcd", "syrk", "flop_model", "truncation_rank",
+           "tlr_gemm_fast", "trsm", "potrf", "gemmbdcd", "uncompress"]
 
 _PFX = {np.dtype(np.float64): "d", np.dtype(np.float32): "s", np.dtype(np.complex128): "z"}
 
@@ -64,7 +65,7 @@ def qrb(cv, av, bu, bv):
     return _geqrf(np.hstack([cv, g]))
 
 
-def truncation_rank(sigma, rk, acc, fixed_rank_if_positive=False):
+def truncation_rank(sigma, rk, acc, fixed_rank_if_positive=False, scan_from=1):
     """Truncation rule of ``__svd`` (reference src/compute/hcore_dgemm.c:444-464).
 
     ``rk != 0`` -> ``min(rk, n)``; otherwise the first index ``i >= 1`` with
@@ -74,13 +75,13 @@ def truncation_rank(sigma, rk, acc, fixed_rank_if_positive=False):
     fixed = (rk > 0) if fixed_rank_if_positive else (rk != 0)
     if fixed:
         return min(rk, n)
-    for i in range(1, n):
+    for i in range(scan_from, n):          # HCORE_dgemm_fast starts at 2 (reference src/compute/hcore_dgemm_fast.c:314)
         if sigma[i] < acc:
             return i
     return n
 
 
-def core_svd(qr_u, qr_v, rk, acc):
+def core_svd(qr_u, qr_v, rk, acc, scan_from=1):
     """``__svd`` (reference src/compute/hcore_dgemm.c:296-503).
 
     ``R_u, R_v`` = upper triangles (:330-336, :358-361); ``T = R_u * R_v^T`` (:384);
@@ -94,7 +95,7 @@ def core_svd(qr_u, qr_v, rk, acc):
     t = ru @ rv.T
     u, s, vt, info = _lp("gesvd", t.dtype)(np.asfortranarray(t), compute_uv=1, full_matrices=1)
     assert info == 0
-    r = truncation_rank(s, rk, acc, fixed_rank_if_positive=np.iscomplexobj(t))
+    r = truncation_rank(s, rk, acc, fixed_rank_if_positive=np.iscomplexobj(t), scan_from=scan_from)
     return u[:, :r], vt[:r, :] * s[:r, None], s, r
 
 
@@ -151,6 +152,66 @@ def tlr_gemm(au, av, bu, bv, cu, cv, *, alpha, beta, rk, maxrk, acc):
     if r > maxrk:
         raise ValueError("rank after truncation exceeds maxrk")
     return newu(qr_u, tau_u, u_r), newv(qr_v, tau_v, sv_r), r, sigma
+
+
+def tlr_gemm_fast(au, av, bu, bv, cu, cv, *, alpha, beta, rk, maxrk, acc):
+    """``HCORE_dgemm_fast`` (reference src/compute/hcore_dgemm_fast.c:59-426) on one tile.
+
+    Same stages as ``HCORE_dgemm`` -- stack + ``dgeqrf`` (:150-160, :170-206), core product by ``dtrmm`` on the two R
+    factors (:226-229, the same matrix as ``R_u R_v^T``), ``dgesvd`` (:291-300), ``dormqr`` (:355-414) -- with three
+    observable differences: the accuracy scan starts at index 2 (:314), there is no ``maxrk`` check on either the stack
+    width or the new rank, and no flop counter.  Returns ``(cu_new, cv_new, r, sigma)``."""
+    qr_u, tau_u = qra(cu, au, alpha, beta)
+    qr_v, tau_v = qrb(cv, av, bu, bv)
+    u_r, sv_r, sigma, r = core_svd(qr_u, qr_v, rk, acc, scan_from=2)
+    return newu(qr_u, tau_u, u_r), newv(qr_v, tau_v, sv_r), r, sigma
+
+
+def trsm(side, uplo, trans, diag, alpha, a, b):
+    """``HCORE_dtrsm`` (reference src/compute/hcore_dtrsm.c:24-48): ``cblas_dtrsm`` on the factor ``b`` (M x Brank).
+
+    ``side/uplo/trans/diag`` are the HCORE_enum values (141/142, 121/122, 111/112, 131/132).  Returns
+    ``(x, flops)`` with the reference's count ``n m^2`` (left) or ``m n^2`` (right) (:42-45, flop_counts 't')."""
+    from scipy.linalg import blas
+    m, n = b.shape
+    x = blas.dtrsm(alpha, np.asfortranarray(a), np.asfortranarray(b), side=int(side == 142), lower=int(uplo == 122),
+                   trans_a=int(trans != 111), diag=int(diag == 132))
+    return x, (n * m * m if side == 141 else m * n * n)
+
+
+def potrf(uplo, a):
+    """``HCORE_dpotrf`` (reference src/compute/hcore_dpotrf.c:23-35): ``LAPACKE_dpotrf_work`` in place; the other
+    triangle is left untouched.  QUIRK: the reference forwards its ``HCORE_enum uplo`` argument unchanged to LAPACKE's
+    ``char uplo`` (:29-32), so only the CHARACTER codes 'L' / 'U' (any case) select a triangle; the enum values
+    HCORE_Lower = 122 ('z') and HCORE_Upper = 121 ('y') make LAPACK reject the argument: ``LAPACKE_dpotrf_work``
+    returns ``info = -2`` (LAPACK's -1, shifted by the LAPACKE wrapper) with the matrix untouched.
+    ``uplo`` here is that integer.  Returns ``(a_out, info, flops)``, flops = ``n^3/3 - n^2/2.0 + n/6`` evaluated the
+    way ``flop_counts('c', ...)`` does (src/misc/descutil/flop_counts.c:11-14; counted even when info != 0)."""
+    n = a.shape[0]
+    flops = int(n * n * n // 3 - n * n / 2.0 + n // 6)
+    ch = chr(uplo).upper() if 0 < uplo < 128 else "?"
+    if ch not in ("L", "U"):
+        return np.array(a, copy=True), -2, flops
+    c, info = lapack.dpotrf(np.asfortranarray(a), lower=int(ch == "L"), clean=0, overwrite_a=0)
+    return c, info, flops
+
+
+def gemmbdcd(trans_a, alpha, au, av, bd, beta, cd):
+    """``HCORE_dgemmbdcd`` (reference src/compute/hcore_dgemmbdcd.c:35-122): ``CD <- alpha AU (AV^T BD) + beta CD``
+    (:78-90 / :99-111; the two ``transA`` branches differ only in which of M, LDA, LDB they use as sizes and agree
+    when LDA = LDB = M).  Returns ``(cd_out, flops)`` with ``flops->update`` as the reference counts it (:91-92)."""
+    k, n, m = au.shape[1], bd.shape[1], au.shape[0]
+    w = av.T @ bd
+    out = alpha * (au @ w) + (beta * cd if beta != 0 else 0.0)
+    return out, 2 * k * n * bd.shape[0] + 2 * m * n * k
+
+
+def uncompress(au, bv):
+    """``HCORE_duncompress`` / ``HCORE_zuncompress`` (reference src/compute/hcore_duncompress.c:33-85,
+    hcore_zuncompress.c:35-95): ``CD = AU BV^T`` with a PLAIN transpose also for complex data; the reference passes
+    one / zero to ``?gemm`` whatever ``alpha`` / ``beta`` the caller gives (:72-78) and asserts equal ranks (:69)."""
+    assert au.shape[1] == bv.shape[1], "ranks must be the same"
+    return au @ bv.T
 
 
 def tlr_gemm_colmajor(au, av, bu, bv, cu, cv, crk, **kw):

@@ -14,6 +14,8 @@ Fixtures:
   ref_ctest_dsyrk.npz    testing/testing_dsyrk.c (nrows 10, rank 7).
   ref_tlr_small.npz      compiled-reference outputs (full factors) for seeded tilegen batches
                          at nb=64/k=8 and nb=96/k=(5,7,6) (ragged ranks), fixed-rank mode too.
+  ref_cholstep.npz       compiled-reference outputs of HCORE_dtrsm / dpotrf / dgemmbdcd / d,zuncompress / dgemm_fast on
+                         the seeded inputs of tests/cholstep_cases.py (`python tests/golden/make_golden.py cholstep`).
   ref_tlr_large.npz      compiled-reference ranks, singular-value-free summaries (errors,
                          flop counts) at nb=500/k=25 and nb=1024/k=64 (inputs are regenerated
                          from the seed by hcore_b200.tilegen).
@@ -234,8 +236,65 @@ def tlr_complex():
     print("tlr_complex:", {k_: int(v) for k_, v in rec.items() if k_.endswith("_rank")})
 
 
+def cholstep():
+    """Compiled-reference outputs of HCORE_dtrsm (all 16 side/uplo/trans/diag variants + two multi-block sizes),
+    HCORE_dpotrf ('L', 'U', a non-positive-definite tile, the enum-valued uplo the reference rejects), HCORE_dgemmbdcd
+    (both transA branches, beta 0 / 1 / -0.5, a non-square CD), HCORE_duncompress / HCORE_zuncompress and HCORE_dgemm_fast
+    on the seeded inputs of tests/cholstep_cases.py.  The reference ships no test for any of them."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cholstep_cases as cc
+    cm = lambda x: np.ascontiguousarray(x.T)          # math orientation -> column-major storage
+    rec = {}
+    for (side, uplo, tr, dg) in cc.TRSM_VARIANTS:
+        a, b = cc.trsm_case(70, 9, side, uplo)
+        out, fl = rb.hcore_dtrsm(side, uplo, tr, dg, 0.7, cm(a), cm(b))
+        rec[f"trsm_{side}_{uplo}_{tr}_{dg}"] = out.T
+        rec[f"trsm_{side}_{uplo}_{tr}_{dg}_flops"] = fl
+    for (m, k, side, uplo, tr) in ((200, 20, 141, 122, 111), (200, 20, 142, 121, 112), (130, 70, 142, 122, 111), (257, 33, 141, 121, 111)):
+        a, b = cc.trsm_case(m, k, side, uplo)
+        out, fl = rb.hcore_dtrsm(side, uplo, tr, 131, -1.25, cm(a), cm(b))
+        rec[f"trsmbig_{m}_{k}_{side}_{uplo}_{tr}"] = out.T
+    for n in (100, 64, 200):
+        s_ = cc.spd_matrix(n)
+        for ch in ("L", "U"):
+            out, info, fl = rb.hcore_dpotrf(ord(ch), cm(s_))
+            assert info == 0
+            rec[f"potrf_{n}_{ch}"] = out.T
+            rec[f"potrf_{n}_{ch}_flops"] = fl
+    s_ = cc.spd_matrix(100); s_[50, 50] = -1.0
+    out, info, fl = rb.hcore_dpotrf(ord("L"), cm(s_))
+    rec["potrf_notpd"] = out.T; rec["potrf_notpd_info"] = info
+    out, info, fl = rb.hcore_dpotrf(122, cm(cc.spd_matrix(100)))         # HCORE_Lower as an enum: rejected by LAPACK
+    rec["potrf_enum_info"] = info
+    for (m, n, k) in ((96, 96, 7), (130, 80, 12)):
+        au, av, bd, cd = cc.bdcd_case(m, n, k)
+        for ta in (111, 112):
+            for beta in (0.0, 1.0, -0.5):
+                out, fl = rb.hcore_dgemmbdcd(ta, 0.3, cm(au), cm(av), cm(bd), beta, cm(cd))
+                rec[f"bdcd_{m}_{n}_{k}_{ta}_{beta}"] = out.T
+                rec[f"bdcd_{m}_{n}_{k}_{ta}_{beta}_flops"] = fl
+    for dt, nm in ((np.float64, "d"), (np.complex128, "z")):
+        for (m, n, k) in ((96, 80, 7), (130, 200, 33)):
+            au, bv = cc.uncompress_case(m, n, k, dt)
+            rec[f"unc_{nm}_{m}_{n}_{k}"] = rb.hcore_uncompress(cm(au), cm(bv)).T
+    for (name, au, av, bu, bv, cu, cv, acc) in cc.fast_cases():
+        a, c = au.shape[1], cu.shape[1]
+        mk = 2 * max(a, c, bu.shape[1])
+        cu2, cv2, r = rb.hcore_dgemm_fast(cm(au), cm(av), cm(bu), cm(bv), cm(cu), cm(cv), c, alpha=-1.0, beta=1.0, rk=0, maxrk=mk, acc=acc)
+        _, _, r_gemm, _ = rb.hcore_gemm(cm(au), cm(av), cm(bu), cm(bv), np.vstack([cm(cu), np.zeros((mk, cu.shape[0]))]),
+                                        np.vstack([cm(cv), np.zeros((mk, cu.shape[0]))]), c, alpha=-1.0, beta=1.0, rk=0, maxrk=mk, acc=acc)
+        rec[f"fast_{name}_cu"] = cu2[:r].T; rec[f"fast_{name}_cv"] = cv2[:r].T
+        rec[f"fast_{name}_rank"] = r; rec[f"fast_{name}_rank_dgemm"] = r_gemm
+        print("dgemm_fast", name, "rank", r, "HCORE_dgemm rank", r_gemm)
+    np.savez_compressed(os.path.join(HERE, "ref_cholstep.npz"), **rec)
+    print("cholstep:", len(rec), "arrays")
+
+
 if __name__ == "__main__":
     rb.set_blas_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "cholstep":
+        cholstep()
+        sys.exit(0)
     ctest_dgemm()
     ctest_sgemm()
     ctest_dgemmcd()
@@ -243,3 +302,4 @@ if __name__ == "__main__":
     tlr_small()
     tlr_large()
     tlr_complex()
+    cholstep()

@@ -219,3 +219,70 @@ def test_device_model_wide_stack_virtual_rows():
     q = dm.tsqr_apply(f, np.eye(n))
     assert np.abs(q.T @ q - np.eye(n)).max() < 1e-13
     assert np.abs(q @ R - x).max() < 1e-13
+
+
+# ---- the remaining TLR-Cholesky tile kernels + HCORE_dgemm_fast: oracle vs committed compiled-reference outputs ------
+
+def _chol_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_cholstep.npz"))
+
+
+def test_oracle_trsm_vs_compiled_reference(golden_dir):
+    import cholstep_cases as cc
+    g = _chol_golden(golden_dir)
+    for (side, uplo, tr, dg) in cc.TRSM_VARIANTS:
+        a, b = cc.trsm_case(70, 9, side, uplo)
+        x, fl = orc.trsm(side, uplo, tr, dg, 0.7, a, b)
+        assert np.abs(x - g[f"trsm_{side}_{uplo}_{tr}_{dg}"]).max() < 1e-13
+        assert fl == int(g[f"trsm_{side}_{uplo}_{tr}_{dg}_flops"])
+    for (m, k, side, uplo, tr) in ((200, 20, 141, 122, 111), (200, 20, 142, 121, 112), (130, 70, 142, 122, 111), (257, 33, 141, 121, 111)):
+        a, b = cc.trsm_case(m, k, side, uplo)
+        x, _ = orc.trsm(side, uplo, tr, 131, -1.25, a, b)
+        assert np.abs(x - g[f"trsmbig_{m}_{k}_{side}_{uplo}_{tr}"]).max() < 1e-12
+
+
+def test_oracle_potrf_vs_compiled_reference(golden_dir):
+    import cholstep_cases as cc
+    g = _chol_golden(golden_dir)
+    for n in (100, 64, 200):
+        for ch in ("L", "U"):
+            c, info, fl = orc.potrf(ord(ch), cc.spd_matrix(n))
+            assert info == 0 and fl == int(g[f"potrf_{n}_{ch}_flops"])
+            assert np.abs(c - g[f"potrf_{n}_{ch}"]).max() < 1e-13
+    s_ = cc.spd_matrix(100); s_[50, 50] = -1.0
+    c, info, _ = orc.potrf(ord("L"), s_)
+    assert info == int(g["potrf_notpd_info"]) == 51
+    # the reference forwards the HCORE_enum to LAPACKE's `char uplo` (hcore_dpotrf.c:29-32): the enum value is rejected
+    assert orc.potrf(122, cc.spd_matrix(100))[1] == int(g["potrf_enum_info"]) == -2
+
+
+def test_oracle_gemmbdcd_uncompress_vs_compiled_reference(golden_dir):
+    import cholstep_cases as cc
+    g = _chol_golden(golden_dir)
+    for (m, n, k) in ((96, 96, 7), (130, 80, 12)):
+        au, av, bd, cd = cc.bdcd_case(m, n, k)
+        for ta in (111, 112):
+            for beta in (0.0, 1.0, -0.5):
+                out, fl = orc.gemmbdcd(ta, 0.3, au, av, bd, beta, cd)
+                assert np.abs(out - g[f"bdcd_{m}_{n}_{k}_{ta}_{beta}"]).max() < 1e-13
+                assert fl == int(g[f"bdcd_{m}_{n}_{k}_{ta}_{beta}_flops"])
+    for dt, nm in ((np.float64, "d"), (np.complex128, "z")):
+        for (m, n, k) in ((96, 80, 7), (130, 200, 33)):
+            au, bv = cc.uncompress_case(m, n, k, dt)
+            assert np.abs(orc.uncompress(au, bv) - g[f"unc_{nm}_{m}_{n}_{k}"]).max() < 1e-13
+
+
+def test_oracle_dgemm_fast_vs_compiled_reference(golden_dir):
+    """HCORE_dgemm_fast (reference src/compute/hcore_dgemm_fast.c:59-426): same factors as HCORE_dgemm except that
+    the accuracy scan starts at index 2 (:314) -- the two crafted tiles get rank 2 where HCORE_dgemm gives 1."""
+    import cholstep_cases as cc
+    g = _chol_golden(golden_dir)
+    for (name, au, av, bu, bv, cu, cv, acc) in cc.fast_cases():
+        mk = 2 * max(au.shape[1], cu.shape[1], bu.shape[1])
+        cu2, cv2, r, _ = orc.tlr_gemm_fast(au, av, bu, bv, cu, cv, alpha=-1.0, beta=1.0, rk=0, maxrk=mk, acc=acc)
+        assert r == int(g[f"fast_{name}_rank"])
+        assert np.abs(cu2 @ cv2.T - g[f"fast_{name}_cu"] @ g[f"fast_{name}_cv"].T).max() < 1e-13
+        r_gemm = orc.tlr_gemm(au, av, bu, bv, cu, cv, alpha=-1.0, beta=1.0, rk=0, maxrk=mk, acc=acc)[2]
+        assert r_gemm == int(g[f"fast_{name}_rank_dgemm"])
+    assert int(g["fast_width2_rank"]) == 2 and int(g["fast_width2_rank_dgemm"]) == 1
+    assert int(g["fast_width3_rank"]) == 2 and int(g["fast_width3_rank_dgemm"]) == 1

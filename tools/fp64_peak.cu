@@ -81,6 +81,57 @@ __global__ void dmma1684_kernel(double *out, int iters, double x, double y) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA interleaved in one instruction stream (independent chains): if the tensor path and the scalar
+// FP64 pipe were separate units the combined rate would exceed either alone.
+template <int ILP>
+__global__ void mix_kernel(double *out, int iters, double x, double y) {
+    double d[ILP][2], acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { d[i][0] = d[i][1] = threadIdx.x * 1e-9; acc[i] = threadIdx.x * 1e-9 + i; }
+    double a = x + threadIdx.x * 1e-12, b = y;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(d[i][0]), "+d"(d[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[(i + j) % ILP] = fma(acc[(i + j) % ILP], x, y);   // 8 DFMA = the flops of one DMMA
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += d[i][0] + d[i][1] + acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// half of the CTA's warps issue DMMA only, the other half DFMA only
+template <int ILP>
+__global__ void split_kernel(double *out, int iters, double x, double y) {
+    double d[ILP][2], acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { d[i][0] = d[i][1] = threadIdx.x * 1e-9; acc[i] = threadIdx.x * 1e-9 + i; }
+    double a = x + threadIdx.x * 1e-12, b = y;
+    if ((threadIdx.x >> 5) & 1) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < ILP; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(d[i][0]), "+d"(d[i][1]) : "d"(a), "d"(b));
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], x, y);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += d[i][0] + d[i][1] + acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 double time_ms(F launch) {
     cudaEvent_t e0, e1;
@@ -111,6 +162,12 @@ int main() {
             ms = time_ms([&] { dmma884_kernel<8><<<grid, threads>>>(out, iters, 1.0000001, 1e-9); });
             fl = 2.0 * 8 * 8 * 4 * 8 * iters * (double)(threads / 32) * grid;
             printf("DMMA.884  threads=%4d ctas/sm=%d : %8.2f TFLOP/s\n", threads, bps, fl / ms * 1e-9);
+            ms = time_ms([&] { mix_kernel<8><<<grid, threads>>>(out, iters / 2, 1.0000001, 1e-9); });
+            fl = (2.0 * 8 * 8 * 4 + 2.0 * 8 * 32) * 8 * (iters / 2) * (double)(threads / 32) * grid;
+            printf("DMMA+DFMA interleaved threads=%4d ctas/sm=%d : %8.2f TFLOP/s (sum of both)\n", threads, bps, fl / ms * 1e-9);
+            ms = time_ms([&] { split_kernel<8><<<grid, threads>>>(out, iters, 1.0000001, 1e-9); });
+            fl = (2.0 * 8 * 8 * 4 + 2.0 * 8 * 32) * 8 * iters * (double)(threads / 64) * grid;
+            printf("DMMA | DFMA by warp parity threads=%4d ctas/sm=%d : %8.2f TFLOP/s (sum of both)\n", threads, bps, fl / ms * 1e-9);
             ms = time_ms([&] { dmma1684_kernel<4><<<grid, threads>>>(out, iters, 1.0000001, 1e-9); });
             fl = 2.0 * 16 * 8 * 4 * 4 * iters * (double)(threads / 32) * grid;
             printf("DMMA.1684 threads=%4d ctas/sm=%d : %8.2f TFLOP/s\n", threads, bps, fl / ms * 1e-9);
