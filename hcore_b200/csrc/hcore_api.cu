@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <dlfcn.h>
 
 #include "tlr_kernels.cuh"
 #include "dense_kernels.cuh"
@@ -257,6 +258,69 @@ void hcore_b200_shard_range(int64_t ntiles, int world, int rank, int64_t *first,
     const int64_t f = rank * base + std::min<int64_t>(rank, rem);
     if (first) *first = f;
     if (count) *count = base + (rank < rem ? 1 : 0);
+}
+
+// ---- multi-GPU: the final {rank, status} gather over NCCL (north star: "NCCL only for the final rank/status gather") ----
+// NCCL is resolved at run time (the symbols of an already loaded libnccl -- the application's or torch's -- else
+// dlopen("libnccl.so.2")): the library itself has no link-time dependency on it.
+namespace {
+typedef int (*nccl_allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+nccl_allgather_fn resolve_nccl_allgather() {
+    static nccl_allgather_fn fn = nullptr;
+    if (!fn) {
+        void *sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+        if (!sym) {
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (h) sym = dlsym(h, "ncclAllGather");
+        }
+        fn = reinterpret_cast<nccl_allgather_fn>(sym);
+    }
+    return fn;
+}
+// dst[i * cmax + j] blocks -> contiguous tile order (the first `rem` ranks own base + 1 tiles, the others base)
+__global__ void gather_compact_kernel(const int32_t *padded, int32_t *out, int64_t ntiles, int world, int64_t cmax) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ntiles) return;
+    const int64_t base = ntiles / world, rem = ntiles % world;
+    int r; int64_t off;
+    if (i < rem * (base + 1)) { r = (int)(i / (base + 1)); off = i - r * (base + 1); }
+    else { r = (int)(rem + (i - rem * (base + 1)) / (base > 0 ? base : 1)); off = i - rem * (base + 1) - (r - rem) * base; }
+    out[i] = padded[r * cmax + off];
+}
+}  // namespace
+
+int hcore_b200_gather_status(hcore_b200_handle_t ctx, void *nccl_comm, int world, int rank, int64_t ntiles,
+                             const int32_t *d_rank_local, const int32_t *d_status_local,
+                             int32_t *d_rank_all, int32_t *d_status_all, void *stream) {
+    if (!ctx || world <= 0 || rank < 0 || rank >= world || ntiles < 0) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t first, count;
+    hcore_b200_shard_range(ntiles, world, rank, &first, &count);
+    if (world == 1 && !nccl_comm) {                      // single rank: plain copies
+        if (d_rank_all && d_rank_local) CUDA_TRY(ctx, cudaMemcpyAsync(d_rank_all, d_rank_local, ntiles * 4, cudaMemcpyDeviceToDevice, st));
+        if (d_status_all && d_status_local) CUDA_TRY(ctx, cudaMemcpyAsync(d_status_all, d_status_local, ntiles * 4, cudaMemcpyDeviceToDevice, st));
+        return HCORE_B200_OK;
+    }
+    nccl_allgather_fn allgather = resolve_nccl_allgather();
+    if (!allgather || !nccl_comm) { ctx->err = "hcore_b200_gather_status: NCCL (libnccl.so.2) not available or null communicator"; return HCORE_B200_ERR_ARG; }
+    const int64_t cmax = (ntiles + world - 1) / world;
+    CUDA_TRY(ctx, ctx->info.reserve((size_t)(world + 1) * cmax * sizeof(int32_t)));
+    int32_t *send = (int32_t *)ctx->info.p, *recv = send + cmax;
+    const int32_t *src[2] = {d_rank_local, d_status_local};
+    int32_t *dst[2] = {d_rank_all, d_status_all};
+    for (int q = 0; q < 2; ++q) {
+        if (!src[q] || !dst[q]) continue;
+        CUDA_TRY(ctx, cudaMemsetAsync(send, 0, cmax * 4, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(send, src[q], count * 4, cudaMemcpyDeviceToDevice, st));
+        const int rc = allgather(send, recv, (size_t)cmax, /*ncclInt32*/ 2, nccl_comm, st);
+        if (rc != 0) { ctx->err = "ncclAllGather failed (" + std::to_string(rc) + ")"; return HCORE_B200_ERR_CUDA; }
+        gather_compact_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(recv, dst[q], ntiles, world, cmax);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
 }
 
 uint64_t hcore_b200_gemm_flops(int m_, int a_, int b_, int c_, int r_) {

@@ -106,23 +106,26 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     //                     i+1+warp, +16, ...; batches of 4 columns share one DMMA all-reduce),
     //                     down-date their squared norms (recomputed exactly every 8th step) and
     //                     leave the warp's best candidate for the next step
-    // The factorisation stops at step kq when the exact Frobenius norm of the remaining block is
-    // below 1% of the truncation threshold (singular values move by less than that, Weyl), or at
-    // rounding level of the largest column in fixed-rank mode.
+    // The squared norms of the trailing columns are recomputed EXACTLY in every step (they fall out of the update
+    // loop: one more DMMA all-reduce per batch of four columns, no down-dating and none of its cancellation).
+    // The factorisation stops at the first step kq at which the Frobenius norm of the remaining block -- the sum of
+    // those norms -- is below 1% of the truncation threshold (singular values move by less than that, Weyl), or
+    // at rounding level of the largest column in fixed-rank mode.
     constexpr int RPL = N / 32;                        // rows per lane
     double *candv = sig;                               // [16] per-warp best squared norm (sig is free until later)
+    double *cands = sig + 16;                          // [16] per-warp sum of the squared norms of its columns
     int *candi = reinterpret_cast<int *>(ssort);       // [16] and its column
     {
         // exact norms of all columns; warp w owns columns w, w+16, ... like phase D of "step -1"
-        double best = -1.0; int bi = 0;
+        double best = -1.0, wsum = 0.0; int bi = 0;
         for (int cc = warp; cc < n16; cc += nwarps) {
             double s2 = 0.0;
             for (int rr = lane; rr < n16; rr += 32) { const double x = L[rr + cc * LDL]; s2 = fma(x, x, s2); }
             s2 = warp_sum(s2);
-            if (lane == 0) vn[cc] = s2;
+            wsum += s2;
             if (s2 > best) { best = s2; bi = cc; }
         }
-        if (lane == 0) { candv[warp] = best; candi[warp] = bi; }
+        if (lane == 0) { candv[warp] = best; candi[warp] = bi; cands[warp] = wsum; }
     }
     __syncthreads();
     double tol2;
@@ -134,7 +137,6 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     int kq = n16;
     PROF_ADD(11);
     for (int i = 0; i < n16; ++i) {
-        const int ki = i >> 5, li = i & 31;
         if (warp == 0) {
             // -- pivot --
             double best = (lane < nwarps) ? candv[lane] : -1.0;
@@ -147,8 +149,11 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
             }
             best = __shfl_sync(0xffffffffu, best, 0);
             const int piv = __shfl_sync(0xffffffffu, bi, 0);
-            const bool exact = (i & 7) == 0;           // candidates come from exactly recomputed norms
-            const bool stop = exact && best * (double)(n16 - i) < tol2;
+            double fro2 = (lane < nwarps) ? cands[lane] : 0.0;       // squared Frobenius norm of the remaining block
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) fro2 += __shfl_xor_sync(0xffffffffu, fro2, o);
+            fro2 = __shfl_sync(0xffffffffu, fro2, 0);
+            const bool stop = fro2 < tol2;
             if (lane == 0) misc[2] = stop ? 1 : 0;
             if (!stop) {
                 // -- swap columns i <-> piv, build the reflector of the pivot column --
@@ -179,10 +184,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
                 }
                 if (lane == 0) {
                     dmisc[0] = h.tau;
-                    if (piv != i) {
-                        const int pi = perm[i]; perm[i] = perm[piv]; perm[piv] = pi;
-                        vn[piv] = vn[i];
-                    }
+                    if (piv != i) { const int pi = perm[i]; perm[i] = perm[piv]; perm[piv] = pi; }
                 }
             }
         }
@@ -190,11 +192,10 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
         if (misc[2]) { kq = i; break; }
         {
             const double tau = dmisc[0];
-            const bool exact_next = ((i + 1) & 7) == 0;
             double vv[RPL];
 #pragma unroll
             for (int e = 0; e < RPL; ++e) { const int rr = lane + 32 * e; vv[e] = (rr >= i && rr < n16) ? vvec[rr] : 0.0; }
-            double best = -1.0; int bi = 0x7fffffff;
+            double best = -1.0, wsum = 0.0; int bi = 0x7fffffff;
             for (int c0 = i + 1 + warp; c0 < n16; c0 += 4 * nwarps) {
                 double x[4][RPL], dot[4];
 #pragma unroll
@@ -225,24 +226,18 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
                     }
                     nrm[q] = s2;
                 }
-                if (exact_next) warp_allsum_dmma<4>(nrm);      // exact norms of rows > i
-                if (lane == li) {
+                warp_allsum_dmma<4>(nrm);                      // exact squared norms of rows > i, in every lane
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int cc = c0 + q * nwarps;
-                        if (cc < n16) {
-                            double top = x[q][0];
-#pragma unroll
-                            for (int e = 1; e < RPL; ++e) top = (e == ki) ? x[q][e] : top;
-                            double v = exact_next ? nrm[q] : vn[cc] - top * top;
-                            v = v > 0.0 ? v : 0.0;
-                            vn[cc] = v;
-                            if (v > best || (v == best && cc < bi)) { best = v; bi = cc; }
-                        }
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = c0 + q * nwarps;
+                    if (cc < n16) {
+                        const double v = nrm[q];
+                        wsum += v;
+                        if (v > best || (v == best && cc < bi)) { best = v; bi = cc; }
                     }
                 }
             }
-            if (lane == li) { candv[warp] = best; candi[warp] = bi; }
+            if (lane == 0) { candv[warp] = best; candi[warp] = bi; cands[warp] = wsum; }
         }
         __syncthreads();
     }
@@ -280,39 +275,35 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step
     int sweeps = 0;
     bool converged = (kq4 < 4);
-    // Two independent rotations A = (ap, aq) and B = (bp, bq) at once.  The six partial sums are reduced
-    // by recursive halving: the lower half of the group ends up with the three totals of A, the upper
-    // half with those of B (12 exchanges instead of 24), each half derives ITS rotation (the scalar chain
-    // runs once for both) and the halves swap (cos, sin).  sin == 0 means "no rotation".
+    // Two independent rotations A = (ap, aq) and B = (bp, bq) at once.  Only the two inner products a_p.a_q are
+    // formed: the squared column norms are CACHED (cn[], recomputed exactly at the start of every sweep and carried
+    // through each rotation by  app' = c^2 app - 2 c s apq + s^2 aqq,  aqq' = s^2 app + 2 c s apq + c^2 aqq; every term
+    // is formed to relative accuracy, so a small column next to a large one keeps a relatively accurate norm).  The
+    // two partial sums are reduced by recursive halving: the lower half of the group ends up with the total of A, the
+    // upper half with that of B (4 exchanges), each half derives ITS rotation (the scalar chain runs once for both)
+    // and the halves swap (cos, sin, new norms).  sin == 0 means "no rotation".
     const bool hi8 = (l16 & (LG / 2)) != 0;
     // the warp's other 16-lane group may be idle: shuffles name the lanes of this group only
     const unsigned hmask = (LG == 32) ? 0xffffffffu : ((tid & 16) ? 0xffff0000u : 0x0000ffffu);
-    auto rotate2 = [&](double2 (&ap)[RP], double2 (&aq)[RP], double2 (&bp)[RP], double2 (&bq)[RP], int &big) {
-        double sa[3] = {0.0, 0.0, 0.0}, ta[3] = {0.0, 0.0, 0.0}, sb[3] = {0.0, 0.0, 0.0}, tb[3] = {0.0, 0.0, 0.0};
+    auto rotate2 = [&](double2 (&ap)[RP], double2 (&aq)[RP], double2 (&bp)[RP], double2 (&bq)[RP],
+                       double &nap, double &naq, double &nbp, double &nbq, int &big) {
+        double sa = 0.0, ta = 0.0, sb = 0.0, tb = 0.0;
 #pragma unroll
         for (int e = 0; e < RP; ++e) {
-            sa[0] = fma(ap[e].x, ap[e].x, sa[0]); ta[0] = fma(ap[e].y, ap[e].y, ta[0]);
-            sa[1] = fma(aq[e].x, aq[e].x, sa[1]); ta[1] = fma(aq[e].y, aq[e].y, ta[1]);
-            sa[2] = fma(ap[e].x, aq[e].x, sa[2]); ta[2] = fma(ap[e].y, aq[e].y, ta[2]);
-            sb[0] = fma(bp[e].x, bp[e].x, sb[0]); tb[0] = fma(bp[e].y, bp[e].y, tb[0]);
-            sb[1] = fma(bq[e].x, bq[e].x, sb[1]); tb[1] = fma(bq[e].y, bq[e].y, tb[1]);
-            sb[2] = fma(bp[e].x, bq[e].x, sb[2]); tb[2] = fma(bp[e].y, bq[e].y, tb[2]);
+            sa = fma(ap[e].x, aq[e].x, sa); ta = fma(ap[e].y, aq[e].y, ta);
+            sb = fma(bp[e].x, bq[e].x, sb); tb = fma(bp[e].y, bq[e].y, tb);
         }
-        double v[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const double a = sa[q] + ta[q], b = sb[q] + tb[q];
-            v[q] = (hi8 ? b : a) + __shfl_xor_sync(hmask, hi8 ? a : b, LG / 2);
+        double v;
+        {
+            const double a = sa + ta, b = sb + tb;
+            v = (hi8 ? b : a) + __shfl_xor_sync(hmask, hi8 ? a : b, LG / 2);
         }
 #pragma unroll
-        for (int o = LG / 4; o > 0; o >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) v[q] += __shfl_xor_sync(hmask, v[q], o);
-        }
+        for (int o = LG / 4; o > 0; o >>= 1) v += __shfl_xor_sync(hmask, v, o);
         // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
-        const double app = v[0], aqq = v[1], apq = v[2];
+        const double app = hi8 ? nbp : nap, aqq = hi8 ? nbq : naq, apq = v;
         const double den2 = app * aqq, apq2 = apq * apq;
-        double cs = 1.0, sn = 0.0;
+        double cs = 1.0, sn = 0.0, npp = app, nqq = aqq;
         if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
             if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
             // d = aqq - app, hyp = sqrt(d^2 + 4 apq^2):  cos^2 = (|d| + hyp) / (2 hyp),
@@ -323,7 +314,14 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
             const double ru = rsqrt(u);
             cs = u * ru;
             sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
+            const double c2 = cs * cs, s2 = sn * sn, x2 = cs * sn * h2;      // 2 c s apq
+            npp = fma(s2, aqq, fma(c2, app, -x2));
+            nqq = fma(s2, app, fma(c2, aqq, x2));
+            npp = npp > 0.0 ? npp : 0.0;
+            nqq = nqq > 0.0 ? nqq : 0.0;
         }
+        const double onp = __shfl_xor_sync(hmask, npp, LG / 2), onq = __shfl_xor_sync(hmask, nqq, LG / 2);
+        nap = hi8 ? onp : npp; naq = hi8 ? onq : nqq; nbp = hi8 ? npp : onp; nbq = hi8 ? nqq : onq;
         const double ocs = __shfl_xor_sync(hmask, cs, LG / 2), osn = __shfl_xor_sync(hmask, sn, LG / 2);
         const double csa = hi8 ? ocs : cs, sna = hi8 ? osn : sn, csb = hi8 ? cs : ocs, snb = hi8 ? sn : osn;
         if (sna != 0.0) {
@@ -343,8 +341,16 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
             }
         }
     };
+    double *cn = vn;                                   // cached squared column norms (vn is free after the QRCP)
     for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
         int big = 0;
+        for (int cc = warp; cc < kq4; cc += nwarps) {      // exact norms at the start of every sweep
+            double s2 = 0.0;
+            for (int rr = lane; rr < n16; rr += 32) { const double x = L[rr + cc * LDL]; s2 = fma(x, x, s2); }
+            s2 = warp_sum(s2);
+            if (lane == 0) cn[cc] = s2;
+        }
+        __syncthreads();
         for (int step = 0; step < nb2 - 1; ++step) {
             auto do_pair = [&](int k) {
                 int p, qq;
@@ -361,9 +367,11 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
                     q0[e] = on ? *reinterpret_cast<const double2 *>(c0q + 2 * LG * e) : z;
                     q1[e] = on ? *reinterpret_cast<const double2 *>(c1q + 2 * LG * e) : z;
                 }
-                if (step == 0) rotate2(p0, p1, q0, q1, big);
-                rotate2(p0, q0, p1, q1, big);
-                rotate2(p0, q1, p1, q0, big);
+                double np0 = cn[2 * p], np1 = cn[2 * p + 1], nq0 = cn[2 * qq], nq1 = cn[2 * qq + 1];
+                if (step == 0) rotate2(p0, p1, q0, q1, np0, np1, nq0, nq1, big);
+                rotate2(p0, q0, p1, q1, np0, nq0, np1, nq1, big);
+                rotate2(p0, q1, p1, q0, np0, nq1, np1, nq0, big);
+                if (l16 == 0) { cn[2 * p] = np0; cn[2 * p + 1] = np1; cn[2 * qq] = nq0; cn[2 * qq + 1] = nq1; }
 #pragma unroll
                 for (int e = 0; e < RP; ++e) {
                     if (2 * l16 + 2 * LG * e < n16) {

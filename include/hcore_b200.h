@@ -81,6 +81,15 @@ int64_t hcore_b200_launch_count(hcore_b200_handle_t handle);
  * (SURVEY.md section 8(e)); rank r owns [*first, *first + *count).                       */
 void hcore_b200_shard_range(int64_t ntiles, int world, int rank, int64_t *first, int64_t *count);
 
+/* After a sharded batch every rank holds the new ranks / status of ITS tiles; this gathers both arrays (int32, tile
+ * order of the unsharded batch) on every rank with ONE ncclAllGather each -- the only collective of the path (SURVEY.md
+ * section 8(e)).  nccl_comm is the caller's ncclComm_t (world ranks, one per GPU); NCCL is looked up at run time
+ * (symbols already in the process, else libnccl.so.2).  d_*_local hold `count` entries (hcore_b200_shard_range),
+ * d_*_all `ntiles`; either pair may be NULL.  world == 1 with a NULL communicator degenerates to a copy. */
+int hcore_b200_gather_status(hcore_b200_handle_t handle, void *nccl_comm, int world, int rank, int64_t ntiles,
+                             const int32_t *d_rank_local, const int32_t *d_status_local,
+                             int32_t *d_rank_all, int32_t *d_status_all, void *stream);
+
 /* ---- batched TLR update + recompression (device pointers) ----------------------------- */
 /* Batched HCORE_dgemm (reference src/compute/hcore_dgemm.c:703-1012) over `ntiles`
  * independent tiles.

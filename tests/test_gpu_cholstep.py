@@ -137,7 +137,8 @@ def test_dpotrf_legacy_not_positive_definite(gold):
     info = api.hcore_dpotrf(ord("L"), 100, A, 100)
     assert info == int(gold["potrf_notpd_info"]) == 51
     ref = gold["potrf_notpd"]
-    assert np.abs(np.tril(A.T)[:, :50] - np.tril(ref)[:, :50]).max() < 1e-12       # the 50 columns factored before the failure
+    # what LAPACK defines on failure: the Cholesky factor of the positive definite leading minor of order info - 1
+    assert np.abs(np.tril(A.T)[:50, :50] - np.tril(ref)[:50, :50]).max() < 1e-12
 
 
 def test_dpotrf_legacy_invalid_uplo_like_lapack():

@@ -149,21 +149,26 @@ def test_stage4_reflector_application(ctx, nb, k, kind):
     acc = 1e-8
     b, maxrk = _batch(nb, k, kind)
     N = _width(maxrk)
+    # the small factors U_r, W and the R factors as the SVD stage leaves them (the apply kernel updates Y in place)
+    _, status = _run_stages(ctx, b, 3, -1.0, 1.0, 0, maxrk, acc)
+    assert (status.cpu().numpy() == 0).all()
+    small = []
+    for t in range(b.ntiles):
+        r = int(ctx.debug_fetch(9, t, 4)[1])
+        small.append([ctx.debug_fetch(w, t, N * N).reshape(N, N).T.copy() for w in (4, 5, 2, 3)] + [r])
     t_, status = _run_stages(ctx, b, 4, -1.0, 1.0, 0, maxrk, acc)
     assert (status.cpu().numpy() == 0).all()
     cu, cv, crk = t_["cu"].cpu().numpy(), t_["cv"].cpu().numpy(), t_["crk"].cpu().numpy()
     for t in range(b.ntiles):
         xu, xv, _ = _stacks(b, t, -1.0, 1.0)
         n, r = xu.shape[1], int(crk[t])
+        assert r == small[t][4]
         CU, CV = cu[t, :r].T, cv[t, :r].T
         assert np.abs(CU.T @ CU - np.eye(r)).max() < 1e-13
-        Yu = ctx.debug_fetch(4, t, N * N).reshape(N, N).T[:n, :r]
-        Yv = ctx.debug_fetch(5, t, N * N).reshape(N, N).T[:n, :r]
-        Rud = ctx.debug_fetch(2, t, N * N).reshape(N, N).T[:n, :n]
-        Rvd = ctx.debug_fetch(3, t, N * N).reshape(N, N).T[:n, :n]
+        Yu, Yv, Rud, Rvd = small[t][0][:n, :r], small[t][1][:n, :r], small[t][2][:n, :n], small[t][3][:n, :n]
         nx = np.linalg.norm(xu, 2) * np.linalg.norm(xv, 2)
         # Q_u^T X_u = R_u  =>  CU^T X_u = U_r^T R_u ; likewise CV^T X_v = W^T R_v
-        assert np.abs(CU.T @ xu - Yu.T @ Rud).max() <= 1e-12 * np.linalg.norm(xu, 2)
-        assert np.abs(CV.T @ xv - Yv.T @ Rvd).max() <= 1e-12 * nx
+        assert np.abs(CU.T @ xu - Yu.T @ Rud).max() <= 1e-11 * np.linalg.norm(xu, 2)
+        assert np.abs(CV.T @ xv - Yv.T @ Rvd).max() <= 1e-11 * nx
         # and the product is the stacked update restricted to the kept subspace: error below the dropped singular values
         assert np.linalg.norm(CU @ CV.T - xu @ xv.T) <= max(acc * np.sqrt(n), 1e-13 * nx)
