@@ -389,7 +389,14 @@ def main():
     value = total_tiles / (ms_per_step * 1e-3)
 
     # results of the last step: ranks / status gathered with NCCL (the only collective on this path)
-    ranks_all, stat_all = sched.gather_results(d["crk"], d["status"])
+    # through the library's own C entry point (hcore_b200_gather_status: ncclAllGather on a raw ncclComm_t); the
+    # torch.distributed gather is only the fallback when NCCL's C API cannot be reached from this process
+    try:
+        ranks_all, stat_all = sched.gather_results_c(ctx, d["crk"], d["status"])
+        gather_via = "hcore_b200_gather_status (C ABI, ncclAllGather)" if world > 1 else "hcore_b200_gather_status (single rank: copy)"
+    except Exception as e:  # pragma: no cover
+        ranks_all, stat_all = sched.gather_results(d["crk"], d["status"])
+        gather_via = f"torch.distributed all_gather (C-ABI gather unavailable: {e!r})"
     ranks_np = ranks_all.cpu().numpy()
     nfail = int((stat_all != 0).sum().item())
     mean_rank = float(ranks_np.mean())
@@ -450,7 +457,7 @@ def main():
             traffic_src = tj.get("source")
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": f"tlr_{dom}_kernel", "achieved": stages[dom]["model_tflops"],
+    roofline = {"bound": "fp64", "kernel": f"tlr_{dom}_kernel", "achieved": stages[dom]["model_tflops"],
                 "peak": peak_tflops, "unit": "TFLOP/s", "frac": stages[dom]["model_tflops"] / peak_tflops,
                 "traffic": traffic,
                 "note": "FP64: peak = max(DMMA m8n8k4 micro-benchmark 37.1 TF (profiles/fp64_peak_r1.txt), cuBLAS DGEMM "
@@ -468,14 +475,14 @@ def main():
                        "parallelism": f"tile-sharded x{world}", "l2": "inputs (>60 GB per GPU) exceed L2",
                        "c_restore_between_steps": "untimed device copy of the pristine C factors"},
             "gflops_effective": value * flops_tile / 1e9, "flops_per_tile_model": flops_tile,
-            "mean_new_rank": mean_rank, "failed_tiles": nfail, "sample_abs_err_fro": errs, "accuracy": accuracy,
+            "mean_new_rank": mean_rank, "failed_tiles": nfail, "status_gather": gather_via, "sample_abs_err_fro": errs, "accuracy": accuracy,
             "gpu_launches": launches, "stages": stages, "roofline": roofline, "clocks": clocks,
             "wall_s_timed_region": wall}
 
     # ---- end to end through the C ABI with HOST buffers (H2D + D2H inside the timed region) ----
     # every rank runs it on its own GPU at the same time; the time is the max over ranks
     if not args.no_e2e:
-        Te = min(args.e2e_tiles if world == 1 else min(args.e2e_tiles, 1024), T_local)
+        Te = min(args.e2e_tiles, T_local)                   # the same tile count per GPU at every N
         host = {}
         for nm in ("au", "av", "bu", "bv"):
             host[nm] = d[nm][:Te].cpu().pin_memory()
@@ -505,19 +512,31 @@ def main():
             dist.all_reduce(nf, op=dist.ReduceOp.SUM)
         # bytes that actually cross PCIe (the library copies only the columns that carry data: Crk columns of
         # C in, max new rank of each slice out)
+        # bytes that actually cross PCIe (the library copies only the columns that carry data: Crk columns of C in,
+        # min(maxrk, Ark + Crk) columns of C out -- fixed before the new ranks are known, so nothing waits for them)
         per_tile_in = (4 * k + 2 * k) * nb * 8
-        out_bytes = 0
-        crk_np = crk.numpy()
-        hc = max(int(torch.cuda.get_device_properties(dev).multi_processor_count), 64)   # the library's slice size
-        for s0 in range(0, Te, hc):
-            sl = crk_np[s0:s0 + hc]
-            out_bytes += 2 * len(sl) * nb * int(sl.max()) * 8
+        out_bytes = 2 * Te * nb * min(2 * k, 2 * k) * 8
         line["e2e"] = {"value": world * Te / float(te.item()), "unit": "tiles/s",
                        "h2d_bytes_per_step": world * (Te * per_tile_in + 3 * 4 * Te),
                        "d2h_bytes_per_step": world * (out_bytes + 2 * 4 * Te),
                        "tiles_per_step": world * Te, "failed_tiles": int(nf.item()), "rank0_numa_node": numa,
-                       "note": "HCORE_dgemm_batched_host on every rank at once: pinned host buffers, sliced "
-                               "H2D/compute/D2H pipeline on two streams; host wall clock, max over ranks"}
+                       "note": "HCORE_dgemm_batched_host on every rank at once: pinned host buffers, slices of 148 tiles "
+                               "through three staging buffers on three streams (H2D / kernels / D2H, event-chained, no "
+                               "host synchronisation inside the loop); host wall clock, max over ranks"}
+        # the transfer roofline of the end-to-end path: bytes moved / time against the raw concurrent H2D + D2H ceiling
+        # of this box measured with the same slice sizes (tools/pcie_ceiling.py -> profiles/pcie_ceiling_n*.json)
+        e = line["e2e"]
+        ach = (e["h2d_bytes_per_step"] + e["d2h_bytes_per_step"]) / float(te.item()) / 1e9
+        ceil_gbs, src = None, None
+        for cand in (os.path.join(ROOT, "profiles", f"pcie_ceiling_n{world}.json"),):
+            if os.path.exists(cand):
+                pj = json.load(open(cand))
+                # the H2D direction is the one that binds: the ceiling in tiles/s is the H2D rate / bytes in per tile
+                ceil_gbs = pj["both_h2d_gbs"] * (1.0 + e["d2h_bytes_per_step"] / e["h2d_bytes_per_step"])
+                src = os.path.relpath(cand, ROOT)
+        e["roofline"] = {"bound": "pcie", "achieved_gbs": ach, "ceiling_gbs": ceil_gbs, "frac": (ach / ceil_gbs) if ceil_gbs else None,
+                         "ceiling_source": src, "note": "ceiling = measured H2D rate with D2H running concurrently, scaled to "
+                                                        "this call's H2D:D2H byte mix (H2D is the binding direction)"}
         del host
     if rank == 0 and world == 1:
         # ---- CPU baseline: the reference on the host cores ----

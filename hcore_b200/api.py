@@ -370,17 +370,31 @@ class Context:
         self._check(rc)
 
     def dgemm_batched_host(self, alpha, AU, AV, Ark, BU, BV, Brk, beta, CU, CV, Crk, *, rk, maxrk, acc, status=None):
-        """Same on HOST tensors/arrays (pinned torch tensors recommended): the end-to-end path."""
+        """Same on HOST tensors/arrays (pinned torch tensors recommended): the end-to-end path.  float32 arrays go to
+        ``HCORE_sgemm_batched_host``, complex128 ones to ``HCORE_zgemm_batched_host``."""
         T, ka, nb = AU.shape
         kb, kc = BU.shape[1], CU.shape[1]
 
         def hp(x):
             return None if x is None else C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data)
 
-        rc = self._L.HCORE_dgemm_batched_host(
-            self._h, T, nb, float(alpha), hp(AU), hp(AV), hp(Ark), nb, ka * nb, hp(BU), hp(BV), hp(Brk), nb, kb * nb,
-            float(beta), hp(CU), hp(CV), hp(Crk), nb, kc * nb, int(rk), int(maxrk), float(acc), hp(status))
+        dt = str(AU.dtype).replace("torch.", "")
+        if dt == "complex128":
+            fn, al, be = self._L.HCORE_zgemm_batched_host, _lib.DComplex.of(alpha), _lib.DComplex.of(beta)
+        elif dt == "float32":
+            fn, al, be = self._L.HCORE_sgemm_batched_host, float(alpha), float(beta)
+        else:
+            fn, al, be = self._L.HCORE_dgemm_batched_host, float(alpha), float(beta)
+        rc = fn(self._h, T, nb, al, hp(AU), hp(AV), hp(Ark), nb, ka * nb, hp(BU), hp(BV), hp(Brk), nb, kb * nb,
+                be, hp(CU), hp(CV), hp(Crk), nb, kc * nb, int(rk), int(maxrk), float(acc), hp(status))
         self._check(rc)
+
+    def gather_status(self, nccl_comm, world, rank, ntiles, rank_local, status_local, rank_all, status_all, stream=None):
+        """``hcore_b200_gather_status``: the NCCL all-gather of {new rank, status} through the C ABI (``nccl_comm`` is
+        a raw ``ncclComm_t`` as an integer / void pointer, or None with world == 1)."""
+        self._check(self._L.hcore_b200_gather_status(self._h, C.c_void_p(nccl_comm) if nccl_comm else None, int(world), int(rank),
+                                                     int(ntiles), _ptr(rank_local), _ptr(status_local), _ptr(rank_all),
+                                                     _ptr(status_all), self._stream_ptr(stream)))
 
     # -- batched dense-C updates --
     def dgemmcd_batched(self, AU, AV, Ark, BU, BV, Brk, CD, stream=None):

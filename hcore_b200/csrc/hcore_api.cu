@@ -52,6 +52,13 @@ struct DevBuf {
     }
 };
 
+constexpr int kHostBufs = 3;
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[kHostBufs], comp_done[kHostBufs], out_done[kHostBufs];
+    bool ready = false;
+};
+
 }  // namespace
 
 struct hcore_b200_context {
@@ -72,6 +79,9 @@ struct hcore_b200_context {
     // host-staging (HCORE_dgemm_batched_host and the legacy wrappers)
     DevBuf stage[2];
     DevBuf stage_ints[2];
+    // the three-stream host pipeline (HCORE_*_batched_host): staging buffers, rank / status words, streams, events
+    DevBuf hstage[3], hstage_ints[3];
+    HostPipe hpipe;
     cudaStream_t streams[2] = {nullptr, nullptr};
     // debug / profiling
     int debug_stages = 4;
@@ -237,6 +247,11 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
     for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->Lcore, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->Ywork, &ctx->Winv, &ctx->info, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
+    for (int b = 0; b < kHostBufs; ++b) { ctx->hstage[b].release(); ctx->hstage_ints[b].release(); }
+    if (ctx->hpipe.ready) {
+        for (cudaStream_t st : {ctx->hpipe.s_in, ctx->hpipe.s_comp, ctx->hpipe.s_out}) cudaStreamDestroy(st);
+        for (int b = 0; b < kHostBufs; ++b) { cudaEventDestroy(ctx->hpipe.in_done[b]); cudaEventDestroy(ctx->hpipe.comp_done[b]); cudaEventDestroy(ctx->hpipe.out_done[b]); }
+    }
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &s : ctx->streams) if (s) cudaStreamDestroy(s);
     delete ctx;
@@ -599,90 +614,185 @@ int HCORE_sgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, flo
                                d_CU, d_CV, d_Crk, ldc, strideC, rk, maxrk, acc, d_status, stream, 1);
 }
 
+}  // extern "C"
+
+// =====================================================================================================
+// Host-buffer forms: every array is a HOST array (pinned memory gives full overlap).  Slices of the batch travel
+// through kHostBufs device staging buffers on THREE streams -- host-to-device copies, kernels, device-to-host copies --
+// chained by events only: the calling thread never blocks inside the loop, so the copy engines of both directions
+// and the SMs stay busy at the same time (PCIe is full duplex).  The number of C columns that come back is fixed per
+// slice from what the host knows (the stack width Ark + Crk bounds the new rank), so no rank has to reach the host
+// before the copy is enqueued; the columns between a tile's new rank and that bound are zero-filled on the device.
+// =====================================================================================================
+namespace {
+
+// zero the byte range [lo[t], hi) of two strided arrays per tile (columns past the new rank)
+__global__ void zero_tail_kernel(char *CU, char *CV, size_t stride_bytes, size_t col_bytes, const int *rank_new,
+                                 const int *status, const int *rank_old, int ncopy, int ntiles) {
+    const int t = blockIdx.y;
+    if (t >= ntiles) return;
+    const int r = (status && status[t] != HCORE_B200_OK) ? rank_old[t] : rank_new[t];
+    if (r >= ncopy) return;
+    const size_t lo = (size_t)r * col_bytes, n16 = ((size_t)(ncopy - r) * col_bytes) >> 4;
+    for (int a = 0; a < 2; ++a) {
+        uint4 *dst = reinterpret_cast<uint4 *>((a ? CV : CU) + (size_t)t * stride_bytes + lo);
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+            dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+template <class FIn, class FComp, class FOut>
+int host_pipeline(hcore_b200_context *ctx, HostPipe &hp, int ntiles, int hc, size_t stage_bytes, FIn &&in, FComp &&comp,
+                  FOut &&out) {
+    if (!hp.ready) {
+        for (cudaStream_t *st : {&hp.s_in, &hp.s_comp, &hp.s_out}) CUDA_TRY(ctx, cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+        for (int b = 0; b < kHostBufs; ++b) {
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&hp.in_done[b], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&hp.comp_done[b], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&hp.out_done[b], cudaEventDisableTiming));
+        }
+        hp.ready = true;
+    }
+    const int nb_used = std::min(kHostBufs, (ntiles + hc - 1) / hc);
+    for (int b = 0; b < nb_used; ++b) {
+        CUDA_TRY(ctx, ctx->hstage[b].reserve(stage_bytes * hc));
+        CUDA_TRY(ctx, ctx->hstage_ints[b].reserve((size_t)hc * 5 * sizeof(int)));
+    }
+    int slice = 0;
+    for (int t0 = 0; t0 < ntiles; t0 += hc, ++slice) {
+        const int b = slice % kHostBufs, cnt = std::min(hc, ntiles - t0);
+        if (slice >= kHostBufs) CUDA_TRY(ctx, cudaStreamWaitEvent(hp.s_in, hp.out_done[b], 0));   // staging buffer b is free again
+        CUDA_TRY(ctx, in(t0, cnt, b, hp.s_in));
+        CUDA_TRY(ctx, cudaEventRecord(hp.in_done[b], hp.s_in));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(hp.s_comp, hp.in_done[b], 0));
+        const int rc = comp(t0, cnt, b, hp.s_comp);
+        if (rc != HCORE_B200_OK) { cudaDeviceSynchronize(); return rc; }
+        CUDA_TRY(ctx, cudaEventRecord(hp.comp_done[b], hp.s_comp));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(hp.s_out, hp.comp_done[b], 0));
+        CUDA_TRY(ctx, out(t0, cnt, b, hp.s_out));
+        CUDA_TRY(ctx, cudaEventRecord(hp.out_done[b], hp.s_out));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(hp.s_out));
+    CUDA_TRY(ctx, cudaStreamSynchronize(hp.s_comp));
+    CUDA_TRY(ctx, cudaStreamSynchronize(hp.s_in));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+inline cudaError_t first_error(std::initializer_list<cudaError_t> es) {
+    for (cudaError_t e : es) if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// kind: 0 = double, 1 = float (HCORE_sgemm), 2 = complex double (HCORE_zgemm); es = element size in bytes
+int tlr_host(hcore_b200_handle_t ctx, int kind, int ntiles, int nb, const void *alpha, const void *h_AU, const void *h_AV,
+             const int32_t *h_Ark, int lda, int64_t strideA, const void *h_BU, const void *h_BV, const int32_t *h_Brk, int ldb,
+             int64_t strideB, const void *beta, void *h_CU, void *h_CV, int32_t *h_Crk, int ldc, int64_t strideC, int rk, int maxrk,
+             double acc, int32_t *h_status) {
+    if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t es = kind == 0 ? 8 : (kind == 1 ? 4 : 16);
+    // Slice = one wave of the SVD kernel (one CTA per SM): the path is PCIe-bound (3.1 MB in, 1.5-2.1 MB out per tile
+    // against ~17 us of GPU time at nb = 1024, rank 64), so small slices only shorten the pipeline fill and drain.
+    const int hc = std::min(ntiles, std::max(ctx->num_sms, 64));
+    const size_t perA = (size_t)strideA * es, perB = (size_t)strideB * es, perC = (size_t)strideC * es;
+    const size_t per_tile = 2 * perA + 2 * perB + 2 * perC;
+    auto carve = [&](int b, char *&dAU, char *&dAV, char *&dBU, char *&dBV, char *&dCU, char *&dCV, int *&di) {
+        char *base = (char *)ctx->hstage[b].p;
+        dAU = base; dAV = base + perA * hc; dBU = base + 2 * perA * hc; dBV = dBU + perB * hc;
+        dCU = base + 2 * perA * hc + 2 * perB * hc; dCV = dCU + perC * hc;
+        di = (int *)ctx->hstage_ints[b].p;
+    };
+    std::vector<int> ncopy_of;       // C columns that travel back, per slice
+    auto in = [&](int t0, int cnt, int b, cudaStream_t st) {
+        char *dAU, *dAV, *dBU, *dBV, *dCU, *dCV; int *di;
+        carve(b, dAU, dAV, dBU, dBV, dCU, dCV, di);
+        // only the columns that carry data cross PCIe: the first max(Crk) columns of CU / CV go in
+        int cmax = 1;
+        for (int t = 0; t < cnt; ++t) cmax = std::max(cmax, (int)h_Crk[t0 + t]);
+        const size_t win = std::min(perC, (size_t)ldc * cmax * es);
+        return first_error({
+            cudaMemcpyAsync(dAU, (const char *)h_AU + (size_t)t0 * perA, perA * cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpyAsync(dAV, (const char *)h_AV + (size_t)t0 * perA, perA * cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpyAsync(dBU, (const char *)h_BU + (size_t)t0 * perB, perB * cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpyAsync(dBV, (const char *)h_BV + (size_t)t0 * perB, perB * cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpy2DAsync(dCU, perC, (const char *)h_CU + (size_t)t0 * perC, perC, win, cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpy2DAsync(dCV, perC, (const char *)h_CV + (size_t)t0 * perC, perC, win, cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpyAsync(di, h_Ark + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpyAsync(di + hc, h_Brk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st),
+            cudaMemcpyAsync(di + 2 * hc, h_Crk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st)});
+    };
+    // the ranks that go in are read again when the results come back: keep a private copy (h_Crk is overwritten)
+    std::vector<int32_t> crk_in(h_Crk, h_Crk + ntiles);
+    auto comp = [&](int t0, int cnt, int b, cudaStream_t st) -> int {
+        char *dAU, *dAV, *dBU, *dBV, *dCU, *dCV; int *di;
+        carve(b, dAU, dAV, dBU, dBV, dCU, dCV, di);
+        int *dArk = di, *dBrk = di + hc, *dCrk = di + 2 * hc, *dOld = di + 3 * hc, *dSt = di + 4 * hc;
+        int nmax = 1;
+        for (int t = 0; t < cnt; ++t) nmax = std::max(nmax, (int)h_Ark[t0 + t] + (int)crk_in[t0 + t]);
+        const int ncopy = (int)std::min<int64_t>({(int64_t)nmax, (int64_t)maxrk, strideC / ldc});
+        ncopy_of.push_back(ncopy);
+        // a failed tile keeps its old rank: a copy of the ranks is taken before the update overwrites them
+        int rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dOld, dCrk, sizeof(int) * cnt, cudaMemcpyDeviceToDevice, st));
+        if (kind == 2) {
+            const hcore_b200_dcomplex *al = (const hcore_b200_dcomplex *)alpha, *be = (const hcore_b200_dcomplex *)beta;
+            rc = HCORE_zgemm_batched_strided(ctx, cnt, nb, *al, dAU, dAV, dArk, lda, strideA, dBU, dBV, dBrk, ldb, strideB, *be, dCU,
+                                             dCV, dCrk, ldc, strideC, rk, maxrk, acc, dSt, st);
+        } else {
+            rc = tlr_batched_strided(ctx, cnt, nb, *(const double *)alpha, dAU, dAV, dArk, lda, strideA, dBU, dBV, dBrk, ldb, strideB,
+                                     *(const double *)beta, dCU, dCV, dCrk, ldc, strideC, rk, maxrk, acc, dSt, st, kind == 1);
+        }
+        if (rc != HCORE_B200_OK) return rc;
+        zero_tail_kernel<<<dim3(8, cnt), 256, 0, st>>>(dCU, dCV, perC, (size_t)ldc * es, dCrk, dSt, dOld, ncopy, cnt);
+        ctx->launches++;
+        return HCORE_B200_OK;
+    };
+    size_t slice_idx = 0;
+    auto out = [&](int t0, int cnt, int b, cudaStream_t st) {
+        char *dAU, *dAV, *dBU, *dBV, *dCU, *dCV; int *di;
+        carve(b, dAU, dAV, dBU, dBV, dCU, dCV, di);
+        const size_t wout = std::min(perC, (size_t)ldc * ncopy_of[slice_idx++] * es);
+        return first_error({
+            cudaMemcpy2DAsync((char *)h_CU + (size_t)t0 * perC, perC, dCU, perC, wout, cnt, cudaMemcpyDeviceToHost, st),
+            cudaMemcpy2DAsync((char *)h_CV + (size_t)t0 * perC, perC, dCV, perC, wout, cnt, cudaMemcpyDeviceToHost, st),
+            cudaMemcpyAsync(h_Crk + t0, di + 2 * hc, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st),
+            h_status ? cudaMemcpyAsync(h_status + t0, di + 4 * hc, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st) : cudaSuccess});
+    };
+    return host_pipeline(ctx, ctx->hpipe, ntiles, hc, per_tile, in, comp, out);
+}
+
+}  // namespace
+
+extern "C" {
+
 int HCORE_dgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, double alpha,
                         const double *h_AU, const double *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
                         const double *h_BU, const double *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
                         double beta, double *h_CU, double *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
                         int rk, int maxrk, double acc, int32_t *h_status) {
-    if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0) return HCORE_B200_ERR_ARG;
-    if (ntiles == 0) return HCORE_B200_OK;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    // Slices of `hc` tiles ping-pong over two device staging buffers / streams so that the
-    // H2D copy of slice i+1 and the D2H copy of slice i-1 overlap the kernels of slice i.
-    // The kernels themselves share the context workspace, so they are serialised by an
-    // event chain (compute of slice i+1 waits for compute of slice i).
-    // Slice = one wave of the SVD kernel (one CTA per SM): the path is PCIe-bound (3.1 MB in, 1.5 MB out per
-    // tile against ~10 us of GPU time), so small slices only shorten the pipeline fill and drain.
-    const int hc = std::min(ntiles, std::max(ctx->num_sms, 64));
-    const size_t perA = (size_t)strideA * 8, perB = (size_t)strideB * 8, perC = (size_t)strideC * 8;
-    const size_t per_tile = 2 * perA + 2 * perB + 2 * perC;
-    for (int s = 0; s < 2; ++s) {
-        CUDA_TRY(ctx, ctx->stage[s].reserve(per_tile * hc));
-        CUDA_TRY(ctx, ctx->stage_ints[s].reserve((size_t)hc * 4 * sizeof(int)));
-    }
-    cudaError_t first_err = cudaSuccess;
-    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && first_err == cudaSuccess) first_err = e; };
-    cudaEvent_t done[2];
-    for (auto &e : done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    int rc = HCORE_B200_OK;
-    int slice = 0;
-    struct Pending { int t0, cnt; double *dCU, *dCV; } pending[2] = {{0, 0, nullptr, nullptr}, {0, 0, nullptr, nullptr}};
-    auto flush = [&](int s) {
-        Pending &p = pending[s];
-        if (p.cnt == 0) return;
-        cudaStream_t st = ctx->streams[s];
-        cudaStreamSynchronize(st);                       // ranks of this slice are on the host now
-        int rmax = 1;
-        for (int t = 0; t < p.cnt; ++t) rmax = std::max(rmax, (int)h_Crk[p.t0 + t]);
-        const size_t wout = std::min(perC, (size_t)ldc * rmax * 8);
-        ck(cudaMemcpy2DAsync(h_CU + (size_t)p.t0 * strideC, perC, p.dCU, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st));
-        ck(cudaMemcpy2DAsync(h_CV + (size_t)p.t0 * strideC, perC, p.dCV, perC, wout, p.cnt, cudaMemcpyDeviceToHost, st));
-        p.cnt = 0;
-    };
-    for (int t0 = 0; t0 < ntiles && rc == HCORE_B200_OK; t0 += hc, ++slice) {
-        const int s = slice & 1;
-        const int cnt = std::min(hc, ntiles - t0);
-        cudaStream_t st = ctx->streams[s];
-        char *base = (char *)ctx->stage[s].p;
-        double *dAU = (double *)base, *dAV = (double *)(base + perA * hc);
-        double *dBU = (double *)(base + 2 * perA * hc), *dBV = (double *)(base + 2 * perA * hc + perB * hc);
-        double *dCU = (double *)(base + 2 * perA * hc + 2 * perB * hc);
-        double *dCV = (double *)(base + 2 * perA * hc + 2 * perB * hc + perC * hc);
-        int *di = (int *)ctx->stage_ints[s].p;
-        int *dArk = di, *dBrk = di + hc, *dCrk = di + 2 * hc, *dSt = di + 3 * hc;
-        ck(cudaMemcpyAsync(dAU, h_AU + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpyAsync(dAV, h_AV + (size_t)t0 * strideA, perA * cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpyAsync(dBU, h_BU + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpyAsync(dBV, h_BV + (size_t)t0 * strideB, perB * cnt, cudaMemcpyHostToDevice, st));
-        // Only the columns that carry data cross PCIe: the first max(Crk) columns of CU/CV go in,
-        // the first max(new Crk) columns come back (2-D copies, one row per tile).
-        int cmax = 1;
-        for (int t = 0; t < cnt; ++t) cmax = std::max(cmax, (int)h_Crk[t0 + t]);
-        const size_t win = std::min(perC, (size_t)ldc * cmax * 8);
-        ck(cudaMemcpy2DAsync(dCU, perC, h_CU + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpy2DAsync(dCV, perC, h_CV + (size_t)t0 * strideC, perC, win, cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpyAsync(dArk, h_Ark + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpyAsync(dBrk, h_Brk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
-        ck(cudaMemcpyAsync(dCrk, h_Crk + t0, sizeof(int) * cnt, cudaMemcpyHostToDevice, st));
-        if (slice > 0) cudaStreamWaitEvent(st, done[s ^ 1], 0);   // workspace is shared
-        rc = HCORE_dgemm_batched_strided(ctx, cnt, nb, alpha, dAU, dAV, dArk, lda, strideA, dBU, dBV, dBrk, ldb,
-                                         strideB, beta, dCU, dCV, dCrk, ldc, strideC, rk, maxrk, acc, dSt, st);
-        cudaEventRecord(done[s], st);
-        ck(cudaMemcpyAsync(h_Crk + t0, dCrk, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
-        if (h_status) cudaMemcpyAsync(h_status + t0, dSt, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st);
-        pending[s] = {t0, cnt, dCU, dCV};
-        // while slice `slice` computes, finish the previous one: its new ranks are known once its
-        // stream has drained, then its factors come back on that stream
-        if (slice >= 1) flush(s ^ 1);
-    }
-    if (slice >= 1) flush((slice - 1) & 1);
-    cudaStreamSynchronize(ctx->streams[0]);
-    cudaStreamSynchronize(ctx->streams[1]);
-    for (auto &e : done) cudaEventDestroy(e);
-    if (rc != HCORE_B200_OK) return rc;
-    CUDA_TRY(ctx, first_err);
-    CUDA_TRY(ctx, cudaGetLastError());
-    return HCORE_B200_OK;
+    return tlr_host(ctx, 0, ntiles, nb, &alpha, h_AU, h_AV, h_Ark, lda, strideA, h_BU, h_BV, h_Brk, ldb, strideB, &beta, h_CU, h_CV,
+                    h_Crk, ldc, strideC, rk, maxrk, acc, h_status);
+}
+
+int HCORE_sgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, float alpha,
+                        const float *h_AU, const float *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
+                        const float *h_BU, const float *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
+                        float beta, float *h_CU, float *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, float acc, int32_t *h_status) {
+    const double al = alpha, be = beta;
+    return tlr_host(ctx, 1, ntiles, nb, &al, h_AU, h_AV, h_Ark, lda, strideA, h_BU, h_BV, h_Brk, ldb, strideB, &be, h_CU, h_CV,
+                    h_Crk, ldc, strideC, rk, maxrk, acc, h_status);
+}
+
+int HCORE_zgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_dcomplex alpha,
+                        const void *h_AU, const void *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
+                        const void *h_BU, const void *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
+                        hcore_b200_dcomplex beta, void *h_CU, void *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *h_status) {
+    return tlr_host(ctx, 2, ntiles, nb, &alpha, h_AU, h_AV, h_Ark, lda, strideA, h_BU, h_BV, h_Brk, ldb, strideB, &beta, h_CU, h_CV,
+                    h_Crk, ldc, strideC, rk, maxrk, acc, h_status);
 }
 
 // ---- complex double (HCORE_zgemm) ------------------------------------------------------------

@@ -55,3 +55,42 @@ class TileScheduler:
         ranks = torch.cat([out[r, 0, :c] for r, (_, c) in enumerate(ranges)])
         stats = torch.cat([out[r, 1, :c] for r, (_, c) in enumerate(ranges)])
         return ranks, stats
+
+    # ---- the same gather through the C ABI (hcore_b200_gather_status: ncclAllGather on a raw ncclComm_t) ------------
+    def nccl_comm(self):
+        """A raw ``ncclComm_t`` over the ranks of this job, created with NCCL's own C API through ctypes (the unique id
+        travels over the existing torch.distributed group).  What a C caller would pass to ``hcore_b200_gather_status``."""
+        import ctypes as C
+        import torch
+        if getattr(self, "_comm", None):
+            return self._comm
+        nccl = C.CDLL("libnccl.so.2")
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]
+
+        nccl.ncclGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+        nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        uid = UniqueId()
+        if self.rank == 0:
+            assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+        buf = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone().cuda()
+        self.dist.broadcast(buf, 0)
+        C.memmove(C.byref(uid), bytes(buf.cpu().numpy().tobytes()), 128)
+        comm = C.c_void_p()
+        rc = nccl.ncclCommInitRank(C.byref(comm), self.world, uid, self.rank)
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed ({rc})")
+        self._nccl, self._comm = nccl, comm.value
+        return self._comm
+
+    def gather_results_c(self, ctx, local_rank_i32, local_status_i32):
+        """``gather_results`` through ``hcore_b200_gather_status`` (C ABI, one ncclAllGather per array)."""
+        import torch
+        dev = local_rank_i32.device
+        ranks = torch.empty(self.ntiles, dtype=torch.int32, device=dev)
+        stats = torch.empty(self.ntiles, dtype=torch.int32, device=dev)
+        comm = self.nccl_comm() if (self.dist is not None and self.world > 1) else None
+        ctx.gather_status(comm, self.world, self.rank, self.ntiles, local_rank_i32, local_status_i32, ranks, stats)
+        torch.cuda.synchronize()
+        return ranks, stats

@@ -152,16 +152,35 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         int rk, int maxrk, double acc,
                         int32_t *d_status, void *stream);
 
-/* Host-buffer variant: every pointer is a HOST pointer (pinned memory gives overlap);
- * the call stages chunks through the device (H2D, compute, D2H overlapped on internal
- * streams) and returns when the results are back in host memory.  This is the
- * "reference-facing" end-to-end path bench.py reports as `e2e`.                          */
+/* Host-buffer variants: every pointer is a HOST pointer (pinned memory gives full overlap).  Slices of the batch are
+ * staged through the device on three internal streams (host-to-device copies, kernels, device-to-host copies, chained
+ * by events: both PCIe directions and the SMs are busy at the same time) and the call returns when the results are
+ * back in host memory.  This is the "reference-facing" end-to-end path bench.py reports as `e2e`.
+ * Columns of CU / CV: the first Crk[t] columns go in; on return the first (new) Crk[t] columns hold the factors and the
+ * columns from there up to min(maxrk, max over the slice of Ark + Crk) are ZERO (the copy size is fixed before the
+ * ranks are known, so nothing has to wait for them).  A failed tile keeps its first Crk[t] columns and its rank. */
 int HCORE_dgemm_batched_host(hcore_b200_handle_t handle, int ntiles, int nb,
                         double alpha,
                         const double *h_AU, const double *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
                         const double *h_BU, const double *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
                         double beta,
                         double *h_CU, double *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc,
+                        int32_t *h_status);
+int HCORE_sgemm_batched_host(hcore_b200_handle_t handle, int ntiles, int nb,
+                        float alpha,
+                        const float *h_AU, const float *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
+                        const float *h_BU, const float *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
+                        float beta,
+                        float *h_CU, float *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, float acc,
+                        int32_t *h_status);
+int HCORE_zgemm_batched_host(hcore_b200_handle_t handle, int ntiles, int nb,
+                        hcore_b200_dcomplex alpha,
+                        const void *h_AU, const void *h_AV, const int32_t *h_Ark, int lda, int64_t strideA,
+                        const void *h_BU, const void *h_BV, const int32_t *h_Brk, int ldb, int64_t strideB,
+                        hcore_b200_dcomplex beta,
+                        void *h_CU, void *h_CV, int32_t *h_Crk, int ldc, int64_t strideC,
                         int rk, int maxrk, double acc,
                         int32_t *h_status);
 

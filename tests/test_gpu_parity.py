@@ -436,6 +436,31 @@ def test_host_buffer_path_matches_device_path(ctx):
     for t in range(T):
         r = int(crk_d[t])
         assert np.array_equal(cu_h[t, :r], cu_d[t, :r]) and np.array_equal(cv_h[t, :r], cv_d[t, :r])
+        assert not cu_h[t, r:2 * k].any() and not cv_h[t, r:2 * k].any()      # columns past the new rank come back zeroed
+
+
+@pytest.mark.parametrize("dt,acc", [(np.float32, 1e-4), (np.complex128, 1e-8)])
+def test_host_buffer_path_single_and_complex(ctx, dt, acc):
+    """HCORE_sgemm_batched_host / HCORE_zgemm_batched_host: the same three-stream pipeline, bit-identical to the device call."""
+    nb, k, T = 192, 12, 400
+    b = make_lr_batch(4, nb, k, base_seed=33, dtype=dt, decades=4.0 if dt == np.float32 else 8.0)
+    rep = lambda x: np.ascontiguousarray(np.tile(x, (T // 4 + 1,) + (1,) * (x.ndim - 1))[:T])
+    h = {n: rep(getattr(b, n)) for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
+    t = {n: torch.from_numpy(h[n]).to("cuda:0") for n in h}
+    st_d = torch.full((T,), -7, dtype=torch.int32, device="cuda:0")
+    call = ctx.sgemm_batched if dt == np.float32 else ctx.zgemm_batched
+    al, be = (-1.0, 1.0) if dt == np.float32 else (-1.0 + 0.5j, 1.0 - 0.25j)
+    call(al, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], be, t["cu"], t["cv"], t["crk"], rk=0, maxrk=2 * k, acc=acc,
+         status=st_d)
+    torch.cuda.synchronize()
+    st_h = np.full(T, -1, np.int32)
+    ctx.dgemm_batched_host(al, h["au"], h["av"], h["ark"], h["bu"], h["bv"], h["brk"], be, h["cu"], h["cv"], h["crk"], rk=0,
+                           maxrk=2 * k, acc=acc, status=st_h)
+    assert (st_h == 0).all() and np.array_equal(h["crk"], t["crk"].cpu().numpy())
+    cu_d, cv_d = t["cu"].cpu().numpy(), t["cv"].cpu().numpy()
+    for i in range(T):
+        r = int(h["crk"][i])
+        assert np.array_equal(h["cu"][i, :r], cu_d[i, :r]) and np.array_equal(h["cv"][i, :r], cv_d[i, :r])
 
 
 # ---- dense-C updates (BASELINE.json configs[2]) ----------------------------------------------------------------

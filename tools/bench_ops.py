@@ -98,6 +98,59 @@ if ONLY in ("", "cov"):
     print("covariance", out["covariance"], flush=True)
     del t, cu0, cv0
     torch.cuda.empty_cache()
+# ---- the remaining tile kernels of one TLR-Cholesky step: device-resident, CUDA events --------------
+if ONLY in ("", "chol"):
+    nb, k = 1024, 64
+    FP64 = 37.1e12
+    rng = torch.Generator(device=dev); rng.manual_seed(7)
+    # dtrsm: ONE lower triangular diagonal tile, T V-factors (the trsm of a Cholesky panel step)
+    T = 2048
+    Lt = torch.tril(torch.rand((nb, nb), dtype=torch.float64, device=dev, generator=rng) - 0.5) / 32 + torch.eye(nb, dtype=torch.float64, device=dev)
+    A1 = Lt.T.contiguous()[None]                         # column-major storage of L
+    BV0 = torch.rand((T, k, nb), dtype=torch.float64, device=dev, generator=rng) - 0.5
+    BV = BV0.clone()
+    ms = timed(lambda: ctx.dtrsm_batched(141, 122, 111, 131, 1.0, A1, BV), lambda: BV.copy_(BV0))
+    byts, fl = (nb * nb // 2 + 2 * nb * k) * 8, nb * nb * k
+    out["dtrsm_shared_L"] = {"nb": nb, "rank": k, "tiles": T, "calls_per_s": T / ms * 1e3, "tflops": T * fl / ms / 1e9,
+                             "frac_fp64_peak": T * fl / ms / 1e9 / (FP64 / 1e12), "note": "L (4 MB) stays in L2; B in/out 1 MB per tile"}
+    print("dtrsm", out["dtrsm_shared_L"], flush=True)
+    # dpotrf: a single tile (the diagonal tile of a step) and a batch
+    for T in (1, 64):
+        X = torch.rand((T, nb, nb), dtype=torch.float64, device=dev, generator=rng) - 0.5
+        S0 = (X @ X.transpose(1, 2)) / nb + torch.eye(nb, dtype=torch.float64, device=dev)
+        S = S0.clone()
+        info = torch.zeros(T, dtype=torch.int32, device=dev)
+        ms = timed(lambda: ctx.dpotrf_batched(122, S, info), lambda: S.copy_(S0), reps=5)
+        out[f"dpotrf_T{T}"] = {"n": nb, "tiles": T, "ms_per_call": ms, "calls_per_s": T / ms * 1e3,
+                               "tflops": T * (nb ** 3 / 3) / ms / 1e9, "info_nonzero": int((info != 0).sum().item())}
+        print("dpotrf", out[f"dpotrf_T{T}"], flush=True)
+        del X, S0, S
+    # dgemmbdcd and uncompress: HBM-bound dense output
+    T = 1024
+    d = bench.make_device_batch(torch, T, nb, k, dev, seed=6)
+    BD = torch.rand((T, nb, nb), dtype=torch.float64, device=dev, generator=rng) - 0.5
+    CD = torch.rand((T, nb, nb), dtype=torch.float64, device=dev, generator=rng)
+    ms = timed(lambda: ctx.dgemmbdcd_batched(-1.0, d["au"], d["av"], d["ark"], BD, 1.0, CD), lambda: None)
+    byts = (3 * nb * nb + 2 * nb * k) * 8
+    out["dgemmbdcd"] = {"nb": nb, "rank": k, "tiles": T, "calls_per_s": T / ms * 1e3, "algorithmic_GBps": T * byts / ms / 1e6,
+                        "frac_of_measured_hbm": T * byts / ms / 1e6 / HBM}
+    print("dgemmbdcd", out["dgemmbdcd"], flush=True)
+    ms = timed(lambda: ctx.uncompress_batched(d["au"], d["ark"], d["bv"], d["brk"], CD), lambda: None)
+    byts = (nb * nb + 2 * nb * k) * 8
+    out["duncompress"] = {"nb": nb, "rank": k, "tiles": T, "calls_per_s": T / ms * 1e3, "algorithmic_GBps": T * byts / ms / 1e6,
+                          "frac_of_measured_hbm": T * byts / ms / 1e6 / HBM}
+    print("duncompress", out["duncompress"], flush=True)
+    del BD, CD
+    T = 512
+    zu = torch.complex(d["au"][:T], d["av"][:T]).contiguous(); zv = torch.complex(d["bu"][:T], d["bv"][:T]).contiguous()
+    ZD = torch.zeros((T, nb, nb), dtype=torch.complex128, device=dev)
+    ms = timed(lambda: ctx.uncompress_batched(zu, d["ark"][:T], zv, d["brk"][:T], ZD), lambda: None)
+    byts = (nb * nb + 2 * nb * k) * 16
+    out["zuncompress"] = {"nb": nb, "rank": k, "tiles": T, "calls_per_s": T / ms * 1e3, "algorithmic_GBps": T * byts / ms / 1e6,
+                          "frac_of_measured_hbm": T * byts / ms / 1e6 / HBM, "tflops": T * 8.0 * nb * nb * k / ms / 1e9}
+    print("zuncompress", out["zuncompress"], flush=True)
+    del d, zu, zv, ZD
+    torch.cuda.empty_cache()
 # ---- dense-C updates (config 3) ---------------------------------------------------------------------------
 nb, k, T = 1024, 32, (2048 if ONLY in ("", "dense") else 0)
 if T == 0:
@@ -108,7 +161,9 @@ cd = torch.rand((T, nb, nb), dtype=torch.float64, device=dev)
 for name, fn in (("dgemmcd", lambda: ctx.dgemmcd_batched(d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], cd)),
                  ("dsyrk", lambda: ctx.dsyrk_batched(-1.0, d["au"], d["av"], d["ark"], cd))):
     ms = timed(fn, lambda: None)
-    byts = (2 * nb * nb + (4 if name == "dgemmcd" else 2) * nb * k) * 8
+    # dsyrk reads only the blocks that touch the lower triangle and writes the whole tile (the strict upper blocks are
+    # zero-filled): with 128 x 64 blocks at nb = 1024 that is 72 of 128 blocks read, 128 written
+    byts = (2 * nb * nb + 4 * nb * k) * 8 if name == "dgemmcd" else (int(nb * nb * (1 + 72 / 128)) + 2 * nb * k) * 8
     out[name] = {"nb": nb, "rank": k, "tiles": T, "calls_per_s": T / ms * 1e3, "algorithmic_GBps": T * byts / ms / 1e6,
                  "frac_of_measured_hbm": T * byts / ms / 1e6 / HBM}
     print(name, out[name], flush=True)
