@@ -36,6 +36,9 @@ struct DenseArgs {
     int nb, ncols;                       // rows and columns of CD
     double su, beta;                     // beta == 0: CD is not read
     int syrk;                            // 1: lower triangle only + zero strict upper
+    // pointer-array form (HCORE_dgemmcd_batched / HCORE_dsyrk_batched): per-tile pointers replace base + t * stride
+    const double *const *pAU, *const *pAV, *const *pBU, *const *pBV;
+    double *const *pCD;
 };
 
 // X = scale * Au (Av^T Bv)  (m x b, ld m_pad)      reference hcore_dgemmcd.c:66-78, hcore_dsyrk.c:103-144.
@@ -51,8 +54,8 @@ __global__ void __launch_bounds__(256, 2) dense_prep_kernel(DenseArgs ar) {
         for (int idx = threadIdx.x; idx < ar.m_pad * b; idx += blockDim.x) X[idx] = 0.0;
         return;
     }
-    const double *AU = ar.AU + (size_t)t * ar.strideA, *AV = ar.AV + (size_t)t * ar.strideA;
-    const double *BV = ar.BV + (size_t)t * ar.strideB;
+    const double *AU = ar.pAU ? ar.pAU[t] : ar.AU + (size_t)t * ar.strideA, *AV = ar.pAV ? ar.pAV[t] : ar.AV + (size_t)t * ar.strideA;
+    const double *BV = ar.pBV ? ar.pBV[t] : ar.BV + (size_t)t * ar.strideB;
     pg_body(smem, BV, AU, AV, b, a, m, ar.ldb, ar.lda, ar.m_pad, 0, ar.scale, ar.X + (size_t)t * ar.m_pad * ar.kcap, ar.mc);
 }
 
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
     if (ar.Krk[t] < 0) return;                 // tile flagged by the caller (uncompress with mismatched ranks): untouched
     const int m = ar.nb, nn = ar.ncols, ldc = ar.ldc, ldy = ar.ldy;
     const int rows = (m - i0 < kDuRows) ? (m - i0) : kDuRows, cols = (nn - j0 < kDuCols) ? (nn - j0) : kDuCols;
-    double *CD = ar.CD + (size_t)t * ar.strideC + i0 + (size_t)j0 * ldc;   // block origin
-    const double *BU = ar.Yop + (size_t)t * ar.strideY + j0;
+    double *CD = (ar.pCD ? ar.pCD[t] : ar.CD + (size_t)t * ar.strideC) + i0 + (size_t)j0 * ldc;   // block origin
+    const double *BU = (ar.pBU ? ar.pBU[t] : ar.Yop + (size_t)t * ar.strideY) + j0;
     const int tid = threadIdx.x, warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, tg = lane & 3;
     const bool cd_bulk = ((m & 1) == 0) && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(CD) & 15) == 0);

@@ -64,6 +64,7 @@ struct HostPipe {
 struct hcore_b200_context {
     int device = 0;
     int chunk_limit = 0;            // user override, 0 = default
+    int host_slice = 0;             // tiles per slice of the host-buffer pipeline (0 = default; HCORE_B200_HOST_SLICE)
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -234,6 +235,7 @@ int hcore_b200_create(hcore_b200_handle_t *handle, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HCORE_B200_ERR_CUDA; }
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char *e = getenv("HCORE_B200_TSQR_WARPS")) ctx->tsqr_warps = atoi(e);
+    if (const char *e = getenv("HCORE_B200_HOST_SLICE")) ctx->host_slice = atoi(e);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &s : ctx->streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     *handle = ctx;
@@ -693,9 +695,10 @@ int tlr_host(hcore_b200_handle_t ctx, int kind, int ntiles, int nb, const void *
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t es = kind == 0 ? 8 : (kind == 1 ? 4 : 16);
-    // Slice = one wave of the SVD kernel (one CTA per SM): the path is PCIe-bound (3.1 MB in, 1.5-2.1 MB out per tile
-    // against ~17 us of GPU time at nb = 1024, rank 64), so small slices only shorten the pipeline fill and drain.
-    const int hc = std::min(ntiles, std::max(ctx->num_sms, 64));
+    // The path is PCIe-bound (3.1 MB in, 2.1 MB out per tile against ~17 us of GPU time at nb = 1024, rank 64): what a
+    // slice costs is its share of the pipeline fill (the first H2D) and drain (the last kernels + D2H), so slices are
+    // small -- 64 tiles keep the kernels (latency-bound below one wave of 148 CTAs) ahead of the copies with margin.
+    const int hc = std::min(ntiles, ctx->host_slice > 0 ? ctx->host_slice : 64);
     const size_t perA = (size_t)strideA * es, perB = (size_t)strideB * es, perC = (size_t)strideC * es;
     const size_t per_tile = 2 * perA + 2 * perB + 2 * perC;
     auto carve = [&](int b, char *&dAU, char *&dAV, char *&dBU, char *&dBV, char *&dCU, char *&dCV, int *&di) {
@@ -796,11 +799,12 @@ int HCORE_zgemm_batched_host(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_
 }
 
 // ---- complex double (HCORE_zgemm) ------------------------------------------------------------
-int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_dcomplex alpha,
+}  // extern "C"
+static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_dcomplex alpha,
                         const void *d_AU, const void *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
                         const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
                         hcore_b200_dcomplex beta, void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
-                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream, const void *const *d_ptrs = nullptr) {
     if (!ctx || ntiles < 0 || nb <= 0 || maxrk <= 0 || lda < nb || ldb < nb || ldc < nb) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -839,6 +843,7 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hco
         ar.nb = nb; ar.lda = lda; ar.ldb = ldb; ar.ldc = ldc;
         ar.alpha = make_double2(alpha.re, alpha.im); ar.beta = make_double2(beta.re, beta.im);
         ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc; ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
+        ar.ptrs = (const zc *const *)d_ptrs; ar.ptr_stride = ntiles;
         ztlr_stack_kernel<<<ar.ntiles, 256, 0, st>>>(ar, ws);
         if (nb <= 32 * kZRows) ztlr_qr_blocked_kernel<<<2 * ar.ntiles, 256, sm_qrb, st>>>(ar, ws);
         else ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
@@ -850,12 +855,44 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hco
     return HCORE_B200_OK;
 }
 
+extern "C" {
+int HCORE_zgemm_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_dcomplex alpha,
+                        const void *d_AU, const void *d_AV, const int32_t *d_Ark, int lda, int64_t strideA,
+                        const void *d_BU, const void *d_BV, const int32_t *d_Brk, int ldb, int64_t strideB,
+                        hcore_b200_dcomplex beta, void *d_CU, void *d_CV, int32_t *d_Crk, int ldc, int64_t strideC,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    return zgemm_launch(ctx, ntiles, nb, alpha, d_AU, d_AV, d_Ark, lda, strideA, d_BU, d_BV, d_Brk, ldb, strideB, beta, d_CU, d_CV,
+                        d_Crk, ldc, strideC, rk, maxrk, acc, d_status, stream);
+}
+
+// pointer-array form: six device arrays of per-tile pointers (complex arrays, interleaved re / im)
+int HCORE_zgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_dcomplex alpha,
+                        const void *const *d_AU, const void *const *d_AV, const int32_t *d_Ark, int lda,
+                        const void *const *d_BU, const void *const *d_BV, const int32_t *d_Brk, int ldb,
+                        hcore_b200_dcomplex beta, void *const *d_CU, void *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // the six tables are gathered into one [6][ntiles] table the kernels index (device-to-device, 48 bytes per tile)
+    CUDA_TRY(ctx, ctx->ptrs.reserve(6ull * ntiles * sizeof(void *)));
+    const void *const *src[6] = {d_AU, d_AV, d_BU, d_BV, (const void *const *)d_CU, (const void *const *)d_CV};
+    for (int q = 0; q < 6; ++q)
+        CUDA_TRY(ctx, cudaMemcpyAsync((void **)ctx->ptrs.p + (size_t)q * ntiles, src[q], (size_t)ntiles * sizeof(void *),
+                                      cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return zgemm_launch(ctx, ntiles, nb, alpha, nullptr, nullptr, d_Ark, lda, 0, nullptr, nullptr, d_Brk, ldb, 0, beta, nullptr, nullptr,
+                        d_Crk, ldc, 0, rk, maxrk, acc, d_status, stream, (const void *const *)ctx->ptrs.p);
+}
+}  // extern "C"
+
 // ---- dense-C updates ----------------------------------------------------------------------
 // kcap = upper bound of the B-side rank (columns of the X workspace).  mc = rows contracted by AV^T BV.
 static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scale, int syrk,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA, int lda,
                         const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB, int ldb, int mc,
-                        double *d_CD, int64_t strideC, int ldc, int kcap, void *stream) {
+                        double *d_CD, int64_t strideC, int ldc, int kcap, void *stream,
+                        const double *const *p_AU = nullptr, const double *const *p_AV = nullptr, const double *const *p_BU = nullptr,
+                        const double *const *p_BV = nullptr, double *const *p_CD = nullptr) {
     if (!ctx || ntiles < 0 || nb <= 0 || lda < nb || ldb < nb || ldc < nb || kcap <= 0) return HCORE_B200_ERR_ARG;
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -885,6 +922,7 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
         ar.Krk = d_Brk + t0;
         ar.CD = d_CD + (size_t)t0 * strideC; ar.strideC = strideC; ar.ldc = ldc;
         ar.nb = nb; ar.ncols = nb; ar.su = 1.0; ar.beta = 1.0; ar.syrk = syrk;
+        if (p_CD) { ar.pAU = p_AU + t0; ar.pAV = p_AV + t0; ar.pBU = p_BU + t0; ar.pBV = p_BV + t0; ar.pCD = p_CD + t0; }
         dense_prep_kernel<<<cnt, 256, sm_prep, st>>>(ar);
         dense_update_kernel<<<dim3((nb + kDuRows - 1) / kDuRows, (nb + kDuCols - 1) / kDuCols, cnt), 256, sm_upd, st>>>(ar);
         ctx->launches += 2;
@@ -921,6 +959,8 @@ static int rank_cap(int64_t stride, int ld, int fallback) {      // columns a st
     return stride > 0 ? (int)std::max<int64_t>(1, stride / ld) : fallback;
 }
 
+extern "C" {
+
 int HCORE_dgemmcd_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
                         const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB,
@@ -934,6 +974,24 @@ int HCORE_dsyrk_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, dou
                         double *d_CD, int64_t strideC, void *stream) {
     return dense_launch(ctx, ntiles, nb, alpha, 1, d_AU, d_AV, d_Ark, strideA, nb, d_AU, d_AV, d_Ark, strideA, nb, nb, d_CD,
                         strideC, nb, rank_cap(strideA, nb, HCORE_B200_MAX_STACK), stream);
+}
+
+// pointer-array forms (device arrays of per-tile device pointers); kmax = largest rank in the batch (workspace sizing)
+int HCORE_dgemmcd_batched(hcore_b200_handle_t ctx, int ntiles, int nb, int kmax,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk,
+                        double *const *d_CD, void *stream) {
+    if (!d_AU || !d_AV || !d_BU || !d_BV || !d_CD || kmax <= 0) return HCORE_B200_ERR_ARG;
+    return dense_launch(ctx, ntiles, nb, -1.0, 0, nullptr, nullptr, d_Ark, 0, nb, nullptr, nullptr, d_Brk, 0, nb, nb, nullptr, 0, nb, kmax,
+                        stream, d_AU, d_AV, d_BU, d_BV, d_CD);
+}
+
+int HCORE_dsyrk_batched(hcore_b200_handle_t ctx, int ntiles, int nb, int kmax, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark,
+                        double *const *d_CD, void *stream) {
+    if (!d_AU || !d_AV || !d_CD || kmax <= 0) return HCORE_B200_ERR_ARG;
+    return dense_launch(ctx, ntiles, nb, alpha, 1, nullptr, nullptr, d_Ark, 0, nb, nullptr, nullptr, d_Ark, 0, nb, nb, nullptr, 0, nb, kmax,
+                        stream, d_AU, d_AV, d_AU, d_AV, d_CD);
 }
 
 // ---- HCORE_dgemmbdcd / HCORE_duncompress / HCORE_zuncompress (device pointers) -------------------------------------

@@ -48,6 +48,8 @@ struct ZArgs {
     const zc *AU, *AV, *BU, *BV;     // strided factor arrays
     zc *CU, *CV;
     long strideA, strideB, strideC;
+    const zc *const *ptrs;           // pointer-array form: [6][ntiles_total] tables (AU, AV, BU, BV, CU, CV), else null
+    long ptr_stride;                 // entries per table
     const int *Ark, *Brk;
     int *Crk;
     int *status;
@@ -86,9 +88,12 @@ __global__ void __launch_bounds__(256) ztlr_stack_kernel(ZArgs ar, ZWorkspace ws
         if (ar.status) ar.status[gt] = st;
     }
     if (st != HCORE_B200_OK) return;
-    const zc *AU = ar.AU + (size_t)gt * ar.strideA, *AV = ar.AV + (size_t)gt * ar.strideA;
-    const zc *BU = ar.BU + (size_t)gt * ar.strideB, *BV = ar.BV + (size_t)gt * ar.strideB;
-    const zc *CU = ar.CU + (size_t)gt * ar.strideC, *CV = ar.CV + (size_t)gt * ar.strideC;
+    const zc *AU = ar.ptrs ? ar.ptrs[gt] : ar.AU + (size_t)gt * ar.strideA;
+    const zc *AV = ar.ptrs ? ar.ptrs[ar.ptr_stride + gt] : ar.AV + (size_t)gt * ar.strideA;
+    const zc *BU = ar.ptrs ? ar.ptrs[2 * ar.ptr_stride + gt] : ar.BU + (size_t)gt * ar.strideB;
+    const zc *BV = ar.ptrs ? ar.ptrs[3 * ar.ptr_stride + gt] : ar.BV + (size_t)gt * ar.strideB;
+    const zc *CU = ar.ptrs ? ar.ptrs[4 * ar.ptr_stride + gt] : ar.CU + (size_t)gt * ar.strideC;
+    const zc *CV = ar.ptrs ? ar.ptrs[5 * ar.ptr_stride + gt] : ar.CV + (size_t)gt * ar.strideC;
     zc *XU = zpanel(ws, 0, t, m), *XV = zpanel(ws, 1, t, m);
     zc *P = ws.T + (size_t)t * N * N;                     // P[i + j*N], i < a, j < b
 
@@ -495,7 +500,8 @@ __global__ void __launch_bounds__(256) ztlr_apply_kernel(ZArgs ar, ZWorkspace ws
     const zc *y = ws.Y + ((size_t)pnl * ws.chunk + t) * N * N + (size_t)col * N;
     zc *z = reinterpret_cast<zc *>(zsm) + (size_t)warp * m;
     zc *vbuf = reinterpret_cast<zc *>(zsm) + (size_t)W * m;   // [2][m]
-    zc *out = (pnl == 0 ? ar.CU : ar.CV) + (size_t)gt * ar.strideC + (size_t)col * ar.ldc;
+    zc *out = (ar.ptrs ? const_cast<zc *>(ar.ptrs[(4 + pnl) * ar.ptr_stride + gt]) : (pnl == 0 ? ar.CU : ar.CV) + (size_t)gt * ar.strideC) +
+              (size_t)col * ar.ldc;
     if (on)
         for (int r = lane; r < m; r += 32) z[r] = (r < n) ? y[r] : zmake(0.0, 0.0);
     auto stage = [&](int j, int b) {                          // rows j+1 .. m-1 of reflector j -> vbuf[b]

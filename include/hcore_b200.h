@@ -152,6 +152,16 @@ int HCORE_zgemm_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         int rk, int maxrk, double acc,
                         int32_t *d_status, void *stream);
 
+/* Pointer-array form of the same: six device arrays of per-tile device pointers. */
+int HCORE_zgemm_batched(hcore_b200_handle_t handle, int ntiles, int nb,
+                        hcore_b200_dcomplex alpha,
+                        const void *const *d_AU, const void *const *d_AV, const int32_t *d_Ark, int lda,
+                        const void *const *d_BU, const void *const *d_BV, const int32_t *d_Brk, int ldb,
+                        hcore_b200_dcomplex beta,
+                        void *const *d_CU, void *const *d_CV, int32_t *d_Crk, int ldc,
+                        int rk, int maxrk, double acc,
+                        int32_t *d_status, void *stream);
+
 /* Host-buffer variants: every pointer is a HOST pointer (pinned memory gives full overlap).  Slices of the batch are
  * staged through the device on three internal streams (host-to-device copies, kernels, device-to-host copies, chained
  * by events: both PCIe directions and the SMs are busy at the same time) and the call returns when the results are
@@ -258,6 +268,16 @@ int HCORE_dsyrk_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
                         double alpha,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA,
                         double *d_CD, int64_t strideC, void *stream);
+
+/* Pointer-array forms (device arrays of per-tile device pointers, every leading dimension = nb as in the reference);
+ * kmax = the largest rank in the batch (sizes the workspace). */
+int HCORE_dgemmcd_batched(hcore_b200_handle_t handle, int ntiles, int nb, int kmax,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark,
+                        const double *const *d_BU, const double *const *d_BV, const int32_t *d_Brk,
+                        double *const *d_CD, void *stream);
+int HCORE_dsyrk_batched(hcore_b200_handle_t handle, int ntiles, int nb, int kmax, double alpha,
+                        const double *const *d_AU, const double *const *d_AV, const int32_t *d_Ark,
+                        double *const *d_CD, void *stream);
 
 /* ---- the remaining tile kernels of one TLR-Cholesky step (device pointers) ------------ */
 /* Batched HCORE_dgemmbdcd (reference src/compute/hcore_dgemmbdcd.c:35-122):

@@ -296,3 +296,52 @@ def test_dense_batched_ranks_above_128(ctx):
     ref = orc.gemmcd(AU[0].T, AV[0].T, BU[0].T, BV[0].T, CD[0].T)
     assert np.abs(c1[0].cpu().numpy().T - ref).max() <= 1e-11 * np.abs(ref).max()
     assert np.array_equal(c1[1].cpu().numpy(), CD[1])
+
+
+# ---- pointer-array forms (HCORE_{d,s,z}gemm_batched, HCORE_dgemmcd_batched, HCORE_dsyrk_batched) -----------
+
+def _ptr_table(tensors):
+    return torch.tensor([x.data_ptr() for x in tensors], dtype=torch.int64, device="cuda:0")
+
+
+def test_pointer_array_forms_equal_strided_forms(ctx):
+    import ctypes as C
+    from hcore_b200 import _lib
+    from hcore_b200.tilegen import make_lr_batch, make_dense_batch
+    L = _lib.load()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    T, nb, k = 5, 160, 10
+    # complex update: tiles scattered in separately allocated arrays, in reverse order
+    b = make_lr_batch(T, nb, k, base_seed=91, dtype=np.complex128)
+    t = {n: dev(getattr(b, n)) for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
+    ctx.zgemm_batched(-1.0 + 0.5j, t["au"], t["av"], t["ark"], t["bu"], t["bv"], t["brk"], 1.0, t["cu"], t["cv"], t["crk"], rk=0,
+                      maxrk=2 * k, acc=1e-8)
+    torch.cuda.synchronize()
+    sep = {n: [dev(getattr(b, n)[i]) for i in range(T)] for n in ("au", "av", "bu", "bv", "cu", "cv")}
+    tabs = {n: _ptr_table(sep[n]) for n in sep}
+    crk2, st = dev(b.crk), torch.full((T,), -3, dtype=torch.int32, device="cuda:0")
+    rc = L.HCORE_zgemm_batched(ctx._h, T, nb, _lib.DComplex.of(-1.0 + 0.5j), vp(tabs["au"]), vp(tabs["av"]), vp(t["ark"]), nb,
+                               vp(tabs["bu"]), vp(tabs["bv"]), vp(t["brk"]), nb, _lib.DComplex.of(1.0), vp(tabs["cu"]), vp(tabs["cv"]),
+                               vp(crk2), nb, 0, 2 * k, 1e-8, vp(st), None)
+    torch.cuda.synchronize()
+    assert rc == 0 and (st.cpu().numpy() == 0).all() and torch.equal(crk2, t["crk"])
+    for i in range(T):
+        r = int(crk2[i].item())
+        assert torch.equal(sep["cu"][i][:r], t["cu"][i, :r]) and torch.equal(sep["cv"][i][:r], t["cv"][i, :r])
+    # dense updates
+    bd = make_lr_batch(T, nb, k, base_seed=92)
+    td = {n: dev(getattr(bd, n)) for n in ("au", "av", "bu", "bv", "ark", "brk")}
+    cd = make_dense_batch(T, nb)
+    c1, c2 = dev(cd), dev(cd)
+    ctx.dgemmcd_batched(td["au"], td["av"], td["ark"], td["bu"], td["bv"], td["brk"], c1)
+    ctx.dsyrk_batched(-1.0, td["au"], td["av"], td["ark"], c2)
+    sepd = {n: [dev(getattr(bd, n)[i]) for i in range(T)] for n in ("au", "av", "bu", "bv")}
+    cds1, cds2 = [dev(cd[i]) for i in range(T)], [dev(cd[i]) for i in range(T)]
+    tb = {n: _ptr_table(sepd[n]) for n in sepd}
+    t1, t2 = _ptr_table(cds1), _ptr_table(cds2)
+    assert L.HCORE_dgemmcd_batched(ctx._h, T, nb, k, vp(tb["au"]), vp(tb["av"]), vp(td["ark"]), vp(tb["bu"]), vp(tb["bv"]), vp(td["brk"]),
+                                   vp(t1), None) == 0
+    assert L.HCORE_dsyrk_batched(ctx._h, T, nb, k, -1.0, vp(tb["au"]), vp(tb["av"]), vp(td["ark"]), vp(t2), None) == 0
+    torch.cuda.synchronize()
+    for i in range(T):
+        assert torch.equal(cds1[i], c1[i]) and torch.equal(cds2[i], c2[i])
