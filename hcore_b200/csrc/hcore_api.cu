@@ -83,6 +83,17 @@ struct hcore_b200_context {
     // the three-stream host pipeline (HCORE_*_batched_host): staging buffers, rank / status words, streams, events
     DevBuf hstage[3], hstage_ints[3];
     HostPipe hpipe;
+    // pinned host mirror of the legacy wrappers' staging block
+    void *pin = nullptr;
+    size_t pin_bytes = 0;
+    cudaError_t pin_reserve(size_t need) {
+        if (need <= pin_bytes) return cudaSuccess;
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr; pin_bytes = 0;
+        cudaError_t e = cudaHostAlloc(&pin, need, cudaHostAllocDefault);
+        if (e == cudaSuccess) pin_bytes = need;
+        return e;
+    }
     cudaStream_t streams[2] = {nullptr, nullptr};
     // debug / profiling
     int debug_stages = 4;
@@ -250,6 +261,7 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
     for (int b = 0; b < kHostBufs; ++b) { ctx->hstage[b].release(); ctx->hstage_ints[b].release(); }
+    if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->hpipe.ready) {
         for (cudaStream_t st : {ctx->hpipe.s_in, ctx->hpipe.s_comp, ctx->hpipe.s_out}) cudaStreamDestroy(st);
         for (int b = 0; b < kHostBufs; ++b) { cudaEventDestroy(ctx->hpipe.in_done[b]); cudaEventDestroy(ctx->hpipe.comp_done[b]); cudaEventDestroy(ctx->hpipe.out_done[b]); }
@@ -696,9 +708,9 @@ int tlr_host(hcore_b200_handle_t ctx, int kind, int ntiles, int nb, const void *
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t es = kind == 0 ? 8 : (kind == 1 ? 4 : 16);
     // The path is PCIe-bound (3.1 MB in, 2.1 MB out per tile against ~17 us of GPU time at nb = 1024, rank 64): what a
-    // slice costs is its share of the pipeline fill (the first H2D) and drain (the last kernels + D2H), so slices are
-    // small -- 64 tiles keep the kernels (latency-bound below one wave of 148 CTAs) ahead of the copies with margin.
-    const int hc = std::min(ntiles, ctx->host_slice > 0 ? ctx->host_slice : 64);
+    // slice costs is its share of the pipeline fill (the first H2D) and drain (the last kernels + D2H).  One wave of the
+    // SVD kernel (148 tiles) per slice measured best: 64-tile slices lose 4 % (14.1 k vs 14.7 k tiles/s, 2048 tiles).
+    const int hc = std::min(ntiles, ctx->host_slice > 0 ? ctx->host_slice : std::max(ctx->num_sms, 64));
     const size_t perA = (size_t)strideA * es, perB = (size_t)strideB * es, perC = (size_t)strideC * es;
     const size_t per_tile = 2 * perA + 2 * perB + 2 * perC;
     auto carve = [&](int b, char *&dAU, char *&dAV, char *&dBU, char *&dBV, char *&dCU, char *&dCV, int *&di) {
@@ -1300,25 +1312,33 @@ static int legacy_gemm(const char *who, int es, int M, double alpha, const void 
     char *dAU = base, *dAV = base + fa16, *dBU = base + 2 * fa16, *dBV = base + 2 * fa16 + fb16,
          *dCU = base + 2 * fa16 + 2 * fb16, *dCV = base + 2 * fa16 + 2 * fb16 + fc;
     int *di = (int *)ctx->stage_ints[0].p;
-    int hi[4] = {a, b, c, 0};
+    // The caller's arrays are pageable: they are gathered into a PINNED mirror of the device staging block (same
+    // layout) and travel in ONE asynchronous copy on this thread's stream.  A pageable cudaMemcpyAsync goes through a
+    // driver-wide staging buffer and serialises the worker threads of a task runtime against each other.
+    const size_t total = 2 * fa16 + 2 * fb16 + 2 * fc;
+    if (ctx->pin_reserve(total + 64) != cudaSuccess) legacy_fail(who, "pinned host allocation failed", HCORE_B200_ERR_CUDA);
+    char *hb = (char *)ctx->pin;
+    int *hi = (int *)(hb + total);
+    hi[0] = a; hi[1] = b; hi[2] = c; hi[3] = 0;
+    memcpy(hb, AU, fa); memcpy(hb + fa16, AV, fa);
+    memcpy(hb + 2 * fa16, BU, fb); memcpy(hb + 2 * fa16 + fb16, BV, fb);
+    memcpy(hb + 2 * fa16 + 2 * fb16, CU, fcin); memcpy(hb + 2 * fa16 + 2 * fb16 + fc, CV, fcin);
     cudaStream_t st = ctx->streams[0];
-    lchk(who, cudaMemcpyAsync(dAU, AU, fa, cudaMemcpyHostToDevice, st));
-    lchk(who, cudaMemcpyAsync(dAV, AV, fa, cudaMemcpyHostToDevice, st));
-    lchk(who, cudaMemcpyAsync(dBU, BU, fb, cudaMemcpyHostToDevice, st));
-    lchk(who, cudaMemcpyAsync(dBV, BV, fb, cudaMemcpyHostToDevice, st));
-    lchk(who, cudaMemcpyAsync(dCU, CU, fcin, cudaMemcpyHostToDevice, st));
-    lchk(who, cudaMemcpyAsync(dCV, CV, fcin, cudaMemcpyHostToDevice, st));
-    lchk(who, cudaMemcpyAsync(di, hi, sizeof(hi), cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(base, hb, 2 * fa16 + 2 * fb16 + fcin, cudaMemcpyHostToDevice, st));          // A, B factors and CU
+    lchk(who, cudaMemcpyAsync(dCV, hb + 2 * fa16 + 2 * fb16 + fc, fcin, cudaMemcpyHostToDevice, st));
+    lchk(who, cudaMemcpyAsync(di, hi, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
     int rc = tlr_batched_strided(ctx, 1, M, alpha, dAU, dAV, di, LDA, 0, dBU, dBV, di + 1, LDB, 0, beta, dCU, dCV, di + 2,
                                  LDC, 0, rk, maxrk, acc, di + 3, st, es == 4, 0, nullptr, scan_from);
     if (rc != HCORE_B200_OK) legacy_fail(who, hcore_b200_last_error(ctx), rc);
-    lchk(who, cudaMemcpyAsync(hi, di, sizeof(hi), cudaMemcpyDeviceToHost, st));
+    lchk(who, cudaMemcpyAsync(hi, di, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
     if (hi[3] != HCORE_B200_OK) legacy_fail(who, "tile update failed", hi[3]);
     const int rnew = hi[2];
-    lchk(who, cudaMemcpyAsync(CU, dCU, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st));
-    lchk(who, cudaMemcpyAsync(CV, dCV, (size_t)LDC * rnew * es, cudaMemcpyDeviceToHost, st));
+    const size_t fout = (size_t)LDC * rnew * es;
+    lchk(who, cudaMemcpyAsync(hb, dCU, fout, cudaMemcpyDeviceToHost, st));
+    lchk(who, cudaMemcpyAsync(hb + fc, dCV, fout, cudaMemcpyDeviceToHost, st));
     if (cudaStreamSynchronize(st) != cudaSuccess) legacy_fail(who, "CUDA failure", HCORE_B200_ERR_CUDA);
+    memcpy(CU, hb, fout); memcpy(CV, hb + fc, fout);
     return rnew;
 }
 

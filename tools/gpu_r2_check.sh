@@ -13,6 +13,7 @@ import json;d=json.load(open('gpurun_out/quick_$TAG.json'));print(d['value'],{k:
  bench)  timeout 1200 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 3000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err ;;
  ops)    timeout 1500 python tools/bench_ops.py gpurun_out/ops_$TAG.json 2>&1 | tail -30 ;;
  chol)   OPS_ONLY=chol timeout 900 python tools/bench_ops.py gpurun_out/chol_$TAG.json 2>&1 | tail -20 ;;
+ choldemo) timeout 900 python tools/chol_step_demo.py 16 512 256 1e-8 gpurun_out/chol_demo_$TAG.json 2>&1 | tail -6 ;;
  legacy) timeout 600 python tools/legacy_latency.py 2>&1 | tail -12 | tee gpurun_out/legacy_$TAG.txt ;;
  ctests) timeout 600 python -m pytest tests/test_c_boundary.py -m gpu -q 2>&1 | tail -15 ;;
  sanitize) for tool in memcheck racecheck; do timeout 1200 compute-sanitizer --tool $tool --print-limit 10 python tools/sanitize_run.py 2>&1 | tail -6; done | tee gpurun_out/sanitize_$TAG.txt ;;
