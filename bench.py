@@ -41,7 +41,10 @@ def parse_args():
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--acc", type=float, default=1e-8)
-    ap.add_argument("--e2e-tiles", type=int, default=2048, help="tiles per end-to-end (host buffer) step")
+    ap.add_argument("--e2e-tiles", type=int, default=4096, help="tiles per GPU per end-to-end (host buffer) step")
+    ap.add_argument("--config", default="dgemm", choices=["dgemm", "sgemm", "zgemm", "dgemmcd", "dsyrk", "dtrsm", "dpotrf"],
+                    help="dgemm = the headline (BASELINE.json configs[1]); the others are the secondary configs "
+                         "(configs[2], configs[3]) and the Cholesky-step kernels, one JSON line each, N = 1")
     ap.add_argument("--cpu-sample", type=int, default=0, help="CPU baseline tiles per worker (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -317,10 +320,135 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_secondary(args):
+    """--config sgemm | zgemm | dgemmcd | dsyrk | dtrsm | dpotrf: the secondary configs of BASELINE.json through the same
+    C ABI, one GPU, the same JSON schema (value = device-resident rate by CUDA events; e2e = host buffers where the
+    library has a host form)."""
+    import torch
+    from hcore_b200 import api
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ctx = api.Context(0)
+    nb, cfg = args.nb, args.config
+    k = args.rank if cfg in ("sgemm", "zgemm", "dtrsm") else 32
+    hbm = 6463.3
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    sampler = ClockSampler(0)
+    e2e = None
+    restore = lambda: None
+    if cfg in ("sgemm", "zgemm"):
+        T = min(args.tiles, 4736 if cfg == "sgemm" else 1184)
+        acc = 1e-4 if cfg == "sgemm" else args.acc
+        d = make_device_batch(torch, T, nb, k, dev, seed=4)
+        conv = {}
+        for nm in ("au", "av", "bu", "bv", "cu0", "cv0", "cu", "cv"):
+            x = d.pop(nm)
+            conv[nm] = (torch.complex(x, torch.roll(x, 1, dims=2) * 0.5) if cfg == "zgemm" else x.to(torch.float32)).contiguous()
+            del x
+
+        def restore():
+            conv["cu"][:, :k].copy_(conv["cu0"]); conv["cv"][:, :k].copy_(conv["cv0"]); d["crk"].fill_(k)
+        call = ctx.sgemm_batched if cfg == "sgemm" else ctx.zgemm_batched
+        fn = lambda: call(-1.0, conv["au"], conv["av"], d["ark"], conv["bu"], conv["bv"], d["brk"], 1.0, conv["cu"], conv["cv"],
+                          d["crk"], rk=0, maxrk=2 * k, acc=acc, status=d["status"])
+        unit, work = "tiles/s", f"batched HCORE_{cfg}, {T} tiles, nb={nb}, rank {k}, acc {acc:g} (BASELINE.json configs[3])"
+        flops_unit = (8.0 if cfg == "zgemm" else 1.0) * (api.gemm_flops(nb, k, k, k, 93) + 2 * (2 * k) ** 3) / (4.0 if cfg == "zgemm" else 1.0)
+        es = 4 if cfg == "sgemm" else 16
+        bytes_unit = es * nb * (6 * k + 2 * 93)
+    elif cfg in ("dgemmcd", "dsyrk"):
+        T = min(args.tiles, 2048)
+        d = make_device_batch(torch, T, nb, k, dev, seed=5)
+        cd = torch.rand((T, nb, nb), dtype=torch.float64, device=dev)
+        fn = (lambda: ctx.dgemmcd_batched(d["au"], d["av"], d["ark"], d["bu"], d["bv"], d["brk"], cd)) if cfg == "dgemmcd" else \
+             (lambda: ctx.dsyrk_batched(-1.0, d["au"], d["av"], d["ark"], cd))
+        unit, work = "calls/s", f"batched HCORE_{cfg}, {T} dense {nb} x {nb} tiles, rank {k} (BASELINE.json configs[2])"
+        flops_unit = 2.0 * nb * nb * k + 4.0 * nb * k * k
+        bytes_unit = (2 * nb * nb + 4 * nb * k) * 8 if cfg == "dgemmcd" else (int(nb * nb * (1 + 72 / 128)) + 2 * nb * k) * 8
+    elif cfg == "dtrsm":
+        T = min(args.tiles, 2048)
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        Lt = torch.tril(torch.rand((nb, nb), dtype=torch.float64, device=dev, generator=g) - 0.5) / 32 + torch.eye(nb, dtype=torch.float64, device=dev)
+        A1 = Lt.T.contiguous()[None]
+        B0 = torch.rand((T, k, nb), dtype=torch.float64, device=dev, generator=g) - 0.5
+        B = B0.clone()
+        restore = lambda: B.copy_(B0)
+        fn = lambda: ctx.dtrsm_batched(141, 122, 111, 131, 1.0, A1, B)
+        unit, work = "calls/s", f"batched HCORE_dtrsm (Left, Lower, NoTrans), one shared {nb} x {nb} triangle, {T} factors of rank {k}"
+        flops_unit, bytes_unit = float(nb) * nb * k, 2 * nb * k * 8
+    else:
+        T = min(args.tiles, 64)
+        X = torch.rand((T, nb, nb), dtype=torch.float64, device=dev) - 0.5
+        S0 = (X @ X.transpose(1, 2)) / nb + torch.eye(nb, dtype=torch.float64, device=dev)
+        S = S0.clone()
+        info = torch.zeros(T, dtype=torch.int32, device=dev)
+        restore = lambda: S.copy_(S0)
+        fn = lambda: ctx.dpotrf_batched(122, S, info)
+        unit, work = "calls/s", f"batched HCORE_dpotrf (Lower), {T} dense {nb} x {nb} tiles"
+        flops_unit, bytes_unit = nb ** 3 / 3.0, nb * nb * 8
+    for _ in range(max(args.warmup, 3)):
+        restore(); fn()
+    torch.cuda.synchronize()
+    sampler.start()
+    l0, ms = ctx.launches, 0.0
+    for _ in range(args.steps):
+        restore()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    ms /= args.steps
+    value = T / (ms * 1e-3)
+    tf, gbs = value * flops_unit / 1e12, value * bytes_unit / 1e9
+    fp_frac, hbm_frac = tf / FP64_PEAK_FALLBACK_TFLOPS, gbs / hbm
+    bound = "fp64" if fp_frac >= hbm_frac else "hbm"
+    roofline = {"bound": bound, "achieved": tf if bound == "fp64" else gbs, "peak": FP64_PEAK_FALLBACK_TFLOPS if bound == "fp64" else hbm,
+                "unit": "TFLOP/s" if bound == "fp64" else "GB/s", "frac": max(fp_frac, hbm_frac), "traffic": None,
+                "note": f"model flops {flops_unit:.4g} and algorithmic bytes {bytes_unit:.4g} per unit; FP64 peak 37.1 TF (profiles/fp64_peak_r1.txt), "
+                        f"HBM {hbm:.0f} GB/s (MEASURED_PEAKS.json); the binding roof is the one with the larger fraction "
+                        f"(fp64 {fp_frac:.3f}, hbm {hbm_frac:.3f})"}
+    if cfg in ("sgemm", "zgemm") and not args.no_e2e:
+        Te = min(1024 if cfg == "zgemm" else 2048, T)
+        host = {nm: conv[nm][:Te].cpu().pin_memory() for nm in ("au", "av", "bu", "bv")}
+        host["cu"] = torch.zeros((Te, 2 * k, nb), dtype=conv["cu"].dtype).pin_memory()
+        host["cv"] = torch.zeros_like(host["cu"]).pin_memory()
+        cu0h, cv0h = conv["cu0"][:Te].cpu(), conv["cv0"][:Te].cpu()
+        ark = torch.full((Te,), k, dtype=torch.int32).pin_memory(); brk = ark.clone().pin_memory(); crk = ark.clone().pin_memory()
+        sth = torch.zeros((Te,), dtype=torch.int32).pin_memory()
+        times = []
+        for it in range(2 + args.steps):
+            host["cu"][:, :k].copy_(cu0h); host["cv"][:, :k].copy_(cv0h); crk.fill_(k)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.dgemm_batched_host(-1.0, host["au"], host["av"], ark, host["bu"], host["bv"], brk, 1.0, host["cu"], host["cv"], crk,
+                                   rk=0, maxrk=2 * k, acc=acc, status=sth)
+            if it >= 2:
+                times.append(time.perf_counter() - t0)
+        es = 4 if cfg == "sgemm" else 16
+        e2e = {"value": Te / float(np.mean(times)), "unit": unit, "h2d_bytes_per_step": Te * 6 * k * nb * es,
+               "d2h_bytes_per_step": Te * 2 * 2 * k * nb * es, "tiles_per_step": Te, "failed_tiles": int((sth != 0).sum().item()),
+               "note": f"HCORE_{cfg}_batched_host, pinned host buffers, three-stream pipeline"}
+    line = {"metric": f"HCORE_{cfg} batched {unit} (nb={nb}, rank {k})", "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"sgemm": "f32 in/out, f64 arithmetic", "zgemm": "c128"}.get(cfg, "f64"), "data": "synthetic",
+            "config": {"workload": work, "nb": nb, "rank": k, "units_per_step": T, "l2": "inputs exceed L2"},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "e2e": e2e}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config != "dgemm":
+        run_secondary(args)
         return
 
     import torch
@@ -448,13 +576,19 @@ def main():
     dom = max(names, key=lambda nm: stages[nm]["ms"])
     # DRAM bytes of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one
     # `ncu --set full` capture (per tile, profiles/roofline_traffic.json) x the tiles one launch processes
-    traffic, traffic_src = None, None
+    traffic, traffic_src, pipe_ncu = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         ent = tj.get(f"tlr_{dom}_kernel")
         if ent and (nb, k) == (tj.get("nb"), tj.get("rank")):
             traffic = ent["dram_bytes_per_tile"] * (T_local / nchunks)
             traffic_src = tj.get("source")
+            pipe_ncu = ent.get("fp64_pipe_active_pct")
+            for nm in names:                     # ncu-measured FP64 pipe utilisation of each stage's kernel (committed capture)
+                e2 = tj.get(f"tlr_{nm}_kernel")
+                if e2 and "fp64_pipe_active_pct" in e2:
+                    stages[nm]["ncu_fp64_pipe_active_pct"] = e2["fp64_pipe_active_pct"]
+                    stages[nm]["ncu_dram_bytes_per_tile"] = e2["dram_bytes_per_tile"]
     except Exception:
         pass
     roofline = {"bound": "fp64", "kernel": f"tlr_{dom}_kernel", "achieved": stages[dom]["model_tflops"],
@@ -464,6 +598,9 @@ def main():
                         f"8192^3 measured in this run = {cublas_tflops:.1f} TF); MEASURED_PEAKS.json has no FP64 entry. "
                         "achieved = reference flop model of the stage x tiles / CUDA-event time of the stage's launches",
                 "traffic_source": traffic_src, "launches_per_step": nchunks,
+                "ncu_fp64_pipe_active_pct": pipe_ncu,
+                "ncu_note": "sm__pipe_shared_cycles_active (the FP64 pipe DMMA and DFMA share) of the committed ncu --set full capture: what "
+                            "the kernel keeps busy, counting every FP64 instruction -- `frac` counts only the reference's model flops",
                 "pipeline_frac": value / world * flops_tile / 1e12 / peak_tflops}
 
     line = {"metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
