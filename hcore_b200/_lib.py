@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "hcore_b200_version", "hcore_b200_launch_count", "hcore_b200_shard_range",
     "HCORE_dgemm_batched", "HCORE_dgemm_batched_strided", "HCORE_dgemm_batched_host",
     "HCORE_sgemm_batched_host", "HCORE_zgemm_batched_host", "hcore_b200_gather_status",
-    "HCORE_zgemm_batched", "HCORE_dgemmcd_batched", "HCORE_dsyrk_batched",
+    "HCORE_zgemm_batched", "HCORE_dgemmcd_batched", "HCORE_dsyrk_batched", "HCORE_dcompress_batched_strided",
     "HCORE_sgemm_batched", "HCORE_sgemm_batched_strided", "HCORE_sgemm",
     "HCORE_zgemm_batched_strided", "HCORE_zgemm",
     "sgemm_use_trmm", "sgemm_print_index", "sgemm_print_mat",
@@ -107,6 +107,7 @@ def load():
     L.HCORE_zgemm_batched.argtypes = [vp, i, i, DComplex, vp, vp, vp, i, vp, vp, vp, i, DComplex, vp, vp, vp, i, i, i, d, vp, vp]
     L.HCORE_dgemmcd_batched.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.HCORE_dsyrk_batched.argtypes = [vp, i, i, i, d, vp, vp, vp, vp, vp]
+    L.HCORE_dcompress_batched_strided.argtypes = [vp, i, i, vp, i, i64, d, i, i, vp, vp, i, i64, vp, vp, vp]
     L.hcore_b200_gather_status.argtypes = [vp, vp, i, i, i64, vp, vp, vp, vp, vp]
     L.HCORE_dgemmcd_batched_strided.argtypes = [vp, i, i, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp]
     L.HCORE_dsyrk_batched_strided.argtypes = [vp, i, i, d, vp, vp, vp, i64, vp, i64, vp]

@@ -463,3 +463,17 @@ class Context:
         rc = fn(self._h, T, M, N, _ptr(AU), _ptr(Ark), M, ka * M, _ptr(BV), _ptr(Brk), N, kb * N, _ptr(CD), M, N * M,
                 _ptr(status), self._stream_ptr(stream))
         self._check(rc)
+
+    def dcompress_batched(self, A, acc, maxrk, U, V, rank, status=None, power_iters=1, stream=None):
+        """``HCORE_dcompress_batched_strided``: dense tiles ``A`` (T, nb, nb) column-major -> ``U, V`` (T, maxrk, nb) with
+        ``A[t] ~ U[t].T @ V[t]`` in numpy orientation (U orthonormal), ``rank`` (T,) int32 out."""
+        T, nb, _ = A.shape
+        for nm, x in (("A", A), ("U", U), ("V", V)):
+            self._dev_f64(x, nm)
+        self._dev_i32(rank, "rank")
+        if U.shape[1] < maxrk:
+            raise ValueError("U/V need room for maxrk columns")
+        rc = self._L.HCORE_dcompress_batched_strided(self._h, T, nb, _ptr(A), nb, nb * nb, float(acc), int(maxrk), int(power_iters),
+                                                     _ptr(U), _ptr(V), nb, U.shape[1] * nb, _ptr(rank), _ptr(status),
+                                                     self._stream_ptr(stream))
+        self._check(rc)

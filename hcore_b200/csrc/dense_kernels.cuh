@@ -67,8 +67,9 @@ struct BdtAvArgs {
     const int *Ark;
     long strideA, strideB;
     int lda, ldb, mc, ncols;             // contraction length (rows of AV and BD), columns of BD
-    double *Y;                           // [ntiles][n_pad * kcap]
-    int n_pad, kcap;
+    double *Y;                           // per tile: ncols x a, leading dimension ldy, element stride strideY
+    long strideY;
+    int ldy, n_pad;                      // n_pad = ncols rounded up to the 64-row blocks of the grid
 };
 __global__ void __launch_bounds__(256) dense_bdtav_kernel(BdtAvArgs ar) {
     const int t = blockIdx.y, a = ar.Ark[t];
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) dense_bdtav_kernel(BdtAvArgs ar) {
     const int i0 = blockIdx.x * 64 + 8 * warp;                     // row of Y = column of BD
     if (i0 >= ar.n_pad) return;
     const double *AV = ar.AV + (size_t)t * ar.strideA, *BD = ar.BD + (size_t)t * ar.strideB;
-    double *Y = ar.Y + (size_t)t * ar.n_pad * ar.kcap;
+    double *Y = ar.Y + (size_t)t * ar.strideY;
     const bool ron = i0 + g < ar.ncols;
     const double *bp = BD + (size_t)(i0 + g) * ar.ldb + tg;
     for (int q0 = 0; q0 < a; q0 += 64) {                            // 8 column tiles of Y at a time
@@ -100,9 +101,94 @@ __global__ void __launch_bounds__(256) dense_bdtav_kernel(BdtAvArgs ar) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int col = q0 + 8 * q + 2 * tg + e;
-                if (col < a) Y[(i0 + g) + (size_t)col * ar.n_pad] = acc[q][e];
+                if (col < a && (ron || ar.ldy >= ar.n_pad)) Y[(i0 + g) + (size_t)col * ar.ldy] = acc[q][e];   // padding rows only if they exist
             }
         }
+    }
+}
+
+// Y = A X for a dense tile A (m x n, ld lda) and a skinny X (n x p, ld ldx; strideX = 0: one X for the whole batch):
+// the range-finder / projection products of the tile compression (HCORE_dcompress_batched_strided).
+// grid = (64-row blocks of Y, tiles), 256 threads; warp w owns rows 8 w .. 8 w + 7 of the block.
+struct AxArgs {
+    const double *A, *X;
+    const int *Prk;                      // columns of X per tile (may be null: p for every tile)
+    long strideA, strideX, strideY;
+    int lda, ldx, ldy, m, n, p;
+    double *Y;
+};
+__global__ void __launch_bounds__(256) dense_ax_kernel(AxArgs ar) {
+    const int t = blockIdx.y, p = ar.Prk ? ar.Prk[t] : ar.p;
+    if (p <= 0) return;
+    const int warp = warp_id(), lane = lane_id(), g = lane >> 2, tg = lane & 3;
+    const int i0 = blockIdx.x * 64 + 8 * warp;
+    if (i0 >= ar.m) return;
+    const double *A = ar.A + (size_t)t * ar.strideA, *X = ar.X + (size_t)t * ar.strideX;
+    double *Y = ar.Y + (size_t)t * ar.strideY;
+    const bool ron = i0 + g < ar.m;
+    const double *ap = A + (i0 + g) + (size_t)tg * ar.lda;
+    for (int q0 = 0; q0 < p; q0 += 64) {
+        double acc[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
+        for (int k = 0; k < ar.n; k += 4) {
+            const double av = (ron && k + tg < ar.n) ? __ldg(ap + (size_t)k * ar.lda) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = q0 + 8 * q + g;
+                if (q0 + 8 * q < p) {
+                    const double xv = (col < p && k + tg < ar.n) ? __ldg(X + (size_t)col * ar.ldx + k + tg) : 0.0;
+                    dmma_884(acc[q][0], acc[q][1], av, xv);
+                }
+            }
+        }
+        if (ron) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = q0 + 8 * q + 2 * tg + e;
+                    if (col < p) Y[(i0 + g) + (size_t)col * ar.ldy] = acc[q][e];
+                }
+            }
+        }
+    }
+}
+
+// deterministic test matrix of the range finder: entries in (-1, 1) from a counter-based hash (splitmix64)
+__global__ void fill_omega_kernel(double *X, int n, int p, int ldx, unsigned long long seed) {
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= (long)n * p) return;
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    X[(idx % n) + (idx / n) * (long)ldx] = (double)(long long)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
+// E = [I_p; 0] (n x p, ld lde) per tile, and the per-tile rank words of a compression pass
+__global__ void fill_identity_kernel(double *E, long strideE, int lde, int n, int p) {
+    const int t = blockIdx.y;
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= (long)n * p) return;
+    const int r = idx % n, c = idx / n;
+    E[(size_t)t * strideE + r + (size_t)c * lde] = (r == c) ? 1.0 : 0.0;
+}
+// the first min(rank, maxrk) columns of the internal factors -> the caller's arrays; rank capped at maxrk
+// (reference testing/testing_dgemm.c:202-205: rank > storage_maxrank -> storage_maxrank)
+__global__ void compress_copy_out_kernel(const double *CU, const double *CV, long strideI, int ldi, double *U, double *V, long strideO,
+                                         int ldo, int nb, const int *rank_in, const int *status_in, int maxrk, int *rank_out,
+                                         int *status_out) {
+    const int t = blockIdx.y;
+    const int st = status_in[t];
+    const int r = st == HCORE_B200_OK ? (rank_in[t] < maxrk ? rank_in[t] : maxrk) : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rank_out[t] = r;
+        if (status_out) status_out[t] = st;
+    }
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < (long)nb * r; idx += (long)gridDim.x * blockDim.x) {
+        const int row = idx % nb, c = idx / nb;
+        U[(size_t)t * strideO + row + (size_t)c * ldo] = CU[(size_t)t * strideI + row + (size_t)c * ldi];
+        V[(size_t)t * strideO + row + (size_t)c * ldo] = CV[(size_t)t * strideI + row + (size_t)c * ldi];
     }
 }
 

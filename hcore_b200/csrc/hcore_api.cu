@@ -74,6 +74,8 @@ struct hcore_b200_context {
     DevBuf X, Ywork;
     // trsm / potrf workspace (inverses of the 64 x 64 diagonal blocks, per-tile info)
     DevBuf Winv, info;
+    // tile compression workspace (test matrix, internal factor buffers, a zero vector, rank words)
+    DevBuf cmpOm, cmpCU, cmpCV, cmpZero, cmpInts;
     bool attr_done[8] = {false, false, false, false, false, false, false, false};
     // complex (zgemm) workspace
     DevBuf zpanel, ztau, zT, zY, zsigma, zints;
@@ -257,7 +259,7 @@ int hcore_b200_destroy(hcore_b200_handle_t ctx) {
     if (!ctx) return HCORE_B200_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->Lcore, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->Ywork, &ctx->Winv, &ctx->info, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
+    for (DevBuf *b : {&ctx->rec, &ctx->G, &ctx->R, &ctx->Y, &ctx->Lcore, &ctx->sigma, &ctx->ints, &ctx->ptrs, &ctx->X, &ctx->Ywork, &ctx->Winv, &ctx->info, &ctx->cmpOm, &ctx->cmpCU, &ctx->cmpCV, &ctx->cmpZero, &ctx->cmpInts, &ctx->zpanel, &ctx->ztau, &ctx->zT, &ctx->zY, &ctx->zsigma, &ctx->zints,
                       &ctx->stage[0], &ctx->stage[1], &ctx->stage_ints[0], &ctx->stage_ints[1]})
         b->release();
     for (int b = 0; b < kHostBufs; ++b) { ctx->hstage[b].release(); ctx->hstage_ints[b].release(); }
@@ -1025,7 +1027,7 @@ static int gemmbdcd_launch(hcore_b200_handle_t ctx, int ntiles, int M, int mc, i
         BdtAvArgs pa{};
         pa.AV = d_AV + (size_t)t0 * strideA; pa.BD = d_BD + (size_t)t0 * strideB; pa.Ark = d_Ark + t0;
         pa.strideA = strideA; pa.strideB = strideB; pa.lda = lda; pa.ldb = ldb; pa.mc = mc; pa.ncols = N;
-        pa.Y = (double *)ctx->Ywork.p; pa.n_pad = n_pad; pa.kcap = kcap;
+        pa.Y = (double *)ctx->Ywork.p; pa.n_pad = n_pad; pa.ldy = n_pad; pa.strideY = (long)n_pad * kcap;
         dense_bdtav_kernel<<<dim3(n_pad / 64, cnt), 256, 0, st>>>(pa);
         ctx->launches++;
         int rc = dense_xyt(ctx, cnt, M, N, alpha, d_AU + (size_t)t0 * strideA, lda, strideA, (const double *)ctx->Ywork.p, n_pad,
@@ -1092,6 +1094,101 @@ int HCORE_zuncompress_batched_strided(hcore_b200_handle_t ctx, int ntiles, int M
         ctx->launches++;
     }
     ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return HCORE_B200_OK;
+}
+
+// ---- tile compression: dense nb x nb tile -> U V^T ------------------------------------------
+// The reference declares a generate-and-compress kernel (HCORE_zgytlr, src/include/hcore_z.h:63-75) but never defines it;
+// its tests compress with LAPACKE_dgesvd and keep rank = #{sigma >= acc}, capped at the storage rank
+// (testing/testing_dgemm.c:119-236).  Here, built from the kernels of the update path:
+//   1. Y = A Omega (Omega: nb x p deterministic test matrix, p = maxrk + 16), Q = orth(Y) -- the orthonormalisation IS one
+//      pass of the update pipeline on the tile (CU = Y, CV = [I; 0]) with a zero update and fixed rank p: its new CU are
+//      the left singular vectors of Y;
+//   2. optional power iteration (default 1): Q <- orth(A orth(A^T Q)), which makes the captured subspace accurate to
+//      far below acc even for slowly decaying spectra;
+//   3. V0 = A^T Q, so Q V0^T = Q Q^T A; one more pass of the update pipeline with the caller's accuracy truncates it by
+//      the update path's own rule: U orthonormal, V carries the singular values, new rank in d_rank (capped at maxrk).
+__global__ void fill_int_kernel(int *p, int v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int HCORE_dcompress_batched_strided(hcore_b200_handle_t ctx, int ntiles, int nb, const double *d_A, int lda, int64_t strideA,
+                        double acc, int maxrk, int power_iters, double *d_U, double *d_V, int ldu, int64_t strideUV,
+                        int32_t *d_rank, int32_t *d_status, void *stream) {
+    if (!ctx || ntiles < 0 || nb < 16 || lda < nb || ldu < nb || maxrk < 1 || power_iters < 0 || !d_rank) return HCORE_B200_ERR_ARG;
+    if (strideUV > 0 && strideUV < (int64_t)ldu * maxrk) return HCORE_B200_ERR_ARG;
+    if (ntiles == 0) return HCORE_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int p = std::min(round_up(maxrk + 16, 8), 248);
+    p = std::min(p, (nb - 1) & ~7);                      // the stack [Q | 0] has p + 1 columns and must not be wider than the tile
+    if (p < 8) return HCORE_B200_ERR_ARG;
+    const int pc = p + 1;
+    const size_t per = 2ull * nb * pc * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)ntiles, (size_t)592, (3ull << 30) / per}));
+    CUDA_TRY(ctx, ctx->cmpOm.reserve((size_t)nb * p * 8));
+    CUDA_TRY(ctx, ctx->cmpCU.reserve((size_t)chunk * nb * pc * 8));
+    CUDA_TRY(ctx, ctx->cmpCV.reserve((size_t)chunk * nb * pc * 8));
+    CUDA_TRY(ctx, ctx->cmpZero.reserve((size_t)nb * 8));
+    CUDA_TRY(ctx, ctx->cmpInts.reserve((size_t)chunk * 4 * sizeof(int)));
+    double *Om = (double *)ctx->cmpOm.p, *bufA = (double *)ctx->cmpCU.p, *bufB = (double *)ctx->cmpCV.p, *zero = (double *)ctx->cmpZero.p;
+    int *ones = (int *)ctx->cmpInts.p, *crk = ones + chunk, *stw = crk + chunk;
+    const long strideI = (long)nb * pc;
+    CUDA_TRY(ctx, cudaMemsetAsync(zero, 0, (size_t)nb * 8, st));
+    fill_omega_kernel<<<(unsigned)(((size_t)nb * p + 255) / 256), 256, 0, st>>>(Om, nb, p, nb, 0x243F6A8885A308D3ull);
+    fill_int_kernel<<<(chunk + 255) / 256, 256, 0, st>>>(ones, 1, chunk);
+    ctx->launches += 2;
+    const int n_pad = round_up(nb, 64);
+    // one pass of the update pipeline on (CU, CV) with a zero update: rk > 0 = fixed rank (orthonormalisation), rk = 0 = accuracy
+    auto pass = [&](int cnt, double *CU, double *CV, int rk, double a) -> int {
+        fill_int_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(crk, p, cnt);
+        ctx->launches++;
+        return tlr_batched_strided(ctx, cnt, nb, 0.0, zero, zero, ones, nb, 0, zero, zero, ones, nb, 0, 1.0, CU, CV, crk, nb, strideI, rk,
+                                   pc, a, stw, st, 0);
+    };
+    auto identity = [&](int cnt, double *E) {
+        fill_identity_kernel<<<dim3((unsigned)(((size_t)nb * p + 255) / 256), cnt), 256, 0, st>>>(E, strideI, nb, nb, p);
+        ctx->launches++;
+    };
+    auto ax = [&](int cnt, const double *A, const double *X, long strideX, double *Y) {       // Y = A X
+        AxArgs a{};
+        a.A = A; a.X = X; a.Prk = nullptr; a.strideA = strideA; a.strideX = strideX; a.strideY = strideI;
+        a.lda = lda; a.ldx = nb; a.ldy = nb; a.m = nb; a.n = nb; a.p = p; a.Y = Y;
+        dense_ax_kernel<<<dim3(n_pad / 64, cnt), 256, 0, st>>>(a);
+        ctx->launches++;
+    };
+    auto atq = [&](int cnt, const double *A, const double *Q, double *Y) {                      // Y = A^T Q
+        BdtAvArgs a{};
+        a.AV = Q; a.BD = A; a.Ark = crk; a.strideA = strideI; a.strideB = strideA; a.lda = nb; a.ldb = lda; a.mc = nb; a.ncols = nb;
+        a.Y = Y; a.strideY = strideI; a.ldy = nb; a.n_pad = n_pad;
+        dense_bdtav_kernel<<<dim3(n_pad / 64, cnt), 256, 0, st>>>(a);
+        ctx->launches++;
+    };
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        const int cnt = std::min(chunk, ntiles - t0);
+        const double *A = d_A + (size_t)t0 * strideA;
+        int rc;
+        ax(cnt, A, Om, 0, bufA);                                   // Y = A Omega
+        identity(cnt, bufB);
+        if ((rc = pass(cnt, bufA, bufB, p, acc)) != HCORE_B200_OK) return rc;      // bufA <- Q
+        for (int it = 0; it < power_iters; ++it) {
+            atq(cnt, A, bufA, bufB);                                // Z = A^T Q
+            identity(cnt, bufA);
+            if ((rc = pass(cnt, bufB, bufA, p, acc)) != HCORE_B200_OK) return rc;  // bufB <- orth(Z)
+            ax(cnt, A, bufB, strideI, bufA);                       // Y = A orth(Z)
+            identity(cnt, bufB);
+            if ((rc = pass(cnt, bufA, bufB, p, acc)) != HCORE_B200_OK) return rc;  // bufA <- Q
+        }
+        fill_int_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(crk, p, cnt);          // atq reads the column count from crk
+        atq(cnt, A, bufA, bufB);                                    // V0 = A^T Q
+        if ((rc = pass(cnt, bufA, bufB, 0, acc)) != HCORE_B200_OK) return rc;      // truncation to acc
+        compress_copy_out_kernel<<<dim3(16, cnt), 256, 0, st>>>(bufA, bufB, strideI, nb, d_U + (size_t)t0 * strideUV,
+                                                                 d_V + (size_t)t0 * strideUV, strideUV, ldu, nb, crk, stw, maxrk,
+                                                                 d_rank + t0, d_status ? d_status + t0 : nullptr);
+        ctx->launches += 2;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return HCORE_B200_OK;
 }

@@ -317,6 +317,21 @@ int HCORE_dtrsm_batched_strided(hcore_b200_handle_t handle, int ntiles, int side
 int HCORE_dpotrf_batched_strided(hcore_b200_handle_t handle, int ntiles, int uplo, int N,
                         double *d_A, int lda, int64_t strideA, int32_t *d_info, void *stream);
 
+/* ---- tile compression: dense -> U V^T (device pointers) -------------------------------- */
+/* The step before the update path.  The reference only DECLARES a generate-and-compress kernel (HCORE_zgytlr,
+ * src/include/hcore_z.h:63-75, never defined); its tests compress with LAPACKE_dgesvd and keep
+ * rank = #{sigma >= acc}, capped at the storage rank (testing/testing_dgemm.c:119-236).  This entry point gives the
+ * same factors on the device: A[t] (nb x nb, ld lda) ~ U[t] V[t]^T with U orthonormal (nb x rank) and V carrying the
+ * singular values, truncated by the update path's rule (first i >= 1 with sigma_i < acc, absolute), rank capped at
+ * maxrk.  Randomised range finder (p = maxrk + 16 columns, `power_iters` power iterations: 1 is the safe default)
+ * whose orthonormalisation and truncation steps are passes of the update pipeline itself.
+ * d_U / d_V: buffers of ldu x maxrk per tile (element stride strideUV); d_rank: int32 out; d_status may be NULL. */
+int HCORE_dcompress_batched_strided(hcore_b200_handle_t handle, int ntiles, int nb,
+                        const double *d_A, int lda, int64_t strideA,
+                        double acc, int maxrk, int power_iters,
+                        double *d_U, double *d_V, int ldu, int64_t strideUV,
+                        int32_t *d_rank, int32_t *d_status, void *stream);
+
 /* ---- flop model ------------------------------------------------------------------------ */
 /* The reference's own accounting of one HCORE_dgemm call (flops->update; reference
  * src/misc/descutil/flop_counts.c:3-70 with the call sites of hcore_dgemm.c), used for

@@ -27,7 +27,7 @@ from scipy.linalg import lapack
 
 __all__ = ["qra", "qrb", "core_svd", "newu", "newv", "tlr_gemm", "tlr_gemm_colmajor",
            "gemmcd", "syrk", "flop_model", "truncation_rank",
-           "tlr_gemm_fast", "trsm", "potrf", "gemmbdcd", "uncompress"]
+           "tlr_gemm_fast", "trsm", "potrf", "gemmbdcd", "uncompress", "compress"]
 
 _PFX = {np.dtype(np.float64): "d", np.dtype(np.float32): "s", np.dtype(np.complex128): "z"}
 
@@ -212,6 +212,21 @@ def uncompress(au, bv):
     one / zero to ``?gemm`` whatever ``alpha`` / ``beta`` the caller gives (:72-78) and asserts equal ranks (:69)."""
     assert au.shape[1] == bv.shape[1], "ranks must be the same"
     return au @ bv.T
+
+
+def compress(a, acc, storage_maxrank):
+    """Dense tile -> ``(U, V, rank)`` the way the reference's tests do it (reference testing/testing_dgemm.c:119-236; the
+    library itself only declares ``HCORE_zgytlr``, src/include/hcore_z.h:63-75, and never defines it): ``dgesvd('A','A')``
+    (:172), rows of ``V^T`` scaled by sigma (:176-179), ``rank = #{sigma_i >= acc}`` counted from i = 0 (:201), capped at
+    ``storage_maxrank`` (:202-205), ``U`` = first rank left vectors (:212), ``V = (Sigma V^T)^T`` (:217).
+    Returns math-orientation ``U`` (m x rank), ``V`` (n x rank) with ``a ~ U @ V.T``."""
+    u, s, vt, info = lapack.dgesvd(np.asfortranarray(a), compute_uv=1, full_matrices=1)
+    assert info == 0
+    rank = 0
+    while rank < min(a.shape) and s[rank] >= acc:
+        rank += 1
+    rank = min(rank, storage_maxrank)
+    return u[:, :rank].copy(), (vt[:rank] * s[:rank, None]).T.copy(), rank
 
 
 def tlr_gemm_colmajor(au, av, bu, bv, cu, cv, crk, **kw):

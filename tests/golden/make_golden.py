@@ -290,10 +290,39 @@ def cholstep():
     print("cholstep:", len(rec), "arrays")
 
 
+def compress_cases():
+    """The reference's compression procedure (testing/testing_dgemm.c:119-236: LAPACKE_dlatms + LAPACKE_dgesvd + rank rule),
+    replayed through the same OpenBLAS the reference is linked with: the three 10 x 10 matrices of testing_dgemm.c and
+    two larger dlatms matrices.  Stored: the dense matrices and the factors (pins oracle.compress)."""
+    rec = {}
+    iseed = np.array([0, 0, 0, 1], dtype=np.int32)
+    for i in range(3):
+        a, U, V, r = generate_compress(10, iseed, 6, 1e-4)
+        rec[f"c10_{i}_a"] = a.T.copy(); rec[f"c10_{i}_u"] = U.T.copy(); rec[f"c10_{i}_v"] = V.T.copy(); rec[f"c10_{i}_rank"] = r
+    for n, smr, acc in ((64, 40, 1e-8), (96, 12, 1e-6)):
+        d = np.array([10.0 ** (-i / 3.0) for i in range(n)])
+        a = np.zeros((n, n))
+        assert _blas.scipy_LAPACKE_dlatms(102, n, n, b"U", iseed.ctypes.data_as(ip), b"N", _p(d), 0, -1.0, -1.0, n - 1, n - 1, b"N", _p(a), n) == 0
+        clone = a.copy()
+        s_, u, vt, sb = np.zeros(n), np.zeros((n, n)), np.zeros((n, n)), np.zeros(n)
+        assert _blas.scipy_LAPACKE_dgesvd(102, b"A", b"A", n, n, _p(clone), n, _p(s_), _p(u), n, _p(vt), n, _p(sb)) == 0
+        rank = 0
+        while rank < n and s_[rank] >= acc:
+            rank += 1
+        rank = min(rank, smr)
+        rec[f"c{n}_a"] = a.T.copy(); rec[f"c{n}_u"] = u[:rank].T.copy(); rec[f"c{n}_v"] = (vt.T * s_[:, None])[:rank].T.copy()
+        rec[f"c{n}_rank"] = rank; rec[f"c{n}_par"] = np.array([smr, acc])
+    np.savez_compressed(os.path.join(HERE, "ref_compress.npz"), **rec)
+    print("compress:", {k_: int(v) for k_, v in rec.items() if k_.endswith("_rank")})
+
+
 if __name__ == "__main__":
     rb.set_blas_threads(1)
     if len(sys.argv) > 1 and sys.argv[1] == "cholstep":
         cholstep()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "compress":
+        compress_cases()
         sys.exit(0)
     ctest_dgemm()
     ctest_sgemm()
@@ -303,3 +332,4 @@ if __name__ == "__main__":
     tlr_large()
     tlr_complex()
     cholstep()
+    compress_cases()

@@ -286,3 +286,16 @@ def test_oracle_dgemm_fast_vs_compiled_reference(golden_dir):
         assert r_gemm == int(g[f"fast_{name}_rank_dgemm"])
     assert int(g["fast_width2_rank"]) == 2 and int(g["fast_width2_rank_dgemm"]) == 1
     assert int(g["fast_width3_rank"]) == 2 and int(g["fast_width3_rank_dgemm"]) == 1
+
+
+def test_oracle_compress_vs_reference_procedure(golden_dir):
+    """oracle.compress against the reference's own compression procedure (testing/testing_dgemm.c:119-236) replayed
+    through the LAPACKE of the reference build (tests/golden/make_golden.py compress)."""
+    g = np.load(os.path.join(golden_dir, "ref_compress.npz"))
+    cases = [(f"c10_{i}", 6, 1e-4) for i in range(3)] + [(f"c{n}", int(g[f"c{n}_par"][0]), float(g[f"c{n}_par"][1])) for n in (64, 96)]
+    for name, smr, acc in cases:
+        a = g[name + "_a"]
+        u, v, r = orc.compress(a, acc, smr)
+        assert r == int(g[name + "_rank"])
+        assert np.abs(u @ v.T - g[name + "_u"] @ g[name + "_v"].T).max() < 1e-13 * max(1.0, np.abs(a).max())
+        assert np.abs(u.T @ u - np.eye(r)).max() < 1e-13

@@ -125,6 +125,20 @@ if ONLY in ("", "chol"):
                                "tflops": T * (nb ** 3 / 3) / ms / 1e9, "info_nonzero": int((info != 0).sum().item())}
         print("dpotrf", out[f"dpotrf_T{T}"], flush=True)
         del X, S0, S
+    # tile compression (dense 1024 x 1024 -> rank <= 64): covariance-like tiles = low-rank + decaying tail
+    T = 296
+    gu = torch.linalg.qr(torch.rand((T, nb, 96), dtype=torch.float64, device=dev, generator=rng) - 0.5)[0]
+    gv = torch.linalg.qr(torch.rand((T, nb, 96), dtype=torch.float64, device=dev, generator=rng) - 0.5)[0]
+    sg = 10.0 ** (-torch.arange(96, dtype=torch.float64, device=dev) / 5.0)
+    Ad = ((gu * sg) @ gv.transpose(1, 2)).transpose(1, 2).contiguous()
+    Uo = torch.zeros((T, 64, nb), dtype=torch.float64, device=dev); Vo = torch.zeros_like(Uo)
+    ro = torch.zeros(T, dtype=torch.int32, device=dev)
+    for q in (1, 0):
+        ms = timed(lambda: ctx.dcompress_batched(Ad, 1e-8, 64, Uo, Vo, ro, power_iters=q), lambda: None, reps=2, warm=1)
+        out[f"dcompress_q{q}"] = {"nb": nb, "maxrk": 64, "tiles": T, "power_iters": q, "tiles_per_s": T / ms * 1e3,
+                                  "mean_rank": float(ro.float().mean().item())}
+        print("dcompress", out[f"dcompress_q{q}"], flush=True)
+    del gu, gv, Ad, Uo, Vo
     # dgemmbdcd and uncompress: HBM-bound dense output
     T = 1024
     d = bench.make_device_batch(torch, T, nb, k, dev, seed=6)

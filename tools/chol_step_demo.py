@@ -1,5 +1,6 @@
 """Device-resident TLR Cholesky built ONLY from this library's batched tile kernels (GPU box):
 
+    HCORE_dcompress (every off-diagonal tile, dense -> U V^T)
     for k:  HCORE_dpotrf(A_kk)                                   dense diagonal tile
             HCORE_dtrsm (V_ik <- L_kk^-1 V_ik, i > k)            one shared triangle, ragged ranks
             HCORE_dsyrk (A_ii -= A_ik A_ik^T, i > k)             dense diagonal tiles
@@ -22,7 +23,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hcore_b200 import api  # noqa: E402
-from hcore_b200.tilegen import _morton_points, compress_tile  # noqa: E402
+from hcore_b200.tilegen import _morton_points  # noqa: E402
 
 nt = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 512
@@ -37,17 +38,25 @@ rng = np.random.default_rng(7)
 pts = _morton_points(N, rng)
 dd = torch.from_numpy(pts).to(dev)
 K = torch.exp(-(torch.cdist(dd, dd) / 0.1) ** 2) + 1e-2 * torch.eye(N, dtype=torch.float64, device=dev)   # SPD, well inside acc
-Kh = K.cpu().numpy()
-U = np.zeros((nt * nt, maxrk, nb)); V = np.zeros_like(U); rk = np.ones(nt * nt, np.int32)
-for k in range(nt):
-    for i in range(k + 1, nt):
-        u, v, r = compress_tile(Kh[i * nb:(i + 1) * nb, k * nb:(k + 1) * nb], acc, maxrk // 4)
-        U[k * nt + i, :r], V[k * nt + i, :r], rk[k * nt + i] = u, v, r                 # tile (i, k) at index k * nt + i
-D = np.stack([np.ascontiguousarray(Kh[i * nb:(i + 1) * nb, i * nb:(i + 1) * nb].T) for i in range(nt)])
-print(f"N = {N} ({nt} x {nt} tiles of {nb}), acc {acc:g}: ranks min/mean/max = {rk[rk > 1].min()}/{rk[rk > 1].mean():.1f}/{rk.max()}")
-Ud, Vd, rkd, Dd = (torch.from_numpy(x).to(dev) for x in (U, V, rk, D))
-info = torch.zeros(nt, dtype=torch.int32, device=dev)
 ctx = api.Context(0)
+# the off-diagonal tiles are compressed ON THE DEVICE (HCORE_dcompress_batched_strided): tile (i, k) at index k * nt + i
+idx = [(i, k) for k in range(nt) for i in range(k + 1, nt)]
+Adense = torch.stack([K[i * nb:(i + 1) * nb, k * nb:(k + 1) * nb].T.contiguous() for (i, k) in idx])     # column-major tiles
+Uc = torch.zeros((len(idx), maxrk, nb), dtype=torch.float64, device=dev); Vc = torch.zeros_like(Uc)
+rkc = torch.zeros(len(idx), dtype=torch.int32, device=dev); stc = torch.zeros_like(rkc)
+torch.cuda.synchronize(); tc0 = time.perf_counter()
+ctx.dcompress_batched(Adense, acc, maxrk // 4, Uc, Vc, rkc, status=stc)
+torch.cuda.synchronize(); t_compress = time.perf_counter() - tc0
+assert int(stc.abs().sum().item()) == 0
+Ud = torch.zeros((nt * nt, maxrk, nb), dtype=torch.float64, device=dev); Vd = torch.zeros_like(Ud)
+rkd = torch.ones(nt * nt, dtype=torch.int32, device=dev)
+sel = torch.tensor([k * nt + i for (i, k) in idx], device=dev)
+Ud[sel], Vd[sel], rkd[sel] = Uc, Vc, rkc
+del Adense, Uc, Vc
+Dd = torch.stack([K[i * nb:(i + 1) * nb, i * nb:(i + 1) * nb].T.contiguous() for i in range(nt)])
+print(f"N = {N} ({nt} x {nt} tiles of {nb}), acc {acc:g}: {len(idx)} tiles compressed on the device in {t_compress * 1e3:.1f} ms, "
+      f"ranks min/mean/max = {int(rkc.min())}/{float(rkc.float().mean()):.1f}/{int(rkc.max())}")
+info = torch.zeros(nt, dtype=torch.int32, device=dev)
 L = ctx._L
 import ctypes as C  # noqa: E402
 vp = lambda t: C.c_void_p(t.data_ptr())
@@ -94,10 +103,10 @@ for k in range(nt):
         r = int(rkd[k * nt + i].item())
         Lm[i * nb:(i + 1) * nb, k * nb:(k + 1) * nb] = Ud[k * nt + i, :r].T @ Vd[k * nt + i, :r]
 err = (torch.linalg.norm(Lm @ Lm.T - K) / torch.linalg.norm(K)).item()
-res = {"N": N, "nt": nt, "nb": nb, "maxrk": maxrk, "acc": acc, "seconds": dt, "gemm_tile_updates": ngemm,
+res = {"N": N, "nt": nt, "nb": nb, "maxrk": maxrk, "acc": acc, "seconds": dt, "compress_seconds": t_compress, "tiles_compressed": len(idx), "gemm_tile_updates": ngemm,
        "kernel_launches": ctx.launches - launch0, "rel_err_LLt": err, "final_rank_mean": float(rkd[rkd > 1].float().mean().item()),
        "final_rank_max": int(rkd.max().item()),
-       "note": "potrf / trsm / syrk / gemm all through libhcore_b200 on device-resident tiles; wall clock incl. host-side pointer tables"}
+       "note": "compress / potrf / trsm / syrk / gemm all through libhcore_b200 on device-resident tiles; wall clock incl. host-side pointer tables"}
 print(json.dumps(res))
 if outp:
     json.dump(res, open(outp, "w"), indent=1)
