@@ -823,7 +823,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     if (ntiles == 0) return HCORE_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = pick_width(maxrk);
+    const int N = pick_width(maxrk, HCORE_B200_MAX_STACK_Z);
     const size_t per = (2ull * nb * N + 2ull * N + 3ull * N * N) * sizeof(zc) + N * 8 + 16;
     int chunk = ctx->chunk_limit > 0 ? ctx->chunk_limit : (int)std::min<size_t>(ctx->num_sms * 4, (4ull << 30) / per);
     chunk = std::max(1, std::min(chunk, ntiles));
@@ -861,7 +861,8 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
         ztlr_stack_kernel<<<ar.ntiles, 256, 0, st>>>(ar, ws);
         if (nb <= 32 * kZRows) ztlr_qr_blocked_kernel<<<2 * ar.ntiles, 256, sm_qrb, st>>>(ar, ws);
         else ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
-        ztlr_svd_kernel<<<ar.ntiles, 512, 0, st>>>(ar, ws);
+        if (N <= 128) ztlr_svd_kernel<8><<<ar.ntiles, 512, 0, st>>>(ar, ws);
+        else ztlr_svd_kernel<16><<<ar.ntiles, 256, 0, st>>>(ar, ws);
         ztlr_apply_kernel<<<dim3((N + apw - 1) / apw, 2, ar.ntiles), 32 * apw, sm_ap, st>>>(ar, ws);
         ctx->launches += 4;
     }

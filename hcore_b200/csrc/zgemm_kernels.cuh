@@ -337,9 +337,12 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
 constexpr double kZTolRot = 1e-15, kZTolStop = 1e-7;
 constexpr int kZMaxSweeps = 60;
 
-__global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) {
-    __shared__ double sig[HCORE_B200_MAX_STACK], ssort[HCORE_B200_MAX_STACK];
-    __shared__ int posof[HCORE_B200_MAX_STACK], misc[4];
+// RPL = rows per lane of a 16-lane column pair: 8 (stacks up to 128, 512 threads) or 16 (stacks up to 256: ranks up to
+// 128, 256 threads so that the two columns of a pair -- 64 doubles per lane -- stay in registers)
+template <int RPL>
+__global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) {
+    __shared__ double sig[HCORE_B200_MAX_STACK_Z], ssort[HCORE_B200_MAX_STACK_Z];
+    __shared__ int posof[HCORE_B200_MAX_STACK_Z], misc[4];
     const int t = blockIdx.x;
     if (ws.st[t] != HCORE_B200_OK) return;
     const int gt = ar.tile0 + t;
@@ -373,17 +376,17 @@ __global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) 
                 rr_pair(n2, step, k, p, q);
                 if (q >= n) continue;
                 zc *cp = T + (size_t)p * N, *cq = T + (size_t)q * N;
-                zc xp[8], xq[8];
+                zc xp[RPL], xq[RPL];
                 double app = 0.0, aqq = 0.0;
                 zc apq = zmake(0.0, 0.0);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < RPL; ++e) {
                     const int r = l16 + 16 * e;
                     xp[e] = (r < n) ? cp[r] : zmake(0.0, 0.0);
                     xq[e] = (r < n) ? cq[r] : zmake(0.0, 0.0);
                 }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < RPL; ++e) {
                     app += zabs2(xp[e]); aqq += zabs2(xq[e]);
                     apq = zcfma(xp[e], xq[e], apq);                  // p^H q
                 }
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(512) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) 
                     const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
+                    for (int e = 0; e < RPL; ++e) {
                         const int r = l16 + 16 * e;
                         if (r < n) {
                             const zc qt = zmul(xq[e], ph);

@@ -47,7 +47,7 @@ extern "C" {
 #define HCORE_B200_OK                0
 #define HCORE_B200_ERR_ZERO_RANK     1  /* Ark, Brk or Crk == 0   (ref hcore_dgemm.c:743-746: exit)      */
 #define HCORE_B200_ERR_MAXRK         2  /* maxrk < Ark + Crk      (ref hcore_dgemm.c:924-927: exit)      */
-#define HCORE_B200_ERR_UNSUPPORTED   3  /* Ark+Crk above the compiled stack width (256; complex 128) or > nb */
+#define HCORE_B200_ERR_UNSUPPORTED   3  /* Ark+Crk above the compiled stack width (256) or > nb              */
 #define HCORE_B200_ERR_NEWRANK       4  /* rank after truncation > maxrk (ref hcore_dgemm.c:465-468)     */
 #define HCORE_B200_ERR_NO_CONVERGE   5  /* Jacobi SVD hit its sweep limit (ref: dgesvd info != 0, :407)  */
 #define HCORE_B200_ERR_RANK_MISMATCH 6  /* uncompress: Ark != Brk (ref hcore_duncompress.c:69: assert)    */
@@ -55,7 +55,8 @@ extern "C" {
 #define HCORE_B200_ERR_ARG         101  /* invalid argument           (function return value only)       */
 
 /* Largest stacked width Ark + Crk the kernels are compiled for. */
-#define HCORE_B200_MAX_STACK       128   /* complex path, dense-C ranks */
+#define HCORE_B200_MAX_STACK       128   /* default X-workspace rank of the dense-C kernels when no stride tells it */
+#define HCORE_B200_MAX_STACK_Z     256   /* HCORE_zgemm: Ark + Crk up to 256 (ranks up to 128) */
 #define HCORE_B200_MAX_STACK_D     256   /* HCORE_dgemm / HCORE_sgemm: Ark + Crk up to 256 (ranks up to 128) */
 
 typedef struct hcore_b200_context *hcore_b200_handle_t;
