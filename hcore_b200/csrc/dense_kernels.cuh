@@ -222,7 +222,6 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
     double *Cs = smem + SM::kC, *Bs = smem + SM::kB;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::kBar);      // [0] block of CD, [1] Y chunk
     const int t = blockIdx.z, i0 = blockIdx.x * kDuRows, j0 = blockIdx.y * kDuCols;
-    if (ar.Krk[t] < 0) return;                 // tile flagged by the caller (uncompress with mismatched ranks): untouched
     const int m = ar.nb, nn = ar.ncols, ldc = ar.ldc, ldy = ar.ldy;
     const int rows = (m - i0 < kDuRows) ? (m - i0) : kDuRows, cols = (nn - j0 < kDuCols) ? (nn - j0) : kDuCols;
     double *CD = (ar.pCD ? ar.pCD[t] : ar.CD + (size_t)t * ar.strideC) + i0 + (size_t)j0 * ldc;   // block origin
@@ -231,7 +230,9 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
     const int g = lane >> 2, tg = lane & 3;
     const bool cd_bulk = ((m & 1) == 0) && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(CD) & 15) == 0);
     const bool bulk_ok = cd_bulk && ((nn & 1) == 0) && ((ldy & 1) == 0) && ((reinterpret_cast<uintptr_t>(BU) & 15) == 0);
-    const bool readc = ar.beta != 0.0;
+    // A tile flagged by the caller (contraction length < 0: uncompress with mismatched ranks) must come out untouched:
+    // it is processed as CD <- 1 * CD + 0.  (Short-circuit: with beta != 0 the rank word is not needed before the loads.)
+    const bool readc = ar.beta != 0.0 || ar.Krk[t] < 0;
 
     if (ar.syrk && j0 > i0 + rows - 1) {      // every entry is strictly above the diagonal: the reference zeroes it
         if (cd_bulk) {
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
         }
     }
     // ---- product^T: warp w owns rows 16 w .. 16 w + 15 of the block (two row tiles) x 64 columns ----------
-    const int b = ar.Krk[t] > 0 ? ar.Krk[t] : 0, b8 = round_up(b, 8);
+    const int kraw = ar.Krk[t];
+    const int b = kraw > 0 ? kraw : 0, b8 = round_up(b, 8);
     const double *X = ar.Xop + (size_t)t * ar.strideX + i0 + 16 * warp + g;
     const bool r0on = 16 * warp + g < rows, r1on = 16 * warp + 8 + g < rows;
     double acc[8][2][2];      // [column tile][row tile][row 2 tg + h]
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
     // ---- update in shared memory, write back -----------------------------------------------------------
     if (bulk_ok && readc) mbar_wait(&bars[0], 0);
     else __syncthreads();
-    const double su = ar.su, beta = ar.beta;
+    const double su = ar.su, beta = kraw < 0 ? 1.0 : ar.beta;
     const bool plain = (rows == kDuRows) && (cols == kDuCols) && !(ar.syrk && j0 + cols - 1 > i0);
     if (plain) {
 #pragma unroll

@@ -58,6 +58,132 @@ struct SvdSmem {
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
 
+// ---- one-sided BLOCK Jacobi step on a pair of 4-column blocks, everything GEMM-shaped on the FP64 tensor pipe ----
+// One warp owns the pair (blocks p, q of the column-major core matrix L, n16 rows):
+//   1. G = X^T X (8 x 8 Gram matrix of the pair's eight columns): 2 DMMAs per 8 rows, the same register is A and B
+//      operand (lane (g, t) holds rows 2t, 2t+1 of column g of the 8-row slice);
+//   2. the cross rotations of the pair (4 rounds of 4 disjoint rotations; in the first step of a sweep also the
+//      3 rounds of in-block rotations) are derived from G ALONE: each rotation is computed redundantly by the lanes
+//      of its two rows, G <- J_r^T G J_r and J <- J J_r are 2 DMMAs each with G, K = J_r^T G and J kept in
+//      accumulator-fragment layout (an accumulator fragment is the A operand of the next product, and -- G being
+//      symmetric -- also its B operand), so a round needs three shuffles (two diagonal entries, one off-diagonal);
+//   3. X <- X J: 4 DMMAs per 16 rows, in place.
+// Compared with rotating the columns one pair at a time this trades the shuffle reductions, the scalar updates and
+// three quarters of the barriers for DMMAs.  Column index inside the solver: m = 0..3 -> column mu4(m) of block p,
+// m = 4..7 -> column mu4(m - 4) of block q, mu4 = (0, 2, 1, 3): this relabelling makes both shared-memory access
+// patterns (16-byte loads) bank-conflict free with the leading dimension N + 4.
+//   Accuracy: G is formed from the current columns in every step (entry-wise error eps ||x_i|| ||x_j||, i.e. the
+// cosines are accurate to rounding even between columns of very different norms); the two-sided updates keep that
+// scaled accuracy unless a rotation cancels a column almost completely, which only costs an inexact ANGLE in the
+// remaining rounds of the step (J is a product of plane rotations whatever the angles: orthogonal to rounding).
+template <int N>
+__device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int q, bool inblock, int lane, int &big) {
+    constexpr int LDL = N + 4, RB = N / 8;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int g = lane >> 2, t = lane & 3;
+    // ---- 1. Gram matrix ----------------------------------------------------------------------------------------
+    double gx, gy;                                     // G(g, 2t), G(g, 2t + 1)
+    {
+        const int mu = ((g & 1) << 1) | ((g >> 1) & 1);
+        const double *gc = L + (size_t)(4 * ((g & 4) ? q : p) + mu) * LDL + 2 * t;
+        double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            if (8 * j < n16) {
+                const double2 v = *reinterpret_cast<const double2 *>(gc + 8 * j);
+                dmma_884(ax[j & 3], ay[j & 3], v.x, v.x);
+                dmma_884(ax[j & 3], ay[j & 3], v.y, v.y);
+            }
+        }
+        gx = (ax[0] + ax[1]) + (ax[2] + ax[3]);
+        gy = (ay[0] + ay[1]) + (ay[2] + ay[3]);
+    }
+    // ---- 2. rotations ----------------------------------------------------------------------------------------
+    double jx = 0.0, jy = 0.0;                         // accumulated J(g, 2t), J(g, 2t + 1)
+    bool first = true;
+    auto round = [&](const int pg, const bool last) {  // pg: partner of row / column g in this round
+        const double dsel = (g & 1) ? gy : gx;         // lane (g, g / 2) holds G(g, g) here
+        const double dg = __shfl_sync(kFull, dsel, 4 * g + (g >> 1));
+        const double dp = __shfl_sync(kFull, dsel, 4 * pg + (pg >> 1));
+        const double osel = (pg & 1) ? gy : gx;        // lane (g, pg / 2) holds G(g, pg) here
+        const double apq = __shfl_sync(kFull, osel, 4 * g + (pg >> 1));
+        const bool lo = g < pg;
+        const double app = lo ? dg : dp, aqq = lo ? dp : dg;
+        const double den2 = app * aqq, apq2 = apq * apq;
+        double cs = 1.0, sn = 0.0;
+        if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
+            if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
+            const double dd = aqq - app, h2 = 2.0 * apq;
+            const double rh = rsqrt(fma(dd, dd, h2 * h2));
+            const double u = 0.5 * fma(fabs(dd), rh, 1.0);
+            const double ru = rsqrt(u);
+            cs = u * ru;
+            sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
+        }
+        // x_lo' = cs x_lo - sn x_hi, x_hi' = sn x_lo + cs x_hi: column g of J_r is cs at row g and sg at row pg
+        const double sg = lo ? -sn : sn;
+        const double j0 = (2 * t == g) ? cs : ((2 * t == pg) ? sg : 0.0);          // J_r(2t, g)
+        const double j1 = (2 * t + 1 == g) ? cs : ((2 * t + 1 == pg) ? sg : 0.0);  // J_r(2t + 1, g)
+        if (!last) {
+            double kx = 0.0, ky = 0.0, nx = 0.0, ny = 0.0;
+            dmma_884(kx, ky, j0, gx);                  // K = J_r^T G   (B operand: G(2t + s, g) = G(g, 2t + s))
+            dmma_884(kx, ky, j1, gy);
+            dmma_884(nx, ny, kx, j0);                  // G' = K J_r
+            dmma_884(nx, ny, ky, j1);
+            gx = nx; gy = ny;
+        }
+        if (first) {                                   // J = J_r: row g of J_r is cs at column g and -sg at column pg
+            jx = (2 * t == g) ? cs : ((2 * t == pg) ? -sg : 0.0);
+            jy = (2 * t + 1 == g) ? cs : ((2 * t + 1 == pg) ? -sg : 0.0);
+            first = false;
+        } else {
+            double nx = 0.0, ny = 0.0;
+            dmma_884(nx, ny, jx, j0);                  // J <- J J_r
+            dmma_884(nx, ny, jy, j1);
+            jx = nx; jy = ny;
+        }
+    };
+    if (inblock) {
+#pragma unroll
+        for (int b = 1; b < 4; ++b) round(g ^ b, false);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) round((g < 4) ? 4 + ((g + r) & 3) : ((g - r) & 3), r == 3);
+    // ---- 3. X <- X J ------------------------------------------------------------------------------------------
+    // B operand of k-chunk h: J(4h + t, n(g)) with n(g) = 4 (g & 1) + g / 2, so that accumulator column 2t + s is
+    // solver column 4 s + t: the results land exactly where the A operands came from.
+    double bj[2];
+    {
+        const int csrc = 2 * (g & 1) + (g >> 2);
+        const bool odd = ((g >> 1) & 1) != 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int src = 4 * (4 * h + t) + csrc;
+            const double vx = __shfl_sync(kFull, jx, src), vy = __shfl_sync(kFull, jy, src);
+            bj[h] = odd ? vy : vx;
+        }
+    }
+    {
+        const int mu = ((t & 1) << 1) | (t >> 1);
+        double *cp = L + (size_t)(4 * p + mu) * LDL + 2 * g;
+        double *cq = L + (size_t)(4 * q + mu) * LDL + 2 * g;
+#pragma unroll
+        for (int e = 0; e < RB / 2; ++e) {
+            if (16 * e < n16) {
+                const double2 vp = *reinterpret_cast<const double2 *>(cp + 16 * e);
+                const double2 vq = *reinterpret_cast<const double2 *>(cq + 16 * e);
+                double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
+                dmma_884(d0x, d0y, vp.x, bj[0]);
+                dmma_884(d0x, d0y, vq.x, bj[1]);
+                dmma_884(d1x, d1y, vp.y, bj[0]);
+                dmma_884(d1x, d1y, vq.y, bj[1]);
+                *reinterpret_cast<double2 *>(cp + 16 * e) = make_double2(d0x, d1x);
+                *reinterpret_cast<double2 *>(cq + 16 * e) = make_double2(d0y, d1y);
+            }
+        }
+    }
+}
+
 // One CTA per tile.  Threads = 4 N (one 16-lane group per Jacobi block pair), capped at 512: the narrow stacks
 // (N = 32, 64: ranks up to 16 / 32) run four / two tiles per SM at a time instead of one mostly idle 512-thread
 // CTA -- their SVD is pure latency (QRCP steps, Jacobi rounds), so co-resident tiles overlap it.
@@ -262,6 +388,29 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     PROF_ADD(13);
     const int kq4 = (kq + 3) & ~3;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq4
 
+    int sweeps = 0;
+    bool converged;
+    if constexpr (N <= 128) {
+    // ---- one-sided block Jacobi on the columns of L: blocks of four columns, a warp per block pair, rotations
+    //      derived from the pair's Gram matrix and applied with DMMAs (jacobi_pair_step).  Blocks meet in
+    //      round-robin order: kq8/4 - 1 barrier steps per sweep, every column pair is rotated once per sweep.
+    const int kq8 = (kq + 7) & ~7;                    // columns kq .. kq8-1 of L are zero
+    const int nb4 = kq8 >> 2, npair = nb4 >> 1;       // blocks (even), block pairs per step (<= number of warps)
+    converged = (kq8 < 8);
+    for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
+        int big = 0;
+        for (int step = 0; step < nb4 - 1; ++step) {
+            if (warp < npair) {
+                int p, qq;
+                rr_pair(nb4, step, warp, p, qq);
+                jacobi_pair_step<N>(L, n16, p, qq, step == 0, lane, big);
+            }
+            __syncthreads();
+        }
+        ++sweeps;
+        converged = (__syncthreads_or(big) == 0);
+    }
+    } else {
     // ---- one-sided Jacobi on the columns of L, in blocks of two columns -----------------------------
     // A group of 16 lanes owns one PAIR OF BLOCKS (four columns) per step and holds it in registers
     // (lane l16: row pairs 2 l16 + 32 e, e < N/32): the four cross rotations run as two rounds of two
@@ -273,8 +422,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     const int l16 = tid & (LG - 1), grp = tid / LG;    // lane l16 of its group: row pairs 2 l16 + 2 LG e
     const int ngrp = blockDim.x / LG;
     const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step
-    int sweeps = 0;
-    bool converged = (kq4 < 4);
+    converged = (kq4 < 4);
     // Two independent rotations A = (ap, aq) and B = (bp, bq) at once.  Only the two inner products a_p.a_q are
     // formed: the squared column norms are CACHED (cn[], recomputed exactly at the start of every sweep and carried
     // through each rotation by  app' = c^2 app - 2 c s apq + s^2 aqq,  aqq' = s^2 app + 2 c s apq + c^2 aqq; every term
@@ -392,6 +540,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
         ++sweeps;
         converged = (__syncthreads_or(big) == 0);
     }
+    }   // N > 128
 
     PROF_ADD(14);
     PROF_COUNT(21, sweeps);

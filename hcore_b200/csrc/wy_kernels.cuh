@@ -802,17 +802,20 @@ __global__ void __launch_bounds__(32 * NW, (NW == 2 ? 6 : 16 / NW)) tlr_tsqr_ker
     PROF_DECL(tid == NT - 32)
     PROF_COUNT(9, 1);
 
-    for (int gc0 = 0; gc0 < n16; gc0 += GW) {
-        const int gcols = (n16 - gc0 < GW) ? (n16 - gc0) : GW;      // multiple of 16
-        const int nsub = gcols / kSubW;                             // sub-panels (= active warps) of the group
-        const int lc = 8 * warp;                                    // my first slice column
-        const bool have_cols = warp < nsub;
-        const int mycol = gc0 + lc + g;
-        const ColSrc src = panel_column(ar, Gt, m_pad, gt, pnl, mycol, c, n);
-        const int nprev = gc0 / kSubW;                              // records of earlier groups
-        for (int j = 0; j < ws.nblk; ++j) {
-            const bool blk0 = (j == 0);
-            double *recj = recg + (size_t)j * NSP * kRecDoubles;
+    // Loop order: ROW BLOCK outer, column group inner.  The records a group streams (those of the earlier groups of
+    // the SAME row block) were written by this CTA a moment ago, so the TMA reads hit L2 instead of re-streaming
+    // 8 MB per tile from HBM as the group-outer order did (the running R lives in L2 either way).
+    for (int j = 0; j < ws.nblk; ++j) {
+        const bool blk0 = (j == 0);
+        double *recj = recg + (size_t)j * NSP * kRecDoubles;
+        for (int gc0 = 0; gc0 < n16; gc0 += GW) {
+            const int gcols = (n16 - gc0 < GW) ? (n16 - gc0) : GW;      // multiple of 16
+            const int nsub = gcols / kSubW;                             // sub-panels (= active warps) of the group
+            const int lc = 8 * warp;                                    // my first slice column
+            const bool have_cols = warp < nsub;
+            const int mycol = gc0 + lc + g;
+            const ColSrc src = panel_column(ar, Gt, m_pad, gt, pnl, mycol, c, n);
+            const int nprev = gc0 / kSubW;                              // records of earlier groups
             // prefetch the first earlier record while the slice is loaded
             if (nprev > 0 && tid == 0) {
                 mbar_expect_tx(&bars[0], kRecBytes);
@@ -920,13 +923,15 @@ __global__ void __launch_bounds__(32 * NW, (NW == 2 ? 6 : 16 / NW)) tlr_tsqr_ker
                 }
                 PROF_ADD(5);
             }
-        }  // row blocks
-        // the records of this group (generic-proxy stores) are streamed by TMA (async proxy) in the next group
-        __threadfence();
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) asm volatile("fence.proxy.async.global;" ::: "memory");
-    }  // column groups
+            // the records of this group (generic-proxy stores) are streamed by TMA (async proxy) in the next group
+            if (gc0 + GW < n16) {
+                __threadfence();
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+        }  // column groups
+    }  // row blocks
     // padding columns n16..N-1 of R
     for (int idx = tid; idx < N * (N - n16); idx += NT) Rg[(size_t)n16 * N + idx] = 0.0;
 }

@@ -268,6 +268,69 @@ def jacobi_svd_cols(t, max_sweeps=30):
     return g, sweeps
 
 
+def _rot_from_gram(app, aqq, apq):
+    """(cos, sin, big) of the rotation that orthogonalises a column pair with squared norms app, aqq and inner
+    product apq: x_p' = c x_p - s x_q, x_q' = s x_p + c x_q (the kernel's two-rsqrt formulation)."""
+    den2 = app * aqq
+    apq2 = apq * apq
+    if not (den2 > 0.0 and apq2 > TOL_ROT * TOL_ROT * den2):
+        return 1.0, 0.0, False
+    big = apq2 > TOL_STOP * TOL_STOP * den2
+    dd = aqq - app
+    h2 = 2.0 * apq
+    rh = 1.0 / np.sqrt(dd * dd + h2 * h2)
+    u = 0.5 * (abs(dd) * rh + 1.0)
+    ru = 1.0 / np.sqrt(u)
+    return u * ru, (h2 if dd >= 0.0 else -h2) * rh * (0.5 * ru), big
+
+
+def jacobi_pair_step(x, inblock):
+    """One block-pair step of the device kernel (``jacobi_pair_step`` in tlr_kernels.cuh) on the m x 8 slice ``x``
+    (columns 0-3 = block p, 4-7 = block q): Gram matrix, rotations derived from the Gram matrix alone (two-sided
+    updates), accumulated 8 x 8 orthogonal J, x <- x J.  Returns (x J, big)."""
+    g = x.T @ x
+    j = np.eye(8)
+    big = False
+    rounds = []
+    if inblock:
+        rounds += [[(i, i ^ b) for i in range(8) if i < (i ^ b)] for b in (1, 2, 3)]
+    rounds += [[(i, 4 + ((i + r) & 3)) for i in range(4)] for r in range(4)]
+    for pairs in rounds:
+        jr = np.eye(8)
+        for (lo, hi) in pairs:
+            c, s, b = _rot_from_gram(g[lo, lo], g[hi, hi], g[lo, hi])
+            big = big or b
+            jr[lo, lo] = c; jr[hi, hi] = c; jr[hi, lo] = -s; jr[lo, hi] = s
+        g = jr.T @ g @ jr
+        j = j @ jr
+    return x @ j, big
+
+
+def jacobi_svd_block4(t, max_sweeps=30):
+    """Block one-sided Jacobi of the device kernel: 4-column blocks (the column count is padded to a multiple of 8
+    with zero columns), round-robin over the blocks, one ``jacobi_pair_step`` per block pair and step.
+    Returns (t @ J with the padding removed, sweeps)."""
+    n0 = t.shape[1]
+    n8 = (n0 + 7) // 8 * 8
+    g = np.zeros((t.shape[0], n8))
+    g[:, :n0] = t
+    nb4 = n8 // 4
+    steps = round_robin_pairs(nb4)
+    sweeps = 0
+    for sweep in range(max_sweeps):
+        big = False
+        for si, st in enumerate(steps):
+            for (p, q) in st:
+                cols = list(range(4 * p, 4 * p + 4)) + list(range(4 * q, 4 * q + 4))
+                xj, b = jacobi_pair_step(g[:, cols], si == 0)
+                g[:, cols] = xj
+                big = big or b
+        sweeps += 1
+        if not big:
+            break
+    return g[:, :n0], sweeps
+
+
 def core_svd_model(ru, rv, rk, acc):
     """SVD stage of the device pipeline: T' = R_v R_u^T, QRCP, Jacobi on the columns of
     R^T, sort, truncate, U_r = P * normalised columns, W = R_v (R_u^T U_r)."""
@@ -278,11 +341,10 @@ def core_svd_model(ru, rv, rk, acc):
     tpp = np.zeros((n16, n16)); tpp[:n, :n] = tp
     tol2 = 1e-4 * acc * acc if rk == 0 else 1e-30 * float(np.max(np.sum(tpp * tpp, axis=0)))
     r_up, perm, kq = qrcp(tpp, tol2)
-    kq2 = (kq + 1) & ~1
     lt = np.zeros((n16, n16))
     lt[:, :kq] = r_up.T
-    gj, sweeps = jacobi_svd_cols(lt[:, :kq2]) if kq2 >= 2 else (lt[:, :kq2], 0)
-    g = np.zeros((n16, n16)); g[:, :kq2] = gj
+    gj, sweeps = jacobi_svd_block4(lt[:, :kq]) if kq >= 1 else (lt[:, :kq], 0)
+    g = np.zeros((n16, n16)); g[:, :kq] = gj
     sig = np.sqrt(np.sum(g * g, axis=0))
     order = np.argsort(-sig, kind="stable")
     sig = sig[order][:n]
