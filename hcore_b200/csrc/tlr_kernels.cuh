@@ -58,6 +58,197 @@ struct SvdSmem {
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double);
 };
 
+// ---- register-resident QR with column pivoting (stacks up to 128 columns) ---------------------------------------
+// The whole core matrix lives in registers: warp w owns columns 8w .. 8w+7, lane (g, t) holds rows 4e + t
+// (e < N/4) of column 8w + g.  Columns never move: a pivot only marks its column as factored at position `pos`.
+// One CTA barrier per Householder step:
+//   after the update of step i every warp determines its best remaining column (exact squared norms of rows > i
+//   fall out of the update), and SPECULATIVELY publishes that column (rows >= i + 1, raw), its leading entry and
+//   the squared norm of the rest to a per-warp slot; after the barrier all warps pick the same winner among the
+//   per-warp candidates (redundantly, a few shuffles), derive the reflector scalars from the winner's slot and
+//   apply the reflector to their own columns.  Slots are double buffered by step parity and live in the shared-
+//   memory area of the core matrix, which is free while the matrix is in registers.
+// The step body is instantiated per 4-row block E = i / 4, so the rows already factored cost nothing and every
+// register index is static.  Sums over the four lanes of a column use one DMMA (B = ones).
+template <int N>
+struct QrcpScratch {                          // offsets (doubles) inside the L area
+    static constexpr int NW = N / 8;
+    static constexpr int kY = 0;              // [2][NW][N] published columns
+    static constexpr int kV = kY + 2 * NW * N;   // [2][NW] best squared norm (rows >= i + 1)
+    static constexpr int kS = kV + 2 * NW;    // [2][NW] sum of the squared norms of the warp's remaining columns
+    static constexpr int kA = kS + 2 * NW;    // [2][NW] leading entry (row i + 1) of the published column
+    static constexpr int kT = kA + 2 * NW;    // [2][NW] squared norm of its rows > i + 1
+    static constexpr int kI = kT + 2 * NW;    // [2][NW] ints: column index of the candidate
+    static_assert(kI + NW <= N * (N + 4), "QRCP scratch must fit the core-matrix area");
+};
+
+__device__ __forceinline__ double quad_sum_dmma(double v) {      // sum over the four lanes of a column group
+    double d0 = 0.0, d1 = 0.0;
+    dmma_884(d0, d1, v, 1.0);
+    return d0;
+}
+
+// candidates of the step that follows row `inext - 1`: norms of rows >= inext of every remaining column, warp argmax,
+// publication.  ENEXT = inext / 4 may be E or E + 1 of the caller; both are handled by masks on the two row blocks.
+template <int N, int E>
+__device__ __forceinline__ void qrcp_publish(const double (&x)[N / 4], int inext, bool active, int col, int par,
+                                             double *scr, int warp, int lane) {
+    using S = QrcpScratch<N>;
+    constexpr int RE = N / 4, NW = N / 8;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int t = lane & 3;
+    const int en = inext >> 2, tn = inext & 3;            // row inext sits in register en of lane tn; en is E or E + 1
+    // leading entry and squared norm of the rows below it
+    double xl = x[E];
+    if constexpr (E + 1 < RE) xl = (en == E) ? xl : x[E + 1];
+    const double alpha = __shfl_sync(kFull, xl, (lane & ~3) | tn);
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int e = E; e < RE; ++e) {
+        const int row = 4 * e + t;
+        double v = x[e];
+        if (e <= E + 1) v = (row > inext) ? v : 0.0;
+        p[e & 3] = fma(v, v, p[e & 3]);
+    }
+    const double tail2 = quad_sum_dmma((p[0] + p[1]) + (p[2] + p[3]));
+    const double nrm2 = fma(alpha, alpha, tail2);
+    // warp argmax over the eight column groups (ties: smaller column), sum of the remaining norms
+    double key = active ? nrm2 : -1.0, wsum = active ? nrm2 : 0.0;
+    int kc = active ? col : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        const double ov = __shfl_xor_sync(kFull, key, o);
+        const int oc = __shfl_xor_sync(kFull, kc, o);
+        wsum += __shfl_xor_sync(kFull, wsum, o);
+        if (ov > key || (ov == key && oc < kc)) { key = ov; kc = oc; }
+    }
+    const int slot = par * NW + warp;
+    if (active && col == kc) {
+        double *ys = scr + S::kY + (size_t)slot * N;
+#pragma unroll
+        for (int e = E; e < RE; ++e) ys[4 * e + t] = x[e];
+        if (t == 0) { scr[S::kA + slot] = alpha; scr[S::kT + slot] = tail2; }
+    }
+    if (lane == 0) {
+        scr[S::kV + slot] = key;
+        scr[S::kS + slot] = wsum;
+        reinterpret_cast<int *>(scr + S::kI)[slot] = kc;
+    }
+}
+
+// Householder step i (row block E = i / 4).  Returns true when the factorisation stops BEFORE this step (the
+// Frobenius norm of the remaining block is below the tolerance): kq = i.
+template <int N, int E>
+__device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, double &beta, int i, int n16, int col,
+                                          bool in_range, double &tol2, int rk, double acc, double *scr, int warp, int lane) {
+    using S = QrcpScratch<N>;
+    constexpr int RE = N / 4, NW = N / 8;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int t = lane & 3, tt = i & 3, par = i & 1;
+    __syncthreads();
+    // ---- winner among the per-warp candidates (every warp, redundantly) ---------------------------------------
+    double bv = (lane < NW) ? scr[S::kV + par * NW + lane] : -1.0;
+    double fs = (lane < NW) ? scr[S::kS + par * NW + lane] : 0.0;
+    int bi = (lane < NW) ? reinterpret_cast<const int *>(scr + S::kI)[par * NW + lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(kFull, bv, o);
+        const int oi = __shfl_xor_sync(kFull, bi, o);
+        fs += __shfl_xor_sync(kFull, fs, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    bv = __shfl_sync(kFull, bv, 0);
+    fs = __shfl_sync(kFull, fs, 0);
+    const int piv = __shfl_sync(kFull, bi, 0);
+    if (i == 0) tol2 = (rk == 0) ? 1e-4 * acc * acc : 1e-30 * bv;
+    if (fs < tol2 || piv == 0x7fffffff) return true;
+    const int wslot = par * NW + (piv >> 3);
+    const double *ys = scr + S::kY + (size_t)wslot * N;
+    const Householder h = make_householder(scr[S::kA + wslot], scr[S::kT + wslot]);
+    if (col == piv) { pos = i; beta = h.beta; }
+    // ---- apply H = I - tau v v^T, v = [1; scal y], to my column: d = y^T x (rows > i) ----------------------------
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int e = E; e < RE; ++e) {
+        double y = ys[4 * e + t];
+        if (e == E) y = (t > tt) ? y : 0.0;
+        p[e & 3] = fma(x[e], y, p[e & 3]);
+    }
+    const double d = quad_sum_dmma((p[0] + p[1]) + (p[2] + p[3]));
+    const double xi = __shfl_sync(kFull, x[E], (lane & ~3) | tt);
+    const double wv = h.tau * fma(h.scal, d, xi), f = h.scal * wv;
+#pragma unroll
+    for (int e = E; e < RE; ++e) {
+        const double y = ys[4 * e + t];
+        if (e == E) x[e] = (t > tt) ? fma(-y, f, x[e]) : ((t == tt) ? x[e] - wv : x[e]);
+        else x[e] = fma(-y, f, x[e]);
+    }
+    // ---- candidates of the next step ---------------------------------------------------------------------------------
+    if (i + 1 < n16) qrcp_publish<N, E>(x, i + 1, in_range && pos < 0, col, par ^ 1, scr, warp, lane);
+    return false;
+}
+
+template <int N, int E>
+__device__ __forceinline__ int qrcp_blocks(double (&x)[N / 4], int &pos, double &beta, int n16, int col, bool in_range,
+                                           double &tol2, int rk, double acc, double *scr, int warp, int lane) {
+    if constexpr (E < N / 4) {
+#pragma unroll 1
+        for (int tt = 0; tt < 4; ++tt) {
+            const int i = 4 * E + tt;
+            if (i >= n16) return n16;
+            if (qrcp_step<N, E>(x, pos, beta, i, n16, col, in_range, tol2, rk, acc, scr, warp, lane)) return i;
+        }
+        return qrcp_blocks<N, E + 1>(x, pos, beta, n16, col, in_range, tol2, rk, acc, scr, warp, lane);
+    } else {
+        return n16;
+    }
+}
+
+// Truncated QRCP of the n16 x n16 matrix in L (column-major, ld N + 4); on return L holds R^T restricted to the kq
+// factored rows (L(a, b) = R(b, a): row a = pivot position of a column, column b = Householder step; zero for b >= kq
+// and above the diagonal), perm[a] = original column at position a.  Returns kq.
+template <int N>
+__device__ __forceinline__ int qrcp_registers(double *L, int n16, int rk, double acc, int *perm, int *cnt) {
+    constexpr int LDL = N + 4, RE = N / 4;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int warp = warp_id(), lane = lane_id();
+    const int g = lane >> 2, t = lane & 3;
+    const int col = 8 * warp + g;
+    const bool in_range = col < n16;
+    double x[RE];
+#pragma unroll
+    for (int e = 0; e < RE; ++e) x[e] = (in_range && 4 * e + t < n16) ? L[(4 * e + t) + (size_t)col * LDL] : 0.0;
+    __syncthreads();                          // the matrix is in registers: its shared-memory area becomes scratch
+    int pos = -1;
+    double beta = 0.0, tol2 = 0.0;
+    qrcp_publish<N, 0>(x, 0, in_range, col, 0, L, warp, lane);
+    const int kq = qrcp_blocks<N, 0>(x, pos, beta, n16, col, in_range, tol2, rk, acc, L, warp, lane);
+    // ---- positions of the columns that were never selected: kq + rank among them (column order) -------------------
+    const unsigned rest = __ballot_sync(kFull, in_range && pos < 0 && t == 0);
+    if (lane == 0) cnt[warp] = __popc(rest);
+    __syncthreads();                          // also: every warp is done with the scratch
+    if (in_range && pos < 0) {
+        int a = kq;
+        for (int w = 0; w < warp; ++w) a += cnt[w];
+        pos = a + __popc(rest & ((1u << (lane & ~3)) - 1u));      // remaining columns of my warp left of mine
+    }
+    if (in_range) {
+        const bool sel = pos < kq;
+#pragma unroll
+        for (int e = 0; e < RE; ++e) {
+            const int b = 4 * e + t;
+            if (b < n16) {
+                double v = 0.0;
+                if (b < kq) v = sel ? (b < pos ? x[e] : (b == pos ? beta : 0.0)) : x[e];
+                L[pos + (size_t)b * LDL] = v;
+            }
+        }
+        if (t == 0) perm[pos] = col;
+    }
+    __syncthreads();
+    return kq;
+}
+
 // ---- one-sided BLOCK Jacobi step on a pair of 4-column blocks, everything GEMM-shaped on the FP64 tensor pipe ----
 // One warp owns the pair (blocks p, q of the column-major core matrix L, n16 rows):
 //   1. G = X^T X (8 x 8 Gram matrix of the pair's eight columns): 2 DMMAs per 8 rows, the same register is A and B
@@ -225,6 +416,12 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     __syncthreads();
     PROF_ADD(10);
 
+    int kq;
+    if constexpr (N <= 128) {
+        kq = qrcp_registers<N>(L, n16, ar.rk, ar.acc, perm, posof);
+        PROF_ADD(12);
+        PROF_COUNT(20, kq);
+    } else {
     // ---- QR with column pivoting (preconditioner), truncated -----------------------------------
     // Two barriers per step:
     //   phase C (warp 0)  pivot = argmax of the 16 per-warp candidates, swap, Householder vector
@@ -260,7 +457,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
         for (int w = 0; w < nwarps; ++w) mx = fmax(mx, candv[w]);
         tol2 = (ar.rk == 0) ? 1e-4 * ar.acc * ar.acc : 1e-30 * mx;
     }
-    int kq = n16;
+    kq = n16;
     PROF_ADD(11);
     for (int i = 0; i < n16; ++i) {
         if (warp == 0) {
@@ -386,6 +583,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     }
     __syncthreads();
     PROF_ADD(13);
+    }   // N > 128
     const int kq4 = (kq + 3) & ~3;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq4
 
     int sweeps = 0;

@@ -169,6 +169,6 @@ def test_stage4_reflector_application(ctx, nb, k, kind):
         nx = np.linalg.norm(xu, 2) * np.linalg.norm(xv, 2)
         # Q_u^T X_u = R_u  =>  CU^T X_u = U_r^T R_u ; likewise CV^T X_v = W^T R_v
         assert np.abs(CU.T @ xu - Yu.T @ Rud).max() <= 1e-11 * np.linalg.norm(xu, 2)
-        assert np.abs(CV.T @ xv - Yv.T @ Rvd).max() <= 1e-11 * nx
+        assert np.abs(CV.T @ xv - Yv.T @ Rvd).max() <= 1e-11 * np.linalg.norm(Yv, 2) * np.linalg.norm(xv, 2)   # entries of W^T R_v are of the order ||W|| ||X_v||
         # and the product is the stacked update restricted to the kept subspace: error below the dropped singular values
         assert np.linalg.norm(CU @ CV.T - xu @ xv.T) <= max(acc * np.sqrt(n), 1e-13 * nx)

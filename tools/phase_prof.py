@@ -49,5 +49,8 @@ for name, tab, cnt in (("tlr_tsqr_kernel", TSQR, 9), ("  inside panel_factor", P
     print(f"== {name}: {n} CTAs, {tot / n:,.0f} cycles per CTA in the listed phases")
     for s, label in tab.items():
         print(f"   {label:58s} {v[s] / n:12,.0f} cyc/CTA  {100.0 * v[s] / max(tot, 1):5.1f} %")
+if v[53]:
+    print("== jacobi_pair_step (warp 0): %d pair steps; cycles per pair step: Gram %.0f, rotations %.0f, apply %.0f; per step: "
+          "pair step + overhead %.0f, barrier wait %.0f" % (v[53], v[50] / v[53], v[51] / v[53], v[52] / v[53], v[54] / v[53], v[55] / v[53]))
 print(f"QRCP steps per tile {v[20] / max(v[29], 1):.1f}, Jacobi sweeps per tile {v[21] / max(v[29], 1):.2f}")
 ctx.close()
