@@ -59,27 +59,27 @@ struct SvdSmem {
 };
 
 // ---- register-resident QR with column pivoting (stacks up to 128 columns) ---------------------------------------
-// The whole core matrix lives in registers: warp w owns columns 8w .. 8w+7, lane (g, t) holds rows 4e + t
-// (e < N/4) of column 8w + g.  Columns never move: a pivot only marks its column as factored at position `pos`.
-// One CTA barrier per Householder step:
+// The whole core matrix lives in registers: warp w owns columns 8w .. 8w+7, lane (g, t) holds the row pairs
+// 8e + 2t, 8e + 2t + 1 (e < N/8) of column 8w + g.  Columns never move: a pivot only marks its column as factored at
+// position `pos`.  One CTA barrier per Householder step:
 //   after the update of step i every warp determines its best remaining column (exact squared norms of rows > i
-//   fall out of the update), and SPECULATIVELY publishes that column (rows >= i + 1, raw), its leading entry and
-//   the squared norm of the rest to a per-warp slot; after the barrier all warps pick the same winner among the
-//   per-warp candidates (redundantly, a few shuffles), derive the reflector scalars from the winner's slot and
-//   apply the reflector to their own columns.  Slots are double buffered by step parity and live in the shared-
-//   memory area of the core matrix, which is free while the matrix is in registers.
-// The step body is instantiated per 4-row block E = i / 4, so the rows already factored cost nothing and every
-// register index is static.  Sums over the four lanes of a column use one DMMA (B = ones).
+//   fall out of the update), and SPECULATIVELY publishes that column (raw), its leading entry and the squared norm
+//   of the rest to a per-warp slot; after the barrier all warps pick the same winner among the per-warp candidates
+//   (redundantly: two REDUX instructions on the bit pattern of the norm with the column index in its low bits),
+//   derive the reflector scalars from the winner's slot and apply the reflector to their own columns.  Slots are
+//   double buffered by step parity and live in the shared-memory area of the core matrix, which is free while the
+//   matrix is in registers.
+// The step body is instantiated per 8-row block E = i / 8, so the rows already factored cost nothing and every
+// register index is static.  Sums over the four lanes of a column are one DMMA (B = ones), warp totals two.
 template <int N>
 struct QrcpScratch {                          // offsets (doubles) inside the L area
     static constexpr int NW = N / 8;
     static constexpr int kY = 0;              // [2][NW][N] published columns
-    static constexpr int kV = kY + 2 * NW * N;   // [2][NW] best squared norm (rows >= i + 1)
+    static constexpr int kV = kY + 2 * NW * N;   // [2][NW] candidate key: squared norm of rows >= i + 1, column in the low bits
     static constexpr int kS = kV + 2 * NW;    // [2][NW] sum of the squared norms of the warp's remaining columns
     static constexpr int kA = kS + 2 * NW;    // [2][NW] leading entry (row i + 1) of the published column
     static constexpr int kT = kA + 2 * NW;    // [2][NW] squared norm of its rows > i + 1
-    static constexpr int kI = kT + 2 * NW;    // [2][NW] ints: column index of the candidate
-    static_assert(kI + NW <= N * (N + 4), "QRCP scratch must fit the core-matrix area");
+    static_assert(kT + 2 * NW <= N * (N + 4), "QRCP scratch must fit the core-matrix area");
 };
 
 __device__ __forceinline__ double quad_sum_dmma(double v) {      // sum over the four lanes of a column group
@@ -87,101 +87,119 @@ __device__ __forceinline__ double quad_sum_dmma(double v) {      // sum over the
     dmma_884(d0, d1, v, 1.0);
     return d0;
 }
+__device__ __forceinline__ double warp_sum_dmma(double v) {      // sum over the 32 lanes, in every lane
+    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+    dmma_884(d0, d1, 1.0, v);
+    dmma_884(e0, e1, 1.0, d0 + d1);
+    return e0;
+}
+// Warp-wide maximum of non-negative doubles by bit pattern (the order of the patterns is the order of the values),
+// or 0 when every lane passes 0.  Two REDUX instructions.
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+// candidate key of a remaining column: its squared norm with the low 7 bits replaced by 127 - column (ties and
+// near-ties go to the smaller column); 0 = no candidate
+__device__ __forceinline__ unsigned long long qrcp_key(double nrm2, int col) {
+    return ((unsigned long long)__double_as_longlong(nrm2) & ~0x7full) | (unsigned long long)(127 - col);
+}
 
 // candidates of the step that follows row `inext - 1`: norms of rows >= inext of every remaining column, warp argmax,
-// publication.  ENEXT = inext / 4 may be E or E + 1 of the caller; both are handled by masks on the two row blocks.
+// publication.  inext / 8 is E or E + 1; both are handled by masks on the two row blocks.
 template <int N, int E>
 __device__ __forceinline__ void qrcp_publish(const double (&x)[N / 4], int inext, bool active, int col, int par,
                                              double *scr, int warp, int lane) {
     using S = QrcpScratch<N>;
-    constexpr int RE = N / 4, NW = N / 8;
+    constexpr int RB = N / 8, NW = N / 8;
     constexpr unsigned kFull = 0xffffffffu;
     const int t = lane & 3;
-    const int en = inext >> 2, tn = inext & 3;            // row inext sits in register en of lane tn; en is E or E + 1
+    const int en = inext >> 3, rn = inext & 7;            // row inext: row block en, lane rn / 2, element rn & 1
     // leading entry and squared norm of the rows below it
-    double xl = x[E];
-    if constexpr (E + 1 < RE) xl = (en == E) ? xl : x[E + 1];
-    const double alpha = __shfl_sync(kFull, xl, (lane & ~3) | tn);
+    double xl = (rn & 1) ? x[2 * E + 1] : x[2 * E];
+    if constexpr (E + 1 < RB) xl = (en == E) ? xl : x[2 * E + 2];
+    const double alpha = __shfl_sync(kFull, xl, (lane & ~3) | (rn >> 1));
     double p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int e = E; e < RE; ++e) {
-        const int row = 4 * e + t;
-        double v = x[e];
-        if (e <= E + 1) v = (row > inext) ? v : 0.0;
-        p[e & 3] = fma(v, v, p[e & 3]);
+    for (int e = E; e < RB; ++e) {
+        double v0 = x[2 * e], v1 = x[2 * e + 1];
+        if (e <= E + 1) {
+            v0 = (8 * e + 2 * t > inext) ? v0 : 0.0;
+            v1 = (8 * e + 2 * t + 1 > inext) ? v1 : 0.0;
+        }
+        p[(2 * e) & 3] = fma(v0, v0, p[(2 * e) & 3]);
+        p[(2 * e + 1) & 3] = fma(v1, v1, p[(2 * e + 1) & 3]);
     }
     const double tail2 = quad_sum_dmma((p[0] + p[1]) + (p[2] + p[3]));
     const double nrm2 = fma(alpha, alpha, tail2);
-    // warp argmax over the eight column groups (ties: smaller column), sum of the remaining norms
-    double key = active ? nrm2 : -1.0, wsum = active ? nrm2 : 0.0;
-    int kc = active ? col : 0x7fffffff;
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-        const double ov = __shfl_xor_sync(kFull, key, o);
-        const int oc = __shfl_xor_sync(kFull, kc, o);
-        wsum += __shfl_xor_sync(kFull, wsum, o);
-        if (ov > key || (ov == key && oc < kc)) { key = ov; kc = oc; }
-    }
+    const unsigned long long key = active ? qrcp_key(nrm2, col) : 0ull;
+    const unsigned long long best = warp_max_u64(key);
+    const double wsum = 0.25 * warp_sum_dmma(active ? nrm2 : 0.0);      // every column is held by four lanes
     const int slot = par * NW + warp;
-    if (active && col == kc) {
-        double *ys = scr + S::kY + (size_t)slot * N;
+    if (active && key == best) {
+        double *ys = scr + S::kY + (size_t)slot * N + 2 * t;
 #pragma unroll
-        for (int e = E; e < RE; ++e) ys[4 * e + t] = x[e];
+        for (int e = E; e < RB; ++e) *reinterpret_cast<double2 *>(ys + 8 * e) = make_double2(x[2 * e], x[2 * e + 1]);
         if (t == 0) { scr[S::kA + slot] = alpha; scr[S::kT + slot] = tail2; }
     }
     if (lane == 0) {
-        scr[S::kV + slot] = key;
+        reinterpret_cast<unsigned long long *>(scr + S::kV)[slot] = best;
         scr[S::kS + slot] = wsum;
-        reinterpret_cast<int *>(scr + S::kI)[slot] = kc;
     }
 }
 
-// Householder step i (row block E = i / 4).  Returns true when the factorisation stops BEFORE this step (the
+// Householder step i (row block E = i / 8).  Returns true when the factorisation stops BEFORE this step (the
 // Frobenius norm of the remaining block is below the tolerance): kq = i.
 template <int N, int E>
-__device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, double &beta, int i, int n16, int col,
-                                          bool in_range, double &tol2, int rk, double acc, double *scr, int warp, int lane) {
+__device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, int n16, int col, bool in_range,
+                                          double &tol2, int rk, double acc, double *scr, double *betas, int warp, int lane) {
     using S = QrcpScratch<N>;
-    constexpr int RE = N / 4, NW = N / 8;
+    constexpr int RB = N / 8, NW = N / 8;
     constexpr unsigned kFull = 0xffffffffu;
-    const int t = lane & 3, tt = i & 3, par = i & 1;
+    const int t = lane & 3, ri = i & 7, par = i & 1;
     __syncthreads();
     // ---- winner among the per-warp candidates (every warp, redundantly) ---------------------------------------
-    double bv = (lane < NW) ? scr[S::kV + par * NW + lane] : -1.0;
-    double fs = (lane < NW) ? scr[S::kS + par * NW + lane] : 0.0;
-    int bi = (lane < NW) ? reinterpret_cast<const int *>(scr + S::kI)[par * NW + lane] : 0x7fffffff;
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(kFull, bv, o);
-        const int oi = __shfl_xor_sync(kFull, bi, o);
-        fs += __shfl_xor_sync(kFull, fs, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    bv = __shfl_sync(kFull, bv, 0);
-    fs = __shfl_sync(kFull, fs, 0);
-    const int piv = __shfl_sync(kFull, bi, 0);
-    if (i == 0) tol2 = (rk == 0) ? 1e-4 * acc * acc : 1e-30 * bv;
-    if (fs < tol2 || piv == 0x7fffffff) return true;
+    const unsigned long long ck = (lane < NW) ? reinterpret_cast<const unsigned long long *>(scr + S::kV)[par * NW + lane] : 0ull;
+    const double fs = warp_sum_dmma((lane < NW) ? scr[S::kS + par * NW + lane] : 0.0);
+    const unsigned long long best = warp_max_u64(ck);
+    if (i == 0) tol2 = (rk == 0) ? 1e-4 * acc * acc : 1e-30 * __longlong_as_double((long long)best);
+    if (fs < tol2 || best == 0ull) return true;
+    const int piv = 127 - (int)(best & 0x7full);
     const int wslot = par * NW + (piv >> 3);
-    const double *ys = scr + S::kY + (size_t)wslot * N;
+    const double *ys = scr + S::kY + (size_t)wslot * N + 2 * t;
     const Householder h = make_householder(scr[S::kA + wslot], scr[S::kT + wslot]);
-    if (col == piv) { pos = i; beta = h.beta; }
+    if (col == piv) {
+        pos = i;
+        if (t == 0) betas[col] = h.beta;
+    }
     // ---- apply H = I - tau v v^T, v = [1; scal y], to my column: d = y^T x (rows > i) ----------------------------
     double p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int e = E; e < RE; ++e) {
-        double y = ys[4 * e + t];
-        if (e == E) y = (t > tt) ? y : 0.0;
-        p[e & 3] = fma(x[e], y, p[e & 3]);
+    for (int e = E; e < RB; ++e) {
+        double2 y = *reinterpret_cast<const double2 *>(ys + 8 * e);
+        if (e == E) { y.x = (2 * t > ri) ? y.x : 0.0; y.y = (2 * t + 1 > ri) ? y.y : 0.0; }
+        p[(2 * e) & 3] = fma(x[2 * e], y.x, p[(2 * e) & 3]);
+        p[(2 * e + 1) & 3] = fma(x[2 * e + 1], y.y, p[(2 * e + 1) & 3]);
     }
     const double d = quad_sum_dmma((p[0] + p[1]) + (p[2] + p[3]));
-    const double xi = __shfl_sync(kFull, x[E], (lane & ~3) | tt);
+    const double xi = __shfl_sync(kFull, (ri & 1) ? x[2 * E + 1] : x[2 * E], (lane & ~3) | (ri >> 1));
     const double wv = h.tau * fma(h.scal, d, xi), f = h.scal * wv;
+    // second pass over the published column: the address is made to depend on d so that these loads are not hoisted
+    // above the reduction (sixteen 16-byte values in flight on top of the register-resident column would spill)
+    const double *ys2 = ys + (__double2hiint(d) & 0);
 #pragma unroll
-    for (int e = E; e < RE; ++e) {
-        const double y = ys[4 * e + t];
-        if (e == E) x[e] = (t > tt) ? fma(-y, f, x[e]) : ((t == tt) ? x[e] - wv : x[e]);
-        else x[e] = fma(-y, f, x[e]);
+    for (int e = E; e < RB; ++e) {
+        const double2 y = *reinterpret_cast<const double2 *>(ys2 + 8 * e);
+        if (e == E) {
+            const int r0 = 2 * t, r1 = 2 * t + 1;
+            x[2 * e] = (r0 > ri) ? fma(-y.x, f, x[2 * e]) : ((r0 == ri) ? x[2 * e] - wv : x[2 * e]);
+            x[2 * e + 1] = (r1 > ri) ? fma(-y.y, f, x[2 * e + 1]) : ((r1 == ri) ? x[2 * e + 1] - wv : x[2 * e + 1]);
+        } else {
+            x[2 * e] = fma(-y.x, f, x[2 * e]);
+            x[2 * e + 1] = fma(-y.y, f, x[2 * e + 1]);
+        }
     }
     // ---- candidates of the next step ---------------------------------------------------------------------------------
     if (i + 1 < n16) qrcp_publish<N, E>(x, i + 1, in_range && pos < 0, col, par ^ 1, scr, warp, lane);
@@ -189,16 +207,16 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, double &
 }
 
 template <int N, int E>
-__device__ __forceinline__ int qrcp_blocks(double (&x)[N / 4], int &pos, double &beta, int n16, int col, bool in_range,
-                                           double &tol2, int rk, double acc, double *scr, int warp, int lane) {
-    if constexpr (E < N / 4) {
+__device__ __forceinline__ int qrcp_blocks(double (&x)[N / 4], int &pos, int n16, int col, bool in_range, double &tol2,
+                                           int rk, double acc, double *scr, double *betas, int warp, int lane) {
+    if constexpr (E < N / 8) {
 #pragma unroll 1
-        for (int tt = 0; tt < 4; ++tt) {
-            const int i = 4 * E + tt;
+        for (int r = 0; r < 8; ++r) {
+            const int i = 8 * E + r;
             if (i >= n16) return n16;
-            if (qrcp_step<N, E>(x, pos, beta, i, n16, col, in_range, tol2, rk, acc, scr, warp, lane)) return i;
+            if (qrcp_step<N, E>(x, pos, i, n16, col, in_range, tol2, rk, acc, scr, betas, warp, lane)) return i;
         }
-        return qrcp_blocks<N, E + 1>(x, pos, beta, n16, col, in_range, tol2, rk, acc, scr, warp, lane);
+        return qrcp_blocks<N, E + 1>(x, pos, n16, col, in_range, tol2, rk, acc, scr, betas, warp, lane);
     } else {
         return n16;
     }
@@ -206,27 +224,32 @@ __device__ __forceinline__ int qrcp_blocks(double (&x)[N / 4], int &pos, double 
 
 // Truncated QRCP of the n16 x n16 matrix in L (column-major, ld N + 4); on return L holds R^T restricted to the kq
 // factored rows (L(a, b) = R(b, a): row a = pivot position of a column, column b = Householder step; zero for b >= kq
-// and above the diagonal), perm[a] = original column at position a.  Returns kq.
+// and above the diagonal), perm[a] = original column at position a.  Returns kq.  betas[N], cnt[N / 8]: scratch.
 template <int N>
-__device__ __forceinline__ int qrcp_registers(double *L, int n16, int rk, double acc, int *perm, int *cnt) {
-    constexpr int LDL = N + 4, RE = N / 4;
+__device__ __forceinline__ int qrcp_registers(double *L, int n16, int rk, double acc, int *perm, int *cnt, double *betas) {
+    constexpr int LDL = N + 4, RB = N / 8;
     constexpr unsigned kFull = 0xffffffffu;
+    static_assert(N <= 128, "the column index travels in seven bits of the candidate key");
     const int warp = warp_id(), lane = lane_id();
     const int g = lane >> 2, t = lane & 3;
     const int col = 8 * warp + g;
     const bool in_range = col < n16;
-    double x[RE];
+    double x[2 * RB];
 #pragma unroll
-    for (int e = 0; e < RE; ++e) x[e] = (in_range && 4 * e + t < n16) ? L[(4 * e + t) + (size_t)col * LDL] : 0.0;
+    for (int e = 0; e < RB; ++e) {
+        double2 v = make_double2(0.0, 0.0);
+        if (in_range && 8 * e < n16) v = *reinterpret_cast<const double2 *>(L + (size_t)col * LDL + 8 * e + 2 * t);
+        x[2 * e] = v.x; x[2 * e + 1] = v.y;
+    }
     __syncthreads();                          // the matrix is in registers: its shared-memory area becomes scratch
     int pos = -1;
-    double beta = 0.0, tol2 = 0.0;
+    double tol2 = 0.0;
     qrcp_publish<N, 0>(x, 0, in_range, col, 0, L, warp, lane);
-    const int kq = qrcp_blocks<N, 0>(x, pos, beta, n16, col, in_range, tol2, rk, acc, L, warp, lane);
+    const int kq = qrcp_blocks<N, 0>(x, pos, n16, col, in_range, tol2, rk, acc, L, betas, warp, lane);
     // ---- positions of the columns that were never selected: kq + rank among them (column order) -------------------
     const unsigned rest = __ballot_sync(kFull, in_range && pos < 0 && t == 0);
     if (lane == 0) cnt[warp] = __popc(rest);
-    __syncthreads();                          // also: every warp is done with the scratch
+    __syncthreads();                          // also: every warp is done with the scratch, betas[] is complete
     if (in_range && pos < 0) {
         int a = kq;
         for (int w = 0; w < warp; ++w) a += cnt[w];
@@ -234,9 +257,10 @@ __device__ __forceinline__ int qrcp_registers(double *L, int n16, int rk, double
     }
     if (in_range) {
         const bool sel = pos < kq;
+        const double beta = sel ? betas[col] : 0.0;
 #pragma unroll
-        for (int e = 0; e < RE; ++e) {
-            const int b = 4 * e + t;
+        for (int e = 0; e < 2 * RB; ++e) {
+            const int b = 8 * (e >> 1) + 2 * t + (e & 1);
             if (b < n16) {
                 double v = 0.0;
                 if (b < kq) v = sel ? (b < pos ? x[e] : (b == pos ? beta : 0.0)) : x[e];
@@ -247,6 +271,14 @@ __device__ __forceinline__ int qrcp_registers(double *L, int n16, int rk, double
     }
     __syncthreads();
     return kq;
+}
+
+// hardware seed of 1 / sqrt(w) (MUFU.RSQ64H: relative error ~2^-22), no special cases: callers select the result
+// away when w is 0 or not finite
+__device__ __forceinline__ double rsqrt_seed(double w) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+    return y;
 }
 
 // ---- one-sided BLOCK Jacobi step on a pair of 4-column blocks, everything GEMM-shaped on the FP64 tensor pipe ----
@@ -301,16 +333,24 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         const bool lo = g < pg;
         const double app = lo ? dg : dp, aqq = lo ? dp : dg;
         const double den2 = app * aqq, apq2 = apq * apq;
-        double cs = 1.0, sn = 0.0;
-        if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
-            if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
-            const double dd = aqq - app, h2 = 2.0 * apq;
-            const double rh = rsqrt(fma(dd, dd, h2 * h2));
-            const double u = 0.5 * fma(fabs(dd), rh, 1.0);
-            const double ru = rsqrt(u);
-            cs = u * ru;
-            sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
-        }
+        // Branch-free (the lanes of a warp hold four different rotations).  cos^2 = (1 + |d| / hyp) / 2 with
+        // d = aqq - app, hyp = sqrt(d^2 + 4 apq^2); sin = sign(d) apq / (hyp cos).  The two reciprocal square roots
+        // are the bare hardware seeds (~2^-22): the ANGLE only has to be good to a few digits (a rotation by a slightly
+        // wrong angle is still a rotation and the off-diagonal entry still shrinks by 2^-22), what must hold to rounding
+        // is cos^2 + sin^2 = 1, restored by the second-order correction 1 - delta/2 + 3 delta^2/8.  This keeps the
+        // dependent FP64 chain of a round short: it shares the FP64 pipe with the DMMAs of the other warps.
+        const bool rot = den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2;
+        if (rot && apq2 > (kTolStop * kTolStop) * den2) big = 1;
+        const double dd = aqq - app;
+        const double rh = rsqrt_seed(fma(dd, dd, 4.0 * apq2));
+        const double u = fma(0.5 * fabs(dd), rh, 0.5);
+        const double ru = rsqrt_seed(u);
+        double cs = u * ru;
+        double sn = ((dd >= 0.0 ? apq : -apq) * rh) * ru;
+        const double dl = fma(cs, cs, fma(sn, sn, -1.0));
+        const double rn = fma(dl, fma(0.375, dl, -0.5), 1.0);
+        cs = rot ? cs * rn : 1.0;
+        sn = rot ? sn * rn : 0.0;
         // x_lo' = cs x_lo - sn x_hi, x_hi' = sn x_lo + cs x_hi: column g of J_r is cs at row g and sg at row pg
         const double sg = lo ? -sn : sn;
         const double j0 = (2 * t == g) ? cs : ((2 * t == pg) ? sg : 0.0);          // J_r(2t, g)
@@ -418,7 +458,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
 
     int kq;
     if constexpr (N <= 128) {
-        kq = qrcp_registers<N>(L, n16, ar.rk, ar.acc, perm, posof);
+        kq = qrcp_registers<N>(L, n16, ar.rk, ar.acc, perm, posof, vn);
         PROF_ADD(12);
         PROF_COUNT(20, kq);
     } else {
