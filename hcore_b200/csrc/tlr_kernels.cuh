@@ -71,6 +71,28 @@ struct SvdSmem {
 //   matrix is in registers.
 // The step body is instantiated per 8-row block E = i / 8, so the rows already factored cost nothing and every
 // register index is static.  Sums over the four lanes of a column are one DMMA (B = ones), warp totals two.
+// make_householder without library calls: rsqrt() and __drcp_rn() carry out-of-line slow paths, and a call inside the
+// step body makes ptxas spill the register-resident column around it.  Hardware seeds (~2^-22) + two Newton steps:
+// a few ulps, arguments are positive and normal here (sigma2 > 0).
+__device__ __forceinline__ Householder make_householder_inline(double alpha, double sigma2) {
+    Householder h;
+    const double s2 = fma(alpha, alpha, sigma2);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s2));
+    y = fma(0.5 * y, fma(-s2 * y, y, 1.0), y);
+    y = fma(0.5 * y, fma(-s2 * y, y, 1.0), y);
+    const double nrm = s2 * y, aabs = fabs(alpha), den = aabs + nrm;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const bool nz = sigma2 != 0.0;
+    h.beta = nz ? -copysign(nrm, alpha) : alpha;
+    h.tau = nz ? fma(aabs, y, 1.0) : 0.0;
+    h.scal = nz ? copysign(r, alpha) : 0.0;
+    return h;
+}
+
 template <int N>
 struct QrcpScratch {                          // offsets (doubles) inside the L area
     static constexpr int NW = N / 8;
@@ -154,7 +176,7 @@ __device__ __forceinline__ void qrcp_publish(const double (&x)[N / 4], int inext
 // Frobenius norm of the remaining block is below the tolerance): kq = i.
 template <int N, int E>
 __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, int n16, int col, bool in_range,
-                                          double &tol2, int rk, double acc, double *scr, double *betas, int warp, int lane) {
+                                          double &tol2, double *scr, double *betas, int warp, int lane) {
     using S = QrcpScratch<N>;
     constexpr int RB = N / 8, NW = N / 8;
     constexpr unsigned kFull = 0xffffffffu;
@@ -164,12 +186,12 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
     const unsigned long long ck = (lane < NW) ? reinterpret_cast<const unsigned long long *>(scr + S::kV)[par * NW + lane] : 0ull;
     const double fs = warp_sum_dmma((lane < NW) ? scr[S::kS + par * NW + lane] : 0.0);
     const unsigned long long best = warp_max_u64(ck);
-    if (i == 0) tol2 = (rk == 0) ? 1e-4 * acc * acc : 1e-30 * __longlong_as_double((long long)best);
+    if (i == 0 && tol2 < 0.0) tol2 = 1e-30 * __longlong_as_double((long long)best);      // fixed-rank mode
     if (fs < tol2 || best == 0ull) return true;
     const int piv = 127 - (int)(best & 0x7full);
     const int wslot = par * NW + (piv >> 3);
     const double *ys = scr + S::kY + (size_t)wslot * N + 2 * t;
-    const Householder h = make_householder(scr[S::kA + wslot], scr[S::kT + wslot]);
+    const Householder h = make_householder_inline(scr[S::kA + wslot], scr[S::kT + wslot]);
     if (col == piv) {
         pos = i;
         if (t == 0) betas[col] = h.beta;
@@ -182,6 +204,7 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
         if (e == E) { y.x = (2 * t > ri) ? y.x : 0.0; y.y = (2 * t + 1 > ri) ? y.y : 0.0; }
         p[(2 * e) & 3] = fma(x[2 * e], y.x, p[(2 * e) & 3]);
         p[(2 * e + 1) & 3] = fma(x[2 * e + 1], y.y, p[(2 * e + 1) & 3]);
+        if (((e - E) & 3) == 3) asm volatile("" ::: "memory");      // at most four loads in flight: registers
     }
     const double d = quad_sum_dmma((p[0] + p[1]) + (p[2] + p[3]));
     const double xi = __shfl_sync(kFull, (ri & 1) ? x[2 * E + 1] : x[2 * E], (lane & ~3) | (ri >> 1));
@@ -200,6 +223,7 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
             x[2 * e] = fma(-y.x, f, x[2 * e]);
             x[2 * e + 1] = fma(-y.y, f, x[2 * e + 1]);
         }
+        if (((e - E) & 3) == 3) asm volatile("" ::: "memory");
     }
     // ---- candidates of the next step ---------------------------------------------------------------------------------
     if (i + 1 < n16) qrcp_publish<N, E>(x, i + 1, in_range && pos < 0, col, par ^ 1, scr, warp, lane);
@@ -208,15 +232,15 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
 
 template <int N, int E>
 __device__ __forceinline__ int qrcp_blocks(double (&x)[N / 4], int &pos, int n16, int col, bool in_range, double &tol2,
-                                           int rk, double acc, double *scr, double *betas, int warp, int lane) {
+                                           double *scr, double *betas, int warp, int lane) {
     if constexpr (E < N / 8) {
 #pragma unroll 1
         for (int r = 0; r < 8; ++r) {
             const int i = 8 * E + r;
             if (i >= n16) return n16;
-            if (qrcp_step<N, E>(x, pos, i, n16, col, in_range, tol2, rk, acc, scr, betas, warp, lane)) return i;
+            if (qrcp_step<N, E>(x, pos, i, n16, col, in_range, tol2, scr, betas, warp, lane)) return i;
         }
-        return qrcp_blocks<N, E + 1>(x, pos, n16, col, in_range, tol2, rk, acc, scr, betas, warp, lane);
+        return qrcp_blocks<N, E + 1>(x, pos, n16, col, in_range, tol2, scr, betas, warp, lane);
     } else {
         return n16;
     }
@@ -243,9 +267,11 @@ __device__ __forceinline__ int qrcp_registers(double *L, int n16, int rk, double
     }
     __syncthreads();                          // the matrix is in registers: its shared-memory area becomes scratch
     int pos = -1;
-    double tol2 = 0.0;
+    // stop when the squared Frobenius norm of the remaining block is below tol2: 1 % of the truncation threshold, or
+    // (fixed-rank mode, set in step 0) rounding level of the largest column
+    double tol2 = (rk == 0) ? 1e-4 * acc * acc : -1.0;
     qrcp_publish<N, 0>(x, 0, in_range, col, 0, L, warp, lane);
-    const int kq = qrcp_blocks<N, 0>(x, pos, n16, col, in_range, tol2, rk, acc, L, betas, warp, lane);
+    const int kq = qrcp_blocks<N, 0>(x, pos, n16, col, in_range, tol2, L, betas, warp, lane);
     // ---- positions of the columns that were never selected: kq + rank among them (column order) -------------------
     const unsigned rest = __ballot_sync(kFull, in_range && pos < 0 && t == 0);
     if (lane == 0) cnt[warp] = __popc(rest);
