@@ -783,6 +783,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
                 if (step == 0) rotate2(p0, p1, q0, q1, np0, np1, nq0, nq1, big);
                 rotate2(p0, q0, p1, q1, np0, nq0, np1, nq1, big);
                 rotate2(p0, q1, p1, q0, np0, nq1, np1, nq0, big);
+                __syncwarp(hmask);        // every lane of the group has read the cached norms
                 if (l16 == 0) { cn[2 * p] = np0; cn[2 * p + 1] = np1; cn[2 * qq] = nq0; cn[2 * qq + 1] = nq1; }
 #pragma unroll
                 for (int e = 0; e < RP; ++e) {

@@ -9,7 +9,7 @@ from hcore_b200 import api
 from hcore_b200.tilegen import make_lr_batch, make_dense_batch
 dev = torch.device("cuda:0")
 ctx = api.Context(0)
-for nb, k in ((200, 12), (257, 9), (260, 70)):    # the last one: stack width 256 (core matrix in L2)
+for nb, k in ((200, 12), (257, 9), (256, 20), (300, 40), (260, 70)):    # stack widths 32, 32, 64, 128 and 256 (core matrix in L2)
     b = make_lr_batch(3, nb, k)
     t = {n: torch.from_numpy(np.ascontiguousarray(getattr(b, n))).to(dev) for n in ("au", "av", "bu", "bv", "cu", "cv", "ark", "brk", "crk")}
     st = torch.zeros(3, dtype=torch.int32, device=dev)
