@@ -902,6 +902,51 @@ int HCORE_zgemm_batched(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
 
 // ---- dense-C updates ----------------------------------------------------------------------
 // kcap = upper bound of the B-side rank (columns of the X workspace).  mc = rows contracted by AV^T BV.
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn resolve_tmap_encode() {      // cuTensorMapEncodeTiled through the runtime: no link-time dependency on libcuda
+    static tmap_encode_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<tmap_encode_fn>(p);
+    }();
+    return fn;
+}
+// The persistent streaming kernel (dense_stream_kernel) takes strided batches of whole 128 x 32 blocks whose operands
+// the TMA bulk copies can address: everything else goes through dense_update_kernel.  HCORE_B200_DENSE_STREAM=0
+// disables it (A/B measurements).
+static bool dense_stream_ok(const DenseArgs &ar, int kcap) {
+    static const bool enabled = [] { const char *e = getenv("HCORE_B200_DENSE_STREAM"); return !(e && e[0] == '0'); }();
+    if (!enabled || ar.pCD || ar.pBU) return false;
+    if (ar.nb % kDsRows || ar.ncols % kDsCols || kcap > kDsKmax) return false;
+    if ((reinterpret_cast<uintptr_t>(ar.CD) | reinterpret_cast<uintptr_t>(ar.Yop)) & 15) return false;
+    if ((ar.ldc | ar.ldy) & 1) return false;
+    if ((ar.strideC | ar.strideY) & 1) return false;
+    if (!resolve_tmap_encode()) return false;
+    return true;
+}
+static int dense_stream_launch(hcore_b200_context *ctx, const DenseArgs &ar, int cnt, cudaStream_t st) {
+    if (!ctx->attr_done[6]) {
+        ctx->attr_done[6] = true;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(dense_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DenseStreamSmem::kBytes));
+    }
+    // tensor map of the batch of dense tiles: rows x columns x tiles, FP64, 128 x 32 x 1 boxes
+    alignas(64) CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)ar.nb, (cuuint64_t)ar.ncols, (cuuint64_t)cnt};
+    const cuuint64_t strides[2] = {(cuuint64_t)ar.ldc * 8, (cuuint64_t)(cnt > 1 ? ar.strideC : (long)ar.ldc * ar.ncols) * 8};
+    const cuuint32_t box[3] = {kDsRows, kDsCols, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = resolve_tmap_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ar.CD, dims, strides, box, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return HCORE_B200_ERR_CUDA; }
+    const long nstrips = (long)cnt * (ar.nb / kDsRows);
+    const int grid = (int)std::min<long>(nstrips, ctx->num_sms);
+    dense_stream_kernel<<<grid, kDsThreads, DenseStreamSmem::kBytes, st>>>(ar, cnt, tmap);
+    return HCORE_B200_OK;
+}
+
 static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scale, int syrk,
                         const double *d_AU, const double *d_AV, const int32_t *d_Ark, int64_t strideA, int lda,
                         const double *d_BU, const double *d_BV, const int32_t *d_Brk, int64_t strideB, int ldb, int mc,
@@ -939,7 +984,8 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
         ar.nb = nb; ar.ncols = nb; ar.su = 1.0; ar.beta = 1.0; ar.syrk = syrk;
         if (p_CD) { ar.pAU = p_AU + t0; ar.pAV = p_AV + t0; ar.pBU = p_BU + t0; ar.pBV = p_BV + t0; ar.pCD = p_CD + t0; }
         dense_prep_kernel<<<cnt, 256, sm_prep, st>>>(ar);
-        dense_update_kernel<<<dim3((nb + kDuRows - 1) / kDuRows, (nb + kDuCols - 1) / kDuCols, cnt), 256, sm_upd, st>>>(ar);
+        if (dense_stream_ok(ar, kc8)) { const int rc = dense_stream_launch(ctx, ar, cnt, st); if (rc != HCORE_B200_OK) return rc; }
+        else dense_update_kernel<<<dim3((nb + kDuRows - 1) / kDuRows, (nb + kDuCols - 1) / kDuCols, cnt), 256, sm_upd, st>>>(ar);
         ctx->launches += 2;
     }
     CUDA_TRY(ctx, cudaGetLastError());
@@ -949,7 +995,7 @@ static int dense_launch(hcore_b200_handle_t ctx, int ntiles, int nb, double scal
 // CD (m x n, ld ldc) = beta CD + su * X (m x k, ld ldx) Y^T (n x k, ld ldy): the update kernel alone
 static int dense_xyt(hcore_b200_handle_t ctx, int ntiles, int m, int n, double su, const double *d_X, int ldx, int64_t strideX,
                      const double *d_Y, int ldy, int64_t strideY, const int32_t *d_K, double beta, double *d_CD, int ldc,
-                     int64_t strideC, cudaStream_t st) {
+                     int64_t strideC, cudaStream_t st, int kcap = 1 << 30) {      // kcap: upper bound of the contraction lengths
     if (!ctx->attr_done[4]) {
         ctx->attr_done[4] = true;
         CUDA_TRY(ctx, cudaFuncSetAttribute(dense_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PgSmem::kBytes));
@@ -963,7 +1009,8 @@ static int dense_xyt(hcore_b200_handle_t ctx, int ntiles, int m, int n, double s
         ar.Krk = d_K + t0;
         ar.CD = d_CD + (size_t)t0 * strideC; ar.strideC = strideC; ar.ldc = ldc;
         ar.nb = m; ar.ncols = n; ar.su = su; ar.beta = beta; ar.syrk = 0;
-        dense_update_kernel<<<dim3((m + kDuRows - 1) / kDuRows, (n + kDuCols - 1) / kDuCols, cnt), 256, DenseUpdSmem::kBytes, st>>>(ar);
+        if (dense_stream_ok(ar, kcap)) { const int rc = dense_stream_launch(ctx, ar, cnt, st); if (rc != HCORE_B200_OK) return rc; }
+        else dense_update_kernel<<<dim3((m + kDuRows - 1) / kDuRows, (n + kDuCols - 1) / kDuCols, cnt), 256, DenseUpdSmem::kBytes, st>>>(ar);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaGetLastError());
@@ -1032,7 +1079,7 @@ static int gemmbdcd_launch(hcore_b200_handle_t ctx, int ntiles, int M, int mc, i
         dense_bdtav_kernel<<<dim3(n_pad / 64, cnt), 256, 0, st>>>(pa);
         ctx->launches++;
         int rc = dense_xyt(ctx, cnt, M, N, alpha, d_AU + (size_t)t0 * strideA, lda, strideA, (const double *)ctx->Ywork.p, n_pad,
-                           (int64_t)n_pad * kcap, d_Ark + t0, beta, d_CD + (size_t)t0 * strideC, ldc, strideC, st);
+                           (int64_t)n_pad * kcap, d_Ark + t0, beta, d_CD + (size_t)t0 * strideC, ldc, strideC, st, kcap);
         if (rc != HCORE_B200_OK) return rc;
     }
     return HCORE_B200_OK;
@@ -1070,7 +1117,8 @@ int HCORE_duncompress_batched_strided(hcore_b200_handle_t ctx, int ntiles, int M
     uncompress_check_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_Ark, d_Brk, K, d_status, ntiles);
     ctx->launches++;
     // a mismatched tile carries K = -1: the update kernel skips it (see dense_update_kernel)
-    return dense_xyt(ctx, ntiles, M, N, 1.0, d_AU, lda, strideA, d_BV, ldb, strideB, K, 0.0, d_CD, ldc, strideC, st);
+    return dense_xyt(ctx, ntiles, M, N, 1.0, d_AU, lda, strideA, d_BV, ldb, strideB, K, 0.0, d_CD, ldc, strideC, st,
+                     std::min(rank_cap(strideA, lda, 1 << 30), rank_cap(strideB, ldb, 1 << 30)));
 }
 
 int HCORE_zuncompress_batched_strided(hcore_b200_handle_t ctx, int ntiles, int M, int N,
