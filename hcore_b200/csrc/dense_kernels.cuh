@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
 // ---- persistent streaming form of the same update -----------------------------------------------------------------
 // dense_update_kernel gives every 128 x 64 block its own CTA and moves it with one 1 KB bulk copy per column: load,
 // product, update and store of a block follow each other, and the copy engine is limited by the NUMBER of requests
-// (measured: ~10 k cycles per block, the sum of its HBM time and its FP64 time).  Here one 512-thread CTA per SM walks
+// (measured: ~10 k cycles per block, the sum of its HBM time and its FP64 time).  Here persistent CTAs walk
 // over (tile, 128-row strip) pairs and streams the strip's 128 x 32 blocks through a ring of shared-memory slots, each
 // block moved by ONE tiled TMA request in each direction (cp.async.bulk.tensor.3d on a tensor map of the whole batch:
 // rows x columns x tiles):
@@ -385,19 +385,22 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
 //     slot q    :  product X Y^T by DMMA (the strip's X fragments stay in registers, the 32 x k piece of Y is staged by
 //                  the threads themselves one block ahead), update in shared memory
 //     slot q-1  -> tensor store of the finished block
-// Warp w owns rows 8w .. 8w+7 of the strip; the product is formed transposed (DMMA rows = columns of CD) so that a lane
+// Every warp owns a band of rows of the strip; the product is formed transposed (DMMA rows = columns of CD) so that a lane
 // ends up with two consecutive rows of one column and updates the slot with 16-byte accesses.  The strictly upper
 // blocks of HCORE_dsyrk are zeroed with plain stores when a strip starts and never enter the ring.
 // Preconditions (checked on the host, dense_stream_ok): strided batch, m % 128 == 0, n % 32 == 0, contraction
-// length <= 64, 16-byte aligned bases, even leading dimensions and strides.
-constexpr int kDsRows = 128, kDsCols = 32, kDsSlots = 5, kDsAhead = 3, kDsKmax = 64, kDsThreads = 512;
+// length <= 32, 16-byte aligned bases, even leading dimensions and strides.
+// Shape used (hcore_api.cu): two 256-thread CTAs per SM, three slots each, a warp owns 16 rows, contraction lengths up
+// to kDsKmax = 32: while one CTA updates and stores, the other one keeps the FP64 pipe busy.
+constexpr int kDsRows = 128, kDsCols = 32, kDsKmax = 32;
 constexpr int kDsLdY = kDsCols + 4;     // 36
 constexpr int kDsBlock = kDsRows * kDsCols;            // doubles per slot: the TMA box, dense (ld = 128)
+template <int THREADS, int KMAX, int SLOTS, int NYB>
 struct DenseStreamSmem {
     static constexpr int kC = 0;                                            // [slots][32 x 128], 128-byte aligned
-    static constexpr int kY = kC + kDsSlots * kDsBlock;                     // [2][64 x 36]  Y piece: [k][column]
-    static constexpr int kBar = kY + 2 * kDsKmax * kDsLdY;                  // full[slots]
-    static constexpr int kTotal = kBar + kDsSlots;
+    static constexpr int kY = kC + SLOTS * kDsBlock;                        // [NYB][KMAX x 36]  Y piece: [k][column]
+    static constexpr int kBar = kY + NYB * KMAX * kDsLdY;                   // full[slots]
+    static constexpr int kTotal = kBar + SLOTS;
     static constexpr size_t kBytes = (size_t)kTotal * sizeof(double) + 128; // + slack to align the slots to 128 bytes
 };
 
@@ -412,12 +415,17 @@ __device__ __forceinline__ void tma_store_3d(const void *tmap, int c0, int c1, i
 
 // walks over the ring items (blocks that are read-modified-written) of this CTA, in the order every role sees them
 struct DenseCursor {
-    int s;             // current strip (tile * row blocks + row block)
+    int t, ib;         // current strip: tile and row block (advanced without divisions)
     int j, n, k;       // next block of the strip, blocks of the strip that enter the ring, contraction length of the tile
 };
 
-__global__ void __launch_bounds__(kDsThreads, 1) dense_stream_kernel(DenseArgs ar, int ntiles, const __grid_constant__ CUtensorMap tmap) {
-    using SM = DenseStreamSmem;
+template <int THREADS, int KMAX, int SLOTS, int AHEAD, int NYB>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
+dense_stream_kernel(DenseArgs ar, int ntiles, const __grid_constant__ CUtensorMap tmap) {
+    using SM = DenseStreamSmem<THREADS, KMAX, SLOTS, NYB>;
+    constexpr int NWARP = THREADS / 32, RT = 16 / NWARP;             // 8-row tiles per warp
+    constexpr int YPT = 16 * KMAX / THREADS;                         // 16-byte pieces of Y per thread
+    static_assert(RT * NWARP == 16 && YPT * THREADS == 16 * KMAX && SLOTS > AHEAD, "shape");
     extern __shared__ __align__(16) double smem_raw[];
     double *smem = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::kBar);
@@ -425,68 +433,72 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_stream_kernel(DenseArgs a
     const int g = lane >> 2, tg = lane & 3;
     const int m = ar.nb, n = ar.ncols, ldc = ar.ldc, ldy = ar.ldy;
     const int nrb = m / kDsRows, ncb = n / kDsCols;
-    const int nstrips = ntiles * nrb;                 // < 2^31: the host launches at most 32768 tiles at a time
     const bool readc = ar.beta != 0.0;
 
     if (tid == 0) {
-        for (int sl = 0; sl < kDsSlots; ++sl) mbar_init(&full[sl], 1);
+        for (int sl = 0; sl < SLOTS; ++sl) mbar_init(&full[sl], 1);
         fence_mbar_init();
     }
     // stale rows of a Y buffer are multiplied by zero X entries: they only have to be finite
-    for (int idx = tid; idx < 2 * kDsKmax * kDsLdY; idx += kDsThreads) smem[SM::kY + idx] = 0.0;
+    for (int idx = tid; idx < NYB * KMAX * kDsLdY; idx += THREADS) smem[SM::kY + idx] = 0.0;
     __syncthreads();
 
-    auto enter = [&](DenseCursor &c) {              // first strip at or after c.s with blocks for the ring
-        for (; c.s < nstrips; c.s += gridDim.x) {
-            const int t = c.s / nrb, ib = c.s % nrb;
-            c.k = ar.Krk[t];
+    const int dt = gridDim.x / nrb, dib = gridDim.x % nrb;           // strip stride of the CTA as (tiles, row blocks)
+    auto start = [&]() { return DenseCursor{(int)blockIdx.x / nrb, (int)blockIdx.x % nrb, 0, 0, 0}; };
+    auto advance = [&](DenseCursor &c) {            // next strip of this CTA
+        c.t += dt; c.ib += dib;
+        if (c.ib >= nrb) { c.ib -= nrb; ++c.t; }
+    };
+    auto enter = [&](DenseCursor &c) {              // first strip at or after the current one with blocks for the ring
+        for (; c.t < ntiles; advance(c)) {
+            c.k = ar.Krk[c.t];
             c.j = 0;
             // flagged tile (k < 0) or nothing to add: CD untouched (dsyrk still zeroes its upper triangle)
-            c.n = (c.k < 0 || (c.k == 0 && ar.beta == 1.0 && !ar.syrk)) ? 0 : (ar.syrk ? min(ncb, 4 * (ib + 1)) : ncb);
+            c.n = (c.k < 0 || (c.k == 0 && ar.beta == 1.0 && !ar.syrk)) ? 0 : (ar.syrk ? min(ncb, 4 * (c.ib + 1)) : ncb);
             if (c.n > 0) return;
         }
     };
     auto step = [&](DenseCursor &c) {               // to the next ring item
-        if (++c.j >= c.n) { c.s += gridDim.x; enter(c); }
+        if (++c.j >= c.n) { advance(c); enter(c); }
     };
-    // ---- producer (one lane of warp 0): tensor loads kDsAhead items ahead ------------------------------------------------
-    DenseCursor pc{(int)blockIdx.x, 0, 0, 0};
+    // ---- producer (thread 0): tensor loads AHEAD items ahead ---------------------------------------------------------------
+    DenseCursor pc = start();
     int pq = 0;
     auto produce = [&]() {
-        if (pc.s >= nstrips) return;
+        if (pc.t >= ntiles) return;
         if (readc) {
-            const int sl = pq % kDsSlots;
+            const int sl = pq % SLOTS;
             mbar_expect_tx(&full[sl], kDsBlock * 8);
-            tma_load_3d(smem + SM::kC + sl * kDsBlock, &tmap, (pc.s % nrb) * kDsRows, pc.j * kDsCols, pc.s / nrb, &full[sl]);
+            tma_load_3d(smem + SM::kC + sl * kDsBlock, &tmap, pc.ib * kDsRows, pc.j * kDsCols, pc.t, &full[sl]);
         }
         ++pq;
         step(pc);
     };
     if (tid == 0) {
         enter(pc);
-        for (int a = 0; a < kDsAhead; ++a) produce();
+        for (int a = 0; a < AHEAD; ++a) produce();
     }
-    // ---- Y piece of a ring item: 32 columns x k, two 16-byte values per thread, staged one item ahead ------------------------
-    DenseCursor yc{(int)blockIdx.x, 0, 0, 0};
+    // ---- Y piece of a ring item: 32 columns x k, YPT 16-byte values per thread, fetched one item ahead -----------------------
+    DenseCursor yc = start();
     enter(yc);
-    double2 yv[2];
+    double2 yv[YPT];
     auto y_fetch = [&]() {
-        if (yc.s >= nstrips) return;
-        const double *Y = ar.Yop + (size_t)(yc.s / nrb) * ar.strideY + yc.j * kDsCols;
+        if (yc.t >= ntiles || yc.k <= 0) return;
+        const double *Y = ar.Yop + (size_t)yc.t * ar.strideY + yc.j * kDsCols;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < YPT; ++r) {
             // rows >= k are not staged (y_stage): read a valid row instead of selecting after the load, so that nothing
             // depends on the loaded value before the product has been issued
-            const int idx = tid + kDsThreads * r, kk = min(idx >> 4, yc.k > 0 ? yc.k - 1 : 0), cp = idx & 15;
-            if (yc.k > 0) yv[r] = __ldg(reinterpret_cast<const double2 *>(Y + (size_t)kk * ldy) + cp);
+            const int idx = tid + THREADS * r, kk = min(idx >> 4, yc.k - 1), cp = idx & 15;
+            yv[r] = __ldg(reinterpret_cast<const double2 *>(Y + (size_t)kk * ldy) + cp);
         }
     };
     auto y_stage = [&](int buf) {
-        if (yc.s >= nstrips) return;
-        double *Ys = smem + SM::kY + buf * kDsKmax * kDsLdY;
+        if (yc.t >= ntiles) return;
+        double *Ys = smem + SM::kY + buf * KMAX * kDsLdY;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int idx = tid + kDsThreads * r, kk = idx >> 4, cp = idx & 15;
+        for (int r = 0; r < YPT; ++r) {
+            const int idx = tid + THREADS * r, kk = idx >> 4, cp = idx & 15;
             if (kk < yc.k) *reinterpret_cast<double2 *>(Ys + kk * kDsLdY + 2 * cp) = yv[r];
         }
         step(yc);
@@ -498,64 +510,77 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_stream_kernel(DenseArgs a
     // ---- consumer ------------------------------------------------------------------------------------------------
     int cq = 0;
     PROF_DECL(tid == 0)
-    for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
-        const int t = s / nrb, ib = s % nrb, i0 = ib * kDsRows;
+    for (DenseCursor cc0 = start(); cc0.t < ntiles; advance(cc0)) {
+        const int t = cc0.t, ib = cc0.ib, i0 = ib * kDsRows;
         const int k = ar.Krk[t];
         const int nblk = (k < 0 || (k == 0 && ar.beta == 1.0 && !ar.syrk)) ? 0 : (ar.syrk ? min(ncb, 4 * (ib + 1)) : ncb);
         double *CDt = ar.CD + (size_t)t * ar.strideC;
         if (ar.syrk && k >= 0) {                    // strictly upper blocks of the strip: zero (reference hcore_dsyrk.c:174-181)
             const int jz = kDsRows * (ib + 1);      // first column that is above the diagonal for every row of the strip
-            for (long idx = tid; idx < (long)(kDsRows / 2) * (n - jz); idx += kDsThreads) {
+            for (long idx = tid; idx < (long)(kDsRows / 2) * (n - jz); idx += THREADS) {
                 const int rp = (int)(idx % (kDsRows / 2)), c = jz + (int)(idx / (kDsRows / 2));
                 *reinterpret_cast<double2 *>(CDt + i0 + 2 * rp + (size_t)c * ldc) = make_double2(0.0, 0.0);
             }
         }
         if (nblk == 0) continue;
         const int nks = (k + 3) >> 2;
-        // X fragments of the strip: row i0 + 8 warp + g, columns 4 ks + tg
-        double xr[kDsKmax / 4];
+        // X fragments of the strip: rows i0 + 8 (RT warp + rt) + g, columns 4 ks + tg
+        double xr[RT][KMAX / 4];
         {
-            const double *X = ar.Xop + (size_t)t * ar.strideX + i0 + 8 * warp + g;
+            const double *X = ar.Xop + (size_t)t * ar.strideX + i0 + 8 * RT * warp + g;
 #pragma unroll
-            for (int ks = 0; ks < kDsKmax / 4; ++ks) xr[ks] = (4 * ks + tg < k) ? __ldg(X + (size_t)(4 * ks + tg) * ar.ldx) : 0.0;
+            for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+                for (int ks = 0; ks < KMAX / 4; ++ks)
+                    xr[rt][ks] = (4 * ks + tg < k) ? __ldg(X + 8 * rt + (size_t)(4 * ks + tg) * ar.ldx) : 0.0;
         }
         for (int jb = 0; jb < nblk; ++jb, ++cq) {
-            const int sl = cq % kDsSlots, j0 = jb * kDsCols;
+            const int sl = cq % SLOTS, j0 = jb * kDsCols;
             double *Cs = smem + SM::kC + sl * kDsBlock;
-            const double *Ys = smem + SM::kY + (cq & 1) * kDsKmax * kDsLdY;
+            const double *Ys = smem + SM::kY + (NYB == 2 ? (cq & 1) : 0) * KMAX * kDsLdY;
             PROF_ADD(56);
             y_fetch();                              // Y piece of the next item: in flight during the product
-            double acc[4][2];
+            double acc[4][RT][2];
 #pragma unroll
-            for (int tt = 0; tt < 4; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
+            for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) acc[tt][rt][0] = acc[tt][rt][1] = 0.0;
             const double *ya = Ys + g + tg * kDsLdY;
             // a real (warp-uniform) exit, not predication: predicated-off DMMAs still occupy the FP64 pipe
 #pragma unroll
-            for (int ks = 0; ks < kDsKmax / 4; ++ks) {
+            for (int ks = 0; ks < KMAX / 4; ++ks) {
                 if (ks >= nks) break;
 #pragma unroll
-                for (int tt = 0; tt < 4; ++tt) dmma_884(acc[tt][0], acc[tt][1], ya[4 * ks * kDsLdY + 8 * tt], xr[ks]);
+                for (int tt = 0; tt < 4; ++tt) {
+                    const double a = ya[4 * ks * kDsLdY + 8 * tt];
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) dmma_884(acc[tt][rt][0], acc[tt][rt][1], a, xr[rt][ks]);
+                }
             }
             PROF_ADD(57);
-            if (readc) mbar_wait(&full[sl], (uint32_t)((cq / kDsSlots) & 1));
+            if (NYB == 1) __syncthreads();          // every warp has read the Y piece: the next one may replace it
+            if (readc) mbar_wait(&full[sl], (uint32_t)((cq / SLOTS) & 1));
             PROF_ADD(58);
             const double su = ar.su, beta = ar.beta;
             const bool diag = ar.syrk && j0 + kDsCols - 1 > i0;        // the block reaches above the diagonal
 #pragma unroll
             for (int tt = 0; tt < 4; ++tt) {
-                const int cc = 8 * tt + g, rr = 8 * warp + 2 * tg;
-                double2 *p = reinterpret_cast<double2 *>(Cs + rr + cc * kDsRows);
-                double2 v = readc ? *p : make_double2(0.0, 0.0);
-                v.x = fma(su, acc[tt][0], beta * v.x);
-                v.y = fma(su, acc[tt][1], beta * v.y);
-                if (diag) {
-                    if (j0 + cc > i0 + rr) v.x = 0.0;
-                    if (j0 + cc > i0 + rr + 1) v.y = 0.0;
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) {
+                    const int cc = 8 * tt + g, rr = 8 * (RT * warp + rt) + 2 * tg;
+                    double2 *p = reinterpret_cast<double2 *>(Cs + rr + cc * kDsRows);
+                    double2 v = readc ? *p : make_double2(0.0, 0.0);
+                    v.x = fma(su, acc[tt][rt][0], beta * v.x);
+                    v.y = fma(su, acc[tt][rt][1], beta * v.y);
+                    if (diag) {
+                        if (j0 + cc > i0 + rr) v.x = 0.0;
+                        if (j0 + cc > i0 + rr + 1) v.y = 0.0;
+                    }
+                    *p = v;
                 }
-                *p = v;
             }
             PROF_ADD(59);
-            y_stage((cq + 1) & 1);
+            y_stage(NYB == 2 ? ((cq + 1) & 1) : 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic accesses of this slot -> async proxy
             __syncthreads();
             PROF_ADD(60);
@@ -563,9 +588,9 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_stream_kernel(DenseArgs a
             if (tid == 0) {
                 tma_store_3d(&tmap, i0, j0, t, Cs);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // the slot refilled now is the one of item q + kDsAhead - kDsSlots: its store (all groups but the
-                // kDsSlots - kDsAhead most recent ones) must have finished reading shared memory
-                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kDsSlots - kDsAhead) : "memory");
+                // the slot refilled now is the one of item q + AHEAD - SLOTS: its store (all groups but the SLOTS - AHEAD
+                // most recent ones) must have finished reading shared memory
+                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SLOTS - AHEAD) : "memory");
                 PROF_ADD(61);
                 produce();
                 PROF_ADD(62);

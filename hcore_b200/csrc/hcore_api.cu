@@ -928,9 +928,14 @@ static bool dense_stream_ok(const DenseArgs &ar, int kcap) {
     return true;
 }
 static int dense_stream_launch(hcore_b200_context *ctx, const DenseArgs &ar, int cnt, cudaStream_t st) {
+    // two 256-thread CTAs per SM, three slots each, contraction lengths up to 32 (longer ones are bound by the FP64 pipe,
+    // not by HBM, and the one-CTA-per-SM shape that would hold their X fragments is slower than dense_update_kernel:
+    // 166 k vs 174 k calls/s for HCORE_duncompress at k = 64)
+    auto *k32 = dense_stream_kernel<256, kDsKmax, 3, 2, 1>;
+    constexpr size_t sm32 = DenseStreamSmem<256, kDsKmax, 3, 1>::kBytes;
     if (!ctx->attr_done[6]) {
         ctx->attr_done[6] = true;
-        CUDA_TRY(ctx, cudaFuncSetAttribute(dense_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DenseStreamSmem::kBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32));
     }
     // tensor map of the batch of dense tiles: rows x columns x tiles, FP64, 128 x 32 x 1 boxes
     alignas(64) CUtensorMap tmap;
@@ -942,8 +947,10 @@ static int dense_stream_launch(hcore_b200_context *ctx, const DenseArgs &ar, int
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return HCORE_B200_ERR_CUDA; }
     const long nstrips = (long)cnt * (ar.nb / kDsRows);
-    const int grid = (int)std::min<long>(nstrips, ctx->num_sms);
-    dense_stream_kernel<<<grid, kDsThreads, DenseStreamSmem::kBytes, st>>>(ar, cnt, tmap);
+    // an ODD number of CTAs: the strips of a CTA then cycle through all row blocks, which balances HCORE_dsyrk (the
+    // strip of row block i has 4 (i + 1) blocks to update)
+    const int grid = (int)std::min<long>(nstrips, 2l * ctx->num_sms - 1 + ((2 * ctx->num_sms) & 1));
+    k32<<<grid, 256, sm32, st>>>(ar, cnt, tmap);
     return HCORE_B200_OK;
 }
 

@@ -298,6 +298,54 @@ def test_dense_batched_ranks_above_128(ctx):
     assert np.array_equal(c1[1].cpu().numpy(), CD[1])
 
 
+@pytest.mark.parametrize("nb,T", [(128, 1), (384, 5), (1024, 4)])
+def test_dense_streaming_kernel_cases(ctx, nb, T):
+    """Whole 128 x 32 blocks, contraction lengths <= 32, aligned strided batches go through the persistent TMA
+    streaming kernel (dense_stream_kernel): varying ranks per tile, empty factors, the triangle rule of HCORE_dsyrk
+    (reference hcore_dsyrk.c:174-181) on every strip, a single tile, write-only uncompress with a flagged tile."""
+    k = 24
+    rng = np.random.default_rng(100 + nb)
+    f = lambda *s: rng.random(s) - 0.5
+    AU, AV, BU, BV, CD = f(T, k, nb), f(T, k, nb), f(T, k, nb), f(T, k, nb), f(T, nb, nb)
+    ark = np.array(([k, 7, 0, 24, 1] * 2)[:T], np.int32)
+    brk = np.array(([k, 0, 5, 13, 24] * 2)[:T], np.int32)
+    c1, c2 = dev(CD), dev(CD)
+    ctx.dgemmcd_batched(dev(AU), dev(AV), dev(ark), dev(BU), dev(BV), dev(brk), c1)
+    ctx.dsyrk_batched(0.75, dev(AU), dev(AV), dev(ark), c2)
+    torch.cuda.synchronize()
+    for i in range(T):
+        a, b = int(ark[i]), int(brk[i])
+        out = c1[i].cpu().numpy().T
+        if a == 0 or b == 0:
+            assert np.array_equal(out, CD[i].T)                         # nothing to add: the tile is not touched
+        else:
+            ref = orc.gemmcd(AU[i, :a].T, AV[i, :a].T, BU[i, :b].T, BV[i, :b].T, CD[i].T)
+            assert np.abs(out - ref).max() <= 1000 * EPS * max(1.0, np.abs(ref).max())
+        out = c2[i].cpu().numpy().T
+        if a > 0:
+            ref = orc.syrk(AU[i, :a].T, AV[i, :a].T, CD[i].T, 0.75)
+            assert np.abs(out - ref).max() <= 1000 * EPS * max(1.0, np.abs(ref).max())
+            assert np.abs(np.triu(out, 1)).max() == 0.0
+    # write-only form (beta = 0: no tensor loads): CD = AU BV^T, one tile with mismatched ranks, one with rank 0
+    M, N = nb, max(128, nb // 2)
+    AUm, BVm = f(T, k, M), f(T, k, N)
+    ra = np.array(([k, 3, 0, 9, 24] * 2)[:T], np.int32)
+    rb = ra.copy()
+    if T > 3:
+        rb[3] = 10
+    ct, st = dev(np.full((T, N, M), 5.0)), torch.full((T,), -9, dtype=torch.int32, device="cuda:0")
+    ctx.uncompress_batched(dev(AUm), dev(ra), dev(BVm), dev(rb), ct, status=st)
+    torch.cuda.synchronize()
+    out = ct.cpu().numpy()
+    for i in range(T):
+        if ra[i] != rb[i]:
+            assert int(st[i].item()) == 6 and (out[i] == 5.0).all()
+        else:
+            r = int(ra[i])
+            ref = orc.uncompress(AUm[i, :r].T, BVm[i, :r].T) if r > 0 else np.zeros((M, N))
+            assert int(st[i].item()) == 0 and np.abs(out[i].T - ref).max() <= 256 * EPS * max(1.0, np.abs(ref).max())
+
+
 # ---- pointer-array forms (SURVEY.md 8(b): HCORE_{d,s,z}gemm_batched, HCORE_dgemmcd_batched, HCORE_dsyrk_batched) -----------
 
 def _ptr_table(tensors):
