@@ -313,13 +313,12 @@ __global__ void __launch_bounds__(256, 2) dense_update_kernel(DenseArgs ar) {
         const double *ba = Bs + g + tg * kDuLdB;
 #pragma unroll
         for (int ks = 0; ks < kDuKc / 4; ++ks) {
-            if (4 * ks < kc) {
+            if (4 * ks >= kc) break;       // a real exit: predicated-off DMMAs still occupy the FP64 pipe
 #pragma unroll
-                for (int tt = 0; tt < 8; ++tt) {
-                    const double bv = ba[4 * ks * kDuLdB + 8 * tt];
-                    dmma_884(acc[tt][0][0], acc[tt][0][1], bv, xa[ks]);
-                    dmma_884(acc[tt][1][0], acc[tt][1][1], bv, xb[ks]);
-                }
+            for (int tt = 0; tt < 8; ++tt) {
+                const double bv = ba[4 * ks * kDuLdB + 8 * tt];
+                dmma_884(acc[tt][0][0], acc[tt][0][1], bv, xa[ks]);
+                dmma_884(acc[tt][1][0], acc[tt][1][1], bv, xb[ks]);
             }
         }
     }

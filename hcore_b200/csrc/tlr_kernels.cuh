@@ -338,11 +338,10 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
-            if (8 * j < n16) {
-                const double2 v = *reinterpret_cast<const double2 *>(gc + 8 * j);
-                dmma_884(ax[j & 3], ay[j & 3], v.x, v.x);
-                dmma_884(ax[j & 3], ay[j & 3], v.y, v.y);
-            }
+            if (8 * j >= n16) break;       // a real (warp-uniform) exit: predicated-off DMMAs still occupy the FP64 pipe
+            const double2 v = *reinterpret_cast<const double2 *>(gc + 8 * j);
+            dmma_884(ax[j & 3], ay[j & 3], v.x, v.x);
+            dmma_884(ax[j & 3], ay[j & 3], v.y, v.y);
         }
         gx = (ax[0] + ax[1]) + (ax[2] + ax[3]);
         gy = (ay[0] + ay[1]) + (ay[2] + ay[3]);
@@ -426,17 +425,16 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         double *cq = L + (size_t)(4 * q + mu) * LDL + 2 * g;
 #pragma unroll
         for (int e = 0; e < RB / 2; ++e) {
-            if (16 * e < n16) {
-                const double2 vp = *reinterpret_cast<const double2 *>(cp + 16 * e);
-                const double2 vq = *reinterpret_cast<const double2 *>(cq + 16 * e);
-                double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
-                dmma_884(d0x, d0y, vp.x, bj[0]);
-                dmma_884(d0x, d0y, vq.x, bj[1]);
-                dmma_884(d1x, d1y, vp.y, bj[0]);
-                dmma_884(d1x, d1y, vq.y, bj[1]);
-                *reinterpret_cast<double2 *>(cp + 16 * e) = make_double2(d0x, d1x);
-                *reinterpret_cast<double2 *>(cq + 16 * e) = make_double2(d0y, d1y);
-            }
+            if (16 * e >= n16) break;
+            const double2 vp = *reinterpret_cast<const double2 *>(cp + 16 * e);
+            const double2 vq = *reinterpret_cast<const double2 *>(cq + 16 * e);
+            double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
+            dmma_884(d0x, d0y, vp.x, bj[0]);
+            dmma_884(d0x, d0y, vq.x, bj[1]);
+            dmma_884(d1x, d1y, vp.y, bj[0]);
+            dmma_884(d1x, d1y, vq.y, bj[1]);
+            *reinterpret_cast<double2 *>(cp + 16 * e) = make_double2(d0x, d1x);
+            *reinterpret_cast<double2 *>(cq + 16 * e) = make_double2(d0y, d1y);
         }
     }
 }

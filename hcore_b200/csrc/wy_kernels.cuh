@@ -287,10 +287,9 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                             const double av = As[(k + tg) + (i0 + g) * kPgLd];
 #pragma unroll
                             for (int q = 0; q < KC / 8; ++q) {
-                                if (8 * q < bs8) {
-                                    const double bv = Bs[(k + tg) + (8 * q + g) * kPgLd];
-                                    dmma_884(acc[q][0], acc[q][1], av, bv);
-                                }
+                                if (8 * q >= bs8) break;   // a real exit: predicated-off DMMAs still occupy the FP64 pipe
+                                const double bv = Bs[(k + tg) + (8 * q + g) * kPgLd];
+                                dmma_884(acc[q][0], acc[q][1], av, bv);
                             }
                         }
                     }
@@ -331,10 +330,9 @@ __device__ __forceinline__ void pg_body(double *smem, const double *AV, const do
                         const double av = cur[(8 * strip + g) + (k + tg) * kPgLd];
 #pragma unroll
                         for (int q = 0; q < QW; ++q) {
-                            if (8 * (q0 + q) < as8) {
-                                const double bv = P[(8 * (q0 + q) + g) + (k + tg) * kPgLdP];
-                                dmma_884(acc[q][0], acc[q][1], av, bv);
-                            }
+                            if (8 * (q0 + q) >= as8) break;
+                            const double bv = P[(8 * (q0 + q) + g) + (k + tg) * kPgLdP];
+                            dmma_884(acc[q][0], acc[q][1], av, bv);
                         }
                     }
                     const int row = ch * kPgRows + 8 * strip + g;
@@ -474,11 +472,10 @@ __global__ void __launch_bounds__(256, 1) tlr_gdense_kernel(TlrArgs ar, TlrWorks
             const double b0 = bp[k * SM::kLdB], b1 = bp[k * SM::kLdB + 8];
 #pragma unroll
             for (int tt = 0; tt < CT; ++tt) {
-                if (8 * (ct0 + tt) < a8) {
-                    const double av = ap[k + 8 * (ct0 + tt) * SM::kLdA];
-                    dmma_884(acc[0][tt][0], acc[0][tt][1], b0, av);
-                    dmma_884(acc[1][tt][0], acc[1][tt][1], b1, av);
-                }
+                if (8 * (ct0 + tt) >= a8) break;
+                const double av = ap[k + 8 * (ct0 + tt) * SM::kLdA];
+                dmma_884(acc[0][tt][0], acc[0][tt][1], b0, av);
+                dmma_884(acc[1][tt][0], acc[1][tt][1], b1, av);
             }
         }
         __syncthreads();
