@@ -101,7 +101,7 @@ struct GuardedView {
     }
 };
 
-template <int NT, GemmMode MODE, typename AView, typename BView, typename KLim = FullK>
+template <int NT, GemmMode MODE, int UNR = 4, typename AView, typename BView, typename KLim = FullK>
 __device__ __forceinline__ void block_gemm(MatView C, AView A, BView B, int M, int N, int K,
                                            int warp, int nwarps, KLim klim = KLim()) {
     const int lane = lane_id();
@@ -117,7 +117,8 @@ __device__ __forceinline__ void block_gemm(MatView C, AView A, BView B, int M, i
         for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
         int kb = 0, ke = K;
         klim(i0, jt0 << 3, kb, ke);
-#pragma unroll 4
+        // UNR contraction steps of operand loads in flight (operands in global memory / L2: the loop is latency-bound)
+#pragma unroll UNR
         for (int k = kb; k < ke; k += 4) {
             const double a = A.at(i0 + g, k + tg);
 #pragma unroll

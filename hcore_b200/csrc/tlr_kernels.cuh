@@ -14,6 +14,13 @@
 
 namespace hcore_b200 {
 
+#ifndef HCORE_SVD_NT
+#define HCORE_SVD_NT 4
+#endif
+#ifndef HCORE_SVD_UNR
+#define HCORE_SVD_UNR 4
+#endif
+
 template <int N>
 struct Geometry {
     static constexpr int kLdL = N + 4;            // leading dim of the N x N core matrix
@@ -474,7 +481,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     PROF_DECL(tid == 0)
     PROF_COUNT(29, 1);
     // ---- T' = R_v * R_u^T --------------------------------------------------------------
-    block_gemm<2, kGemmSet>(mview(L, 1, LDL), cview(Rv, 1, N), cview(Ru, N, 1), n16, n16, n16, warp, nwarps,
+    block_gemm<HCORE_SVD_NT, kGemmSet, HCORE_SVD_UNR>(mview(L, 1, LDL), cview(Rv, 1, N), cview(Ru, N, 1), n16, n16, n16, warp, nwarps,
                             UpperTimesUpperT());
     if (tid < n16) perm[tid] = tid;
     __syncthreads();
@@ -864,10 +871,10 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     PROF_ADD(16);
 
     // ---- W = R_v * (R_u^T * U_r) -> Yv ----------------------------------------------------------
-    block_gemm<2, kGemmSet>(mview(L, 1, LDL), cview(Ru, N, 1), cview(Yu, 1, N), n16, r8, n16, warp, nwarps,
+    block_gemm<HCORE_SVD_NT, kGemmSet, HCORE_SVD_UNR>(mview(L, 1, LDL), cview(Ru, N, 1), cview(Yu, 1, N), n16, r8, n16, warp, nwarps,
                             UpperTransK{n16});
     __syncthreads();
-    block_gemm<2, kGemmSet>(mview(Yv, 1, N), cview(Rv, 1, N), cview(L, 1, LDL), n16, r8, n16, warp, nwarps,
+    block_gemm<HCORE_SVD_NT, kGemmSet, HCORE_SVD_UNR>(mview(Yv, 1, N), cview(Rv, 1, N), cview(L, 1, LDL), n16, r8, n16, warp, nwarps,
                             UpperK());
     PROF_ADD(17);
 }
