@@ -353,6 +353,18 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         gx = (ax[0] + ax[1]) + (ax[2] + ax[3]);
         gy = (ay[0] + ay[1]) + (ay[2] + ay[3]);
     }
+    // ---- nothing to rotate?  In the last sweeps most pairs (in the final, checking sweep: all of them) have every
+    // cosine below the rotation threshold: all rounds would produce the identity, G would stay as it is and X J = X
+    // exactly, so the step ends here -- bit-identical to going through the motions, at a third of the cost.
+    {
+        const double dsel = (g & 1) ? gy : gx;         // lane (g, g / 2) holds G(g, g) here
+        const double dg = __shfl_sync(kFull, dsel, 4 * g + (g >> 1));
+        const double d0 = __shfl_sync(kFull, gx, 9 * t), d1 = __shfl_sync(kFull, gy, 9 * t + 4);   // G(2t, 2t), G(2t+1, 2t+1)
+        const bool rel0 = inblock ? (g != 2 * t) : ((g < 4) != (t < 2));       // entries some round looks at
+        const bool rel1 = inblock ? (g != 2 * t + 1) : ((g < 4) != (t < 2));
+        const bool any = (rel0 && gx * gx > (kTolRot * kTolRot) * (dg * d0)) || (rel1 && gy * gy > (kTolRot * kTolRot) * (dg * d1));
+        if (!__any_sync(kFull, any)) return;
+    }
     // ---- 2. rotations ----------------------------------------------------------------------------------------
     double jx = 0.0, jy = 0.0;                         // accumulated J(g, 2t), J(g, 2t + 1)
     bool first = true;
