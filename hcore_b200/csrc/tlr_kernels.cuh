@@ -320,9 +320,9 @@ __device__ __forceinline__ double rsqrt_seed(double w) {
 //      operand (lane (g, t) holds rows 2t, 2t+1 of column g of the 8-row slice);
 //   2. the cross rotations of the pair (4 rounds of 4 disjoint rotations; in the first step of a sweep also the
 //      3 rounds of in-block rotations) are derived from G ALONE: each rotation is computed redundantly by the lanes
-//      of its two rows, G <- J_r^T G J_r and J <- J J_r are 2 DMMAs each with G, K = J_r^T G and J kept in
-//      accumulator-fragment layout (an accumulator fragment is the A operand of the next product, and -- G being
-//      symmetric -- also its B operand), so a round needs three shuffles (two diagonal entries, one off-diagonal);
+//      of its two rows; G and J stay in accumulator-fragment layout (an accumulator fragment is the A operand of the
+//      next product): G J_r and J J_r are two DMMAs each, the row mix J_r^T (G J_r) one shuffle per entry (the lane of
+//      the partner row), so a round needs five shuffles;
 //   3. X <- X J: 4 DMMAs per 16 rows, in place.
 // Compared with rotating the columns one pair at a time this trades the shuffle reductions, the scalar updates and
 // three quarters of the barriers for DMMAs.  Column index inside the solver: m = 0..3 -> column mu4(m) of block p,
@@ -400,12 +400,14 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         const double j0 = (2 * t == g) ? cs : ((2 * t == pg) ? sg : 0.0);          // J_r(2t, g)
         const double j1 = (2 * t + 1 == g) ? cs : ((2 * t + 1 == pg) ? sg : 0.0);  // J_r(2t + 1, g)
         if (!last) {
-            double kx = 0.0, ky = 0.0, nx = 0.0, ny = 0.0;
-            dmma_884(kx, ky, j0, gx);                  // K = J_r^T G   (B operand: G(2t + s, g) = G(g, 2t + s))
-            dmma_884(kx, ky, j1, gy);
-            dmma_884(nx, ny, kx, j0);                  // G' = K J_r
-            dmma_884(nx, ny, ky, j1);
-            gx = nx; gy = ny;
+            // G' = J_r^T (G J_r): the column mix M = G J_r by two DMMAs (G as A operand), the row mix
+            // G'(i, j) = cs_i M(i, j) + sg_i M(P(i), j) with this lane's own rotation and the partner row's lane (pg, t)
+            double mx = 0.0, my = 0.0;
+            dmma_884(mx, my, gx, j0);
+            dmma_884(mx, my, gy, j1);
+            const double px = __shfl_sync(kFull, mx, 4 * pg + t), py = __shfl_sync(kFull, my, 4 * pg + t);
+            gx = fma(sg, px, cs * mx);
+            gy = fma(sg, py, cs * my);
         }
         if (first) {                                   // J = J_r: row g of J_r is cs at column g and -sg at column pg
             jx = (2 * t == g) ? cs : ((2 * t == pg) ? -sg : 0.0);
