@@ -314,6 +314,44 @@ __device__ __forceinline__ double rsqrt_seed(double w) {
     return y;
 }
 
+// Two-warp named barrier k + 1 (k = 0 .. 7) with a literal id (ptxas reserves highest id + 1 barriers per CTA):
+// ARRIVE = true signals without waiting, false waits for the partner's signal.
+template <bool ARRIVE>
+__device__ __forceinline__ void pair_barrier(int k) {
+#define HCORE_PAIR_CASE(i) case i: if (ARRIVE) asm volatile("bar.arrive " #i " + 1, 64;" ::: "memory"); else asm volatile("bar.sync " #i " + 1, 64;" ::: "memory"); break;
+    switch (k) {
+        HCORE_PAIR_CASE(0) HCORE_PAIR_CASE(1) HCORE_PAIR_CASE(2) HCORE_PAIR_CASE(3)
+        HCORE_PAIR_CASE(4) HCORE_PAIR_CASE(5) HCORE_PAIR_CASE(6) HCORE_PAIR_CASE(7)
+        default: break;
+    }
+#undef HCORE_PAIR_CASE
+}
+
+// X <- X J for the eight columns of blocks p, q (in place): b0 / b1 = B operands J(t, n(g)), J(4 + t, n(g)) with
+// n(g) = 4 (g & 1) + g / 2, so that accumulator column 2t + s is solver column 4 s + t and the results land exactly
+// where the A operands came from.  4 DMMAs per 16 rows.
+template <int N>
+__device__ __forceinline__ void jacobi_pair_apply(double *L, int n16, int p, int q, double b0, double b1, int lane) {
+    constexpr int LDL = N + 4, RB = N / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const int mu = ((t & 1) << 1) | (t >> 1);
+    double *cp = L + (size_t)(4 * p + mu) * LDL + 2 * g;
+    double *cq = L + (size_t)(4 * q + mu) * LDL + 2 * g;
+#pragma unroll
+    for (int e = 0; e < RB / 2; ++e) {
+        if (16 * e >= n16) break;          // a real (warp-uniform) exit: predicated-off DMMAs still occupy the FP64 pipe
+        const double2 vp = *reinterpret_cast<const double2 *>(cp + 16 * e);
+        const double2 vq = *reinterpret_cast<const double2 *>(cq + 16 * e);
+        double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
+        dmma_884(d0x, d0y, vp.x, b0);
+        dmma_884(d0x, d0y, vq.x, b1);
+        dmma_884(d1x, d1y, vp.y, b0);
+        dmma_884(d1x, d1y, vq.y, b1);
+        *reinterpret_cast<double2 *>(cp + 16 * e) = make_double2(d0x, d1x);
+        *reinterpret_cast<double2 *>(cq + 16 * e) = make_double2(d0y, d1y);
+    }
+}
+
 // ---- one-sided BLOCK Jacobi step on a pair of 4-column blocks, everything GEMM-shaped on the FP64 tensor pipe ----
 // One warp owns the pair (blocks p, q of the column-major core matrix L, n16 rows):
 //   1. G = X^T X (8 x 8 Gram matrix of the pair's eight columns): 2 DMMAs per 8 rows, the same register is A and B
@@ -333,7 +371,8 @@ __device__ __forceinline__ double rsqrt_seed(double w) {
 // scaled accuracy unless a rotation cancels a column almost completely, which only costs an inexact ANGLE in the
 // remaining rounds of the step (J is a product of plane rotations whatever the angles: orthogonal to rounding).
 template <int N>
-__device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int q, bool inblock, int lane, int &big) {
+__device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int q, bool inblock, int lane, int &big,
+                                                 double *jb, int jbar) {
     constexpr int LDL = N + 4, RB = N / 8;
     constexpr unsigned kFull = 0xffffffffu;
     const int g = lane >> 2, t = lane & 3;
@@ -363,7 +402,13 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         const bool rel0 = inblock ? (g != 2 * t) : ((g < 4) != (t < 2));       // entries some round looks at
         const bool rel1 = inblock ? (g != 2 * t + 1) : ((g < 4) != (t < 2));
         const bool any = (rel0 && gx * gx > (kTolRot * kTolRot) * (dg * d0)) || (rel1 && gy * gy > (kTolRot * kTolRot) * (dg * d1));
-        if (!__any_sync(kFull, any)) return;
+        if (!__any_sync(kFull, any)) {
+            if (jb) {
+                if (lane == 0) jb[64] = 0.0;
+                pair_barrier<true>(jbar);
+            }
+            return;
+        }
     }
     // ---- 2. rotations ----------------------------------------------------------------------------------------
     double jx = 0.0, jy = 0.0;                         // accumulated J(g, 2t), J(g, 2t + 1)
@@ -440,24 +485,14 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
             bj[h] = odd ? vy : vx;
         }
     }
-    {
-        const int mu = ((t & 1) << 1) | (t >> 1);
-        double *cp = L + (size_t)(4 * p + mu) * LDL + 2 * g;
-        double *cq = L + (size_t)(4 * q + mu) * LDL + 2 * g;
-#pragma unroll
-        for (int e = 0; e < RB / 2; ++e) {
-            if (16 * e >= n16) break;
-            const double2 vp = *reinterpret_cast<const double2 *>(cp + 16 * e);
-            const double2 vq = *reinterpret_cast<const double2 *>(cq + 16 * e);
-            double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
-            dmma_884(d0x, d0y, vp.x, bj[0]);
-            dmma_884(d0x, d0y, vq.x, bj[1]);
-            dmma_884(d1x, d1y, vp.y, bj[0]);
-            dmma_884(d1x, d1y, vq.y, bj[1]);
-            *reinterpret_cast<double2 *>(cp + 16 * e) = make_double2(d0x, d1x);
-            *reinterpret_cast<double2 *>(cq + 16 * e) = make_double2(d0y, d1y);
-        }
+    if (jb) {                                          // a helper warp on a less loaded scheduler applies J (see the kernel)
+        jb[lane] = bj[0];
+        jb[32 + lane] = bj[1];
+        if (lane == 0) jb[64] = 1.0;
+        pair_barrier<true>(jbar);
+        return;
     }
+    jacobi_pair_apply<N>(L, n16, p, q, bj[0], bj[1], lane);
 }
 
 // One CTA per tile.  Threads = 4 N (one 16-lane group per Jacobi block pair), capped at 512: the narrow stacks
@@ -680,13 +715,40 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     const int kq8 = (kq + 7) & ~7;                    // columns kq .. kq8-1 of L are zero
     const int nb4 = kq8 >> 2, npair = nb4 >> 1;       // blocks (even), block pairs per step (<= number of warps)
     converged = (kq8 < 8);
+    // Helpers (one 512-thread CTA per SM).  Warp w runs on scheduler w % 4, so with npair pairs the first npair % 4
+    // schedulers carry one pair more than the others, and every step would wait for them while the idle warps
+    // npair .. 15 sit on the lighter schedulers.  Idle warp npair + i therefore takes over the update phase X <- X J of
+    // pair own(i) = (i % r) + 4 (i / r), r = npair % 4 (the pairs of the overloaded schedulers, in turn): the owner
+    // hands J over through shared memory and a two-warp named barrier and is done after its rotations.
+    constexpr bool kHelp = (N == 128);
+    constexpr int kJbLd = 72, kMaxHelp = 5;            // per helper: 64 operand values + flag; vvec | sig | ssort hold 5 x 72
+    int help_own = -1, help_idx = -1;                  // helper warp: the pair it helps / owner warp: its helper's index
+    if constexpr (kHelp) {
+        const int r = npair & 3, nidle = nwarps - npair;
+        if (r != 0) {
+            const int nh = nidle < kMaxHelp ? nidle : kMaxHelp;
+            if (warp >= npair && warp - npair < nh) {
+                const int i = warp - npair, o = (i % r) + 4 * (i / r);
+                if (o < npair) { help_own = o; help_idx = i; }
+            } else if (warp < npair && (warp & 3) < r) {
+                const int i = (warp & 3) + r * (warp >> 2);      // inverse of own(i)
+                if (i < nh) help_idx = i;
+            }
+        }
+    }
     for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
         int big = 0;
         for (int step = 0; step < nb4 - 1; ++step) {
             if (warp < npair) {
                 int p, qq;
                 rr_pair(nb4, step, warp, p, qq);
-                jacobi_pair_step<N>(L, n16, p, qq, step == 0, lane, big);
+                jacobi_pair_step<N>(L, n16, p, qq, step == 0, lane, big, help_idx >= 0 ? vvec + kJbLd * help_idx : nullptr, help_idx);
+            } else if (help_own >= 0) {
+                int p, qq;
+                rr_pair(nb4, step, help_own, p, qq);
+                const double *jb = vvec + kJbLd * help_idx;
+                pair_barrier<false>(help_idx);
+                if (jb[64] != 0.0) jacobi_pair_apply<N>(L, n16, p, qq, jb[lane], jb[32 + lane], lane);
             }
             __syncthreads();
         }
