@@ -177,6 +177,28 @@ __device__ __forceinline__ Householder make_householder(double alpha, double sig
     return h;
 }
 
+// make_householder without library calls: rsqrt() and __drcp_rn() carry out-of-line slow paths, and a call inside the
+// step body makes ptxas spill the register-resident column around it.  Hardware seeds (~2^-22) + two Newton steps:
+// a few ulps, arguments are positive and normal here (sigma2 > 0).
+__device__ __forceinline__ Householder make_householder_inline(double alpha, double sigma2) {
+    Householder h;
+    const double s2 = fma(alpha, alpha, sigma2);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s2));
+    y = fma(0.5 * y, fma(-s2 * y, y, 1.0), y);
+    y = fma(0.5 * y, fma(-s2 * y, y, 1.0), y);
+    const double nrm = s2 * y, aabs = fabs(alpha), den = aabs + nrm;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const bool nz = sigma2 != 0.0;
+    h.beta = nz ? -copysign(nrm, alpha) : alpha;
+    h.tau = nz ? fma(aabs, y, 1.0) : 0.0;
+    h.scal = nz ? copysign(r, alpha) : 0.0;
+    return h;
+}
+
 // Named barrier for a subset of the CTA's warps (ids 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

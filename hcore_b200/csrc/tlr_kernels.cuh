@@ -78,28 +78,6 @@ struct SvdSmem {
 //   matrix is in registers.
 // The step body is instantiated per 8-row block E = i / 8, so the rows already factored cost nothing and every
 // register index is static.  Sums over the four lanes of a column are one DMMA (B = ones), warp totals two.
-// make_householder without library calls: rsqrt() and __drcp_rn() carry out-of-line slow paths, and a call inside the
-// step body makes ptxas spill the register-resident column around it.  Hardware seeds (~2^-22) + two Newton steps:
-// a few ulps, arguments are positive and normal here (sigma2 > 0).
-__device__ __forceinline__ Householder make_householder_inline(double alpha, double sigma2) {
-    Householder h;
-    const double s2 = fma(alpha, alpha, sigma2);
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s2));
-    y = fma(0.5 * y, fma(-s2 * y, y, 1.0), y);
-    y = fma(0.5 * y, fma(-s2 * y, y, 1.0), y);
-    const double nrm = s2 * y, aabs = fabs(alpha), den = aabs + nrm;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-    r = fma(r, fma(-den, r, 1.0), r);
-    r = fma(r, fma(-den, r, 1.0), r);
-    const bool nz = sigma2 != 0.0;
-    h.beta = nz ? -copysign(nrm, alpha) : alpha;
-    h.tau = nz ? fma(aabs, y, 1.0) : 0.0;
-    h.scal = nz ? copysign(r, alpha) : 0.0;
-    return h;
-}
-
 template <int N>
 struct QrcpScratch {                          // offsets (doubles) inside the L area
     static constexpr int NW = N / 8;
