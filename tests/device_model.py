@@ -4,8 +4,9 @@ The CUDA pipeline in ``hcore_b200/csrc`` does not call LAPACK; it uses
   1. a flat-tree tall-skinny Householder QR (first row block: plain blocked
      Householder; every further row block: triangular-on-top-of-dense "TPQRT" step
      against the running R), column sub-panels of width W with compact-WY T factors,
-  2. a one-sided Jacobi SVD of ``T = R_u R_v^T`` (columns), sorted, truncated with the
-     reference's rule, ``W = T^T U_r`` instead of accumulating V,
+  2. a pivoted, truncated Householder QR of the core ``T' = R_v R_u^T`` and a one-sided BLOCK Jacobi SVD of its
+     ``R^T`` (4-column blocks, rotations derived from the 8 x 8 Gram matrix of a block pair), sorted, truncated with
+     the reference's rule, ``W = T' U_r`` instead of accumulating V,
   3. application of the stored block reflectors to ``[Y; 0]``.
 This file restates exactly that arithmetic in numpy so that (a) the math can be
 validated against the oracle on the CPU, and (b) per-stage device dumps can be
@@ -178,31 +179,29 @@ def tsqr_apply(f, y):
 
 
 def qrcp(a, tol2=0.0):
-    """Householder QR with column pivoting on squared partial column norms that are
-    down-dated and recomputed exactly every 8th step (no LAPACK-style safeguard: the
-    permutation only has to be a good *preconditioner* for the Jacobi sweeps, any
-    permutation is backward stable).  The factorisation is TRUNCATED: at a step ``i`` that is
-    a multiple of 8 (exact norms) it stops when ``max_norm2 * (n - i) < tol2``, i.e. when the
-    Frobenius norm of the remaining block is below ``sqrt(tol2)``; the remaining block is
-    dropped.  Returns (R of shape (kq, n) upper trapezoidal, perm, kq) with
-    ``a[:, perm] = Q R + O(sqrt(tol2))``."""
+    """Householder QR with column pivoting as the device runs it (``qrcp_registers`` in tlr_kernels.cuh): the squared
+    norms of the remaining columns (rows >= i) are recomputed EXACTLY in every step, the pivot is the largest one
+    (ties: the smaller original column), and the factorisation is TRUNCATED at the first step whose remaining block
+    has a squared Frobenius norm -- the sum of those norms -- below ``tol2``; the remaining block is dropped.  Any
+    permutation is backward stable: it only has to be a good *preconditioner* for the Jacobi sweeps.  The device never
+    moves columns (a pivot only marks its column) and numbers the columns that were never selected in column order;
+    this model swaps, which only orders the dropped-block columns differently.
+    Returns (R of shape (kq, n) upper trapezoidal, perm, kq) with ``a[:, perm] = Q R + O(sqrt(tol2))``."""
     a = np.array(a, dtype=np.float64, copy=True)
     n = a.shape[1]
     perm = np.arange(n)
-    vn = np.sum(a * a, axis=0)
     kq = n
     for i in range(n):
-        if i % 8 == 0:
-            if i > 0:
-                vn[i:] = np.sum(a[i:, i:] ** 2, axis=0)
-            if vn[i:].max() * (n - i) < tol2:
-                kq = i
-                break
-        p = i + int(np.argmax(vn[i:]))
+        vn = np.sum(a[i:, i:] ** 2, axis=0)
+        if vn.sum() < tol2:
+            kq = i
+            break
+        best = vn.max()
+        cand = [j for j in range(n - i) if vn[j] == best]
+        p = i + min(cand, key=lambda j: perm[i + j])
         if p != i:
             a[:, [i, p]] = a[:, [p, i]]
             perm[[i, p]] = perm[[p, i]]
-            vn[[i, p]] = vn[[p, i]]
         x = a[i:, i]
         beta, tau, scal = _house(x[0], float(x[1:] @ x[1:]))
         if tau != 0.0:
@@ -211,7 +210,6 @@ def qrcp(a, tol2=0.0):
             a[i:, i + 1:] -= np.outer(v, wv)
         a[i, i] = beta
         a[i + 1:, i] = 0.0
-        vn[i + 1:] = np.maximum(vn[i + 1:] - a[i, i + 1:] ** 2, 0.0)
     return np.triu(a)[:kq], perm, kq
 
 
