@@ -86,15 +86,36 @@ __global__ void __launch_bounds__(256) dense_bdtav_kernel(BdtAvArgs ar) {
         double acc[8][2];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-        for (int k = 0; k < ar.mc; k += 4) {
+        // whole 32-deep contraction chunks: the eight BD loads of a chunk are in flight together (BD is streamed from HBM
+        // exactly once), AV fragments come out of L1 / L2; columns >= a of Y are never stored, so their AV operand is read
+        // from a clamped (valid) column instead of being masked
+        const double *avp[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int col = q0 + 8 * q + g;
+            avp[q] = AV + (size_t)(col < a ? col : a - 1) * ar.lda + tg;
+        }
+        int k = 0;
+        for (; k + 32 <= ar.mc; k += 32) {
+            double bv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bv[u] = ron ? __ldg(bp + k + 4 * u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q0 + 8 * q >= a) break;        // a real exit: predicated-off DMMAs still occupy the FP64 pipe
+                    dmma_884(acc[q][0], acc[q][1], bv[u], __ldg(avp[q] + k + 4 * u));
+                }
+            }
+        }
+        for (; k < ar.mc; k += 4) {
             const double bv = (ron && k + tg < ar.mc) ? __ldg(bp + k) : 0.0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int col = q0 + 8 * q + g;
-                if (q0 + 8 * q < a) {
-                    const double av = (col < a && k + tg < ar.mc) ? __ldg(AV + (size_t)col * ar.lda + k + tg) : 0.0;
-                    dmma_884(acc[q][0], acc[q][1], bv, av);
-                }
+                if (q0 + 8 * q >= a) break;
+                const double av = (k + tg < ar.mc) ? __ldg(avp[q] + k) : 0.0;
+                dmma_884(acc[q][0], acc[q][1], bv, av);
             }
         }
 #pragma unroll
