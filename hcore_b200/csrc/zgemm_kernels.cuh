@@ -8,8 +8,8 @@
 //                      hcore_zgemm.c:65-137, :138-215; PLAIN transposes, :165, :189)
 //   ztlr_qr_kernel     unblocked Householder QR (zgeqr2 semantics: zlarfg, H^H applied) of both panels
 //                      (replaces LAPACKE_zgeqrf, hcore_zgemm.c:123, :205)
-//   ztlr_svd_kernel    T = R_u R_v^T (plain transpose, :309), one-sided Jacobi on its columns with
-//                      complex rotations, sort, truncation (rk > 0 = fixed rank, :376), U_r,
+//   ztlr_svd_kernel    T = R_u R_v^T (plain transpose, :309), truncated pivoted QR of T^H as preconditioner, one-sided
+//                      Jacobi on the columns of R^H with complex rotations, sort, truncation (rk > 0 = fixed rank, :376), U_r,
 //                      W = R_v (R_u^T conj(U_r))  (replaces LAPACKE_zgesvd + the conj/zunmqr/conj dance
 //                      of __znewv, :593-632: CV = Q_v W)
 //   ztlr_apply_kernel  CU = Q_u [U_r; 0], CV = Q_v [W; 0] by applying the reflectors to one output
@@ -341,8 +341,9 @@ constexpr int kZMaxSweeps = 60;
 // 128, 256 threads so that the two columns of a pair -- 64 doubles per lane -- stay in registers)
 template <int RPL>
 __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar, ZWorkspace ws) {
-    __shared__ double sig[HCORE_B200_MAX_STACK_Z], ssort[HCORE_B200_MAX_STACK_Z];
-    __shared__ int posof[HCORE_B200_MAX_STACK_Z], misc[4];
+    __shared__ double sig[HCORE_B200_MAX_STACK_Z], ssort[HCORE_B200_MAX_STACK_Z], vn[HCORE_B200_MAX_STACK_Z], red[40];
+    __shared__ zc vref[HCORE_B200_MAX_STACK_Z];
+    __shared__ int posof[HCORE_B200_MAX_STACK_Z], perm[HCORE_B200_MAX_STACK_Z], misc[4];
     const int t = blockIdx.x;
     if (ws.st[t] != HCORE_B200_OK) return;
     const int gt = ar.tile0 + t;
@@ -352,29 +353,125 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
     zc *T = ws.T + (size_t)t * N * N;                                 // ld N
     zc *Yu = ws.Y + ((size_t)0 * ws.chunk + t) * N * N, *Yv = ws.Y + ((size_t)1 * ws.chunk + t) * N * N;
 
-    // T = R_u R_v^T (plain transpose): T(i,j) = sum_{k >= max(i,j)} Ru(i,k) Rv(j,k)
+    // A = T^H with T = R_u R_v^T (plain transpose): T(i,j) = sum_{k >= max(i,j)} Ru(i,k) Rv(j,k), A(j,i) = conj(T(i,j)).
+    // The left singular vectors of T are wanted: with A P = Q R (pivoted QR), T = P R^H Q^H, so they are P times the
+    // left singular vectors of X = R^H, which one-sided Jacobi on the columns of X delivers without accumulating
+    // anything -- the preconditioning of the real path (tlr_kernels.cuh), in complex arithmetic.
     for (int idx = tid; idx < n * n; idx += blockDim.x) {
         const int i = idx % n, j = idx / n;
         zc acc = zmake(0.0, 0.0);
         for (int k = (i > j ? i : j); k < n; ++k) acc = zfma(Ru[i + (size_t)k * m], Rv[j + (size_t)k * m], acc);
-        T[i + (size_t)j * N] = acc;
+        T[j + (size_t)i * N] = zconj(acc);
+    }
+    if (tid < n) perm[tid] = tid;
+    __syncthreads();
+
+    // ---- truncated QR with column pivoting of A (in place, in global memory / L2) -----------------------------------------
+    // Exact squared norms of the remaining columns in every step (they fall out of the update), pivot = the largest,
+    // stop when the Frobenius norm of the remaining block is below 1 % of the truncation threshold (or, fixed-rank mode,
+    // rounding level of the largest column).  zlarfg / H^H as in ztlr_qr_kernel.
+    for (int cc = warp; cc < n; cc += nwarps) {
+        double s2 = 0.0;
+        for (int r = lane; r < n; r += 32) s2 += zabs2(T[r + (size_t)cc * N]);
+        s2 = warp_sum(s2);
+        if (lane == 0) vn[cc] = s2;
+    }
+    __syncthreads();
+    int kq = n;
+    double tol2 = 0.0;
+    for (int j = 0; j < n; ++j) {
+        // pivot and stop test (every warp, redundantly)
+        double best = -1.0, fro2 = 0.0; int bi = 0x7fffffff;
+        for (int cc = j + lane; cc < n; cc += 32) {
+            const double v = vn[cc];
+            fro2 += v;
+            if (v > best) { best = v; bi = cc; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            fro2 += __shfl_xor_sync(0xffffffffu, fro2, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (j == 0) tol2 = (ar.rk > 0) ? 1e-30 * best : 1e-4 * ar.acc * ar.acc;
+        if (fro2 < tol2) { kq = j; break; }
+        const int piv = bi;
+        __syncthreads();                                   // everybody has read vn[] before it is swapped / rewritten
+        zc *xj = T + (size_t)j * N, *xp = T + (size_t)piv * N;
+        if (piv != j) {
+            for (int r = tid; r < n; r += blockDim.x) { const zc a = xj[r]; xj[r] = xp[r]; xp[r] = a; }
+            if (tid == 0) { const int pi = perm[j]; perm[j] = perm[piv]; perm[piv] = pi; vn[piv] = vn[j]; }
+        }
+        __syncthreads();
+        // reflector of column j (rows j .. n-1)
+        double sloc = 0.0;
+        for (int r = j + 1 + tid; r < n; r += blockDim.x) { const zc x = xj[r]; vref[r] = x; sloc += zabs2(x); }
+        sloc = warp_sum(sloc);
+        if (lane == 0) red[warp] = sloc;
+        __syncthreads();
+        if (tid == 0) {
+            double xn2 = 0.0;
+            for (int w = 0; w < nwarps; ++w) xn2 += red[w];
+            const zc alpha = xj[j];
+            zc tau = zmake(0.0, 0.0), scale = zmake(0.0, 0.0);
+            if (xn2 != 0.0 || alpha.y != 0.0) {                           // LAPACK zlarfg
+                const double beta = -copysign(sqrt(zabs2(alpha) + xn2), alpha.x);
+                tau = zmake((beta - alpha.x) / beta, -alpha.y / beta);
+                const zc d = zmake(alpha.x - beta, alpha.y);
+                const double dn = zabs2(d);
+                scale = zmake(d.x / dn, -d.y / dn);
+                xj[j] = zmake(beta, 0.0);
+            }
+            red[32] = tau.x; red[33] = tau.y; red[34] = scale.x; red[35] = scale.y;
+        }
+        __syncthreads();
+        const zc tau = zmake(red[32], red[33]), scale = zmake(red[34], red[35]);
+        for (int r = j + 1 + tid; r < n; r += blockDim.x) vref[r] = zmul(vref[r], scale);
+        __syncthreads();
+        // H^H = I - conj(tau) v v^H on the remaining columns (a warp per column), new squared norms of rows > j
+        const zc ctau = zconj(tau);
+        for (int c = j + 1 + warp; c < n; c += nwarps) {
+            zc *xc = T + (size_t)c * N;
+            zc dot = zmake(0.0, 0.0);
+            for (int r = j + 1 + lane; r < n; r += 32) dot = zcfma(vref[r], xc[r], dot);
+            dot = zwarp_sum(dot);
+            dot = zadd(dot, xc[j]);
+            const zc tw = zmul(ctau, dot), ntw = zmake(-tw.x, -tw.y);
+            __syncwarp();
+            if (lane == 0) xc[j] = zsub(xc[j], tw);
+            double s2 = 0.0;
+            for (int r = j + 1 + lane; r < n; r += 32) { const zc x = zfma(ntw, vref[r], xc[r]); xc[r] = x; s2 += zabs2(x); }
+            s2 = warp_sum(s2);
+            if (lane == 0) vn[c] = s2;
+        }
+        __syncthreads();
+    }
+    // ---- X = R^H restricted to the kq factored rows (the reflectors below the diagonal are overwritten) -------------------
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;                // entry (i, j) of R, i <= j
+        if (i <= j) {
+            const zc x = (i < kq) ? zconj(T[i + (size_t)j * N]) : zmake(0.0, 0.0);
+            if (i < j) T[i + (size_t)j * N] = zmake(0.0, 0.0);
+            T[j + (size_t)i * N] = x;
+        }
     }
     __syncthreads();
 
-    // one-sided Jacobi on the columns of T; a warp per pair, lane l owns rows l, l+32, ...
-    const int n2 = n + (n & 1);
+    // one-sided Jacobi on the first kq columns of X; a half-warp per pair, lane l16 owns rows l16, l16+16, ...
+    const int n2 = kq + (kq & 1);
     int sweeps = 0;
     bool converged = (n2 < 2);
     for (int sweep = 0; sweep < kZMaxSweeps && !converged; ++sweep) {
         int big = 0;
         for (int step = 0; step < n2 - 1; ++step) {
             // 16 lanes per column pair (lane l16 owns rows l16, l16 + 16, ...): two pairs per warp, the
-            // 64 pairs of a step at N = 128 in two rounds of the CTA's 32 half-warps
+            // pairs of a step in rounds of the CTA's half-warps
             const int l16 = lane & 15, hw = (warp << 1) | (lane >> 4), nhw = nwarps << 1;
             for (int k = hw; k < n2 / 2; k += nhw) {
                 int p, q;
                 rr_pair(n2, step, k, p, q);
-                if (q >= n) continue;
+                if (q >= kq) continue;
                 zc *cp = T + (size_t)p * N, *cq = T + (size_t)q * N;
                 zc xp[RPL], xq[RPL];
                 double app = 0.0, aqq = 0.0;
@@ -460,7 +557,7 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
         const int i = idx % n, cc = idx / n, pos = posof[cc];
         if (pos < rnew) {
             const double sg = sig[cc];
-            Yu[i + (size_t)pos * N] = sg > 0.0 ? zscale(T[i + (size_t)cc * N], 1.0 / sg) : zmake(0.0, 0.0);
+            Yu[perm[i] + (size_t)pos * N] = sg > 0.0 ? zscale(T[i + (size_t)cc * N], 1.0 / sg) : zmake(0.0, 0.0);
         }
     }
     __syncthreads();
