@@ -75,7 +75,7 @@ __device__ __forceinline__ zc *zpanel(const ZWorkspace &ws, int pnl, int t, int 
 }
 
 // ---- 1. stacking ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ztlr_stack_kernel(ZArgs ar, ZWorkspace ws) {
+__global__ void __launch_bounds__(256, 2) ztlr_stack_kernel(ZArgs ar, ZWorkspace ws) {      // 128 registers: two CTAs per SM (the kernel waits on global loads)
     const int t = blockIdx.x, gt = ar.tile0 + t, tid = threadIdx.x;
     const int a = ar.Ark[gt], b = ar.Brk[gt], c = ar.Crk[gt];
     const int n = a + c, m = ar.nb, N = ws.N;
