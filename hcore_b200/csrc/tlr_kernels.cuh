@@ -315,6 +315,30 @@ __device__ __forceinline__ void jacobi_pair_apply(double *L, int n16, int p, int
     const int mu = ((t & 1) << 1) | (t >> 1);
     double *cp = L + (size_t)(4 * p + mu) * LDL + 2 * g;
     double *cq = L + (size_t)(4 * q + mu) * LDL + 2 * g;
+    if constexpr (N > 128) {               // core matrix in L2: eight loads in flight per group of 64 rows
+#pragma unroll
+        for (int e0 = 0; e0 < RB / 2; e0 += 4) {
+            if (16 * e0 >= n16) break;
+            double2 vp[4], vq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = (16 * (e0 + u) < n16) ? e0 + u : e0;
+                vp[u] = *reinterpret_cast<const double2 *>(cp + 16 * e);
+                vq[u] = *reinterpret_cast<const double2 *>(cq + 16 * e);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (16 * (e0 + u) >= n16) break;
+                double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
+                dmma_884(d0x, d0y, vp[u].x, b0);
+                dmma_884(d0x, d0y, vq[u].x, b1);
+                dmma_884(d1x, d1y, vp[u].y, b0);
+                dmma_884(d1x, d1y, vq[u].y, b1);
+                *reinterpret_cast<double2 *>(cp + 16 * (e0 + u)) = make_double2(d0x, d1x);
+                *reinterpret_cast<double2 *>(cq + 16 * (e0 + u)) = make_double2(d0y, d1y);
+            }
+        }
+    } else {
 #pragma unroll
     for (int e = 0; e < RB / 2; ++e) {
         if (16 * e >= n16) break;          // a real (warp-uniform) exit: predicated-off DMMAs still occupy the FP64 pipe
@@ -327,6 +351,7 @@ __device__ __forceinline__ void jacobi_pair_apply(double *L, int n16, int p, int
         dmma_884(d1x, d1y, vq.y, b1);
         *reinterpret_cast<double2 *>(cp + 16 * e) = make_double2(d0x, d1x);
         *reinterpret_cast<double2 *>(cq + 16 * e) = make_double2(d0y, d1y);
+    }
     }
 }
 
@@ -360,12 +385,30 @@ __device__ __forceinline__ void jacobi_pair_step(double *L, int n16, int p, int 
         const int mu = ((g & 1) << 1) | ((g >> 1) & 1);
         const double *gc = L + (size_t)(4 * ((g & 4) ? q : p) + mu) * LDL + 2 * t;
         double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
+        if constexpr (N > 128) {
+            // core matrix in L2: eight 16-byte loads in flight before the first use (a load behind every loop exit would
+            // expose the L2 latency 32 times per Gram matrix); rows beyond n16 are read from a valid row and not used
+#pragma unroll
+            for (int j0 = 0; j0 < RB; j0 += 8) {
+                if (8 * j0 >= n16) break;
+                double2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2 *>(gc + 8 * ((8 * (j0 + u) < n16) ? j0 + u : j0));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (8 * (j0 + u) >= n16) break;
+                    dmma_884(ax[u & 3], ay[u & 3], v[u].x, v[u].x);
+                    dmma_884(ax[u & 3], ay[u & 3], v[u].y, v[u].y);
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             if (8 * j >= n16) break;       // a real (warp-uniform) exit: predicated-off DMMAs still occupy the FP64 pipe
             const double2 v = *reinterpret_cast<const double2 *>(gc + 8 * j);
             dmma_884(ax[j & 3], ay[j & 3], v.x, v.x);
             dmma_884(ax[j & 3], ay[j & 3], v.y, v.y);
+        }
         }
         gx = (ax[0] + ax[1]) + (ax[2] + ax[3]);
         gy = (ay[0] + ay[1]) + (ay[2] + ay[3]);
@@ -682,16 +725,15 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
     __syncthreads();
     PROF_ADD(13);
     }   // N > 128
-    const int kq4 = (kq + 3) & ~3;        // columns kq .. n16-1 of L are zero; Jacobi runs on the first kq4
 
     int sweeps = 0;
     bool converged;
-    if constexpr (N <= 128) {
+    {
     // ---- one-sided block Jacobi on the columns of L: blocks of four columns, a warp per block pair, rotations
     //      derived from the pair's Gram matrix and applied with DMMAs (jacobi_pair_step).  Blocks meet in
     //      round-robin order: kq8/4 - 1 barrier steps per sweep, every column pair is rotated once per sweep.
     const int kq8 = (kq + 7) & ~7;                    // columns kq .. kq8-1 of L are zero
-    const int nb4 = kq8 >> 2, npair = nb4 >> 1;       // blocks (even), block pairs per step (<= number of warps)
+    const int nb4 = kq8 >> 2, npair = nb4 >> 1;       // blocks (even), block pairs per step (N = 256: up to two per warp)
     converged = (kq8 < 8);
     // Helpers (one 512-thread CTA per SM).  Warp w runs on scheduler w % 4, so with npair pairs the first npair % 4
     // schedulers carry one pair more than the others, and every step would wait for them while the idle warps
@@ -718,9 +760,11 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
         int big = 0;
         for (int step = 0; step < nb4 - 1; ++step) {
             if (warp < npair) {
-                int p, qq;
-                rr_pair(nb4, step, warp, p, qq);
-                jacobi_pair_step<N>(L, n16, p, qq, step == 0, lane, big, help_idx >= 0 ? vvec + kJbLd * help_idx : nullptr, help_idx);
+                for (int k = warp; k < npair; k += nwarps) {       // one pair per warp unless N = 256 (core matrix in L2)
+                    int p, qq;
+                    rr_pair(nb4, step, k, p, qq);
+                    jacobi_pair_step<N>(L, n16, p, qq, step == 0, lane, big, help_idx >= 0 ? vvec + kJbLd * help_idx : nullptr, help_idx);
+                }
             } else if (help_own >= 0) {
                 int p, qq;
                 rr_pair(nb4, step, help_own, p, qq);
@@ -733,138 +777,7 @@ __global__ void __launch_bounds__(SvdThreads<N>::value, 512 / SvdThreads<N>::val
         ++sweeps;
         converged = (__syncthreads_or(big) == 0);
     }
-    } else {
-    // ---- one-sided Jacobi on the columns of L, in blocks of two columns -----------------------------
-    // A group of 16 lanes owns one PAIR OF BLOCKS (four columns) per step and holds it in registers
-    // (lane l16: row pairs 2 l16 + 32 e, e < N/32): the four cross rotations run as two rounds of two
-    // independent rotations without touching shared memory, the two in-block rotations are added in
-    // the first step of a sweep.  Blocks meet in round-robin order, so a sweep has kq4/2 - 1 barrier
-    // steps instead of kq - 1, and every column pair is rotated exactly once per sweep.
-    constexpr int LG = (N > 128) ? 32 : 16;            // lanes per block pair (N = 256: a whole warp, 8 rows per lane)
-    constexpr int RP = N / (2 * LG);                   // row pairs per lane and column
-    const int l16 = tid & (LG - 1), grp = tid / LG;    // lane l16 of its group: row pairs 2 l16 + 2 LG e
-    const int ngrp = blockDim.x / LG;
-    const int nb2 = kq4 >> 1, nbp = nb2 >> 1;          // blocks, block pairs per step
-    converged = (kq4 < 4);
-    // Two independent rotations A = (ap, aq) and B = (bp, bq) at once.  Only the two inner products a_p.a_q are
-    // formed: the squared column norms are CACHED (cn[], recomputed exactly at the start of every sweep and carried
-    // through each rotation by  app' = c^2 app - 2 c s apq + s^2 aqq,  aqq' = s^2 app + 2 c s apq + c^2 aqq; every term
-    // is formed to relative accuracy, so a small column next to a large one keeps a relatively accurate norm).  The
-    // two partial sums are reduced by recursive halving: the lower half of the group ends up with the total of A, the
-    // upper half with that of B (4 exchanges), each half derives ITS rotation (the scalar chain runs once for both)
-    // and the halves swap (cos, sin, new norms).  sin == 0 means "no rotation".
-    const bool hi8 = (l16 & (LG / 2)) != 0;
-    // the warp's other 16-lane group may be idle: shuffles name the lanes of this group only
-    const unsigned hmask = (LG == 32) ? 0xffffffffu : ((tid & 16) ? 0xffff0000u : 0x0000ffffu);
-    auto rotate2 = [&](double2 (&ap)[RP], double2 (&aq)[RP], double2 (&bp)[RP], double2 (&bq)[RP],
-                       double &nap, double &naq, double &nbp, double &nbq, int &big) {
-        double sa = 0.0, ta = 0.0, sb = 0.0, tb = 0.0;
-#pragma unroll
-        for (int e = 0; e < RP; ++e) {
-            sa = fma(ap[e].x, aq[e].x, sa); ta = fma(ap[e].y, aq[e].y, ta);
-            sb = fma(bp[e].x, bq[e].x, sb); tb = fma(bp[e].y, bq[e].y, tb);
-        }
-        double v;
-        {
-            const double a = sa + ta, b = sb + tb;
-            v = (hi8 ? b : a) + __shfl_xor_sync(hmask, hi8 ? a : b, LG / 2);
-        }
-#pragma unroll
-        for (int o = LG / 4; o > 0; o >>= 1) v += __shfl_xor_sync(hmask, v, o);
-        // rotate when |cos| = |apq| / sqrt(app*aqq) > kTolRot (compared squared, no sqrt)
-        const double app = hi8 ? nbp : nap, aqq = hi8 ? nbq : naq, apq = v;
-        const double den2 = app * aqq, apq2 = apq * apq;
-        double cs = 1.0, sn = 0.0, npp = app, nqq = aqq;
-        if (den2 > 0.0 && apq2 > (kTolRot * kTolRot) * den2) {
-            if (apq2 > (kTolStop * kTolStop) * den2) big = 1;
-            // d = aqq - app, hyp = sqrt(d^2 + 4 apq^2):  cos^2 = (|d| + hyp) / (2 hyp),
-            // sin = sign(d) apq / (hyp cos)   -- two reciprocal square roots, no division
-            const double dd = aqq - app, h2 = 2.0 * apq;
-            const double rh = rsqrt(fma(dd, dd, h2 * h2));
-            const double u = 0.5 * fma(fabs(dd), rh, 1.0);
-            const double ru = rsqrt(u);
-            cs = u * ru;
-            sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
-            const double c2 = cs * cs, s2 = sn * sn, x2 = cs * sn * h2;      // 2 c s apq
-            npp = fma(s2, aqq, fma(c2, app, -x2));
-            nqq = fma(s2, app, fma(c2, aqq, x2));
-            npp = npp > 0.0 ? npp : 0.0;
-            nqq = nqq > 0.0 ? nqq : 0.0;
-        }
-        const double onp = __shfl_xor_sync(hmask, npp, LG / 2), onq = __shfl_xor_sync(hmask, nqq, LG / 2);
-        nap = hi8 ? onp : npp; naq = hi8 ? onq : nqq; nbp = hi8 ? npp : onp; nbq = hi8 ? nqq : onq;
-        const double ocs = __shfl_xor_sync(hmask, cs, LG / 2), osn = __shfl_xor_sync(hmask, sn, LG / 2);
-        const double csa = hi8 ? ocs : cs, sna = hi8 ? osn : sn, csb = hi8 ? cs : ocs, snb = hi8 ? sn : osn;
-        if (sna != 0.0) {
-#pragma unroll
-            for (int e = 0; e < RP; ++e) {
-                const double px = ap[e].x, py = ap[e].y, qx = aq[e].x, qy = aq[e].y;
-                ap[e].x = csa * px - sna * qx; ap[e].y = csa * py - sna * qy;
-                aq[e].x = fma(sna, px, csa * qx); aq[e].y = fma(sna, py, csa * qy);
-            }
-        }
-        if (snb != 0.0) {
-#pragma unroll
-            for (int e = 0; e < RP; ++e) {
-                const double px = bp[e].x, py = bp[e].y, qx = bq[e].x, qy = bq[e].y;
-                bp[e].x = csb * px - snb * qx; bp[e].y = csb * py - snb * qy;
-                bq[e].x = fma(snb, px, csb * qx); bq[e].y = fma(snb, py, csb * qy);
-            }
-        }
-    };
-    double *cn = vn;                                   // cached squared column norms (vn is free after the QRCP)
-    for (int sweep = 0; sweep < kMaxSweeps && !converged; ++sweep) {
-        int big = 0;
-        for (int cc = warp; cc < kq4; cc += nwarps) {      // exact norms at the start of every sweep
-            double s2 = 0.0;
-            for (int rr = lane; rr < n16; rr += 32) { const double x = L[rr + cc * LDL]; s2 = fma(x, x, s2); }
-            s2 = warp_sum(s2);
-            if (lane == 0) cn[cc] = s2;
-        }
-        __syncthreads();
-        for (int step = 0; step < nb2 - 1; ++step) {
-            auto do_pair = [&](int k) {
-                int p, qq;
-                rr_pair(nb2, step, k, p, qq);
-                double *c0p = L + (size_t)(2 * p) * LDL + 2 * l16, *c1p = c0p + LDL;
-                double *c0q = L + (size_t)(2 * qq) * LDL + 2 * l16, *c1q = c0q + LDL;
-                double2 p0[RP], p1[RP], q0[RP], q1[RP];
-#pragma unroll
-                for (int e = 0; e < RP; ++e) {
-                    const bool on = 2 * l16 + 2 * LG * e < n16;
-                    const double2 z = make_double2(0.0, 0.0);
-                    p0[e] = on ? *reinterpret_cast<const double2 *>(c0p + 2 * LG * e) : z;
-                    p1[e] = on ? *reinterpret_cast<const double2 *>(c1p + 2 * LG * e) : z;
-                    q0[e] = on ? *reinterpret_cast<const double2 *>(c0q + 2 * LG * e) : z;
-                    q1[e] = on ? *reinterpret_cast<const double2 *>(c1q + 2 * LG * e) : z;
-                }
-                double np0 = cn[2 * p], np1 = cn[2 * p + 1], nq0 = cn[2 * qq], nq1 = cn[2 * qq + 1];
-                if (step == 0) rotate2(p0, p1, q0, q1, np0, np1, nq0, nq1, big);
-                rotate2(p0, q0, p1, q1, np0, nq0, np1, nq1, big);
-                rotate2(p0, q1, p1, q0, np0, nq1, np1, nq0, big);
-                __syncwarp(hmask);        // every lane of the group has read the cached norms
-                if (l16 == 0) { cn[2 * p] = np0; cn[2 * p + 1] = np1; cn[2 * qq] = nq0; cn[2 * qq + 1] = nq1; }
-#pragma unroll
-                for (int e = 0; e < RP; ++e) {
-                    if (2 * l16 + 2 * LG * e < n16) {
-                        *reinterpret_cast<double2 *>(c0p + 2 * LG * e) = p0[e];
-                        *reinterpret_cast<double2 *>(c1p + 2 * LG * e) = p1[e];
-                        *reinterpret_cast<double2 *>(c0q + 2 * LG * e) = q0[e];
-                        *reinterpret_cast<double2 *>(c1q + 2 * LG * e) = q1[e];
-                    }
-                }
-            };
-            if constexpr (LG == 16) {                       // N <= 128: 32 groups >= nbp, a single pass
-                if (grp < nbp) do_pair(grp);
-            } else {
-                for (int k = grp; k < nbp; k += ngrp) do_pair(k);
-            }
-            __syncthreads();
-        }
-        ++sweeps;
-        converged = (__syncthreads_or(big) == 0);
     }
-    }   // N > 128
 
     PROF_ADD(14);
     PROF_COUNT(21, sweeps);
