@@ -1,10 +1,12 @@
 // Core SVD kernel of the batched tile-low-rank update (FP64, sm_100a).
 //
-//   tlr_svd_kernel     T' = R_v R_u^T, QR with column pivoting as preconditioner,
-//                      one-sided Jacobi on the columns of R^T, sort, rank truncation,
-//                      U_r and W = R_v (R_u^T U_r)         (replaces the core product,
-//                      LAPACKE_dgesvd, the truncation loop and the sigma scaling,
-//                      reference src/compute/hcore_dgemm.c:330-489)
+//   tlr_svd_kernel     T' = R_v R_u^T, truncated QR with column pivoting as preconditioner
+//                      (register resident, one barrier per Householder step: qrcp_registers),
+//                      one-sided BLOCK Jacobi on the columns of R^T (4-column blocks, rotations
+//                      derived from the Gram matrix of a block pair and applied with DMMAs:
+//                      jacobi_pair_step), sort, rank truncation, U_r and W = R_v (R_u^T U_r)
+//                      (replaces the core product, LAPACKE_dgesvd, the truncation loop and the
+//                      sigma scaling, reference src/compute/hcore_dgemm.c:330-489)
 //
 // The other pipeline stages (P/G products, tall-skinny QR, reflector application) are in
 // wy_kernels.cuh.  tests/device_model.py restates this arithmetic in numpy.
