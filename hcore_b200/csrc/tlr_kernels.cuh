@@ -168,7 +168,9 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
     constexpr int RB = N / 8, NW = N / 8;
     constexpr unsigned kFull = 0xffffffffu;
     const int t = lane & 3, ri = i & 7, par = i & 1;
+    PROF_DECL(threadIdx.x == 0)
     __syncthreads();
+    PROF_ADD(40);
     // ---- winner among the per-warp candidates (every warp, redundantly) ---------------------------------------
     const unsigned long long ck = (lane < NW) ? reinterpret_cast<const unsigned long long *>(scr + S::kV)[par * NW + lane] : 0ull;
     const double fs = warp_sum_dmma((lane < NW) ? scr[S::kS + par * NW + lane] : 0.0);
@@ -178,6 +180,7 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
     const int piv = 127 - (int)(best & 0x7full);
     const int wslot = par * NW + (piv >> 3);
     const double *ys = scr + S::kY + (size_t)wslot * N + 2 * t;
+    PROF_ADD(41);
     const Householder h = make_householder_inline(scr[S::kA + wslot], scr[S::kT + wslot]);
     if (col == piv) {
         pos = i;
@@ -194,6 +197,7 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
         if (((e - E) & 3) == 3) asm volatile("" ::: "memory");      // at most four loads in flight: registers
     }
     const double d = quad_sum_dmma((p[0] + p[1]) + (p[2] + p[3]));
+    PROF_ADD(42);
     const double xi = __shfl_sync(kFull, (ri & 1) ? x[2 * E + 1] : x[2 * E], (lane & ~3) | (ri >> 1));
     const double wv = h.tau * fma(h.scal, d, xi), f = h.scal * wv;
     // second pass over the published column: the address is made to depend on d so that these loads are not hoisted
@@ -212,8 +216,11 @@ __device__ __forceinline__ bool qrcp_step(double (&x)[N / 4], int &pos, int i, i
         }
         if (((e - E) & 3) == 3) asm volatile("" ::: "memory");
     }
+    PROF_ADD(43);
     // ---- candidates of the next step ---------------------------------------------------------------------------------
     if (i + 1 < n16) qrcp_publish<N, E>(x, i + 1, in_range && pos < 0, col, par ^ 1, scr, warp, lane);
+    PROF_ADD(44);
+    PROF_COUNT(45, 1);
     return false;
 }
 

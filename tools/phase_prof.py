@@ -52,5 +52,8 @@ for name, tab, cnt in (("tlr_tsqr_kernel", TSQR, 9), ("  inside panel_factor", P
 if v[53]:
     print("== jacobi_pair_step (warp 0): %d pair steps; cycles per pair step: Gram %.0f, rotations %.0f, apply %.0f; per step: "
           "pair step + overhead %.0f, barrier wait %.0f" % (v[53], v[50] / v[53], v[51] / v[53], v[52] / v[53], v[54] / v[53], v[55] / v[53]))
+if v[45]:
+    print("== qrcp_step (thread 0): %d steps; cycles per step: barrier wait %.0f, winner %.0f, householder + dot %.0f, update %.0f, "
+          "norms + publish %.0f" % (v[45], v[40] / v[45], v[41] / v[45], v[42] / v[45], v[43] / v[45], v[44] / v[45]))
 print(f"QRCP steps per tile {v[20] / max(v[29], 1):.1f}, Jacobi sweeps per tile {v[21] / max(v[29], 1):.2f}")
 ctx.close()
