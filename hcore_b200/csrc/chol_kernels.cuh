@@ -244,7 +244,6 @@ struct PotrfArgs {
 __global__ void __launch_bounds__(256) potrf_diag_kernel(PotrfArgs ar, int j0) {
     extern __shared__ __align__(16) double chol_sm[];
     double *S = chol_sm, *Inv = chol_sm + kTbBlk, *Tm = chol_sm + 2 * kTbBlk;
-    __shared__ int fail;
     const int t = blockIdx.x, tid = threadIdx.x;
     if (ar.info[t] != 0) return;
     double *A = ar.A + (size_t)t * ar.strideA;
@@ -253,30 +252,35 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(PotrfArgs ar, int j0) {
         const int r = idx & (kTb - 1), c = idx >> 6;
         S[r + c * kTbLd] = (r < jb && c < jb && r >= c) ? A[(j0 + r) * ar.si + (j0 + c) * ar.sj] : ((r == c) ? 1.0 : 0.0);
     }
-    if (tid == 0) fail = 0;
     __syncthreads();
+    // One barrier per column (three in the first version: pivot, scaling, update).  Every thread reads the pivot d
+    // itself and derives 1/sqrt(d) and 1/d redundantly; the scaled column L(:, c) = S(:, c) / sqrt(d) goes to a SEPARATE
+    // block (Tm), so the rank-1 update S(r, cc) -= S(r, c) S(cc, c) / d can read the unscaled column while it is
+    // being written out.
+    int bad = 0;
     for (int c = 0; c < jb; ++c) {
-        if (tid == 0) {
-            const double d = S[c + c * kTbLd];
-            if (!(d > 0.0)) fail = c + 1;           // also catches NaN (LAPACK: ajj <= 0 or disnan)
-            else S[c + c * kTbLd] = sqrt(d);
-        }
-        __syncthreads();
-        if (fail) break;
-        const double dinv = 1.0 / S[c + c * kTbLd];
-        if (tid > c && tid < kTb) S[tid + c * kTbLd] *= dinv;
-        __syncthreads();
+        const double d = S[c + c * kTbLd];
+        if (!(d > 0.0)) { bad = c + 1; break; }       // also catches NaN (LAPACK: ajj <= 0 or disnan); uniform over the CTA
+        const double dinv = rsqrt(d), dinv2 = dinv * dinv;
+        if (tid >= c && tid < kTb) Tm[tid + c * kTbLd] = (tid == c) ? d * dinv : S[tid + c * kTbLd] * dinv;
         const int nc = kTb - 1 - c;
         for (int idx = tid; idx < nc * kTb; idx += 256) {
             const int r = idx & (kTb - 1), cc = c + 1 + (idx >> 6);
-            if (r >= cc) S[r + cc * kTbLd] -= S[r + c * kTbLd] * S[cc + c * kTbLd];
+            if (r >= cc) S[r + cc * kTbLd] -= (S[r + c * kTbLd] * S[cc + c * kTbLd]) * dinv2;
         }
         __syncthreads();
     }
-    const int bad = fail;
+    __syncthreads();
+    // the factored columns come from Tm; on failure LAPACK leaves the columns factored so far and the failing column
+    // (and what lies to its right) keeps its updated values
+    const int ngood = bad ? bad - 1 : jb;
     for (int idx = tid; idx < kTb * kTb; idx += 256) {
         const int r = idx & (kTb - 1), c = idx >> 6;
-        // on failure LAPACK leaves the columns factored so far; the failing column keeps its updated values
+        if (r >= c && c < ngood) S[r + c * kTbLd] = Tm[r + c * kTbLd];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kTb * kTb; idx += 256) {
+        const int r = idx & (kTb - 1), c = idx >> 6;
         if (r < jb && c < jb && r >= c) A[(j0 + r) * ar.si + (j0 + c) * ar.sj] = S[r + c * kTbLd];
     }
     if (bad) {
