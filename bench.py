@@ -671,9 +671,13 @@ def main():
                 # the H2D direction is the one that binds: the ceiling in tiles/s is the H2D rate / bytes in per tile
                 ceil_gbs = pj["both_h2d_gbs"] * (1.0 + e["d2h_bytes_per_step"] / e["h2d_bytes_per_step"])
                 src = os.path.relpath(cand, ROOT)
+        note = ("ceiling = measured H2D rate with D2H running concurrently, scaled to this call's H2D:D2H byte mix (H2D is the "
+                "binding direction)")
+        if world > 1:
+            note += ("; the N > 1 ceilings were measured on ONE 8-GPU box (profiles/pcie_ceiling_8gpu_box_n*.json): on a box whose "
+                     "host moves more per GPU the fraction can exceed 1")
         e["roofline"] = {"bound": "pcie", "achieved_gbs": ach, "ceiling_gbs": ceil_gbs, "frac": (ach / ceil_gbs) if ceil_gbs else None,
-                         "ceiling_source": src, "note": "ceiling = measured H2D rate with D2H running concurrently, scaled to "
-                                                        "this call's H2D:D2H byte mix (H2D is the binding direction)"}
+                         "ceiling_source": src, "note": note}
         del host
     if rank == 0 and world == 1:
         # ---- CPU baseline: the reference on the host cores ----
