@@ -106,37 +106,59 @@ __global__ void __launch_bounds__(256, 2) ztlr_stack_kernel(ZArgs ar, ZWorkspace
             XU[r + (size_t)col * m] = zmul(ar.alpha, AU[r + (size_t)(col - c) * ar.lda]);
         }
     }
-    // P = AV^T BV: a warp per 4 x 4 tile of P, lanes along the contraction index (coalesced reads of the
-    // eight columns), sixteen accumulators per lane, warp reductions at the end
+    // P = AV^T BV (plain transpose) on the FP64 tensor pipe: four real DMMAs per complex 8 x 8 x 4 product.  A warp owns
+    // an 8-row strip of P and walks over its column tiles two at a time (the A fragment is reused twice); four
+    // contraction steps (16 rows) of operand loads are in flight together -- the first version, one 4 x 4 tile per warp
+    // with the lanes along the contraction index and no loads in flight across iterations, spent its time waiting for L2.
     {
         const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-        const int ta = (a + 3) / 4, tb = (b + 3) / 4;
-        for (int tile = warp; tile < ta * tb; tile += nwarps) {
-            const int i0 = 4 * (tile % ta), j0 = 4 * (tile / ta);
-            zc acc[4][4];
+        const int g = lane >> 2, tg = lane & 3;
+        const int ta = (a + 7) / 8, tb = (b + 7) / 8;
+        const zc zero = zmake(0.0, 0.0);
+        for (int ti = warp; ti < ta; ti += nwarps) {
+            const int i = 8 * ti + g;
+            const zc *ap = AV + (size_t)(i < a ? i : 0) * ar.lda + tg;
+            for (int tj0 = 0; tj0 < tb; tj0 += 2) {
+                double pr[2][2], pi[2][2];
+                const zc *bp[2];
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+                for (int q = 0; q < 2; ++q) {
+                    pr[q][0] = pr[q][1] = pi[q][0] = pi[q][1] = 0.0;
+                    const int j = 8 * (tj0 + q) + g;
+                    bp[q] = BV + (size_t)(j < b ? j : 0) * ar.ldb + tg;
+                }
+                for (int k0 = 0; k0 < m; k0 += 16) {
+                    zc av[4], bv[2][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[p][q] = zmake(0.0, 0.0);
-            for (int k = lane; k < m; k += 32) {
-                zc av[4], bv[4];
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + 4 * u;
+                        const bool kon = k + tg < m;
+                        av[u] = (kon && i < a) ? ap[k] : zero;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    av[p] = (i0 + p < a) ? AV[k + (size_t)(i0 + p) * ar.lda] : zmake(0.0, 0.0);
-                    bv[p] = (j0 + p < b) ? BV[k + (size_t)(j0 + p) * ar.ldb] : zmake(0.0, 0.0);
+                        for (int q = 0; q < 2; ++q) bv[q][u] = (kon && 8 * (tj0 + q) + g < b) ? bp[q][k] : zero;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (k0 + 4 * u >= m) break;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            if (tj0 + q >= tb) break;      // a real exit: predicated-off DMMAs still occupy the FP64 pipe
+                            dmma_884(pr[q][0], pr[q][1], av[u].x, bv[q][u].x);
+                            dmma_884(pr[q][0], pr[q][1], -av[u].y, bv[q][u].y);
+                            dmma_884(pi[q][0], pi[q][1], av[u].x, bv[q][u].y);
+                            dmma_884(pi[q][0], pi[q][1], av[u].y, bv[q][u].x);
+                        }
+                    }
                 }
 #pragma unroll
-                for (int p = 0; p < 4; ++p)
+                for (int q = 0; q < 2; ++q) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[p][q] = zfma(av[p], bv[q], acc[p][q]);
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 8 * (tj0 + q) + 2 * tg + e;
+                        if (i < a && j < b) P[i + (size_t)j * N] = zmake(pr[q][e], pi[q][e]);
+                    }
+                }
             }
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const zc v = zwarp_sum(acc[p][q]);
-                    if (lane == 0 && i0 + p < a && j0 + q < b) P[(i0 + p) + (size_t)(j0 + q) * N] = v;
-                }
         }
     }
     __syncthreads();
