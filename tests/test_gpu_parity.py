@@ -244,7 +244,9 @@ def test_large_tiles_vs_reference_outputs(ctx, golden_dir, name, nb, k, T):
     # the sweep corners of BASELINE.json configs[4] whose throughput profiles/ops_sweep_*.json quotes
     (2048, 64, -1.0, 1.0, 0, 1e-8), (2048, 128, -1.0, 1.0, 0, 1e-8), (1024, 128, -1.0, 1.0, 0, 1e-8),
     (512, 64, -1.0, 1.0, 0, 1e-8), (512, 16, -1.0, 1.0, 0, 1e-8), (1024, 16, -1.0, 1.0, 0, 1e-8),
-    (1024, 32, -1.0, 1.0, 0, 1e-8), (512, 32, -1.0, 1.0, 0, 1e-8)])
+    (1024, 32, -1.0, 1.0, 0, 1e-8), (512, 32, -1.0, 1.0, 0, 1e-8),
+    # degenerate scalars: half (or all) of the stacked panel is zero, the pivoted QR stops early on exact zeros
+    (256, 24, 0.0, 1.0, 0, 1e-8), (256, 24, -1.0, 0.0, 0, 1e-8), (192, 10, 0.0, 0.0, 0, 1e-8), (1024, 64, 0.0, 1.0, 0, 1e-8)])
 def test_vs_oracle(ctx, nb, k, alpha, beta, rk, acc):
     T = 3
     b = make_lr_batch(T, nb, k, base_seed=7 + nb)
