@@ -840,8 +840,8 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     ws.chunk = chunk; ws.N = N;
     // apply kernel: W column buffers + 2 reflector buffers of nb complex each; W = 8, 4 or 2 warps
     int apw = 8;
-    while (apw > 2 && (size_t)(apw + 2) * nb * sizeof(zc) > 227 * 1024) apw >>= 1;
-    const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = (size_t)(apw + 2) * nb * sizeof(zc);
+    while (apw > 2 && (size_t)(apw + 4) * nb * sizeof(zc) > 227 * 1024) apw >>= 1;      // W columns + two pairs of reflectors
+    const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = (size_t)(apw + 4) * nb * sizeof(zc);
     if (sm_ap > 227 * 1024) { ctx->err = "HCORE_zgemm: nb too large for the apply kernel's shared memory"; return HCORE_B200_ERR_ARG; }
     const size_t sm_qrb = (2ull * kZB * nb + 16 + 2 * kZB) * sizeof(double);
     CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qr));

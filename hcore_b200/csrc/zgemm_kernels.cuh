@@ -605,6 +605,10 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
 // per CTA through a double-buffered cp.async pipeline (reflector j-1 travels while j is applied) and
 // shared by the W columns; the first version had every warp stream every reflector from L2 with
 // dependent loads (86 ms per 592 tiles at nb = 1024, k = 64).
+// Reflectors are applied TWO AT A TIME (the kernel is bound by shared-memory bandwidth: a column and a reflector are
+// 16 KB each): with d = v_j^H z, e = v_{j-1}^H z and g = v_{j-1}^H v_j (all three accumulated in the same pass, by every
+// warp),  H_{j-1} H_j z = z - t_j v_j - t_{j-1} v_{j-1},  t_j = tau_j d,  t_{j-1} = tau_{j-1} (e - t_j g):
+// two passes over z and the two reflectors per PAIR instead of two passes per reflector.
 __global__ void __launch_bounds__(256) ztlr_apply_kernel(ZArgs ar, ZWorkspace ws) {
     extern __shared__ __align__(16) double zsm[];
     const int t = blockIdx.z, pnl = blockIdx.y;
@@ -621,43 +625,74 @@ __global__ void __launch_bounds__(256) ztlr_apply_kernel(ZArgs ar, ZWorkspace ws
     const zc *tau_g = ws.tau + ((size_t)pnl * ws.chunk + t) * N;
     const zc *y = ws.Y + ((size_t)pnl * ws.chunk + t) * N * N + (size_t)col * N;
     zc *z = reinterpret_cast<zc *>(zsm) + (size_t)warp * m;
-    zc *vbuf = reinterpret_cast<zc *>(zsm) + (size_t)W * m;   // [2][m]
+    zc *vbuf = reinterpret_cast<zc *>(zsm) + (size_t)W * m;   // [2 pairs][2 reflectors][m]
     zc *out = (ar.ptrs ? const_cast<zc *>(ar.ptrs[(4 + pnl) * ar.ptr_stride + gt]) : (pnl == 0 ? ar.CU : ar.CV) + (size_t)gt * ar.strideC) +
               (size_t)col * ar.ldc;
     if (on)
         for (int r = lane; r < m; r += 32) z[r] = (r < n) ? y[r] : zmake(0.0, 0.0);
-    auto stage = [&](int j, int b) {                          // rows j+1 .. m-1 of reflector j -> vbuf[b]
-        const zc *v = X + (size_t)j * m;
-        zc *dst = vbuf + (size_t)b * m;
-        for (int r = j + 1 + tid; r < m; r += blockDim.x) cp_async16(dst + r, v + r);
+    // pair p = reflectors (jh, jh - 1), jh = n - 1 - 2p; the last pair of an odd n has only its upper reflector
+    const int npairs = (n + 1) >> 1;
+    auto stage = [&](int p, int b) {                          // rows below the diagonal of both reflectors -> vbuf[b]
+        const int jh = n - 1 - 2 * p;
+        zc *dst = vbuf + (size_t)b * 2 * m;
+        for (int r = jh + 1 + tid; r < m; r += blockDim.x) cp_async16(dst + r, X + (size_t)jh * m + r);
+        if (jh >= 1)
+            for (int r = jh + tid; r < m; r += blockDim.x) cp_async16(dst + m + r, X + (size_t)(jh - 1) * m + r);
         cp_async_commit();
     };
-    stage(n - 1, 0);
-    for (int j = n - 1; j >= 0; --j) {
-        const int b = (n - 1 - j) & 1;
-        if (j > 0) {
-            stage(j - 1, b ^ 1);
+    stage(0, 0);
+    for (int p = 0; p < npairs; ++p) {
+        const int b = p & 1, jh = n - 1 - 2 * p, jl = jh - 1;
+        if (p + 1 < npairs) {
+            stage(p + 1, b ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();                                      // reflector j is in vbuf[b] for every warp
-        const zc tau = tau_g[j];
-        if (on && (tau.x != 0.0 || tau.y != 0.0)) {
-            const zc *v = vbuf + (size_t)b * m;
-            zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
-            int r = j + 1 + lane;
-            for (; r + 32 < m; r += 64) {
-                d0 = zcfma(v[r], z[r], d0);
-                d1 = zcfma(v[r + 32], z[r + 32], d1);
+        __syncthreads();                                      // the pair is in vbuf[b] for every warp
+        const zc *vh = vbuf + (size_t)b * 2 * m, *vl = vh + m;    // vh: rows > jh valid, vl: rows >= jh valid (jl >= 0)
+        const bool two = jl >= 0;
+        // g = v_jl^H v_jh = conj(v_jl[jh]) + sum_{r > jh} conj(v_jl[r]) v_jh[r]: every warp, redundantly (no extra barrier)
+        zc g = zmake(0.0, 0.0);
+        const zc tauh = tau_g[jh], taul = two ? tau_g[jl] : zmake(0.0, 0.0);
+        if (on) {
+            zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0), e0 = zmake(0.0, 0.0), e1 = zmake(0.0, 0.0);
+            zc g0 = zmake(0.0, 0.0), g1 = zmake(0.0, 0.0);
+            int r = jh + 1 + lane;
+            if (two) {
+                for (; r + 32 < m; r += 64) {
+                    const zc z0 = z[r], z1 = z[r + 32], h0 = vh[r], h1 = vh[r + 32], l0 = vl[r], l1 = vl[r + 32];
+                    d0 = zcfma(h0, z0, d0); d1 = zcfma(h1, z1, d1);
+                    e0 = zcfma(l0, z0, e0); e1 = zcfma(l1, z1, e1);
+                    g0 = zcfma(l0, h0, g0); g1 = zcfma(l1, h1, g1);
+                }
+                if (r < m) { const zc z0 = z[r], h0 = vh[r], l0 = vl[r]; d0 = zcfma(h0, z0, d0); e0 = zcfma(l0, z0, e0); g0 = zcfma(l0, h0, g0); }
+            } else {
+                for (; r + 32 < m; r += 64) { d0 = zcfma(vh[r], z[r], d0); d1 = zcfma(vh[r + 32], z[r + 32], d1); }
+                if (r < m) d0 = zcfma(vh[r], z[r], d0);
             }
-            if (r < m) d0 = zcfma(v[r], z[r], d0);
-            zc dot = zwarp_sum(zadd(d0, d1));
-            dot = zadd(dot, z[j]);
-            const zc tw = zmul(tau, dot), ntw = zmake(-tw.x, -tw.y);
+            zc d = zwarp_sum(zadd(d0, d1)), e = zwarp_sum(zadd(e0, e1));
+            g = zwarp_sum(zadd(g0, g1));
+            const zc zjh = z[jh];
+            d = zadd(d, zjh);
+            zc th = zmul(tauh, d), tl = zmake(0.0, 0.0);
+            if (two) {
+                const zc cl = zconj(vl[jh]);
+                g = zadd(g, cl);
+                e = zadd(e, zadd(z[jl], zmul(cl, zjh)));
+                tl = zmul(taul, zsub(e, zmul(th, g)));
+            }
+            const zc nth = zmake(-th.x, -th.y), ntl = zmake(-tl.x, -tl.y);
             __syncwarp();
-            if (lane == 0) z[j] = zsub(z[j], tw);
-            for (int q = j + 1 + lane; q < m; q += 32) z[q] = zfma(ntw, v[q], z[q]);
+            if (lane == 0) {
+                z[jh] = two ? zsub(zsub(zjh, th), zmul(tl, vl[jh])) : zsub(zjh, th);
+                if (two) z[jl] = zsub(z[jl], tl);
+            }
+            if (two) {
+                for (int q = jh + 1 + lane; q < m; q += 32) z[q] = zfma(ntl, vl[q], zfma(nth, vh[q], z[q]));
+            } else {
+                for (int q = jh + 1 + lane; q < m; q += 32) z[q] = zfma(nth, vh[q], z[q]);
+            }
         }
         __syncthreads();                                      // vbuf[b] may be overwritten by the next-but-one stage
     }
