@@ -381,6 +381,8 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
     zc *T = ws.T + (size_t)t * N * N;                                 // ld N
     zc *Yu = ws.Y + ((size_t)0 * ws.chunk + t) * N * N, *Yv = ws.Y + ((size_t)1 * ws.chunk + t) * N * N;
 
+    PROF_DECL(tid == 0)
+    PROF_COUNT(39, 1);
     // A = T^H with T = R_u R_v^T (plain transpose): T(i,j) = sum_{k >= max(i,j)} Ru(i,k) Rv(j,k), A(j,i) = conj(T(i,j)).
     // The left singular vectors of T are wanted: with A P = Q R (pivoted QR), T = P R^H Q^H, so they are P times the
     // left singular vectors of X = R^H, which one-sided Jacobi on the columns of X delivers without accumulating
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
     if (tid < n) perm[tid] = tid;
     __syncthreads();
 
+    PROF_ADD(30);
     // ---- truncated QR with column pivoting of A (in place, in global memory / L2) -----------------------------------------
     // Exact squared norms of the remaining columns in every step (they fall out of the update), pivot = the largest,
     // stop when the Frobenius norm of the remaining block is below 1 % of the truncation threshold (or, fixed-rank mode,
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
         }
         __syncthreads();
     }
+    PROF_ADD(31);
     // ---- X = R^H restricted to the kq factored rows (the reflectors below the diagonal are overwritten) -------------------
     for (int idx = tid; idx < n * n; idx += blockDim.x) {
         const int i = idx % n, j = idx / n;                // entry (i, j) of R, i <= j
@@ -486,6 +490,7 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
     }
     __syncthreads();
 
+    PROF_ADD(32);
     // one-sided Jacobi on the first kq columns of X; a half-warp per pair, lane l16 owns rows l16, l16+16, ...
     const int n2 = kq + (kq & 1);
     int sweeps = 0;
@@ -526,11 +531,16 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
                 const double den2 = app * aqq, g2 = zabs2(apq);
                 if (den2 > 0.0 && g2 > (kZTolRot * kZTolRot) * den2) {
                     if (g2 > (kZTolStop * kZTolStop) * den2) big = 1;
-                    const double g = sqrt(g2);
-                    const zc ph = zmake(apq.x / g, -apq.y / g);     // conj(theta): q <- q conj(theta) makes p^H q real
-                    const double zeta = (aqq - app) / (2.0 * g);
-                    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                    // three reciprocal square roots instead of two square roots and four divisions (the scalar chain of a
+                    // rotation is on the critical path of every round): |apq| = g2 / sqrt(g2); with d = aqq - app and
+                    // hyp = sqrt(d^2 + 4 g^2): cos^2 = (1 + |d| / hyp) / 2, sin = sign(d) g / (hyp cos)
+                    const double rg = rsqrt(g2);
+                    const zc ph = zmake(apq.x * rg, -apq.y * rg);   // conj(theta): q <- q conj(theta) makes p^H q real
+                    const double dd = aqq - app, h2 = 2.0 * (g2 * rg);
+                    const double rh = rsqrt(fma(dd, dd, h2 * h2));
+                    const double u = 0.5 * fma(fabs(dd), rh, 1.0);
+                    const double ru = rsqrt(u);
+                    const double cs = u * ru, sn = (dd >= 0.0 ? h2 : -h2) * rh * (0.5 * ru);
 #pragma unroll
                     for (int e = 0; e < RPL; ++e) {
                         const int r = l16 + 16 * e;
@@ -548,6 +558,9 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
         converged = (__syncthreads_or(big) == 0);
     }
 
+    PROF_ADD(33);
+    PROF_COUNT(38, sweeps);
+    PROF_COUNT(37, kq);
     // singular values, sort (descending, stable), truncation
     for (int cc = warp; cc < n; cc += nwarps) {
         double s2 = 0.0;
@@ -589,6 +602,7 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
         }
     }
     __syncthreads();
+    PROF_ADD(34);
     // tmp = R_u^T conj(U_r)  (n x r) into T;  W = R_v tmp
     for (int idx = tid; idx < n * rnew; idx += blockDim.x) {
         const int k = idx % n, c = idx / n;
@@ -603,6 +617,7 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
         for (int k = j; k < n; ++k) acc = zfma(Rv[j + (size_t)k * m], T[k + (size_t)c * N], acc);
         Yv[j + (size_t)c * N] = acc;
     }
+    PROF_ADD(35);
 }
 
 // ---- 4. reflector application --------------------------------------------------------------------------------
