@@ -361,6 +361,38 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
     }
 }
 
+// Block-level complex product C(i, j) = sum_{k in [klo, khi)} A(i, k) B(k, j) on the FP64 tensor pipe (four real DMMAs
+// per complex 8 x 8 x 4 step).  fa(i, k), fb(k, j) return the operand entries (zero outside their extent), put(i, j, v)
+// stores a result entry, klim(i0, j0, klo, khi) may shrink the contraction range of an 8 x 8 output tile (triangular
+// operands; multiples of 4).  Output tiles are dealt round-robin to the warps; two contraction steps of loads in flight.
+template <typename FA, typename FB, typename PUT, typename KLIM>
+__device__ __forceinline__ void zblock_gemm(int M, int Nc, int K, FA fa, FB fb, PUT put, KLIM klim, int warp, int nwarps, int lane) {
+    const int g = lane >> 2, tg = lane & 3;
+    const int tm = (M + 7) >> 3, tn = (Nc + 7) >> 3;
+    for (int tile = warp; tile < tm * tn; tile += nwarps) {
+        const int i0 = (tile % tm) << 3, j0 = (tile / tm) << 3;
+        int klo = 0, khi = (K + 3) & ~3;
+        klim(i0, j0, klo, khi);
+        double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
+        for (int k = klo; k < khi; k += 8) {
+            const zc a0 = fa(i0 + g, k + tg), b0 = fb(k + tg, j0 + g);
+            const zc a1 = (k + 4 < khi) ? fa(i0 + g, k + 4 + tg) : zmake(0.0, 0.0), b1 = (k + 4 < khi) ? fb(k + 4 + tg, j0 + g) : zmake(0.0, 0.0);
+            dmma_884(cr[0], cr[1], a0.x, b0.x);
+            dmma_884(cr[0], cr[1], -a0.y, b0.y);
+            dmma_884(ci[0], ci[1], a0.x, b0.y);
+            dmma_884(ci[0], ci[1], a0.y, b0.x);
+            if (k + 4 < khi) {                          // warp-uniform
+                dmma_884(cr[0], cr[1], a1.x, b1.x);
+                dmma_884(cr[0], cr[1], -a1.y, b1.y);
+                dmma_884(ci[0], ci[1], a1.x, b1.y);
+                dmma_884(ci[0], ci[1], a1.y, b1.x);
+            }
+        }
+        put(i0 + g, j0 + 2 * tg, zmake(cr[0], ci[0]));
+        put(i0 + g, j0 + 2 * tg + 1, zmake(cr[1], ci[1]));
+    }
+}
+
 // ---- 3. core SVD ------------------------------------------------------------------------------------------
 constexpr double kZTolRot = 1e-15, kZTolStop = 1e-7;
 constexpr int kZMaxSweeps = 60;
@@ -387,11 +419,15 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
     // The left singular vectors of T are wanted: with A P = Q R (pivoted QR), T = P R^H Q^H, so they are P times the
     // left singular vectors of X = R^H, which one-sided Jacobi on the columns of X delivers without accumulating
     // anything -- the preconditioning of the real path (tlr_kernels.cuh), in complex arithmetic.
-    for (int idx = tid; idx < n * n; idx += blockDim.x) {
-        const int i = idx % n, j = idx / n;
-        zc acc = zmake(0.0, 0.0);
-        for (int k = (i > j ? i : j); k < n; ++k) acc = zfma(Ru[i + (size_t)k * m], Rv[j + (size_t)k * m], acc);
-        T[j + (size_t)i * N] = zconj(acc);
+    {
+        const zc zero = zmake(0.0, 0.0);
+        // T(i, j) = sum_{k >= max(i, j)} Ru(i, k) Rv(j, k): A = Ru, B = Rv^T; stored as A^H: T[j + i N] = conj(T(i, j))
+        zblock_gemm(n, n, n,
+                    [&](int i, int k) { return (i < n && k < n && k >= i) ? Ru[i + (size_t)k * m] : zero; },
+                    [&](int k, int j) { return (j < n && k < n && k >= j) ? Rv[j + (size_t)k * m] : zero; },
+                    [&](int i, int j, zc v) { if (i < n && j < n) T[j + (size_t)i * N] = zconj(v); },
+                    [&](int i0, int j0, int &klo, int &) { klo = (i0 > j0 ? i0 : j0) & ~3; },
+                    warp, nwarps, lane);
     }
     if (tid < n) perm[tid] = tid;
     __syncthreads();
@@ -604,18 +640,23 @@ __global__ void __launch_bounds__(RPL == 8 ? 512 : 256) ztlr_svd_kernel(ZArgs ar
     __syncthreads();
     PROF_ADD(34);
     // tmp = R_u^T conj(U_r)  (n x r) into T;  W = R_v tmp
-    for (int idx = tid; idx < n * rnew; idx += blockDim.x) {
-        const int k = idx % n, c = idx / n;
-        zc acc = zmake(0.0, 0.0);
-        for (int i = 0; i <= k; ++i) acc = zfma(Ru[i + (size_t)k * m], zconj(Yu[i + (size_t)c * N]), acc);
-        T[k + (size_t)c * N] = acc;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < n * rnew; idx += blockDim.x) {
-        const int j = idx % n, c = idx / n;
-        zc acc = zmake(0.0, 0.0);
-        for (int k = j; k < n; ++k) acc = zfma(Rv[j + (size_t)k * m], T[k + (size_t)c * N], acc);
-        Yv[j + (size_t)c * N] = acc;
+    {
+        const zc zero = zmake(0.0, 0.0);
+        // tmp(k, c) = sum_{i <= k} Ru(i, k) conj(Yu(i, c)): A = Ru^T (rows k, contraction i), B = conj(Yu)
+        zblock_gemm(n, rnew, n,
+                    [&](int k, int i) { return (k < n && i <= k) ? Ru[i + (size_t)k * m] : zero; },
+                    [&](int i, int c) { return (i < n && c < rnew) ? zconj(Yu[i + (size_t)c * N]) : zero; },
+                    [&](int k, int c, zc v) { if (k < n && c < rnew) T[k + (size_t)c * N] = v; },
+                    [&](int k0, int, int &, int &khi) { const int lim = (k0 + 8 + 3) & ~3; khi = lim < khi ? lim : khi; },
+                    warp, nwarps, lane);
+        __syncthreads();
+        // W(j, c) = sum_{k >= j} Rv(j, k) tmp(k, c)
+        zblock_gemm(n, rnew, n,
+                    [&](int j, int k) { return (j < n && k < n && k >= j) ? Rv[j + (size_t)k * m] : zero; },
+                    [&](int k, int c) { return (k < n && c < rnew) ? T[k + (size_t)c * N] : zero; },
+                    [&](int j, int c, zc v) { if (j < n && c < rnew) Yv[j + (size_t)c * N] = v; },
+                    [&](int j0, int, int &klo, int &) { klo = j0 & ~3; },
+                    warp, nwarps, lane);
     }
     PROF_ADD(35);
 }
