@@ -74,6 +74,41 @@ __device__ __forceinline__ zc *zpanel(const ZWorkspace &ws, int pnl, int t, int 
     return ws.panel + ((size_t)pnl * ws.chunk + t) * (size_t)m * ws.N;
 }
 
+// Block-level complex product C(i, j) = sum_{k in [klo, khi)} A(i, k) B(k, j) on the FP64 tensor pipe (four real DMMAs
+// per complex 8 x 8 x 4 step).  fa(i, k), fb(k, j) return the operand entries (zero outside their extent), put(i, j, v)
+// stores a result entry, klim(i0, j0, klo, khi) may shrink the contraction range of an 8 x 8 output tile (triangular
+// operands; multiples of 4).  Output tiles are dealt round-robin to the warps; four contraction steps of loads in flight.
+template <typename FA, typename FB, typename PUT, typename KLIM>
+__device__ __forceinline__ void zblock_gemm(int M, int Nc, int K, FA fa, FB fb, PUT put, KLIM klim, int warp, int nwarps, int lane) {
+    const int g = lane >> 2, tg = lane & 3;
+    const int tm = (M + 7) >> 3, tn = (Nc + 7) >> 3;
+    for (int tile = warp; tile < tm * tn; tile += nwarps) {
+        const int i0 = (tile % tm) << 3, j0 = (tile / tm) << 3;
+        int klo = 0, khi = (K + 3) & ~3;
+        klim(i0, j0, klo, khi);
+        double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
+        for (int k = klo; k < khi; k += 16) {
+            zc av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {              // four contraction steps of operand loads in flight
+                const bool kon = k + 4 * u < khi;
+                av[u] = kon ? fa(i0 + g, k + 4 * u + tg) : zmake(0.0, 0.0);
+                bv[u] = kon ? fb(k + 4 * u + tg, j0 + g) : zmake(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k + 4 * u >= khi) break;           // warp-uniform: a real exit, not predicated DMMAs
+                dmma_884(cr[0], cr[1], av[u].x, bv[u].x);
+                dmma_884(cr[0], cr[1], -av[u].y, bv[u].y);
+                dmma_884(ci[0], ci[1], av[u].x, bv[u].y);
+                dmma_884(ci[0], ci[1], av[u].y, bv[u].x);
+            }
+        }
+        put(i0 + g, j0 + 2 * tg, zmake(cr[0], ci[0]));
+        put(i0 + g, j0 + 2 * tg + 1, zmake(cr[1], ci[1]));
+    }
+}
+
 // ---- 1. stacking ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) ztlr_stack_kernel(ZArgs ar, ZWorkspace ws) {      // 128 registers: two CTAs per SM (the kernel waits on global loads)
     const int t = blockIdx.x, gt = ar.tile0 + t, tid = threadIdx.x;
@@ -97,6 +132,8 @@ __global__ void __launch_bounds__(256, 2) ztlr_stack_kernel(ZArgs ar, ZWorkspace
     zc *XU = zpanel(ws, 0, t, m), *XV = zpanel(ws, 1, t, m);
     zc *P = ws.T + (size_t)t * N * N;                     // P[i + j*N], i < a, j < b
 
+    PROF_DECL(tid == 0)
+    PROF_COUNT(49, 1);
     for (int idx = tid; idx < m * n; idx += blockDim.x) {
         const int r = idx % m, col = idx / m;
         if (col < c) {
@@ -106,6 +143,7 @@ __global__ void __launch_bounds__(256, 2) ztlr_stack_kernel(ZArgs ar, ZWorkspace
             XU[r + (size_t)col * m] = zmul(ar.alpha, AU[r + (size_t)(col - c) * ar.lda]);
         }
     }
+    PROF_ADD(46);
     // P = AV^T BV (plain transpose) on the FP64 tensor pipe: four real DMMAs per complex 8 x 8 x 4 product.  A warp owns
     // an 8-row strip of P and walks over its column tiles two at a time (the A fragment is reused twice); four
     // contraction steps (16 rows) of operand loads are in flight together -- the first version, one 4 x 4 tile per warp
@@ -162,23 +200,19 @@ __global__ void __launch_bounds__(256, 2) ztlr_stack_kernel(ZArgs ar, ZWorkspace
         }
     }
     __syncthreads();
-    // G = BU P^T -> X_v[:, c : c+a]: one thread per row, 8 outputs at a time
-    for (int r = tid; r < m; r += blockDim.x) {
-        for (int i0 = 0; i0 < a; i0 += 8) {
-            zc acc[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = zmake(0.0, 0.0);
-            for (int j = 0; j < b; ++j) {
-                const zc bu = BU[r + (size_t)j * ar.ldb];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (i0 + q < a) acc[q] = zfma(bu, P[(i0 + q) + (size_t)j * N], acc[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (i0 + q < a) XV[r + (size_t)(c + i0 + q) * m] = acc[q];
-        }
+    PROF_ADD(47);
+    // G = BU P^T -> X_v[:, c : c+a] on the FP64 tensor pipe (zblock_gemm below; the first version, one thread per row with
+    // scalar complex FMAs, was 60 % of this kernel)
+    {
+        const zc zero = zmake(0.0, 0.0);
+        zblock_gemm(m, a, b,
+                    [&](int r, int j) { return (r < m && j < b) ? BU[r + (size_t)j * ar.ldb] : zero; },
+                    [&](int j, int i) { return (i < a && j < b) ? P[i + (size_t)j * N] : zero; },
+                    [&](int r, int i, zc v) { if (r < m && i < a) XV[r + (size_t)(c + i) * m] = v; },
+                    [&](int, int, int &, int &) {},
+                    tid >> 5, blockDim.x >> 5, tid & 31);
     }
+    PROF_ADD(48);
 }
 
 // ---- 2. Householder QR (zgeqr2) --------------------------------------------------------------------------
@@ -358,38 +392,6 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
         for (int c = 0; c < nbk; ++c)
             for (int r = j0 + tid; r < m; r += blockDim.x) X[(size_t)(j0 + c) * m + r] = P[(size_t)c * m + r];
         __syncthreads();
-    }
-}
-
-// Block-level complex product C(i, j) = sum_{k in [klo, khi)} A(i, k) B(k, j) on the FP64 tensor pipe (four real DMMAs
-// per complex 8 x 8 x 4 step).  fa(i, k), fb(k, j) return the operand entries (zero outside their extent), put(i, j, v)
-// stores a result entry, klim(i0, j0, klo, khi) may shrink the contraction range of an 8 x 8 output tile (triangular
-// operands; multiples of 4).  Output tiles are dealt round-robin to the warps; two contraction steps of loads in flight.
-template <typename FA, typename FB, typename PUT, typename KLIM>
-__device__ __forceinline__ void zblock_gemm(int M, int Nc, int K, FA fa, FB fb, PUT put, KLIM klim, int warp, int nwarps, int lane) {
-    const int g = lane >> 2, tg = lane & 3;
-    const int tm = (M + 7) >> 3, tn = (Nc + 7) >> 3;
-    for (int tile = warp; tile < tm * tn; tile += nwarps) {
-        const int i0 = (tile % tm) << 3, j0 = (tile / tm) << 3;
-        int klo = 0, khi = (K + 3) & ~3;
-        klim(i0, j0, klo, khi);
-        double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
-        for (int k = klo; k < khi; k += 8) {
-            const zc a0 = fa(i0 + g, k + tg), b0 = fb(k + tg, j0 + g);
-            const zc a1 = (k + 4 < khi) ? fa(i0 + g, k + 4 + tg) : zmake(0.0, 0.0), b1 = (k + 4 < khi) ? fb(k + 4 + tg, j0 + g) : zmake(0.0, 0.0);
-            dmma_884(cr[0], cr[1], a0.x, b0.x);
-            dmma_884(cr[0], cr[1], -a0.y, b0.y);
-            dmma_884(ci[0], ci[1], a0.x, b0.y);
-            dmma_884(ci[0], ci[1], a0.y, b0.x);
-            if (k + 4 < khi) {                          // warp-uniform
-                dmma_884(cr[0], cr[1], a1.x, b1.x);
-                dmma_884(cr[0], cr[1], -a1.y, b1.y);
-                dmma_884(ci[0], ci[1], a1.x, b1.y);
-                dmma_884(ci[0], ci[1], a1.y, b1.x);
-            }
-        }
-        put(i0 + g, j0 + 2 * tg, zmake(cr[0], ci[0]));
-        put(i0 + g, j0 + 2 * tg + 1, zmake(cr[1], ci[1]));
     }
 }
 

@@ -27,3 +27,5 @@ names = {30: "T^H product", 31: "QRCP", 32: "R^H", 33: "Jacobi", 34: "sort / U_r
 print("tiles", n, "kq", v[37] / n, "sweeps", v[38] / n, "status", int(st.abs().sum()))
 for s_, nm in names.items():
     print(f"  {nm:16s} {v[s_] / n:12,.0f} cycles per tile")
+if v[49]:
+    print("stack kernel: copy %.0f, P %.0f, G %.0f cycles per tile" % (v[46] / v[49], v[47] / v[49], v[48] / v[49]))
