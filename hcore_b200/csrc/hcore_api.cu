@@ -824,17 +824,17 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int N = pick_width(maxrk, HCORE_B200_MAX_STACK_Z);
-    const size_t per = (2ull * nb * N + 2ull * N + 3ull * N * N) * sizeof(zc) + N * 8 + 16;
+    const size_t per = (2ull * nb * N + 2ull * N * (1 + kZB) + 3ull * N * N) * sizeof(zc) + N * 8 + 16;
     int chunk = ctx->chunk_limit > 0 ? ctx->chunk_limit : (int)std::min<size_t>(ctx->num_sms * 4, (4ull << 30) / per);
     chunk = std::max(1, std::min(chunk, ntiles));
     CUDA_TRY(ctx, ctx->zpanel.reserve(2ull * chunk * nb * N * sizeof(zc)));
-    CUDA_TRY(ctx, ctx->ztau.reserve(2ull * chunk * N * sizeof(zc)));
+    CUDA_TRY(ctx, ctx->ztau.reserve(2ull * chunk * N * (1 + kZB) * sizeof(zc)));     // tau + the 8 x 8 compact-WY factors
     CUDA_TRY(ctx, ctx->zT.reserve((size_t)chunk * N * N * sizeof(zc)));
     CUDA_TRY(ctx, ctx->zY.reserve(2ull * chunk * N * N * sizeof(zc)));
     CUDA_TRY(ctx, ctx->zsigma.reserve((size_t)chunk * N * 8));
     CUDA_TRY(ctx, ctx->zints.reserve((size_t)chunk * 4 * sizeof(int)));
     ZWorkspace ws{};
-    ws.panel = (zc *)ctx->zpanel.p; ws.tau = (zc *)ctx->ztau.p; ws.T = (zc *)ctx->zT.p; ws.Y = (zc *)ctx->zY.p;
+    ws.panel = (zc *)ctx->zpanel.p; ws.tau = (zc *)ctx->ztau.p; ws.tfac = ws.tau + 2ull * chunk * N; ws.T = (zc *)ctx->zT.p; ws.Y = (zc *)ctx->zY.p;
     ws.sigma = (double *)ctx->zsigma.p;
     ws.ncols = (int *)ctx->zints.p; ws.newrank = ws.ncols + chunk; ws.st = ws.newrank + chunk; ws.sweeps = ws.st + chunk;
     ws.chunk = chunk; ws.N = N;
@@ -843,7 +843,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     while (apw > 2 && (size_t)(apw + 4) * nb * sizeof(zc) > 227 * 1024) apw >>= 1;      // W columns + two pairs of reflectors
     const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = (size_t)(apw + 4) * nb * sizeof(zc);
     if (sm_ap > 227 * 1024) { ctx->err = "HCORE_zgemm: nb too large for the apply kernel's shared memory"; return HCORE_B200_ERR_ARG; }
-    const size_t sm_qrb = (2ull * kZB * nb + 16 + 2 * kZB) * sizeof(double);
+    const size_t sm_qrb = (2ull * kZB * nb + 16 + 2 * kZB + 2 * kZB * kZB) * sizeof(double);
     CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qr));
     if (nb <= 32 * kZRows)
         CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qrb));
@@ -863,7 +863,8 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
         else ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
         if (N <= 128) ztlr_svd_kernel<8><<<ar.ntiles, 512, 0, st>>>(ar, ws);
         else ztlr_svd_kernel<16><<<ar.ntiles, 256, 0, st>>>(ar, ws);
-        ztlr_apply_kernel<<<dim3((N + apw - 1) / apw, 2, ar.ntiles), 32 * apw, sm_ap, st>>>(ar, ws);
+        if (nb <= 32 * kZRows && !getenv("HCORE_B200_Z_APPLY_SCALAR")) ztlr_apply_wy_kernel<<<dim3((N + 7) / 8, 2, ar.ntiles), 512, 0, st>>>(ar, ws);
+        else ztlr_apply_kernel<<<dim3((N + apw - 1) / apw, 2, ar.ntiles), 32 * apw, sm_ap, st>>>(ar, ws);
         ctx->launches += 4;
     }
     CUDA_TRY(ctx, cudaGetLastError());

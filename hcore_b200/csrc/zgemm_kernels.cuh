@@ -63,6 +63,7 @@ struct ZArgs {
 struct ZWorkspace {
     zc *panel;     // [2][chunk][m * N]     stacked panels -> reflectors + R
     zc *tau;       // [2][chunk][N]
+    zc *tfac;      // [2][chunk][N / 8][8 x 8]  compact-WY triangular factors of the 8-reflector blocks (blocked QR)
     zc *T;         // [chunk][N * N]        P, then the core matrix, then a GEMM temporary
     zc *Y;         // [2][chunk][N * N]     U_r and W
     double *sigma; // [chunk][N]
@@ -293,6 +294,8 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
     zc *P = reinterpret_cast<zc *>(zsm);                       // [kZB][m] block columns (row index absolute)
     double *red = zsm + 2 * (size_t)kZB * m;                   // [8] partial sums, [8..11] tau, scale
     zc *taus = reinterpret_cast<zc *>(red + 16);               // [kZB]
+    zc *Sg = taus + kZB;                                       // [kZB][kZB] v_i^H v_k, i < k
+    zc *tf_g = ws.tfac + ((size_t)pnl * ws.chunk + t) * ws.N * kZB;
     for (int j0 = 0; j0 < n; j0 += kZB) {
         const int nbk = (n - j0 < kZB) ? (n - j0) : kZB;
         for (int c = 0; c < nbk; ++c)
@@ -345,6 +348,43 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
                 }
             }
             __syncthreads();
+        }
+        // ---- compact-WY factor of the block (zlarft, forward / columnwise): H_j0 ... H_{j0+7} = I - V T V^H with
+        //      T(k,k) = tau_k, T(0:k, k) = -tau_k T(0:k, 0:k) (V(:, 0:k)^H v_k); consumed by ztlr_apply_wy_kernel ------
+        {
+            int q = 0;
+            for (int k = 1; k < nbk; ++k)
+                for (int i = 0; i < k; ++i, ++q) {
+                    if (q % nwarps != warp) continue;
+                    const zc *pi = P + (size_t)i * m, *pk = P + (size_t)k * m;
+                    zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
+                    int r = j0 + k + 1 + lane;
+                    for (; r + 32 < m; r += 64) { d0 = zcfma(pi[r], pk[r], d0); d1 = zcfma(pi[r + 32], pk[r + 32], d1); }
+                    if (r < m) d0 = zcfma(pi[r], pk[r], d0);
+                    const zc dot = zadd(zwarp_sum(zadd(d0, d1)), zconj(pi[j0 + k]));   // unit diagonal of v_k
+                    if (lane == 0) Sg[i + kZB * k] = dot;
+                }
+            __syncthreads();
+            if (tid < kZB) {                                   // thread i builds row i of T (rows are independent)
+                const int i = tid;
+                zc Ti[kZB];
+#pragma unroll
+                for (int k = 0; k < kZB; ++k) {
+                    zc v = zmake(0.0, 0.0);
+                    if (i < nbk && k < nbk) {
+                        if (k == i) v = taus[i];
+                        else if (k > i) {
+                            zc acc = zmake(0.0, 0.0);
+#pragma unroll
+                            for (int l = 0; l < kZB; ++l)
+                                if (l >= i && l < k) acc = zfma(Ti[l], Sg[l + kZB * k], acc);
+                            v = zmul(zmake(-taus[k].x, -taus[k].y), acc);
+                        }
+                    }
+                    Ti[k] = v;
+                    tf_g[((size_t)j0 << 3) + i + kZB * k] = v;
+                }
+            }
         }
         // ---- trailing columns: one warp per column, the column in registers ---------------------------
         for (int c = j0 + nbk + warp; c < n; c += nwarps) {
@@ -762,6 +802,138 @@ __global__ void __launch_bounds__(256) ztlr_apply_kernel(ZArgs ar, ZWorkspace ws
     }
     if (on)
         for (int r = lane; r < m; r += 32) out[r] = z[r];
+}
+
+// ---- 4b. blocked reflector application on the FP64 tensor pipe (panels factored by ztlr_qr_blocked_kernel) --------
+// grid = (ceil(N / 8), 2, tiles), 512 threads: a CTA owns 8 output columns, Z = [Y; 0] (m x 8), held TRANSPOSED in
+// DMMA accumulator fragments (warp w owns the row blocks w, w + 16, ..., 8 rows each: 32 doubles per lane; 16 columns
+// per CTA would be the whole register file).  The reflectors are applied eight at a time through their compact-WY
+// factors (T from the QR kernel), last block first:   W = V^H Z,   Z <- Z - V (T W).
+//   step 1  W^T(c, i) = sum_r Z(r, c) conj(V(r, i)): the accumulator fragment of Z^T (lane (g, t): column g, rows 2t,
+//           2t + 1 of the block) IS an A fragment when the contraction chunks are taken as the even / the odd rows, so
+//           Z never leaves its registers; the B fragment is conj(V(8 rb + 2t + e, j0 + g)), loaded from L2.
+//           Per-warp partial tiles are summed through shared memory by 64 threads, which also multiply by T
+//           (eight-lane shuffles: the eight entries of a column of W sit in eight consecutive lanes).
+//   step 2  Z^T(c, r) -= sum_i (T W)(i, c) V(r, i): A = -(T W)^T from shared memory, B = V(8 rb + g, j0 + t + 4h)
+//           (the same 128 KB of V again, in the other fragment layout: L1 hits where the block survived there).
+// 8 real DMMAs per row block and step against two 16-byte loads; the one-column-per-warp kernel above (scalar complex
+// FMAs on operands in shared memory) was bound by shared-memory bandwidth: 42 ms per 592 tiles.
+constexpr int kZApRb = 8;          // row blocks per warp: 16 warps x 8 blocks x 8 rows = 1024 rows
+
+__global__ void __launch_bounds__(512, 1) ztlr_apply_wy_kernel(ZArgs ar, ZWorkspace ws) {
+    __shared__ __align__(16) zc part[16][64];          // per-warp partial W^T tiles [c][i]
+    __shared__ __align__(16) zc ntw[64];               // -(T W)^T [c][i]
+    __shared__ __align__(16) zc Tb[64];                // T(i, k) at i + 8 k
+    const int t = blockIdx.z, pnl = blockIdx.y;
+    if (ws.st[t] != HCORE_B200_OK) return;
+    const int rnew = ws.newrank[t];
+    const int c0 = blockIdx.x * 8;
+    if (c0 >= rnew) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+    const int gt = ar.tile0 + t;
+    const int n = ws.ncols[t], m = ar.nb, N = ws.N;
+    const zc *X = zpanel(ws, pnl, t, m);
+    const zc *tf_g = ws.tfac + ((size_t)pnl * ws.chunk + t) * N * kZB;
+    const zc *Y = ws.Y + ((size_t)pnl * ws.chunk + t) * N * N;
+    zc *out = ar.ptrs ? const_cast<zc *>(ar.ptrs[(4 + pnl) * ar.ptr_stride + gt]) : (pnl == 0 ? ar.CU : ar.CV) + (size_t)gt * ar.strideC;
+    const zc zero = zmake(0.0, 0.0);
+    const int col = c0 + g;
+
+    double zr[kZApRb][2], zi[kZApRb][2];                // Z^T fragments [row block][e]: column g, row 2 tg + e
+#pragma unroll
+    for (int i = 0; i < kZApRb; ++i)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = 8 * (warp + 16 * i) + 2 * tg + e;
+            const zc v = (r < n && col < rnew) ? Y[r + (size_t)col * N] : zero;
+            zr[i][e] = v.x; zi[i][e] = v.y;
+        }
+    // V(r, j): reflector j below its diagonal, unit diagonal, zero above (R lives there) and outside the panel.  The load is
+    // a volatile asm so that it keeps its place in the instruction stream: ONE row block ahead of the DMMAs that consume it.
+    auto vload = [&](int r, int j, bool diag) {
+        const int rc = r < m ? r : m - 1, jc = j < n ? j : n - 1;
+        zc v;
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(X + rc + (size_t)jc * m));
+        if (r >= m || j >= n) v = zero;
+        else if (diag && r <= j) v = zmake(r == j ? 1.0 : 0.0, 0.0);
+        return v;
+    };
+
+    const int nblk = (n + 7) >> 3;
+    for (int bk = nblk - 1; bk >= 0; --bk) {
+        const int j0 = 8 * bk;
+        if (tid < 64) Tb[tid] = tf_g[((size_t)j0 << 3) + tid];
+        // ---- step 1: partial W^T over this warp's row blocks ----
+        double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};  // row c = g, columns i = 2 tg + {0, 1}
+        auto ld1 = [&](int rb, zc *v) {
+            const int r = 8 * rb + 2 * tg;
+            v[0] = vload(r, j0 + g, rb == bk); v[1] = vload(r + 1, j0 + g, rb == bk);
+        };
+        zc vn[2] = {zero, zero};
+        if (warp >= bk && 8 * warp < m) ld1(warp, vn);
+#pragma unroll
+        for (int i = 0; i < kZApRb; ++i) {
+            const int rb = warp + 16 * i;
+            const zc v[2] = {vn[0], vn[1]};
+            if (i + 1 < kZApRb && rb + 16 >= bk && 8 * (rb + 16) < m) ld1(rb + 16, vn);
+            if (rb >= bk && 8 * rb < m) {               // rows above the block: V = 0
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {           // z conj(v) = (zr vr + zi vi) + i (zi vr - zr vi)
+                    dmma_884(wr[0], wr[1], zr[i][e], v[e].x);
+                    dmma_884(wr[0], wr[1], zi[i][e], v[e].y);
+                    dmma_884(wi[0], wi[1], zi[i][e], v[e].x);
+                    dmma_884(wi[0], wi[1], zr[i][e], -v[e].y);
+                }
+            }
+        }
+        part[warp][g * 8 + 2 * tg] = zmake(wr[0], wi[0]);
+        part[warp][g * 8 + 2 * tg + 1] = zmake(wr[1], wi[1]);
+        __syncthreads();
+        if (tid < 64) {                                 // entry (c, k): sum the partials, then row i = k of T W
+            const int i = tid & 7;
+            zc s = zero;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) s = zadd(s, part[w][tid]);
+            zc acc = zero;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {               // (T W)(i, c) = sum_k T(i, k) W(k, c); W^T(c, k) sits in lane (base + k)
+                const zc wk = zmake(__shfl_sync(0xffffffffu, s.x, (lane & ~7) + k), __shfl_sync(0xffffffffu, s.y, (lane & ~7) + k));
+                acc = zfma(Tb[i + 8 * k], wk, acc);
+            }
+            ntw[tid] = zmake(-acc.x, -acc.y);
+        }
+        __syncthreads();
+        // ---- step 2: Z^T += -(T W)^T V^T ----
+        const zc a[2] = {ntw[g * 8 + tg], ntw[g * 8 + tg + 4]};
+        auto ld2 = [&](int rb, zc *v) {
+            const int r = 8 * rb + g;
+            v[0] = vload(r, j0 + tg, rb == bk); v[1] = vload(r, j0 + tg + 4, rb == bk);
+        };
+        if (warp >= bk && 8 * warp < m) ld2(warp, vn);
+#pragma unroll
+        for (int i = 0; i < kZApRb; ++i) {
+            const int rb = warp + 16 * i;
+            const zc v[2] = {vn[0], vn[1]};
+            if (i + 1 < kZApRb && rb + 16 >= bk && 8 * (rb + 16) < m) ld2(rb + 16, vn);
+            if (rb >= bk && 8 * rb < m) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {           // a v = (ar vr - ai vi) + i (ar vi + ai vr)
+                    dmma_884(zr[i][0], zr[i][1], a[h].x, v[h].x);
+                    dmma_884(zr[i][0], zr[i][1], a[h].y, -v[h].y);
+                    dmma_884(zi[i][0], zi[i][1], a[h].x, v[h].y);
+                    dmma_884(zi[i][0], zi[i][1], a[h].y, v[h].x);
+                }
+            }
+        }
+    }
+    if (col < rnew) {
+#pragma unroll
+        for (int i = 0; i < kZApRb; ++i) {
+            const int r = 8 * (warp + 16 * i) + 2 * tg;
+            if (r < m) out[r + (size_t)col * ar.ldc] = zmake(zr[i][0], zi[i][0]);
+            if (r + 1 < m) out[r + 1 + (size_t)col * ar.ldc] = zmake(zr[i][1], zi[i][1]);
+        }
+    }
 }
 
 }  // namespace hcore_b200
