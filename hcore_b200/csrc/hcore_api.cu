@@ -843,7 +843,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     while (apw > 2 && (size_t)(apw + 4) * nb * sizeof(zc) > 227 * 1024) apw >>= 1;      // W columns + two pairs of reflectors
     const size_t sm_qr = (2ull * nb + 40) * sizeof(double), sm_ap = (size_t)(apw + 4) * nb * sizeof(zc);
     if (sm_ap > 227 * 1024) { ctx->err = "HCORE_zgemm: nb too large for the apply kernel's shared memory"; return HCORE_B200_ERR_ARG; }
-    const size_t sm_qrb = (2ull * kZB * nb + 16 + 2 * kZB + 2 * kZB * kZB) * sizeof(double);
+    const size_t sm_qrb = (2ull * kZB * (nb + 1) + 32 + 2 * kZB + 6 * kZB * kZB + 2 * 16 * 64) * sizeof(double);
     CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qr));
     if (nb <= 32 * kZRows)
         CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qrb));
@@ -859,7 +859,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
         ar.rk = rk; ar.maxrk = maxrk; ar.acc = acc; ar.tile0 = t0; ar.ntiles = std::min(chunk, ntiles - t0);
         ar.ptrs = (const zc *const *)d_ptrs; ar.ptr_stride = ntiles;
         ztlr_stack_kernel<<<ar.ntiles, 256, 0, st>>>(ar, ws);
-        if (nb <= 32 * kZRows) ztlr_qr_blocked_kernel<<<2 * ar.ntiles, 256, sm_qrb, st>>>(ar, ws);
+        if (nb <= 32 * kZRows) ztlr_qr_blocked_kernel<<<2 * ar.ntiles, 512, sm_qrb, st>>>(ar, ws);
         else ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
         if (N <= 128) ztlr_svd_kernel<8><<<ar.ntiles, 512, 0, st>>>(ar, ws);
         else ztlr_svd_kernel<16><<<ar.ntiles, 256, 0, st>>>(ar, ws);

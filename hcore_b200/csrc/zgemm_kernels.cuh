@@ -275,36 +275,46 @@ __global__ void __launch_bounds__(512) ztlr_qr_kernel(ZArgs ar, ZWorkspace ws) {
 }
 
 // ---- 2b. blocked Householder QR (nb <= 1024) ----------------------------------------------------------------
-// Same reflectors as ztlr_qr_kernel (zgeqr2 order of operations per column), but the panel is streamed from
-// HBM once per 8-column block instead of once per column: the 8 block columns are factored in shared memory,
-// then every trailing column is loaded into REGISTERS (a warp per column, 32 rows per lane), hit by the 8
-// reflectors in sequence (reflector vectors from shared memory) and written back.  The unblocked kernel
-// moved 268 MB per panel through HBM (66 ms per 592 tiles, HBM-bound); this one moves 33 MB.
+// Same reflectors as ztlr_qr_kernel (zgeqr2 order of operations per column inside a block), but the panel is streamed
+// from HBM once per 8-column block instead of once per column: the 8 block columns are factored in shared memory, their
+// compact-WY factor T is formed (zlarft), and the trailing columns are updated EIGHT AT A TIME on the FP64 tensor pipe,
+//   X <- (I - V T^H V^H) X:   W = V^H X,   X <- X - V (T^H W),
+// with the scheme of ztlr_apply_wy_kernel below: the 8 trailing columns live transposed in DMMA accumulator fragments
+// (16 warps x 8 row blocks), V comes from shared memory (leading dimension m + 1: both fragment layouts conflict-free),
+// the per-warp partial W tiles are summed and multiplied by T^H by 64 threads.  The first blocked version updated one
+// trailing column per warp with scalar complex FMAs (22 ms per 592 tiles); the unblocked kernel moved 268 MB per panel
+// through HBM (66 ms per 592 tiles, HBM-bound), this one moves 33 MB.
 constexpr int kZB = 8;          // block width
-constexpr int kZRows = 32;      // rows per lane of a trailing column: nb - j0 <= 32 * kZRows
+constexpr int kZRows = 32;      // nb <= 32 * kZRows = 1024: 16 warps x 8 row blocks x 8 rows
+constexpr int kZQrRb = 8;       // row blocks per warp
 
-__global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspace ws) {
+__global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspace ws) {
     extern __shared__ __align__(16) double zsm[];
     const int t = blockIdx.x >> 1, pnl = blockIdx.x & 1;
     if (ws.st[t] != HCORE_B200_OK) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const int n = ws.ncols[t], m = ar.nb;
+    const int g = lane >> 2, tg = lane & 3;
+    const int n = ws.ncols[t], m = ar.nb, ldp = m + 1;
     zc *X = zpanel(ws, pnl, t, m);
     zc *tau_g = ws.tau + ((size_t)pnl * ws.chunk + t) * ws.N;
-    zc *P = reinterpret_cast<zc *>(zsm);                       // [kZB][m] block columns (row index absolute)
-    double *red = zsm + 2 * (size_t)kZB * m;                   // [8] partial sums, [8..11] tau, scale
-    zc *taus = reinterpret_cast<zc *>(red + 16);               // [kZB]
-    zc *Sg = taus + kZB;                                       // [kZB][kZB] v_i^H v_k, i < k
     zc *tf_g = ws.tfac + ((size_t)pnl * ws.chunk + t) * ws.N * kZB;
+    zc *P = reinterpret_cast<zc *>(zsm);                       // [kZB][ldp] block columns (row index absolute)
+    double *red = zsm + 2 * (size_t)kZB * ldp;                 // [16] partial sums, [16..19] tau, scale
+    zc *taus = reinterpret_cast<zc *>(red + 32);               // [kZB]
+    zc *Sg = taus + kZB;                                       // [kZB][kZB] v_i^H v_k, i < k
+    zc *Tsm = Sg + kZB * kZB;                                  // T(i, k) at i + 8 k
+    zc *ntw = Tsm + kZB * kZB;                                 // -(T^H W)^T [c][i]
+    zc *part = ntw + kZB * kZB;                                // [16][64] per-warp partial W^T tiles
+    const zc zero = zmake(0.0, 0.0);
     for (int j0 = 0; j0 < n; j0 += kZB) {
-        const int nbk = (n - j0 < kZB) ? (n - j0) : kZB;
+        const int nbk = (n - j0 < kZB) ? (n - j0) : kZB, bk = j0 >> 3;
         for (int c = 0; c < nbk; ++c)
-            for (int r = j0 + tid; r < m; r += blockDim.x) P[(size_t)c * m + r] = X[(size_t)(j0 + c) * m + r];
+            for (int r = j0 + tid; r < m; r += blockDim.x) P[(size_t)c * ldp + r] = X[(size_t)(j0 + c) * m + r];
         __syncthreads();
         // ---- the block's columns, in shared memory -------------------------------------------------
         for (int jj = 0; jj < nbk; ++jj) {
             const int j = j0 + jj;
-            zc *pj = P + (size_t)jj * m;
+            zc *pj = P + (size_t)jj * ldp;
             double s = 0.0;
             for (int r = j + 1 + tid; r < m; r += blockDim.x) s += zabs2(pj[r]);
             s = warp_sum(s);
@@ -325,38 +335,38 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
                 }
                 tau_g[j] = tau;
                 taus[jj] = tau;
-                red[8] = tau.x; red[9] = tau.y; red[10] = scale.x; red[11] = scale.y;
+                red[16] = tau.x; red[17] = tau.y; red[18] = scale.x; red[19] = scale.y;
             }
             __syncthreads();
-            const zc tau = zmake(red[8], red[9]), scale = zmake(red[10], red[11]);
+            const zc tau = zmake(red[16], red[17]), scale = zmake(red[18], red[19]);
             for (int r = j + 1 + tid; r < m; r += blockDim.x) pj[r] = zmul(pj[r], scale);
             __syncthreads();
             if (tau.x != 0.0 || tau.y != 0.0) {
                 const zc ctau = zconj(tau);                                // H^H = I - conj(tau) v v^H
                 for (int c = jj + 1 + warp; c < nbk; c += nwarps) {
-                    zc *pc = P + (size_t)c * m;
+                    zc *pc = P + (size_t)c * ldp;
                     zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
                     int r = j + 1 + lane;
                     for (; r + 32 < m; r += 64) { d0 = zcfma(pj[r], pc[r], d0); d1 = zcfma(pj[r + 32], pc[r + 32], d1); }
                     if (r < m) d0 = zcfma(pj[r], pc[r], d0);
                     zc dot = zwarp_sum(zadd(d0, d1));
                     dot = zadd(dot, pc[j]);
-                    const zc tw = zmul(ctau, dot), ntw = zmake(-tw.x, -tw.y);
+                    const zc tw = zmul(ctau, dot), ntw1 = zmake(-tw.x, -tw.y);
                     __syncwarp();
                     if (lane == 0) pc[j] = zsub(pc[j], tw);
-                    for (int q = j + 1 + lane; q < m; q += 32) pc[q] = zfma(ntw, pj[q], pc[q]);
+                    for (int q = j + 1 + lane; q < m; q += 32) pc[q] = zfma(ntw1, pj[q], pc[q]);
                 }
             }
             __syncthreads();
         }
         // ---- compact-WY factor of the block (zlarft, forward / columnwise): H_j0 ... H_{j0+7} = I - V T V^H with
-        //      T(k,k) = tau_k, T(0:k, k) = -tau_k T(0:k, 0:k) (V(:, 0:k)^H v_k); consumed by ztlr_apply_wy_kernel ------
+        //      T(k,k) = tau_k, T(0:k, k) = -tau_k T(0:k, 0:k) (V(:, 0:k)^H v_k); also consumed by ztlr_apply_wy_kernel ----
         {
             int q = 0;
             for (int k = 1; k < nbk; ++k)
                 for (int i = 0; i < k; ++i, ++q) {
                     if (q % nwarps != warp) continue;
-                    const zc *pi = P + (size_t)i * m, *pk = P + (size_t)k * m;
+                    const zc *pi = P + (size_t)i * ldp, *pk = P + (size_t)k * ldp;
                     zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
                     int r = j0 + k + 1 + lane;
                     for (; r + 32 < m; r += 64) { d0 = zcfma(pi[r], pk[r], d0); d1 = zcfma(pi[r + 32], pk[r + 32], d1); }
@@ -382,55 +392,91 @@ __global__ void __launch_bounds__(256) ztlr_qr_blocked_kernel(ZArgs ar, ZWorkspa
                         }
                     }
                     Ti[k] = v;
+                    Tsm[i + kZB * k] = v;
                     tf_g[((size_t)j0 << 3) + i + kZB * k] = v;
                 }
             }
         }
-        // ---- trailing columns: one warp per column, the column in registers ---------------------------
-        for (int c = j0 + nbk + warp; c < n; c += nwarps) {
-            zc *xc = X + (size_t)c * m;
-            zc x[kZRows];
+        // ---- trailing columns, eight at a time (a full block whenever there are any) --------------------------
+        // V(r, jj) of this block from shared memory: below the diagonal as stored, unit diagonal, zero above
+        auto vsm = [&](int r, int jj, bool diag) {
+            zc v = P[(size_t)jj * ldp + (r < m ? r : m - 1)];
+            if (r >= m) v = zero;
+            else if (diag && r <= j0 + jj) v = zmake(r == j0 + jj ? 1.0 : 0.0, 0.0);
+            return v;
+        };
+        for (int cg0 = j0 + kZB; cg0 < n; cg0 += 8) {
+            const int col = cg0 + g;
+            zc *xc = X + (size_t)(col < n ? col : n - 1) * m;
+            double zr[kZQrRb][2], zi[kZQrRb][2];               // X^T fragments: column g, rows 8 rb + 2 tg + e
 #pragma unroll
-            for (int i = 0; i < kZRows; ++i) {
-                const int r = j0 + lane + 32 * i;
-                x[i] = (r < m) ? xc[r] : zmake(0.0, 0.0);
-            }
-            for (int jj = 0; jj < nbk; ++jj) {
-                const zc tau = taus[jj];
-                if (tau.x == 0.0 && tau.y == 0.0) continue;
-                const int j = j0 + jj;
-                const zc *pj = P + (size_t)jj * m;
-                zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
+            for (int i = 0; i < kZQrRb; ++i)
 #pragma unroll
-                for (int i = 0; i < kZRows; ++i) {
-                    const int r = j0 + lane + 32 * i;
-                    // rows j0 + 32 and beyond lie below every diagonal of the block: only the first register needs the
-                    // unit-diagonal / zero-above cases (the compares and selects were 40 % of the kernel's instructions)
-                    zc v;
-                    if (i == 0) v = (r > j && r < m) ? pj[r] : zmake(r == j ? 1.0 : 0.0, 0.0);
-                    else v = (r < m) ? pj[r] : zmake(0.0, 0.0);
-                    if (i & 1) d1 = zcfma(v, x[i], d1); else d0 = zcfma(v, x[i], d0);
+                for (int e = 0; e < 2; ++e) {
+                    const int rb = warp + 16 * i, r = 8 * rb + 2 * tg + e;
+                    const zc v = (rb >= bk && r < m && col < n) ? xc[r] : zero;
+                    zr[i][e] = v.x; zi[i][e] = v.y;
                 }
-                const zc dot = zwarp_sum(zadd(d0, d1));
-                const zc tw = zmul(zconj(tau), dot), ntw = zmake(-tw.x, -tw.y);
+            double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};     // W^T partial: row c = g, columns i = 2 tg + {0, 1}
 #pragma unroll
-                for (int i = 0; i < kZRows; ++i) {
-                    const int r = j0 + lane + 32 * i;
-                    zc v;
-                    if (i == 0) v = (r > j && r < m) ? pj[r] : zmake(r == j ? 1.0 : 0.0, 0.0);
-                    else v = (r < m) ? pj[r] : zmake(0.0, 0.0);
-                    x[i] = zfma(ntw, v, x[i]);
+            for (int i = 0; i < kZQrRb; ++i) {
+                const int rb = warp + 16 * i;
+                if (rb >= bk && 8 * rb < m) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {              // x conj(v)
+                        const zc v = vsm(8 * rb + 2 * tg + e, g, rb == bk);
+                        dmma_884(wr[0], wr[1], zr[i][e], v.x);
+                        dmma_884(wr[0], wr[1], zi[i][e], v.y);
+                        dmma_884(wi[0], wi[1], zi[i][e], v.x);
+                        dmma_884(wi[0], wi[1], zr[i][e], -v.y);
+                    }
                 }
             }
+            part[warp * 64 + g * 8 + 2 * tg] = zmake(wr[0], wi[0]);
+            part[warp * 64 + g * 8 + 2 * tg + 1] = zmake(wr[1], wi[1]);
+            __syncthreads();
+            if (tid < 64) {                                    // entry (c, k): sum the partials, then row i = k of T^H W
+                const int i = tid & 7;
+                zc s = zero;
+                for (int w = 0; w < nwarps; ++w) s = zadd(s, part[w * 64 + tid]);
+                zc acc = zero;
 #pragma unroll
-            for (int i = 0; i < kZRows; ++i) {
-                const int r = j0 + lane + 32 * i;
-                if (r < m) xc[r] = x[i];
+                for (int k = 0; k < 8; ++k) {                  // (T^H W)(i, c) = sum_k conj(T(k, i)) W(k, c)
+                    const zc wk = zmake(__shfl_sync(0xffffffffu, s.x, (lane & ~7) + k), __shfl_sync(0xffffffffu, s.y, (lane & ~7) + k));
+                    acc = zcfma(Tsm[k + 8 * i], wk, acc);
+                }
+                ntw[tid] = zmake(-acc.x, -acc.y);
+            }
+            __syncthreads();
+            const zc a[2] = {ntw[g * 8 + 2 * tg], ntw[g * 8 + 2 * tg + 1]};   // contraction chunks: reflectors 2 tg + h
+#pragma unroll
+            for (int i = 0; i < kZQrRb; ++i) {
+                const int rb = warp + 16 * i;
+                if (rb >= bk && 8 * rb < m) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {              // a v
+                        const zc v = vsm(8 * rb + g, 2 * tg + h, rb == bk);
+                        dmma_884(zr[i][0], zr[i][1], a[h].x, v.x);
+                        dmma_884(zr[i][0], zr[i][1], a[h].y, -v.y);
+                        dmma_884(zi[i][0], zi[i][1], a[h].x, v.y);
+                        dmma_884(zi[i][0], zi[i][1], a[h].y, v.x);
+                    }
+                }
+            }
+            if (col < n) {
+#pragma unroll
+                for (int i = 0; i < kZQrRb; ++i) {
+                    const int rb = warp + 16 * i, r = 8 * rb + 2 * tg;
+                    if (rb >= bk) {
+                        if (r < m) xc[r] = zmake(zr[i][0], zi[i][0]);
+                        if (r + 1 < m) xc[r + 1] = zmake(zr[i][1], zi[i][1]);
+                    }
+                }
             }
         }
         // ---- the factored block goes back (reflectors below the diagonal, R on and above) -----------------
         for (int c = 0; c < nbk; ++c)
-            for (int r = j0 + tid; r < m; r += blockDim.x) X[(size_t)(j0 + c) * m + r] = P[(size_t)c * m + r];
+            for (int r = j0 + tid; r < m; r += blockDim.x) X[(size_t)(j0 + c) * m + r] = P[(size_t)c * ldp + r];
         __syncthreads();
     }
 }
