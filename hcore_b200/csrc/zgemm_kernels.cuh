@@ -75,6 +75,14 @@ __device__ __forceinline__ zc *zpanel(const ZWorkspace &ws, int pnl, int t, int 
     return ws.panel + ((size_t)pnl * ws.chunk + t) * (size_t)m * ws.N;
 }
 
+// 256-bit global accesses (two consecutive complex numbers, 32-byte aligned: sm_100 LDG/STG.256)
+__device__ __forceinline__ void ldg_z2(const zc *p, zc &a, zc &b) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void stg_z2(zc *p, zc a, zc b) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
 // Block-level complex product C(i, j) = sum_{k in [klo, khi)} A(i, k) B(k, j) on the FP64 tensor pipe (four real DMMAs
 // per complex 8 x 8 x 4 step).  fa(i, k), fb(k, j) return the operand entries (zero outside their extent), put(i, j, v)
 // stores a result entry, klim(i0, j0, klo, khi) may shrink the contraction range of an 8 x 8 output tile (triangular
@@ -306,11 +314,25 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
     zc *ntw = Tsm + kZB * kZB;                                 // -(T^H W)^T [c][i]
     zc *part = ntw + kZB * kZB;                                // [16][64] per-warp partial W^T tiles
     const zc zero = zmake(0.0, 0.0);
+    const bool wide = (m & 1) == 0;                            // columns 32-byte aligned
+    // The panels of a chunk do not fit the L2 (2 MB each, one per SM in flight): the eight trailing columns of the NEXT update
+    // step are pulled into the L2 while the current ones are in the tensor pipe (rows r0.., 128-byte lines dealt to the threads)
+    auto prefetch_cols = [&](int c0, int r0) {
+        const int lpc = ((m - r0) * (int)sizeof(zc) + 127) >> 7;          // lines per column
+        for (int id = tid; id < 8 * lpc; id += blockDim.x) {
+            const int c = c0 + id / lpc;
+            if (c < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(X + (size_t)c * m + r0) + ((size_t)(id % lpc) << 7)));
+        }
+    };
+    PROF_DECL(tid == 0)
+    PROF_COUNT(55, 1);
     for (int j0 = 0; j0 < n; j0 += kZB) {
         const int nbk = (n - j0 < kZB) ? (n - j0) : kZB, bk = j0 >> 3;
         for (int c = 0; c < nbk; ++c)
             for (int r = j0 + tid; r < m; r += blockDim.x) P[(size_t)c * ldp + r] = X[(size_t)(j0 + c) * m + r];
+        if (j0 + kZB < n) prefetch_cols(j0 + kZB, j0);
         __syncthreads();
+        PROF_ADD(50);
         // ---- the block's columns, in shared memory -------------------------------------------------
         for (int jj = 0; jj < nbk; ++jj) {
             const int j = j0 + jj;
@@ -359,6 +381,7 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
             }
             __syncthreads();
         }
+        PROF_ADD(51);
         // ---- compact-WY factor of the block (zlarft, forward / columnwise): H_j0 ... H_{j0+7} = I - V T V^H with
         //      T(k,k) = tau_k, T(0:k, k) = -tau_k T(0:k, 0:k) (V(:, 0:k)^H v_k); also consumed by ztlr_apply_wy_kernel ----
         {
@@ -397,6 +420,7 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                 }
             }
         }
+        PROF_ADD(52);
         // ---- trailing columns, eight at a time (a full block whenever there are any) --------------------------
         // V(r, jj) of this block from shared memory: below the diagonal as stored, unit diagonal, zero above
         auto vsm = [&](int r, int jj, bool diag) {
@@ -408,32 +432,38 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
         for (int cg0 = j0 + kZB; cg0 < n; cg0 += 8) {
             const int col = cg0 + g;
             zc *xc = X + (size_t)(col < n ? col : n - 1) * m;
+            if (cg0 + 8 < n) prefetch_cols(cg0 + 8, j0);
             double zr[kZQrRb][2], zi[kZQrRb][2];               // X^T fragments: column g, rows 8 rb + 2 tg + e
 #pragma unroll
-            for (int i = 0; i < kZQrRb; ++i)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int rb = warp + 16 * i, r = 8 * rb + 2 * tg + e;
-                    const zc v = (rb >= bk && r < m && col < n) ? xc[r] : zero;
-                    zr[i][e] = v.x; zi[i][e] = v.y;
+            for (int i = 0; i < kZQrRb; ++i) {
+                const int rb = warp + 16 * i, r = 8 * rb + 2 * tg;
+                zc v0 = zero, v1 = zero;
+                if (rb >= bk && col < n) {
+                    if (wide) { if (r < m) ldg_z2(xc + r, v0, v1); }          // one 32-byte access per lane instead of two half sectors
+                    else { if (r < m) v0 = xc[r]; if (r + 1 < m) v1 = xc[r + 1]; }
                 }
-            double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};     // W^T partial: row c = g, columns i = 2 tg + {0, 1}
+                zr[i][0] = v0.x; zi[i][0] = v0.y; zr[i][1] = v1.x; zi[i][1] = v1.y;
+            }
+            // W^T partial: row c = g, columns i = 2 tg + {0, 1}; one accumulator pair per contraction chunk e, so that four
+            // independent DMMAs separate every dependent pair (a warp issues in order: back-to-back dependent DMMAs wait 26 cycles)
+            double wr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, wi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
             for (int i = 0; i < kZQrRb; ++i) {
                 const int rb = warp + 16 * i;
-                if (rb >= bk && 8 * rb < m) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {              // x conj(v)
-                        const zc v = vsm(8 * rb + 2 * tg + e, g, rb == bk);
-                        dmma_884(wr[0], wr[1], zr[i][e], v.x);
-                        dmma_884(wr[0], wr[1], zi[i][e], v.y);
-                        dmma_884(wi[0], wi[1], zi[i][e], v.x);
-                        dmma_884(wi[0], wi[1], zr[i][e], -v.y);
-                    }
+                if (rb >= bk && 8 * rb < m) {                  // x conj(v)
+                    const zc v0 = vsm(8 * rb + 2 * tg, g, rb == bk), v1 = vsm(8 * rb + 2 * tg + 1, g, rb == bk);
+                    dmma_884(wr[0][0], wr[0][1], zr[i][0], v0.x);
+                    dmma_884(wi[0][0], wi[0][1], zi[i][0], v0.x);
+                    dmma_884(wr[1][0], wr[1][1], zr[i][1], v1.x);
+                    dmma_884(wi[1][0], wi[1][1], zi[i][1], v1.x);
+                    dmma_884(wr[0][0], wr[0][1], zi[i][0], v0.y);
+                    dmma_884(wi[0][0], wi[0][1], zr[i][0], -v0.y);
+                    dmma_884(wr[1][0], wr[1][1], zi[i][1], v1.y);
+                    dmma_884(wi[1][0], wi[1][1], zr[i][1], -v1.y);
                 }
             }
-            part[warp * 64 + g * 8 + 2 * tg] = zmake(wr[0], wi[0]);
-            part[warp * 64 + g * 8 + 2 * tg + 1] = zmake(wr[1], wi[1]);
+            part[warp * 64 + g * 8 + 2 * tg] = zmake(wr[0][0] + wr[1][0], wi[0][0] + wi[1][0]);
+            part[warp * 64 + g * 8 + 2 * tg + 1] = zmake(wr[0][1] + wr[1][1], wi[0][1] + wi[1][1]);
             __syncthreads();
             if (tid < 64) {                                    // entry (c, k): sum the partials, then row i = k of T^H W
                 const int i = tid & 7;
@@ -454,11 +484,11 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                 const int rb = warp + 16 * i;
                 if (rb >= bk && 8 * rb < m) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {              // a v
+                    for (int h = 0; h < 2; ++h) {              // a v, real and imaginary accumulators alternating
                         const zc v = vsm(8 * rb + g, 2 * tg + h, rb == bk);
                         dmma_884(zr[i][0], zr[i][1], a[h].x, v.x);
-                        dmma_884(zr[i][0], zr[i][1], a[h].y, -v.y);
                         dmma_884(zi[i][0], zi[i][1], a[h].x, v.y);
+                        dmma_884(zr[i][0], zr[i][1], a[h].y, -v.y);
                         dmma_884(zi[i][0], zi[i][1], a[h].y, v.x);
                     }
                 }
@@ -468,16 +498,21 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                 for (int i = 0; i < kZQrRb; ++i) {
                     const int rb = warp + 16 * i, r = 8 * rb + 2 * tg;
                     if (rb >= bk) {
-                        if (r < m) xc[r] = zmake(zr[i][0], zi[i][0]);
-                        if (r + 1 < m) xc[r + 1] = zmake(zr[i][1], zi[i][1]);
+                        if (wide) { if (r < m) stg_z2(xc + r, zmake(zr[i][0], zi[i][0]), zmake(zr[i][1], zi[i][1])); }
+                        else {
+                            if (r < m) xc[r] = zmake(zr[i][0], zi[i][0]);
+                            if (r + 1 < m) xc[r + 1] = zmake(zr[i][1], zi[i][1]);
+                        }
                     }
                 }
             }
         }
+        PROF_ADD(53);
         // ---- the factored block goes back (reflectors below the diagonal, R on and above) -----------------
         for (int c = 0; c < nbk; ++c)
             for (int r = j0 + tid; r < m; r += blockDim.x) X[(size_t)(j0 + c) * m + r] = P[(size_t)c * ldp + r];
         __syncthreads();
+        PROF_ADD(54);
     }
 }
 
@@ -910,7 +945,8 @@ __global__ void __launch_bounds__(512, 1) ztlr_apply_wy_kernel(ZArgs ar, ZWorksp
         const int j0 = 8 * bk;
         if (tid < 64) Tb[tid] = tf_g[((size_t)j0 << 3) + tid];
         // ---- step 1: partial W^T over this warp's row blocks ----
-        double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};  // row c = g, columns i = 2 tg + {0, 1}
+        // row c = g, columns i = 2 tg + {0, 1}; one accumulator pair per contraction chunk (four independent DMMAs between dependent ones)
+        double wr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, wi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
         auto ld1 = [&](int rb, zc *v) {
             const int r = 8 * rb + 2 * tg;
             v[0] = vload(r, j0 + g, rb == bk); v[1] = vload(r + 1, j0 + g, rb == bk);
@@ -923,17 +959,19 @@ __global__ void __launch_bounds__(512, 1) ztlr_apply_wy_kernel(ZArgs ar, ZWorksp
             const zc v[2] = {vn[0], vn[1]};
             if (i + 1 < kZApRb && rb + 16 >= bk && 8 * (rb + 16) < m) ld1(rb + 16, vn);
             if (rb >= bk && 8 * rb < m) {               // rows above the block: V = 0
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {           // z conj(v) = (zr vr + zi vi) + i (zi vr - zr vi)
-                    dmma_884(wr[0], wr[1], zr[i][e], v[e].x);
-                    dmma_884(wr[0], wr[1], zi[i][e], v[e].y);
-                    dmma_884(wi[0], wi[1], zi[i][e], v[e].x);
-                    dmma_884(wi[0], wi[1], zr[i][e], -v[e].y);
-                }
+                // z conj(v) = (zr vr + zi vi) + i (zi vr - zr vi)
+                dmma_884(wr[0][0], wr[0][1], zr[i][0], v[0].x);
+                dmma_884(wi[0][0], wi[0][1], zi[i][0], v[0].x);
+                dmma_884(wr[1][0], wr[1][1], zr[i][1], v[1].x);
+                dmma_884(wi[1][0], wi[1][1], zi[i][1], v[1].x);
+                dmma_884(wr[0][0], wr[0][1], zi[i][0], v[0].y);
+                dmma_884(wi[0][0], wi[0][1], zr[i][0], -v[0].y);
+                dmma_884(wr[1][0], wr[1][1], zi[i][1], v[1].y);
+                dmma_884(wi[1][0], wi[1][1], zr[i][1], -v[1].y);
             }
         }
-        part[warp][g * 8 + 2 * tg] = zmake(wr[0], wi[0]);
-        part[warp][g * 8 + 2 * tg + 1] = zmake(wr[1], wi[1]);
+        part[warp][g * 8 + 2 * tg] = zmake(wr[0][0] + wr[1][0], wi[0][0] + wi[1][0]);
+        part[warp][g * 8 + 2 * tg + 1] = zmake(wr[0][1] + wr[1][1], wi[0][1] + wi[1][1]);
         __syncthreads();
         if (tid < 64) {                                 // entry (c, k): sum the partials, then row i = k of T W
             const int i = tid & 7;
@@ -965,8 +1003,8 @@ __global__ void __launch_bounds__(512, 1) ztlr_apply_wy_kernel(ZArgs ar, ZWorksp
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {           // a v = (ar vr - ai vi) + i (ar vi + ai vr)
                     dmma_884(zr[i][0], zr[i][1], a[h].x, v[h].x);
-                    dmma_884(zr[i][0], zr[i][1], a[h].y, -v[h].y);
                     dmma_884(zi[i][0], zi[i][1], a[h].x, v[h].y);
+                    dmma_884(zr[i][0], zr[i][1], a[h].y, -v[h].y);
                     dmma_884(zi[i][0], zi[i][1], a[h].y, v[h].x);
                 }
             }
