@@ -328,8 +328,23 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
     PROF_COUNT(55, 1);
     for (int j0 = 0; j0 < n; j0 += kZB) {
         const int nbk = (n - j0 < kZB) ? (n - j0) : kZB, bk = j0 >> 3;
-        for (int c = 0; c < nbk; ++c)
-            for (int r = j0 + tid; r < m; r += blockDim.x) P[(size_t)c * ldp + r] = X[(size_t)(j0 + c) * m + r];
+        {                                                      // all sixteen loads of a thread in flight, then the stores
+            zc tmp[kZB][2];                                    // (a loop over the columns waited for every load: 20 k cycles per block)
+#pragma unroll
+            for (int c = 0; c < kZB; ++c)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = j0 + tid + 512 * u;
+                    tmp[c][u] = (c < nbk && r < m) ? X[(size_t)(j0 + c) * m + r] : zero;
+                }
+#pragma unroll
+            for (int c = 0; c < kZB; ++c)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = j0 + tid + 512 * u;
+                    if (c < nbk && r < m) P[(size_t)c * ldp + r] = tmp[c][u];
+                }
+        }
         if (j0 + kZB < n) prefetch_cols(j0 + kZB, j0);
         __syncthreads();
         PROF_ADD(50);
@@ -363,6 +378,16 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
             const zc tau = zmake(red[16], red[17]), scale = zmake(red[18], red[19]);
             for (int r = j + 1 + tid; r < m; r += blockDim.x) pj[r] = zmul(pj[r], scale);
             __syncthreads();
+            if (warp >= kZB && warp - kZB < jj) {                      // warps without a column: S(i, jj) = v_i^H v_jj, i < jj
+                const int i = warp - kZB;
+                const zc *pi = P + (size_t)i * ldp;
+                zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
+                int r = j + 1 + lane;
+                for (; r + 32 < m; r += 64) { d0 = zcfma(pi[r], pj[r], d0); d1 = zcfma(pi[r + 32], pj[r + 32], d1); }
+                if (r < m) d0 = zcfma(pi[r], pj[r], d0);
+                const zc dot = zadd(zwarp_sum(zadd(d0, d1)), zconj(pi[j]));   // unit diagonal of v_jj
+                if (lane == 0) Sg[i + kZB * jj] = dot;
+            }
             if (tau.x != 0.0 || tau.y != 0.0) {
                 const zc ctau = zconj(tau);                                // H^H = I - conj(tau) v v^H
                 for (int c = jj + 1 + warp; c < nbk; c += nwarps) {
@@ -385,19 +410,6 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
         // ---- compact-WY factor of the block (zlarft, forward / columnwise): H_j0 ... H_{j0+7} = I - V T V^H with
         //      T(k,k) = tau_k, T(0:k, k) = -tau_k T(0:k, 0:k) (V(:, 0:k)^H v_k); also consumed by ztlr_apply_wy_kernel ----
         {
-            int q = 0;
-            for (int k = 1; k < nbk; ++k)
-                for (int i = 0; i < k; ++i, ++q) {
-                    if (q % nwarps != warp) continue;
-                    const zc *pi = P + (size_t)i * ldp, *pk = P + (size_t)k * ldp;
-                    zc d0 = zmake(0.0, 0.0), d1 = zmake(0.0, 0.0);
-                    int r = j0 + k + 1 + lane;
-                    for (; r + 32 < m; r += 64) { d0 = zcfma(pi[r], pk[r], d0); d1 = zcfma(pi[r + 32], pk[r + 32], d1); }
-                    if (r < m) d0 = zcfma(pi[r], pk[r], d0);
-                    const zc dot = zadd(zwarp_sum(zadd(d0, d1)), zconj(pi[j0 + k]));   // unit diagonal of v_k
-                    if (lane == 0) Sg[i + kZB * k] = dot;
-                }
-            __syncthreads();
             if (tid < kZB) {                                   // thread i builds row i of T (rows are independent)
                 const int i = tid;
                 zc Ti[kZB];

@@ -31,3 +31,4 @@ if v[49]:
     print("stack kernel: copy %.0f, P %.0f, G %.0f cycles per tile" % (v[46] / v[49], v[47] / v[49], v[48] / v[49]))
 if v[55]:
     print("QR kernel per panel: block load %.0f, in-block %.0f, T factor %.0f, trailing %.0f, write-back %.0f cycles" % tuple(v[i] / v[55] for i in (50, 51, 52, 53, 54)))
+    print("  trailing update per panel (warp 0): load %.0f, step 1 %.0f, reduce + barriers %.0f, step 2 %.0f, store + rest %.0f cycles" % (tuple(v[i] / v[55] for i in (56, 57, 58, 59)) + (v[53] / v[55],)))
