@@ -1,19 +1,22 @@
 // Complex-double tile-low-rank update + recompression (HCORE_zgemm, reference
-// src/compute/hcore_zgemm.c:663-975) -- first, correctness-oriented CUDA path.
+// src/compute/hcore_zgemm.c:663-975).
 //
-// Same pipeline as the FP64 path, complex arithmetic on the FP64 FMA pipe, operands in global
-// memory / L2 (the complex 1024 x 128 panel is 2 MiB, the 128 x 128 core 256 KiB: neither fits
-// one CTA's shared memory):
-//   ztlr_stack_kernel  X_u = [beta CU | alpha AU], P = AV^T BV, X_v = [CV | BU P^T]   (__zqra/__zqrb,
-//                      hcore_zgemm.c:65-137, :138-215; PLAIN transposes, :165, :189)
-//   ztlr_qr_kernel     unblocked Householder QR (zgeqr2 semantics: zlarfg, H^H applied) of both panels
-//                      (replaces LAPACKE_zgeqrf, hcore_zgemm.c:123, :205)
-//   ztlr_svd_kernel    T = R_u R_v^T (plain transpose, :309), truncated pivoted QR of T^H as preconditioner, one-sided
-//                      Jacobi on the columns of R^H with complex rotations, sort, truncation (rk > 0 = fixed rank, :376), U_r,
-//                      W = R_v (R_u^T conj(U_r))  (replaces LAPACKE_zgesvd + the conj/zunmqr/conj dance
-//                      of __znewv, :593-632: CV = Q_v W)
-//   ztlr_apply_kernel  CU = Q_u [U_r; 0], CV = Q_v [W; 0] by applying the reflectors to one output
-//                      column per warp held in shared memory (replaces LAPACKE_zunmqr, :470-530, :600-620)
+// Same pipeline as the FP64 path in complex arithmetic.  Every product runs on the FP64 tensor pipe (four real DMMAs per
+// complex 8 x 8 x 4 step); operands stay in global memory / L2 (the complex 1024 x 128 panel is 2 MiB, the 128 x 128
+// core 256 KiB: neither fits one CTA's shared memory):
+//   ztlr_stack_kernel      X_u = [beta CU | alpha AU], P = AV^T BV, X_v = [CV | BU P^T]   (__zqra/__zqrb,
+//                          hcore_zgemm.c:65-137, :138-215; PLAIN transposes, :165, :189)
+//   ztlr_qr_blocked_kernel Householder QR of both panels in 8-column blocks (zgeqr2 order inside a block, zlarft factor T
+//                          per block, trailing columns updated eight at a time on DMMA); ztlr_qr_kernel (unblocked) for
+//                          nb > 1024 (replaces LAPACKE_zgeqrf, hcore_zgemm.c:123, :205)
+//   ztlr_svd_kernel        T = R_u R_v^T (plain transpose, :309), truncated pivoted QR of T^H as preconditioner, one-sided
+//                          Jacobi on the columns of R^H with complex rotations, sort, truncation (rk > 0 = fixed rank, :376),
+//                          U_r, W = R_v (R_u^T conj(U_r))  (replaces LAPACKE_zgesvd + the conj/zunmqr/conj dance
+//                          of __znewv, :593-632: CV = Q_v W)
+//   ztlr_apply_wy_kernel   CU = Q_u [U_r; 0], CV = Q_v [W; 0]: the reflectors applied eight at a time through the T factors
+//                          of the QR kernel, 8 output columns per CTA in DMMA accumulator fragments; ztlr_apply_kernel
+//                          (one column per warp in shared memory) after the unblocked QR
+//                          (replaces LAPACKE_zunmqr, :470-530, :600-620)
 #pragma once
 #include "common.cuh"
 #include "wy_kernels.cuh"
@@ -456,6 +459,7 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                 }
                 zr[i][0] = v0.x; zi[i][0] = v0.y; zr[i][1] = v1.x; zi[i][1] = v1.y;
             }
+            PROF_ADD(56);
             // W^T partial: row c = g, columns i = 2 tg + {0, 1}; one accumulator pair per contraction chunk e, so that four
             // independent DMMAs separate every dependent pair (a warp issues in order: back-to-back dependent DMMAs wait 26 cycles)
             double wr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, wi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -474,6 +478,7 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                     dmma_884(wi[1][0], wi[1][1], zr[i][1], -v1.y);
                 }
             }
+            PROF_ADD(57);
             part[warp * 64 + g * 8 + 2 * tg] = zmake(wr[0][0] + wr[1][0], wi[0][0] + wi[1][0]);
             part[warp * 64 + g * 8 + 2 * tg + 1] = zmake(wr[0][1] + wr[1][1], wi[0][1] + wi[1][1]);
             __syncthreads();
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                 ntw[tid] = zmake(-acc.x, -acc.y);
             }
             __syncthreads();
+            PROF_ADD(58);
             const zc a[2] = {ntw[g * 8 + 2 * tg], ntw[g * 8 + 2 * tg + 1]};   // contraction chunks: reflectors 2 tg + h
 #pragma unroll
             for (int i = 0; i < kZQrRb; ++i) {
@@ -505,6 +511,7 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                     }
                 }
             }
+            PROF_ADD(59);
             if (col < n) {
 #pragma unroll
                 for (int i = 0; i < kZQrRb; ++i) {
