@@ -404,7 +404,14 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
                     const zc tw = zmul(ctau, dot), ntw1 = zmake(-tw.x, -tw.y);
                     __syncwarp();
                     if (lane == 0) pc[j] = zsub(pc[j], tw);
-                    for (int q = j + 1 + lane; q < m; q += 32) pc[q] = zfma(ntw1, pj[q], pc[q]);
+                    int q = j + 1 + lane;                                  // four rows per lane in flight (pj and pc never alias)
+                    for (; q + 96 < m; q += 128) {
+                        const zc v0 = pj[q], v1 = pj[q + 32], v2 = pj[q + 64], v3 = pj[q + 96];
+                        const zc x0 = pc[q], x1 = pc[q + 32], x2 = pc[q + 64], x3 = pc[q + 96];
+                        pc[q] = zfma(ntw1, v0, x0); pc[q + 32] = zfma(ntw1, v1, x1);
+                        pc[q + 64] = zfma(ntw1, v2, x2); pc[q + 96] = zfma(ntw1, v3, x3);
+                    }
+                    for (; q < m; q += 32) pc[q] = zfma(ntw1, pj[q], pc[q]);
                 }
             }
             __syncthreads();
@@ -484,8 +491,13 @@ __global__ void __launch_bounds__(512, 1) ztlr_qr_blocked_kernel(ZArgs ar, ZWork
             __syncthreads();
             if (tid < 64) {                                    // entry (c, k): sum the partials, then row i = k of T^H W
                 const int i = tid & 7;
-                zc s = zero;
-                for (int w = 0; w < nwarps; ++w) s = zadd(s, part[w * 64 + tid]);
+                zc s0 = zero, s1 = zero, s2 = zero, s3 = zero;     // sixteen loads in flight, four short chains
+#pragma unroll
+                for (int w = 0; w < 16; w += 4) {
+                    s0 = zadd(s0, part[w * 64 + tid]); s1 = zadd(s1, part[(w + 1) * 64 + tid]);
+                    s2 = zadd(s2, part[(w + 2) * 64 + tid]); s3 = zadd(s3, part[(w + 3) * 64 + tid]);
+                }
+                const zc s = zadd(zadd(s0, s1), zadd(s2, s3));
                 zc acc = zero;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {                  // (T^H W)(i, c) = sum_k conj(T(k, i)) W(k, c)
