@@ -116,7 +116,8 @@ def test_sgemm_batched_vs_oracle(ctx, nb, k, acc):
 
 
 @pytest.mark.parametrize("nb,k,acc,rk", [(96, 8, 1e-8, 0), (256, 16, 1e-8, 0), (200, 12, 1e-8, 5), (1024, 64, 1e-8, 0),
-                                         (384, 100, 1e-8, 0), (512, 128, 1e-8, 0), (300, 80, 1e-8, 150)])   # stack width 256
+                                         (384, 100, 1e-8, 0), (512, 128, 1e-8, 0), (300, 80, 1e-8, 150),   # stack width 256
+                                         (257, 9, 1e-8, 0)])                # odd nb: 16-byte access path of the blocked QR
 def test_zgemm_batched_vs_oracle(ctx, nb, k, acc, rk):
     """HCORE_zgemm_batched (config 4, complex leg) against the complex oracle (zgeqrf/zgesvd/zunmqr,
     plain-transpose tiles, reference src/compute/hcore_zgemm.c:165,189,309)."""
