@@ -8,6 +8,8 @@ The CUDA pipeline in ``hcore_b200/csrc`` does not call LAPACK; it uses
      ``R^T`` (4-column blocks, rotations derived from the 8 x 8 Gram matrix of a block pair), sorted, truncated with
      the reference's rule, ``W = T' U_r`` instead of accumulating V,
   3. application of the stored block reflectors to ``[Y; 0]``.
+The complex path (zgemm_kernels.cuh) factors its panels with a plain blocked Householder QR (8-column blocks, zlarft
+factors) and applies Q through the same factors: ``zqr_blocked`` / ``zapply_blocked`` at the end of this file.
 This file restates exactly that arithmetic in numpy so that (a) the math can be
 validated against the oracle on the CPU, and (b) per-stage device dumps can be
 compared with it when debugging.  It is never used by the product.
@@ -366,3 +368,71 @@ def tlr_gemm_model(au, av, bu, bv, cu, cv, *, alpha, beta, rk, maxrk, acc):
     fv = tsqr_factor(xv)
     u, wv, sig, r, sweeps = core_svd_model(fu["R"], fv["R"], rk, acc)
     return tsqr_apply(fu, u), tsqr_apply(fv, wv), r, sig, sweeps
+
+
+# ---- complex path: 8-column blocks with compact-WY factors (hcore_b200/csrc/zgemm_kernels.cuh) ---------------
+ZB = 8      # reflector block width of ztlr_qr_blocked_kernel / ztlr_apply_wy_kernel
+
+
+def _zlarfg(alpha, xn2):
+    """LAPACK zlarfg given alpha and the squared norm of the tail: beta (real), tau, 1 / (alpha - beta)."""
+    if xn2 == 0.0 and alpha.imag == 0.0:
+        return alpha.real, 0.0 + 0.0j, 0.0 + 0.0j
+    beta = -np.copysign(np.sqrt(abs(alpha) ** 2 + xn2), alpha.real)
+    return beta, complex((beta - alpha.real) / beta, -alpha.imag / beta), 1.0 / (alpha - beta)
+
+
+def _unit_lower(blk, j0):
+    """The reflector vectors of a factored block: stored part below the diagonal, unit diagonal, zero above."""
+    v = blk.copy()
+    for c in range(v.shape[1]):
+        v[: j0 + c, c] = 0.0
+        v[j0 + c, c] = 1.0
+    return v
+
+
+def zqr_blocked(x, b=ZB):
+    """Blocked Householder QR of a complex panel the way ztlr_qr_blocked_kernel does it: the b columns of a block are
+    factored column by column (zgeqr2 order, H^H applied inside the block), T is built with the zlarft recurrence
+    T(k,k) = tau_k, T(0:k,k) = -tau_k T(0:k,0:k) (V(:,0:k)^H v_k), and the trailing columns get
+    X <- X - V (T^H (V^H X)).  Returns (factored panel, tau, list of T blocks)."""
+    x = np.array(x, dtype=np.complex128)
+    m, n = x.shape
+    tau = np.zeros(n, dtype=np.complex128)
+    tf = []
+    for j0 in range(0, n, b):
+        nbk = min(b, n - j0)
+        for jj in range(nbk):
+            j = j0 + jj
+            beta, tj, scale = _zlarfg(x[j, j], float(np.vdot(x[j + 1:, j], x[j + 1:, j]).real))
+            tau[j] = tj
+            if tj != 0.0:
+                x[j, j] = beta
+            x[j + 1:, j] *= scale
+            v = np.concatenate(([1.0], x[j + 1:, j]))
+            for c in range(j + 1, j0 + nbk):
+                x[j:, c] -= np.conj(tj) * np.vdot(v, x[j:, c]) * v
+        vb = _unit_lower(x[:, j0:j0 + nbk], j0)
+        s = vb.conj().T @ vb
+        t = np.zeros((b, b), dtype=np.complex128)
+        for k in range(nbk):
+            t[k, k] = tau[j0 + k]
+            t[:k, k] = -tau[j0 + k] * (t[:k, :k] @ s[:k, k])
+        tf.append(t)
+        if j0 + nbk < n:
+            w = vb.conj().T @ x[:, j0 + nbk:]
+            x[:, j0 + nbk:] -= vb @ (t[:nbk, :nbk].conj().T @ w)
+    return x, tau, tf
+
+
+def zapply_blocked(xf, tf, y, b=ZB):
+    """Q [y; 0] the way ztlr_apply_wy_kernel does it: blocks of b reflectors, last block first, Z <- Z - V (T (V^H Z))."""
+    m, n = xf.shape
+    z = np.zeros((m, y.shape[1]), dtype=np.complex128)
+    z[: y.shape[0]] = y
+    for bk in range(len(tf) - 1, -1, -1):
+        j0 = bk * b
+        nbk = min(b, n - j0)
+        vb = _unit_lower(xf[:, j0:j0 + nbk], j0)
+        z -= vb @ (tf[bk][:nbk, :nbk] @ (vb.conj().T @ z))
+    return z

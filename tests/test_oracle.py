@@ -237,6 +237,49 @@ def test_device_model_block_jacobi_and_qrcp():
     assert np.abs(c[:4, 4:]).max() < 0.5                                       # one pass already reduces the cross cosines
 
 
+def test_device_model_complex_compact_wy():
+    """The complex path's blocked QR and reflector application (tests/device_model.py: zqr_blocked, zapply_blocked; device:
+    ztlr_qr_blocked_kernel, ztlr_apply_wy_kernel): 8-reflector blocks through their zlarft factors reproduce the
+    unblocked zgeqr2 / zunmqr results (R, tau, Q [y; 0]), including a partial last block and a column that is already
+    reduced (tau = 0)."""
+    rng = np.random.default_rng(11)
+    for m, n, r in ((64, 20, 7), (40, 16, 16), (33, 5, 3)):
+        x = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+        if n > 10:
+            x[3:, 2] = 0.0                                   # zlarfg: zero tail ...
+            x[2, 2] = x[2, 2].real                           # ... and real alpha -> tau = 0 at column 2 unless updates fill it
+        xf, tau, tf = dm.zqr_blocked(x)
+        # unblocked reference: H_j^H applied column by column to the whole panel
+        xr = x.copy()
+        taur = np.zeros(n, dtype=complex)
+        for j in range(n):
+            beta, tj, scale = dm._zlarfg(xr[j, j], float(np.vdot(xr[j + 1:, j], xr[j + 1:, j]).real))
+            taur[j] = tj
+            if tj != 0.0:
+                xr[j, j] = beta
+            xr[j + 1:, j] *= scale
+            v = np.concatenate(([1.0], xr[j + 1:, j]))
+            for c in range(j + 1, n):
+                xr[j:, c] -= np.conj(tj) * np.vdot(v, xr[j:, c]) * v
+        scale_x = np.linalg.norm(x)
+        assert np.abs(tau - taur).max() < 1e-13 and np.abs(xf - xr).max() < 1e-13 * scale_x
+        rr = np.triu(xf[:n])
+        assert np.allclose(np.abs(rr), np.abs(np.linalg.qr(x)[1]), atol=1e-12 * scale_x)
+        # Q [y; 0]: blocked against reflector-by-reflector (H_0 ... H_{n-1} applied last first)
+        y = rng.standard_normal((n, r)) + 1j * rng.standard_normal((n, r))
+        z = dm.zapply_blocked(xf, tf, y)
+        zr = np.zeros((m, r), dtype=complex)
+        zr[:n] = y
+        for j in range(n - 1, -1, -1):
+            v = np.zeros(m, dtype=complex)
+            v[j] = 1.0
+            v[j + 1:] = xf[j + 1:, j]
+            zr -= tau[j] * np.outer(v, v.conj() @ zr)
+        assert np.abs(z - zr).max() < 1e-13 * np.linalg.norm(y)
+        assert np.abs(z.conj().T @ z - y.conj().T @ y).max() < 1e-12 * np.linalg.norm(y) ** 2   # Q has orthonormal columns
+        assert np.abs(z - zr).max() < 1e-12 and np.linalg.norm(xf[:n, :][np.triu_indices(n)]) > 0
+
+
 def test_device_model_wide_stack_virtual_rows():
     """Stack wider than the TSQR row block (the device's width-256 case: 128-row blocks, up to 256 columns): rows
     h .. n-1 of R are virtual zero rows; R^T R = X^T X, Q has orthonormal columns and Q R = X."""
