@@ -826,7 +826,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     const int N = pick_width(maxrk, HCORE_B200_MAX_STACK_Z);
     const size_t per = (2ull * nb * N + 2ull * N * (1 + kZB) + 3ull * N * N) * sizeof(zc) + N * 8 + 16;
     int chunk = ctx->chunk_limit > 0 ? ctx->chunk_limit : (int)std::min<size_t>(ctx->num_sms * 4, (4ull << 30) / per);
-    chunk = std::max(1, std::min(chunk, ntiles));
+    chunk = std::max(1, std::min(std::min(chunk, ntiles), 32767));     // tile index in gridDim.z (apply) / 2 x tiles in gridDim.x (QR)
     CUDA_TRY(ctx, ctx->zpanel.reserve(2ull * chunk * nb * N * sizeof(zc)));
     CUDA_TRY(ctx, ctx->ztau.reserve(2ull * chunk * N * (1 + kZB) * sizeof(zc)));     // tau + the 8 x 8 compact-WY factors
     CUDA_TRY(ctx, ctx->zT.reserve((size_t)chunk * N * N * sizeof(zc)));
