@@ -848,6 +848,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
     if (nb <= 32 * kZRows)
         CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_qr_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_qrb));
     CUDA_TRY(ctx, cudaFuncSetAttribute(ztlr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_ap));
+    static const bool z_apply_scalar = getenv("HCORE_B200_Z_APPLY_SCALAR") != nullptr;   // measurement switch: one-column-per-warp application
     for (int t0 = 0; t0 < ntiles; t0 += chunk) {
         ZArgs ar{};
         ar.AU = (const zc *)d_AU; ar.AV = (const zc *)d_AV; ar.BU = (const zc *)d_BU; ar.BV = (const zc *)d_BV;
@@ -863,7 +864,7 @@ static int zgemm_launch(hcore_b200_handle_t ctx, int ntiles, int nb, hcore_b200_
         else ztlr_qr_kernel<<<2 * ar.ntiles, 512, sm_qr, st>>>(ar, ws);
         if (N <= 128) ztlr_svd_kernel<8><<<ar.ntiles, 512, 0, st>>>(ar, ws);
         else ztlr_svd_kernel<16><<<ar.ntiles, 256, 0, st>>>(ar, ws);
-        if (nb <= 32 * kZRows && !getenv("HCORE_B200_Z_APPLY_SCALAR")) ztlr_apply_wy_kernel<<<dim3((N + 7) / 8, 2, ar.ntiles), 512, 0, st>>>(ar, ws);
+        if (nb <= 32 * kZRows && !z_apply_scalar) ztlr_apply_wy_kernel<<<dim3((N + 7) / 8, 2, ar.ntiles), 512, 0, st>>>(ar, ws);
         else ztlr_apply_kernel<<<dim3((N + apw - 1) / apw, 2, ar.ntiles), 32 * apw, sm_ap, st>>>(ar, ws);
         ctx->launches += 4;
     }
